@@ -1,0 +1,173 @@
+/* sapio.h -- C-ABI of the B200-native Sapiogenesis world step.
+ *
+ * The reference (edgecase963/Sapiogenesis) has no FFI: its per-tick path is the Python call chain
+ *   Environment.update            physics.py:425-442
+ *     -> sprites.update_organisms sprites.py:1809-1856   (rules: Organism.update :1627-1681, _update_cell :1470-1606,
+ *                                                         neural.activate neural.py:91-366, neural.train_network :369-423,
+ *                                                         reproduction sprites.py:1441-1459)
+ *     -> pymunk.Space.step(0.06)  physics.py:432         (Chipmunk2D: broadphase, narrowphase, sequential impulses)
+ *     -> Sprite.updateSprite      physics.py:250-275     (viscous friction)
+ *     -> updateUI                 Sapiogenesis.py:57-65  (gas clamps, population recount)
+ * Each entry point below replaces one stage of that chain and cites it. All pointers are raw device
+ * pointers (CUDA library) or host pointers (oracle); the caller (PyTorch) owns every buffer including
+ * scratch. No torch types, no exceptions, no allocation, no ownership transfer across this boundary.
+ * Return value: 0 = ok, negative = SAPIO_E_*; message via sapio_last_error().
+ */
+#ifndef SAPIO_H
+#define SAPIO_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SAPIO_ABI_VERSION 1
+
+/* ---- fixed tile sizes ---- */
+#define SAPIO_MAXC   64                         /* cell rows per organism slot */
+#define SAPIO_NPAIR  (SAPIO_MAXC * (SAPIO_MAXC - 1) / 2)
+#define SAPIO_ICAP   192                        /* intra-organism contact slots per organism */
+#define SAPIO_MAXL   12                         /* linear layers per brain (input + <=10 hidden + output) */
+#define SAPIO_NWALL  4
+#define SAPIO_HIST   10                         /* neural.stimulation_memory (neural.py:34) */
+#define SAPIO_STM    30                         /* short-term memory cap (neural.py:315) */
+#define SAPIO_MEMROWS 232                       /* memory_limit 200 (+30 appended before the trim, neural.py:392-404) */
+
+/* ---- cell types: sprites.cell_types (sprites.py:22) + "heart" (sprites.py:573) ---- */
+enum {
+    SAPIO_T_BARRIER = 0, SAPIO_T_CARNIV = 1, SAPIO_T_EYE = 2, SAPIO_T_OLFACTORY = 3,
+    SAPIO_T_CO2C = 4, SAPIO_T_PUSH = 5, SAPIO_T_BODY = 6, SAPIO_T_ROTATE = 7, SAPIO_T_HEART = 8,
+    SAPIO_NTYPES = 9
+};
+
+/* c_alive values */
+enum { SAPIO_CELL_ABSENT = 0, SAPIO_CELL_ALIVE = 1, SAPIO_CELL_DYING = 2 /* died this tick, body not yet moved to the dead pool */ };
+
+/* org_flags bits */
+enum { SAPIO_F_IMMORTAL = 1, SAPIO_F_MALADAPTIVE = 2, SAPIO_F_FINITE_MEMORY = 4, SAPIO_F_MIRROR_X = 8, SAPIO_F_MIRROR_Y = 16 };
+
+/* org_req bits */
+enum { SAPIO_REQ_REPRODUCE = 1, SAPIO_REQ_THOUGHT = 2, SAPIO_REQ_TRAIN = 4 };
+
+/* g_stats slots */
+enum {
+    SAPIO_STAT_BIRTHS = 0, SAPIO_STAT_DEATHS = 1, SAPIO_STAT_CELL_DEATHS = 2, SAPIO_STAT_DEAD_REMOVED = 3,
+    SAPIO_STAT_THINKS = 4, SAPIO_STAT_TRAINS = 5, SAPIO_STAT_XCONTACTS = 6, SAPIO_STAT_ICONTACTS = 7,
+    SAPIO_STAT_BIRTH_FAIL_PLACE = 8, SAPIO_STAT_BIRTH_FAIL_CAPS = 9, SAPIO_STAT_OVERFLOW = 10,
+    SAPIO_STAT_ORG_TICKS = 11, SAPIO_STAT_LEVELS = 12, SAPIO_STAT_COUPLED = 13
+};
+
+/* phase mask for sapio_tick */
+enum {
+    SAPIO_PH_RULES = 1, SAPIO_PH_THINK = 2, SAPIO_PH_TRAIN = 4, SAPIO_PH_REPRODUCE = 8,
+    SAPIO_PH_STEP = 16, SAPIO_PH_FRICTION = 32, SAPIO_PH_POST = 64, SAPIO_PH_ALL = 127
+};
+
+enum { SAPIO_OK = 0, SAPIO_E_ARG = -1, SAPIO_E_CUDA = -2, SAPIO_E_WORKSPACE = -3, SAPIO_E_OVERFLOW = -4, SAPIO_E_NODEVICE = -5 };
+
+/* Frozen world parameters. Defaults and their reference sources: SURVEY.md Appendix B. */
+typedef struct SapioParams {
+    /* capacities */
+    int32_t n_org, n_dead, x_cap, in_cap, brain_cap, adam_cap, width_cap, pad0;
+    /* world: environment_settings.json:1, physics.py:280-345 */
+    float width, height, frame_width, wall_elast, wall_fric;
+    float dt_wall;            /* update_speed/1000 = 0.030 s: the uDiff of every rule (virtual clock) */
+    float dt_phys;            /* Environment.worldSpeed = 0.06 (physics.py:319-320) */
+    float friction_pct;       /* Environment.friction = 60 %/s (physics.py:283) */
+    /* cadences in ticks (virtual clock; sprites.py:41,53,55,62) */
+    int32_t think_ticks, train_ticks, repro_ticks, age_ticks;
+    /* sprites.py:37-65 */
+    float co2_ratio, dispersion_rate, heal_rate, mass_cutoff, break_damage, starvation_rate;
+    float max_push, max_rot, eyesight_mult, olfactory_mult;
+    /* Environment.info (physics.py:298-309), sprites.py:43 */
+    float mutation_severity, brain_mutation_severity, learning_rate;
+    int32_t population_limit, offspring_amount, weight_persistence, memory_limit;
+    /* Chipmunk space defaults */
+    int32_t iterations;
+    float collision_slop, collision_bias, joint_error_bias;
+    /* spawn recipe: add_creature_clicked widget defaults (Sapiogenesis.py:297-320); the size and
+     * mass ranges are also what mutate_cell_count re-uses (sprites.py:937-940) */
+    int32_t cell_lo, cell_hi, size_lo, size_hi, mass_lo, mass_hi, hidden_lo, hidden_hi;
+    float mirror_px, mirror_py;
+    /* RNG */
+    uint64_t seed;
+    /* grid */
+    float grid_cell;          /* broadphase cell edge (>= 2 * max solid radius) */
+    int32_t grid_nx, grid_ny, pad1;
+} SapioParams;
+
+/* The world: one raw pointer per SoA array of include/sapio_fields.def. */
+typedef struct SapioWorld {
+    SapioParams p;
+#define SAPIO_FIELD(name, ctype, scope, per) ctype *name;
+#include "sapio_fields.def"
+#undef SAPIO_FIELD
+} SapioWorld;
+
+/* body id space used for contact keys and canonical ordering */
+static inline uint32_t sapio_body_cell(const SapioParams *p, int org, int k) { (void)p; return (uint32_t)(org * SAPIO_MAXC + k); }
+static inline uint32_t sapio_body_dead(const SapioParams *p, int d) { return (uint32_t)(p->n_org * SAPIO_MAXC + d); }
+static inline uint32_t sapio_body_wall(const SapioParams *p, int w) { return (uint32_t)(p->n_org * SAPIO_MAXC + p->n_dead + w); }
+/* index of joint (i,j), i<j, in lexicographic order == Chipmunk constraint insertion order (sprites.py:1721-1726) */
+static inline int sapio_pair_index(int i, int j) { return i * (2 * SAPIO_MAXC - i - 1) / 2 + (j - i - 1); }
+
+/* ------------------------------------------------------------------------------------------------
+ * CUDA library entry points (libsapio_b200.so). `stream` is a cudaStream_t passed as void*.
+ * ---------------------------------------------------------------------------------------------- */
+int sapio_abi_version(void);
+const char *sapio_last_error(void);
+int sapio_device_count(void);
+
+/* scratch the caller must provide to every call below (grid tables, sort buffers, adjacency, levels) */
+size_t sapio_workspace_bytes(const SapioParams *p);
+
+/* One whole world tick == Environment.update (physics.py:425-442) with the hooks bound as at
+ * Sapiogenesis.py:687-688. `phases` = SAPIO_PH_* mask (SAPIO_PH_ALL for the full step). */
+int sapio_tick(const SapioWorld *w, void *ws, size_t ws_bytes, uint32_t phases, int n_ticks, void *stream);
+
+/* Stages, callable on their own (parity tests drive these one by one):                               */
+/* sprites.update_organisms: per-organism rules incl. think (neural.activate)          sprites.py:1809 */
+int sapio_rules(const SapioWorld *w, void *ws, size_t ws_bytes, uint32_t phases, void *stream);
+/* neural.train_network for every organism whose training is due                       neural.py:369   */
+int sapio_train(const SapioWorld *w, void *ws, size_t ws_bytes, void *stream);
+/* carnivore damage/eating gather, death -> dead bodies, gradual_dispersion, bounds    sprites.py:1326,1752,1849 */
+int sapio_settle(const SapioWorld *w, void *ws, size_t ws_bytes, void *stream);
+/* Organism.reproduce / DNA.mutate / get_new_organism_position / build_body            sprites.py:1441,1068,194,1698 */
+int sapio_reproduce(const SapioWorld *w, void *ws, size_t ws_bytes, void *stream);
+/* pymunk.Space.step(dt_phys)                                                          physics.py:432  */
+int sapio_space_step(const SapioWorld *w, void *ws, size_t ws_bytes, void *stream);
+/* Sprite.updateSprite for every solid sprite                                          physics.py:250  */
+int sapio_friction(const SapioWorld *w, void *stream);
+/* updateUI's simulation-relevant part: gas clamps, population recount                 Sapiogenesis.py:57-65 */
+int sapio_post(const SapioWorld *w, void *stream);
+
+/* Host-buffer variant used for the end-to-end figure and by a GUI host: uploads the per-tick control
+ * block (the values Sapiogenesis.py:82-85 re-reads from widgets each tick), runs n_ticks, downloads
+ * the render state the reference pushes to Qt (Sprite.setPos/setRotation, physics.py:253-272) and the
+ * UI counters (Sapiogenesis.py:62-69). Host pointers must be page-locked for async copies. */
+typedef struct SapioControl {
+    int32_t population_limit, offspring_amount, weight_persistence, repro_ticks;
+    float mutation_severity, brain_mutation_severity, learning_rate, pad;
+} SapioControl;
+typedef struct SapioFrameHeader {
+    double co2, o2; int64_t tick; int32_t population, n_dead_active; int64_t stats[16];
+} SapioFrameHeader;
+int sapio_tick_host(SapioWorld *w_device_resident_params, void *ws, size_t ws_bytes, uint32_t phases, int n_ticks,
+                    const SapioControl *h_control,      /* host, in  */
+                    SapioFrameHeader *h_header,         /* host, out */
+                    float *h_cell_pose,                 /* host, out: n_org*MAXC*4 floats (x, y, angle, alive) */
+                    float *h_dead_pose,                 /* host, out: n_dead*4 floats (x, y, angle, mass) */
+                    void *stream);
+
+/* Islands: pack/unpack one genome (cells table + growth tree + hidden widths + hidden weights) into a
+ * flat record for NCCL send/recv == pickle of sprites.DNA (Sapiogenesis.py:243-254,413-424). */
+size_t sapio_genome_record_floats(const SapioParams *p);
+int sapio_pack_genomes(const SapioWorld *w, const int32_t *d_org_idx, int n, float *d_records, void *stream);
+int sapio_unpack_genomes(const SapioWorld *w, void *ws, size_t ws_bytes, const float *d_records, int n, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAPIO_H */

@@ -1,0 +1,351 @@
+/* brain.c -- CPU oracle: neural.activate (neural.py:91-366), calculateStimulation (:60-75), train_network (:369-423),
+ * networks.Network.forward (networks.py:301-308), Trainer.train_epoch (networks.py:75-87) with torch.optim.Adam defaults.
+ * TEST INFRASTRUCTURE ONLY (see oracle.h). PINNED against the reference's own neural.py / networks.py (tests/golden/).
+ * The network is fp32 like torch's; scalar bookkeeping is double like Python's.
+ */
+#include "oracle.h"
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+static int layer_off(const int32_t *ldim, int layer) {
+    int off = 0;
+    for (int l = 0; l < layer; l++) off += ldim[l + 1] * ldim[l] + ldim[l + 1];
+    return off;
+}
+
+/* Network.forward: out = W_out(...W_1(sigmoid(W_in x + b_in)) + b_1...) + b_out -- sigmoid after the first layer only */
+void oracle_forward(const float *brain, const int32_t *ldim, int nl, const float *x, float *out, float *acts) {
+    float buf[2][1024];
+    const float *cur = x;
+    int off = 0;
+    for (int l = 0; l < nl; l++) {
+        int fin = ldim[l], fout = ldim[l + 1];
+        const float *W = brain + off, *b = W + fout * fin;
+        float *dst = (l == nl - 1) ? out : buf[l & 1];
+        for (int r = 0; r < fout; r++) {
+            float s = 0.0f;
+            for (int c = 0; c < fin; c++) s += W[r * fin + c] * cur[c];
+            s += b[r];
+            if (l == 0) s = 1.0f / (1.0f + expf(-s));
+            dst[r] = s;
+        }
+        if (acts && l == 0) memcpy(acts, dst, sizeof(float) * (size_t)fout);
+        cur = dst;
+        off += fout * fin + fout;
+    }
+}
+
+/* Python round(x, 1) of a float, times 10, as an integer key (neural.py:77-78). Correctly rounded, ties decided on the
+ * exact binary value (glibc printf does exactly that). */
+int oracle_key1(double x) {
+    char s[64];
+    snprintf(s, sizeof(s), "%.1f", x);
+    double r = strtod(s, NULL) * 10.0;
+    return (int)lrint(r);
+}
+/* key of a short-term-memory input: it is a Python float holding the fp32 value (tensor.tolist()) */
+static int key_stm(float x) { return oracle_key1((double)x); }
+/* key of a stored training input: roundList(mem[0], 3) re-rounded the value to the double nearest k/1000 (neural.py:393) */
+static double stored_value(float x) {
+    char s[64];
+    snprintf(s, sizeof(s), "%.3f", (double)x);
+    return strtod(s, NULL);
+}
+static int key_mem(float x) { return oracle_key1(stored_value(x)); }
+
+/* view of one sensor == overlap of the sensor disc (centre: the SENSOR BODY) with solid cells of other organisms and dead
+ * cells not descended from this organism (eye_segment_handler, sprites.py:221-236; contract C3). Calls cb per member in
+ * ascending body id. Predicate in double on fp32 positions, strict (SURVEY A-3). */
+typedef void (*view_cb)(void *ctx, uint32_t body, double x, double y, double r, int alive);
+static void for_each_viewed(const SapioWorld *w, int o, int row, double R, view_cb cb, void *ctx) {
+    const SapioParams *p = &w->p;
+    double sx = w->c_spos[2 * row], sy = w->c_spos[2 * row + 1];
+    for (int oo = 0; oo < p->n_org; oo++) {
+        if (oo == o || w->org_state[oo] != 1) continue;
+        for (int k = 0; k < w->org_ncells[oo]; k++) {
+            int r2 = oo * MAXC + k;
+            if (w->c_alive[r2] == 0) continue;
+            double x = w->c_pos[2 * r2], y = w->c_pos[2 * r2 + 1], rad = w->c_size[r2] * 0.5;
+            double dx = x - sx, dy = y - sy, md = R + rad;
+            if (dx * dx + dy * dy < md * md) cb(ctx, (uint32_t)r2, x, y, rad, 1);
+        }
+    }
+    for (int d = 0; d < p->n_dead; d++) {
+        if (!w->d_state[d] || w->d_owner[d] == w->org_uid[o]) continue;
+        double x = w->d_pos[2 * d], y = w->d_pos[2 * d + 1], rad = w->d_size[d] * 0.5;
+        double dx = x - sx, dy = y - sy, md = R + rad;
+        if (dx * dx + dy * dy < md * md) cb(ctx, (uint32_t)(p->n_org * MAXC + d), x, y, rad, 0);
+    }
+}
+
+typedef struct { double px, py, R, rot; double eye[8]; double smell; uint32_t *hits; int nhits, cap; } SenseCtx;
+
+/* _adv_get_eye_input (neural.py:123-196, SURVEY E-5) */
+static void eye_cb(void *vctx, uint32_t body, double x, double y, double r, int alive) {
+    SenseCtx *c = (SenseCtx *)vctx; (void)alive;
+    if (c->hits && c->nhits < c->cap) c->hits[c->nhits] = body;
+    c->nhits++;
+    double ang = atan2(y - c->py, x - c->px) - c->rot;
+    double dx = cos(ang), dy = sin(ang);
+    double dist = sqrt((x - c->px) * (x - c->px) + (y - c->py) * (y - c->py));
+    double val = fabs((c->R - (dist + r)) / c->R);
+    int idx;
+    if (dx >= 0.0) { if (dy < 0.0) idx = dx < .707 ? 0 : 1; else idx = dx >= .707 ? 2 : 3; }
+    else { if (dy >= 0.0) idx = dy >= .707 ? 4 : 5; else idx = dx < -.707 ? 6 : 7; }
+    if (c->eye[idx] < val) c->eye[idx] = val;
+}
+/* _get_olfactory_input (neural.py:197-218) */
+static void smell_cb(void *vctx, uint32_t body, double x, double y, double r, int alive) {
+    SenseCtx *c = (SenseCtx *)vctx;
+    if (c->hits && c->nhits < c->cap) c->hits[c->nhits] = body;
+    c->nhits++;
+    if (alive) return;
+    double dist = sqrt((x - c->px) * (x - c->px) + (y - c->py) * (y - c->py));
+    double val = fabs((c->R - (dist + r)) / c->R);
+    if (val > c->smell) c->smell = val;
+}
+
+/* parity probe: the view (hit list) of sensor cell `row`; returns the member count */
+int oracle_sensor_view(const SapioWorld *w, int o, int k, uint32_t *hits, int cap) {
+    int row = o * MAXC + k, t = w->c_type[row];
+    SenseCtx c; memset(&c, 0, sizeof(c));
+    c.hits = hits; c.cap = cap; c.px = w->c_pos[2 * row]; c.py = w->c_pos[2 * row + 1];
+    c.R = (double)w->c_size[row] * (t == SAPIO_T_EYE ? w->p.eyesight_mult : w->p.olfactory_mult);
+    for_each_viewed(w, o, row, c.R, t == SAPIO_T_EYE ? eye_cb : smell_cb, &c);
+    return c.nhits;
+}
+
+/* builds the (unrounded) input vector of organism o; returns its length */
+int oracle_inputs(const SapioWorld *w, int o, const double *energy, const uint8_t *alive, double rotation_deg, double *in) {
+    int n = 0;
+    for (int q = 0; q < w->org_nincell[o]; q++) {
+        int k = w->org_incell[o * MAXC + q], row = o * MAXC + k, t = w->c_type[row];
+        SenseCtx c; memset(&c, 0, sizeof(c));
+        c.px = w->c_pos[2 * row]; c.py = w->c_pos[2 * row + 1];
+        c.rot = rotation_deg * (M_PI / 180.0);
+        if (t == SAPIO_T_EYE) {
+            c.R = (double)w->c_size[row] * w->p.eyesight_mult;                  /* sight_range (sprites.py:301) */
+            if (alive[k] == 1) for_each_viewed(w, o, row, c.R, eye_cb, &c);
+            for (int i = 0; i < 8; i++) in[n++] = c.eye[i];
+        } else {
+            c.R = (double)w->c_size[row] * w->p.olfactory_mult;                 /* smell_range (sprites.py:313) */
+            if (alive[k] == 1) for_each_viewed(w, o, row, c.R, smell_cb, &c);
+            in[n++] = c.smell;
+        }
+    }
+    in[n++] = w->org_move[4 * o + 1];                                            /* speed, x_direction, y_direction (neural.py:239-244) */
+    in[n++] = w->org_move[4 * o + 2];
+    in[n++] = w->org_move[4 * o + 3];
+    double cur = 0, mx = 0;                                                      /* _get_energy_input (neural.py:227-233) */
+    for (int k = 0; k < w->org_ncells[o]; k++) { if (alive[k] == 1) cur += energy[k]; mx += w->c_storage[o * MAXC + k]; }
+    in[n++] = (cur / mx * 100.0) / 100.;
+    return n;
+}
+
+/* neural.activate. History/STM are rings indexed by a running count (slot = count % capacity). */
+int oracle_think(SapioWorld *w, int o, const double *health, const double *energy, const uint8_t *alive, double rotation_deg) {
+    (void)health;
+    const SapioParams *p = &w->p;
+    const int IN = p->in_cap;
+    const int32_t *ldim = w->org_ldim + o * 16;
+    int nl = w->org_nlayers[o], I = ldim[0];
+    double raw[1024];
+    float x[1024], out[4];
+    int n = oracle_inputs(w, o, energy, alive, rotation_deg, raw);
+    if (n != I) return -1;
+    for (int i = 0; i < I; i++) x[i] = rintf((float)raw[i] * 1000.0f) / 1000.0f;      /* neural.py:285 (torch.round: half-even) */
+    const float *brain = w->org_brain + (size_t)o * p->brain_cap;
+    oracle_forward(brain, ldim, nl, x, out, NULL);
+    for (int i = 0; i < 4; i++) w->org_out_raw[4 * o + i] = out[i];
+    for (int i = 0; i < 4; i++) out[i] = rintf(out[i] * 1000.0f) / 1000.0f;            /* neural.py:292 */
+    int32_t T = (int32_t)w->g_tick[0];
+    uint32_t r[4];
+    sapio_rng4(p->seed, w->org_uid[o], T, SAPIO_RNG_BOREDOM, 0, r);
+    if ((double)sapio_u01(r[0]) <= (double)w->org_boredom[o]) {                       /* neural.py:294-295 */
+        sapio_rng4(p->seed, w->org_uid[o], T, SAPIO_RNG_RANDN, 0, r);
+        for (int h = 0; h < 2; h++) {                                                  /* Box-Muller on (0,1] x [0,1) */
+            double u1 = ((double)(r[2 * h] >> 8) + 1.0) / 16777216.0, u2 = (double)sapio_u01(r[2 * h + 1]);
+            double rad = sqrt(-2.0 * log(u1)), th = 2.0 * M_PI * u2;
+            out[2 * h] = (float)(rad * cos(th)); out[2 * h + 1] = (float)(rad * sin(th));
+        }
+    }
+    /* previousInputs/Outputs/Dopamine append (neural.py:301-303); list before the append has nv entries */
+    int cnt = w->org_hist_n[o], nv = cnt < SAPIO_HIST ? cnt : SAPIO_HIST;
+    float *hin = w->org_hist_in + (size_t)o * SAPIO_HIST * IN, *hout = w->org_hist_out + o * 40, *hdo = w->org_hist_dopa + o * 10;
+    double dopamine = w->org_dopamine[o], pain = w->org_pain[o];
+    if ((fabs(dopamine) > 0.1 || fabs(pain) > 0.1) && nv + 1 > 3) {                    /* neural.py:305-311 */
+        int s4 = (cnt - 3) % SAPIO_HIST;                                               /* previousInputs[-4] == old[nv-3] */
+        int sc = w->org_stm_n[o], slot = sc % SAPIO_STM;
+        float *sin_ = w->org_stm_in + ((size_t)o * SAPIO_STM + slot) * IN;
+        memcpy(sin_, hin + (size_t)s4 * IN, sizeof(float) * (size_t)I);
+        memcpy(w->org_stm_out + (o * SAPIO_STM + slot) * 4, hout + s4 * 4, sizeof(float) * 4);
+        double d2 = hdo[(cnt - 2) % SAPIO_HIST], d1 = hdo[(cnt - 1) % SAPIO_HIST];
+        w->org_stm_rew[o * SAPIO_STM + slot] = (float)((((0.0 + d2) + d1) + dopamine) / 3);
+        w->org_stm_n[o] = sc + 1;
+    }
+    int slot = cnt % SAPIO_HIST;
+    memcpy(hin + (size_t)slot * IN, x, sizeof(float) * (size_t)I);
+    memcpy(hout + slot * 4, out, sizeof(float) * 4);
+    hdo[slot] = (float)dopamine;
+    w->org_hist_n[o] = cnt + 1;
+    /* outputs -> movement, clamped to [-1, 1] (neural.py:320-349) */
+    for (int i = 0; i < 4; i++) { float v = out[i]; v = v > 1.0f ? 1.0f : (v < -1.0f ? -1.0f : v); w->org_move[4 * o + i] = v; }
+    /* calculateStimulation (neural.py:60-75): fp32 tensor arithmetic, oldest entry first */
+    int nn = (cnt + 1) < SAPIO_HIST ? (cnt + 1) : SAPIO_HIST;
+    float stim_sum = 0.0f;
+    for (int i = 0; i < I; i++) {
+        float s = 0.0f;
+        for (int e = 0; e < nn; e++) { int sl = (cnt + 1 - nn + e) % SAPIO_HIST; s = s + hin[(size_t)sl * IN + i]; }
+        float avg = s / (float)nn;
+        stim_sum = stim_sum + fabsf(avg);
+    }
+    double new_stim = (double)(stim_sum / (float)I);
+    float *sh = w->org_stim_hist + 10 * o;                                             /* neural.py:354-357 */
+    for (int i = 0; i < 9; i++) sh[i] = sh[i + 1];
+    sh[9] = (float)new_stim;
+    double avg = 0; for (int i = 0; i < 10; i++) avg += (double)sh[i];
+    avg /= 10;
+    double stimulation = fabs(new_stim - avg);
+    double cur = w->org_curiosity[o];
+    w->org_stimulation[o] = (float)stimulation;
+    w->org_boredom[o] = (float)((stimulation != 0 && cur != 0) ? (1.0 - stimulation) * cur : 0.0);
+    return 0;
+}
+
+/* neural.train_network (neural.py:369-423) for organism o.
+ * Storage policy for the curated memory (a Python list in the reference): a replaced key is overwritten in place and the
+ * trim moves the last row into the hole, instead of list.pop + append. Keys are unique, so only the fp summation order of the
+ * batch and the tie-break of equal minimal rewards can tell the difference. */
+int oracle_train_one(SapioWorld *w, int o) {
+    const SapioParams *p = &w->p;
+    const int IN = p->in_cap;
+    const int32_t *ldim = w->org_ldim + o * 16;
+    int nl = w->org_nlayers[o], I = ldim[0];
+    int sc = w->org_stm_n[o], sn = sc < SAPIO_STM ? sc : SAPIO_STM;
+    float *min_ = w->org_mem_in + (size_t)o * SAPIO_MEMROWS * IN, *mout = w->org_mem_out + (size_t)o * SAPIO_MEMROWS * 4;
+    float *mrew = w->org_mem_rew + (size_t)o * SAPIO_MEMROWS;
+    int M = w->org_mem_n[o];
+    for (int i = 0; i < sn; i++) {                                                     /* chronological */
+        int si = (sc - sn + i) % SAPIO_STM;
+        const float *xin = w->org_stm_in + ((size_t)o * SAPIO_STM + si) * IN;
+        /* best action among short-term memories with the same 1-dp key; sorted(...)[-1] keeps the LAST of equal maxima */
+        int best = si;
+        double best_r = -INFINITY;
+        for (int j = 0; j < sn; j++) {
+            int sj = (sc - sn + j) % SAPIO_STM;
+            const float *xj = w->org_stm_in + ((size_t)o * SAPIO_STM + sj) * IN;
+            int same = 1;
+            for (int c = 0; c < I && same; c++) same = key_stm(xj[c]) == key_stm(xin[c]);
+            if (!same) continue;
+            double rj = w->org_stm_rew[o * SAPIO_STM + sj];
+            if (rj >= best_r) { best_r = rj; best = sj; }
+        }
+        int add = 1, found = -1;
+        for (int m = 0; m < M && found < 0; m++) {                                      /* rounded_training_data.index (first match) */
+            int same = 1;
+            for (int c = 0; c < I && same; c++) same = key_mem(min_[(size_t)m * IN + c]) == key_stm(xin[c]);
+            if (same) found = m;
+        }
+        int dst = M;
+        if (found >= 0) { if ((double)mrew[found] > best_r) add = 0; else dst = found; }
+        if (add) {
+            if (dst == M) { if (M >= SAPIO_MEMROWS) continue; M++; }
+            memcpy(min_ + (size_t)dst * IN, xin, sizeof(float) * (size_t)I);          /* roundList(mem[0], 3) == the fp32 value again */
+            memcpy(mout + dst * 4, w->org_stm_out + (o * SAPIO_STM + best) * 4, sizeof(float) * 4);
+            mrew[dst] = w->org_stm_rew[o * SAPIO_STM + si];                             /* sic: mem[2], not bestReward (neural.py:395) */
+        }
+    }
+    while (M > p->memory_limit && (w->org_flags[o] & SAPIO_F_FINITE_MEMORY)) {          /* neural.py:399-404 */
+        int lo = 0;
+        for (int m = 1; m < M; m++) if (mrew[m] < mrew[lo]) lo = m;
+        M--;
+        if (lo != M) {
+            memcpy(min_ + (size_t)lo * IN, min_ + (size_t)M * IN, sizeof(float) * (size_t)I);
+            memcpy(mout + lo * 4, mout + M * 4, sizeof(float) * 4);
+            mrew[lo] = mrew[M];
+        }
+    }
+    w->org_mem_n[o] = M;
+    if (M > 0) {
+        /* Trainer.train_epoch (networks.py:75-87): full batch, MSELoss(mean), Adam on input+output layers only */
+        float *brain = w->org_brain + (size_t)o * p->brain_cap;
+        int h0 = ldim[1], hl = ldim[nl - 1];
+        int off_out = layer_off(ldim, nl - 1);
+        float *Win = brain, *bin = brain + h0 * I, *Wout = brain + off_out, *bout = Wout + 4 * hl;
+        int np_in = h0 * I + h0, np_out = 4 * hl + 4;
+        double *g = (double *)calloc((size_t)(np_in + np_out), sizeof(double));
+        float *H = (float *)malloc(sizeof(float) * 1024 * (size_t)(nl + 1));
+        double loss = 0;
+        for (int m = 0; m < M; m++) {
+            const float *x = min_ + (size_t)m * IN, *y = mout + m * 4;
+            /* forward keeping every layer's activation */
+            const float *cur = x; int off = 0;
+            for (int l = 0; l < nl; l++) {
+                int fin = ldim[l], fout = ldim[l + 1];
+                const float *W = brain + off, *b = W + fout * fin;
+                float *dst = H + 1024 * (size_t)(l + 1);
+                for (int r = 0; r < fout; r++) {
+                    float s = 0.0f;
+                    for (int c = 0; c < fin; c++) s += W[r * fin + c] * cur[c];
+                    s += b[r];
+                    if (l == 0) s = 1.0f / (1.0f + expf(-s));
+                    dst[r] = s;
+                }
+                cur = dst; off += fout * fin + fout;
+            }
+            const float *O = H + 1024 * (size_t)nl;
+            float dO[4];
+            for (int q = 0; q < 4; q++) { float e = O[q] - y[q]; loss += (double)e * e; dO[q] = 2.0f * e / (float)(M * 4); }
+            const float *Hl = (nl >= 2) ? H + 1024 * (size_t)(nl - 1) : x;
+            for (int q = 0; q < 4; q++) {
+                for (int c = 0; c < hl; c++) g[np_in + q * hl + c] += (double)(dO[q] * Hl[c]);
+                g[np_in + 4 * hl + q] += (double)dO[q];
+            }
+            /* back through the activation-free hidden chain to the first layer's output */
+            float d[2][1024];
+            int cur_d = 0;
+            for (int c = 0; c < hl; c++) { float s = 0; for (int q = 0; q < 4; q++) s += dO[q] * Wout[q * hl + c]; d[0][c] = s; }
+            for (int l = nl - 2; l >= 1; l--) {
+                int fin = ldim[l], fout = ldim[l + 1];
+                const float *W = brain + layer_off(ldim, l);
+                for (int c = 0; c < fin; c++) { float s = 0; for (int r = 0; r < fout; r++) s += d[cur_d][r] * W[r * fin + c]; d[cur_d ^ 1][c] = s; }
+                cur_d ^= 1;
+            }
+            const float *H0 = H + 1024;
+            for (int r = 0; r < h0; r++) {
+                float dz = d[cur_d][r] * H0[r] * (1.0f - H0[r]);
+                for (int c = 0; c < I; c++) g[r * I + c] += (double)(dz * x[c]);
+                g[h0 * I + r] += (double)dz;
+            }
+        }
+        w->org_loss[o] = (float)(loss / (M * 4));
+        /* torch.optim.Adam defaults: betas (0.9, 0.999), eps 1e-8, no weight decay */
+        int t = ++w->org_adam_t[o];
+        float lr = p->learning_rate, b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
+        double bc1 = 1.0 - pow((double)b1, t), bc2 = 1.0 - pow((double)b2, t);
+        float step_size = (float)((double)lr / bc1), bc2s = (float)sqrt(bc2);
+        float *am = w->org_adam_m + (size_t)o * p->adam_cap, *av = w->org_adam_v + (size_t)o * p->adam_cap;
+        for (int i = 0; i < np_in + np_out; i++) {
+            float gi = (float)g[i];
+            float *prm = i < h0 * I ? &Win[i] : (i < np_in ? &bin[i - h0 * I] : (i < np_in + 4 * hl ? &Wout[i - np_in] : &bout[i - np_in - 4 * hl]));
+            am[i] = b1 * am[i] + (1.0f - b1) * gi;
+            av[i] = b2 * av[i] + (1.0f - b2) * gi * gi;
+            float denom = sqrtf(av[i]) / bc2s + eps;
+            *prm = *prm - step_size * (am[i] / denom);
+        }
+        free(g); free(H);
+    }
+    w->org_train_tick[o] = (int32_t)w->g_tick[0];
+    w->g_stats[SAPIO_STAT_TRAINS]++;
+    return 0;
+}
+
+int oracle_train(SapioWorld *w) {
+    for (int o = 0; o < w->p.n_org; o++) {
+        if (w->org_state[o] != 1 || !(w->org_req[o] & SAPIO_REQ_TRAIN)) continue;
+        oracle_train_one(w, o);
+    }
+    return 0;
+}
