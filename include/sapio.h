@@ -141,7 +141,7 @@ int sapio_space_step(const SapioWorld *w, void *ws, size_t ws_bytes, void *strea
 /* Sprite.updateSprite for every solid sprite                                          physics.py:250  */
 int sapio_friction(const SapioWorld *w, void *stream);
 /* updateUI's simulation-relevant part: gas clamps, population recount                 Sapiogenesis.py:57-65 */
-int sapio_post(const SapioWorld *w, void *stream);
+int sapio_post(const SapioWorld *w, void *ws, size_t ws_bytes, void *stream);
 
 /* Host-buffer variant used for the end-to-end figure and by a GUI host: uploads the per-tick control
  * block (the values Sapiogenesis.py:82-85 re-reads from widgets each tick), runs n_ticks, downloads

@@ -455,6 +455,16 @@ int oracle_space_step(SapioWorld *w) {
     }
     for (int c = 0; c < xn; c++) { w->x_key[c] = xkey[c]; w->x_jn[c] = (float)X[c].jn; w->x_jt[c] = (float)X[c].jt; }
     w->g_x_n[0] = xn;
+    {   /* adjacency by body: partners ascending (smaller ids, then larger ids, walls last); walls own no list */
+        int *cnt = (int *)calloc((size_t)WALL0 + 1, sizeof(int));
+        for (int c = 0; c < xn; c++) { int a = (int)(xkey[c] >> 32), b = (int)(xkey[c] & 0xFFFFFFFFu); cnt[a]++; if (b < WALL0) cnt[b]++; }
+        int acc = 0;
+        for (int b = 0; b <= WALL0; b++) { w->xa_off[b] = acc; acc += (b < WALL0) ? cnt[b] : 0; }
+        memset(cnt, 0, sizeof(int) * ((size_t)WALL0 + 1));
+        for (int c = 0; c < xn; c++) { int a = (int)(xkey[c] >> 32), b = (int)(xkey[c] & 0xFFFFFFFFu); if (b < WALL0) w->xa_other[w->xa_off[b] + cnt[b]++] = (uint32_t)a; }
+        for (int c = 0; c < xn; c++) { int a = (int)(xkey[c] >> 32), b = (int)(xkey[c] & 0xFFFFFFFFu); w->xa_other[w->xa_off[a] + cnt[a]++] = (uint32_t)b; }
+        free(cnt);
+    }
     w->g_stepped[0] = 1;
     w->g_stats[SAPIO_STAT_XCONTACTS] = xn;
     w->g_stats[SAPIO_STAT_ICONTACTS] = n_ic_total;

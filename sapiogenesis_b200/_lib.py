@@ -1,0 +1,56 @@
+"""ctypes binding of libsapio_b200.so -- the hand-written sm_100a CUDA path behind include/sapio.h.
+
+There is no CPU implementation in this package: if the library is missing or no CUDA device is present,
+every compute call raises. (The CPU oracle under oracle/ is test infrastructure and is never imported here.)
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+from .world import SapioParams, SapioWorldStruct
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libsapio_b200.so")
+_lib = None
+
+
+class SapioError(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise SapioError(f"{SO_PATH} is not built: run `python -m sapiogenesis_b200.build` "
+                         "(nvcc, sm_100a). There is no CPU fallback.")
+    L = ctypes.CDLL(SO_PATH)
+    wp, vp, sz, u32, i32 = ctypes.POINTER(SapioWorldStruct), ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_int
+    L.sapio_abi_version.restype = i32
+    L.sapio_last_error.restype = ctypes.c_char_p
+    L.sapio_device_count.restype = i32
+    L.sapio_workspace_bytes.argtypes = [ctypes.POINTER(SapioParams)]; L.sapio_workspace_bytes.restype = sz
+    L.sapio_tick.argtypes = [wp, vp, sz, u32, i32, vp]; L.sapio_tick.restype = i32
+    L.sapio_space_step.argtypes = [wp, vp, sz, vp]; L.sapio_space_step.restype = i32
+    L.sapio_friction.argtypes = [wp, vp]; L.sapio_friction.restype = i32
+    L.sapio_post.argtypes = [wp, vp, sz, vp]; L.sapio_post.restype = i32
+    for name in ("sapio_rules",):
+        if hasattr(L, name):
+            getattr(L, name).argtypes = [wp, vp, sz, u32, vp]; getattr(L, name).restype = i32
+    for name in ("sapio_train", "sapio_settle", "sapio_reproduce"):
+        if hasattr(L, name):
+            getattr(L, name).argtypes = [wp, vp, sz, vp]; getattr(L, name).restype = i32
+    if hasattr(L, "sapio_spawn"):
+        L.sapio_spawn.argtypes = [wp, vp, sz, ctypes.c_void_p, i32, vp]; L.sapio_spawn.restype = i32
+    if L.sapio_abi_version() != 1:
+        raise SapioError("libsapio_b200.so ABI version mismatch")
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().sapio_last_error().decode(errors="replace")
+        raise SapioError(f"{what} failed ({rc}): {msg}")

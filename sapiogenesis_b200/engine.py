@@ -1,0 +1,78 @@
+"""Engine: drives a `World` on one CUDA device through libsapio_b200.so.
+
+This is the object behind `physics.Environment.update` (physics.py:425-442): one call == one world tick
+(rules -> Space.step -> friction -> UI bookkeeping), or any single stage of it. PyTorch supplies the device
+buffers, the stream and the workspace; every kernel is ours.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+from .world import PH_ALL, World
+
+
+class Engine:
+    def __init__(self, world: World, stream: torch.cuda.Stream | None = None):
+        if world.device.type != "cuda":
+            raise _lib.SapioError("Engine needs a CUDA world: this package has no CPU path "
+                                  "(use world.to('cuda'))")
+        self.lib = _lib.load()
+        if self.lib.sapio_device_count() <= 0:
+            raise _lib.SapioError("no CUDA device visible")
+        self.world = world
+        self.stream = stream
+        nbytes = int(self.lib.sapio_workspace_bytes(ctypes.byref(world.p)))
+        self.workspace = torch.zeros(nbytes, dtype=torch.uint8, device=world.device)
+        self._ws = (ctypes.c_void_p(self.workspace.data_ptr()), ctypes.c_size_t(nbytes))
+        self._struct = world.struct()
+
+    def _stream_ptr(self):
+        s = self.stream if self.stream is not None else torch.cuda.current_stream(self.world.device)
+        return ctypes.c_void_p(s.cuda_stream)
+
+    def _ref(self):
+        return ctypes.byref(self._struct)
+
+    def refresh(self):
+        """Call after replacing a tensor of the world (pointers are cached)."""
+        self._struct = self.world.struct()
+
+    # -- whole tick ------------------------------------------------------------------------------
+    def tick(self, n: int = 1, phases: int = PH_ALL):
+        with torch.cuda.device(self.world.device):
+            _lib.check(self.lib.sapio_tick(self._ref(), *self._ws, phases, n, self._stream_ptr()), "sapio_tick")
+
+    # -- stages ----------------------------------------------------------------------------------
+    def space_step(self):
+        with torch.cuda.device(self.world.device):
+            _lib.check(self.lib.sapio_space_step(self._ref(), *self._ws, self._stream_ptr()), "sapio_space_step")
+
+    def friction(self):
+        with torch.cuda.device(self.world.device):
+            _lib.check(self.lib.sapio_friction(self._ref(), self._stream_ptr()), "sapio_friction")
+
+    def post(self):
+        with torch.cuda.device(self.world.device):
+            _lib.check(self.lib.sapio_post(self._ref(), *self._ws, self._stream_ptr()), "sapio_post")
+
+    def rules(self, phases: int = PH_ALL):
+        with torch.cuda.device(self.world.device):
+            _lib.check(self.lib.sapio_rules(self._ref(), *self._ws, phases, self._stream_ptr()), "sapio_rules")
+
+    def train(self):
+        with torch.cuda.device(self.world.device):
+            _lib.check(self.lib.sapio_train(self._ref(), *self._ws, self._stream_ptr()), "sapio_train")
+
+    def settle(self):
+        with torch.cuda.device(self.world.device):
+            _lib.check(self.lib.sapio_settle(self._ref(), *self._ws, self._stream_ptr()), "sapio_settle")
+
+    def reproduce(self):
+        with torch.cuda.device(self.world.device):
+            _lib.check(self.lib.sapio_reproduce(self._ref(), *self._ws, self._stream_ptr()), "sapio_reproduce")
+
+    def synchronize(self):
+        torch.cuda.synchronize(self.world.device)

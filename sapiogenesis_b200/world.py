@@ -125,11 +125,12 @@ def default_params(n_org: int = 16, n_dead: int = 256, width: float = 3180.0, he
 _CT = {
     "uint8_t": (torch.uint8, ctypes.c_uint8), "int8_t": (torch.int8, ctypes.c_int8),
     "int16_t": (torch.int16, ctypes.c_int16), "uint16_t": (torch.int16, ctypes.c_uint16),
-    "int32_t": (torch.int32, ctypes.c_int32), "int64_t": (torch.int64, ctypes.c_int64),
+    "int32_t": (torch.int32, ctypes.c_int32), "uint32_t": (torch.int32, ctypes.c_uint32),
+    "int64_t": (torch.int64, ctypes.c_int64),
     "uint64_t": (torch.int64, ctypes.c_uint64), "float": (torch.float32, ctypes.c_float),
     "double": (torch.float64, ctypes.c_double),
 }
-_NP_VIEW = {"uint16_t": np.uint16, "uint64_t": np.uint64}
+_NP_VIEW = {"uint16_t": np.uint16, "uint32_t": np.uint32, "uint64_t": np.uint64}
 
 
 @dataclass
@@ -160,7 +161,7 @@ class SapioWorldStruct(ctypes.Structure):
 
 def _rows(p: SapioParams, scope: str) -> int:
     return {"ORG": p.n_org, "CELL": p.n_org * MAXC, "PAIR": p.n_org * NPAIR, "ICON": p.n_org * ICAP,
-            "DEAD": p.n_dead, "XCON": p.x_cap, "GLOB": 1}[scope]
+            "DEAD": p.n_dead, "XCON": p.x_cap, "GLOB": 1, "BODY1": p.n_org * MAXC + p.n_dead + 1}[scope]
 
 
 def _per(p: SapioParams, per: str) -> int:
