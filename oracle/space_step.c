@@ -344,7 +344,7 @@ int oracle_space_step(SapioWorld *w) {
         iccode[o] = (uint16_t *)calloc(SAPIO_ICAP, sizeof(uint16_t));
         int n = 0;
         const uint16_t *pcode = w->ic_code + (size_t)o * SAPIO_ICAP;
-        int pcn = fresh[o * MAXC] ? 0 : w->org_ic_n[o];
+        int pcn = w->org_ic_n[o];      /* a newborn's list is empty (ow_materialize), so no freshness test is needed here */
         for (int i = 0; i < nc; i++) {
             int ri = o * MAXC + i;
             if (!solid[ri]) continue;

@@ -24,7 +24,7 @@ __device__ __forceinline__ bool circles_overlap(float x1, float y1, float r1, fl
     return d2 < __dmul_rn(md, md);
 }
 
-struct WallHit { float nx, ny, cx, cy; };   // normal (circle -> wall), closest point on the segment
+struct WallHit { float nx, ny, cx, cy; double d; };   // normal (circle -> wall), closest point on the segment, centre distance
 
 // cpCollision.c CircleToSegment against wall wi (physics.py:328-338: 0 left, 1 bottom, 2 right, 3 top), same double
 // operation sequence as oracle/space_step.c:circle_wall.
@@ -53,7 +53,7 @@ __device__ __forceinline__ bool circle_wall(const SapioParams &p, int wi, float 
     double nx, ny;
     if (d != 0.0) { double inv = __ddiv_rn(1.0, d); nx = __dmul_rn(ddx, inv); ny = __dmul_rn(ddy, inv); }
     else { double L = __dsqrt_rn(den); double inv = __ddiv_rn(1.0, L); nx = -__dmul_rn(sdy, inv); ny = __dmul_rn(sdx, inv); }
-    h->nx = (float)nx; h->ny = (float)ny; h->cx = (float)qx; h->cy = (float)qy;
+    h->nx = (float)nx; h->ny = (float)ny; h->cx = (float)qx; h->cy = (float)qy; h->d = d;
     return true;
 }
 

@@ -9,8 +9,9 @@
 //   exclusive scans    counts -> offsets: deterministic, globally sorted pair list without sorting pairs
 //   k_narrow<true>     per body: writes its sorted adjacency and its (a<b) contact keys
 //   k_cross_links      per body: contact index of every adjacency entry + predecessor links (Gauss-Seidel order)
-//   k_cross_prestep    per cross contact: warm-start match against the previous step's list, bounce, coupling flags
-//   k_org_solve        one warp per organism without cross contacts: intra contacts, sensor pins, all-pairs pins,
+//   k_cross_prestep    per cross contact: warm-start match against the previous step's list, normal/bias/bounce, coupling flags
+//   k_classify         organisms -> coupled list, or one of four size classes (16/32/48/64 cell rows)
+//   k_org_solve<CM>    one warp per organism without cross contacts: intra contacts, sensor pins, all-pairs pins,
 //                      warm start and all iterations with velocities and impulses resident in shared memory
 //   k_coupled          cooperative kernel for organisms / dead cells that share a cross contact: dependency levels of
 //                      the cross contacts (== exact sequential order evaluated in parallel), then the same arithmetic
@@ -35,14 +36,16 @@ struct Workspace {
     int *cnt_up, *cnt_all;          // per body counts [NB + 1]
     int *off_up, *off_all;          // exclusive scans [NB + 1]
     uint64_t *nx_key;               // new contact list [x_cap]
-    float *nx_jn, *nx_jt, *nx_bounce, *nx_jbias;
+    float *nx_jn, *nx_jt, *nx_bounce, *nx_jbias, *nx_bias;
+    float2 *nx_n;                   // contact normal (a -> b)
     int *nx_level, *nx_prev_a, *nx_prev_b;
     uint32_t *adj_other;            // adjacency: partner body id per entry [2*x_cap]
     uint8_t *org_coupled;           // [n_org]
     int *coupled_list;              // [n_org]
+    int *cls_list;                  // [4][n_org] uncoupled organisms by size class (16/32/48/64 cell rows)
     float *ic_bounce, *ic_jbias;    // [n_org * ICAP] (coupled path only)
 };
-enum { FL_NX = 0, FL_NADJ = 1, FL_OVERFLOW = 2, FL_MAXLEVEL = 3, FL_CHANGED = 4, FL_NCOUPLED = 5, FL_NIC = 6 };
+enum { FL_NX = 0, FL_NADJ = 1, FL_OVERFLOW = 2, FL_MAXLEVEL = 3, FL_CHANGED = 4, FL_NCOUPLED = 5, FL_NIC = 6, FL_CLS0 = 8 /* ..11 */, FL_WORK0 = 12 /* ..15 */ };
 
 static size_t carve_workspace(const SapioParams &p, char *base, Workspace *W) {
     size_t off = 0;
@@ -63,10 +66,12 @@ static size_t carve_workspace(const SapioParams &p, char *base, Workspace *W) {
     W->nx_key = (uint64_t *)take(XC * 8);
     W->nx_jn = (float *)take(XC * 4); W->nx_jt = (float *)take(XC * 4);
     W->nx_bounce = (float *)take(XC * 4); W->nx_jbias = (float *)take(XC * 4);
+    W->nx_bias = (float *)take(XC * 4); W->nx_n = (float2 *)take(XC * 8);
     W->nx_level = (int *)take(XC * 4); W->nx_prev_a = (int *)take(XC * 4); W->nx_prev_b = (int *)take(XC * 4);
     W->adj_other = (uint32_t *)take(2 * XC * 4);
     W->org_coupled = (uint8_t *)take((size_t)p.n_org);
     W->coupled_list = (int *)take((size_t)p.n_org * 4);
+    W->cls_list = (int *)take((size_t)p.n_org * 4 * 4);
     W->ic_bounce = (float *)take((size_t)p.n_org * SAPIO_ICAP * 4);
     W->ic_jbias = (float *)take((size_t)p.n_org * SAPIO_ICAP * 4);
     return off;
@@ -157,125 +162,96 @@ __global__ void k_narrow_totals(WORLD_ARG, Workspace W) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// contact arithmetic shared by the shared-memory (organism) and global-memory (cross) paths: cpArbiter.c
+// contact arithmetic (cpArbiter.c) specialised for circles: every contact offset is r1 = ra*n, r2 = -rb*n (a wall
+// counts as rb = frame radius on a static body), so r x n = 0 exactly. Writing that out removes the catastrophic
+// cancellation the general r x j form has in fp32:
+//   k(n) = ma + mb            k(t) = ma + mb + ia*ra^2 + ib*rb^2
+//   v_rel.n = (vb - va).n     v_rel.t = (vb - va).t - rb*wb - ra*wa
+//   torque of impulse (jn, jt): a: -ia*ra*jt   b: -ib*rb*jt      bias impulses (along n) never touch w_bias
 // ------------------------------------------------------------------------------------------------------------------
-struct CBody { float vx, vy, w, vbx, vby, wb, minv, iinv; };
-struct CGeo { float nx, ny, r1x, r1y, r2x, r2y, nMass, tMass, bias; };
+struct StepK { double bc_contact, bc_joint, dt; float dt_coef_unused; };
 
-__device__ __forceinline__ float k_scalar(float minv_a, float iinv_a, float minv_b, float iinv_b, float r1x, float r1y, float r2x, float r2y, float nx, float ny) {
-    float c1 = r1x * ny - r1y * nx, c2 = r2x * ny - r2y * nx;
-    return (minv_a + iinv_a * c1 * c1) + (minv_b + iinv_b * c2 * c2);
+struct CBody { float vx, vy, w, vbx, vby, minv, iinv, r; };
+
+__device__ __forceinline__ float contact_bias(double d, float ra, float rb, const SapioParams &p, const StepK &K) {
+    double dist = d - (double)ra - (double)rb;                            // ((r2 - r1) + (pb - pa)) . n
+    return (float)(-K.bc_contact * fmin(0.0, dist + (double)p.collision_slop) / K.dt);
 }
-// geometry of a circle/circle contact (a at pa radius ra, b at pb radius rb); cpCollision.c CircleToCircle + cpArbiterPreStep
-__device__ __forceinline__ void geo_circles(float pax, float pay, float ra, float pbx, float pby, float rb, float minv_a, float iinv_a, float minv_b, float iinv_b,
-                                            float slop, float bias_coef, float inv_dt, CGeo &g) {
-    float dx = pbx - pax, dy = pby - pay;
-    float d = sqrtf(dx * dx + dy * dy);
-    if (d != 0.f) { float inv = 1.0f / d; g.nx = dx * inv; g.ny = dy * inv; } else { g.nx = 1.f; g.ny = 0.f; }
-    g.r1x = g.nx * ra; g.r1y = g.ny * ra; g.r2x = -g.nx * rb; g.r2y = -g.ny * rb;
-    g.nMass = 1.0f / k_scalar(minv_a, iinv_a, minv_b, iinv_b, g.r1x, g.r1y, g.r2x, g.r2y, g.nx, g.ny);
-    g.tMass = 1.0f / k_scalar(minv_a, iinv_a, minv_b, iinv_b, g.r1x, g.r1y, g.r2x, g.r2y, -g.ny, g.nx);
-    float dist = ((g.r2x - g.r1x) + dx) * g.nx + ((g.r2y - g.r1y) + dy) * g.ny;
-    g.bias = -bias_coef * fminf(0.0f, dist + slop) * inv_dt;
-}
-// circle against a wall (static body at the origin); h from circle_wall()
-__device__ __forceinline__ void geo_wall(float pax, float pay, float ra, const WallHit &h, float fw, float minv_a, float iinv_a, float slop, float bias_coef, float inv_dt, CGeo &g) {
-    g.nx = h.nx; g.ny = h.ny;
-    g.r1x = g.nx * ra; g.r1y = g.ny * ra;
-    g.r2x = h.cx - g.nx * fw; g.r2y = h.cy - g.ny * fw;
-    g.nMass = 1.0f / k_scalar(minv_a, iinv_a, 0.f, 0.f, g.r1x, g.r1y, g.r2x, g.r2y, g.nx, g.ny);
-    g.tMass = 1.0f / k_scalar(minv_a, iinv_a, 0.f, 0.f, g.r1x, g.r1y, g.r2x, g.r2y, -g.ny, g.nx);
-    float dist = ((g.r2x - g.r1x) + (0.f - pax)) * g.nx + ((g.r2y - g.r1y) + (0.f - pay)) * g.ny;
-    g.bias = -bias_coef * fminf(0.0f, dist + slop) * inv_dt;
-}
-__device__ __forceinline__ float contact_bounce(const CBody &A, const CBody &B, const CGeo &g, float e) {
-    float rvx = (B.vx - g.r2y * B.w) - (A.vx - g.r1y * A.w), rvy = (B.vy + g.r2x * B.w) - (A.vy + g.r1x * A.w);
-    return (rvx * g.nx + rvy * g.ny) * e;
-}
-__device__ __forceinline__ void apply_imp(CBody &A, CBody &B, const CGeo &g, float jx, float jy) {
-    A.vx -= jx * A.minv; A.vy -= jy * A.minv; A.w -= A.iinv * (g.r1x * jy - g.r1y * jx);
-    B.vx += jx * B.minv; B.vy += jy * B.minv; B.w += B.iinv * (g.r2x * jy - g.r2y * jx);
-}
+__device__ __forceinline__ float contact_vrn(const CBody &A, const CBody &B, float nx, float ny) { return (B.vx - A.vx) * nx + (B.vy - A.vy) * ny; }
+
 // cpArbiterApplyCachedImpulse
-__device__ __forceinline__ void contact_warm(CBody &A, CBody &B, const CGeo &g, float jn, float jt, float dt_coef) {
-    float jx = (g.nx * jn - g.ny * jt) * dt_coef, jy = (g.nx * jt + g.ny * jn) * dt_coef;
-    apply_imp(A, B, g, jx, jy);
+__device__ __forceinline__ void contact_warm(CBody &A, CBody &B, float nx, float ny, float jn, float jt, float dt_coef) {
+    jn *= dt_coef; jt *= dt_coef;
+    float jx = nx * jn - ny * jt, jy = nx * jt + ny * jn;
+    A.vx -= jx * A.minv; A.vy -= jy * A.minv; A.w -= A.iinv * A.r * jt;
+    B.vx += jx * B.minv; B.vy += jy * B.minv; B.w -= B.iinv * B.r * jt;
 }
 // cpArbiterApplyImpulse (SURVEY A-5)
-__device__ __forceinline__ void contact_apply(CBody &A, CBody &B, const CGeo &g, float bounce, float mu, float &jnAcc, float &jtAcc, float &jBias) {
-    float vb1x = A.vbx - g.r1y * A.wb, vb1y = A.vby + g.r1x * A.wb;
-    float vb2x = B.vbx - g.r2y * B.wb, vb2y = B.vby + g.r2x * B.wb;
-    float rvx = (B.vx - g.r2y * B.w) - (A.vx - g.r1y * A.w), rvy = (B.vy + g.r2x * B.w) - (A.vy + g.r1x * A.w);
-    float vbn = (vb2x - vb1x) * g.nx + (vb2y - vb1y) * g.ny;
-    float vrn = rvx * g.nx + rvy * g.ny;
-    float vrt = -rvx * g.ny + rvy * g.nx;
-    float jbn = (g.bias - vbn) * g.nMass, jbnOld = jBias;
+__device__ __forceinline__ void contact_apply(CBody &A, CBody &B, float nx, float ny, float bias, float bounce, float mu, float &jnAcc, float &jtAcc, float &jBias) {
+    float nMass = 1.0f / (A.minv + B.minv);
+    float tMass = 1.0f / (A.minv + B.minv + A.iinv * A.r * A.r + B.iinv * B.r * B.r);
+    float dvx = B.vx - A.vx, dvy = B.vy - A.vy;
+    float vbn = (B.vbx - A.vbx) * nx + (B.vby - A.vby) * ny;
+    float vrn = dvx * nx + dvy * ny;
+    float vrt = (dvy * nx - dvx * ny) - B.r * B.w - A.r * A.w;
+    float jbn = (bias - vbn) * nMass, jbnOld = jBias;
     jBias = fmaxf(jbnOld + jbn, 0.0f);
-    float jn = -(bounce + vrn) * g.nMass, jnOld = jnAcc;
+    float jn = -(bounce + vrn) * nMass, jnOld = jnAcc;
     jnAcc = fmaxf(jnOld + jn, 0.0f);
     float jtMax = mu * jnAcc;
-    float jt = -vrt * g.tMass, jtOld = jtAcc;
+    float jt = -vrt * tMass, jtOld = jtAcc;
     jtAcc = fminf(fmaxf(jtOld + jt, -jtMax), jtMax);
     float bj = jBias - jbnOld;
-    float bjx = g.nx * bj, bjy = g.ny * bj;
-    A.vbx -= bjx * A.minv; A.vby -= bjy * A.minv; A.wb -= A.iinv * (g.r1x * bjy - g.r1y * bjx);
-    B.vbx += bjx * B.minv; B.vby += bjy * B.minv; B.wb += B.iinv * (g.r2x * bjy - g.r2y * bjx);
+    A.vbx -= nx * bj * A.minv; A.vby -= ny * bj * A.minv;
+    B.vbx += nx * bj * B.minv; B.vby += ny * bj * B.minv;
     float dn = jnAcc - jnOld, dtg = jtAcc - jtOld;
-    apply_imp(A, B, g, g.nx * dn - g.ny * dtg, g.nx * dtg + g.ny * dn);
+    float jx = nx * dn - ny * dtg, jy = nx * dtg + ny * dn;
+    A.vx -= jx * A.minv; A.vy -= jy * A.minv; A.w -= A.iinv * A.r * dtg;
+    B.vx += jx * B.minv; B.vy += jy * B.minv; B.w -= B.iinv * B.r * dtg;
 }
-
-__device__ __forceinline__ float bias_coef_of(float bias, float dt) { return 1.0f - powf(bias, dt); }
 
 // ------------------------------------------------------------------------------------------------------------------
 // cross contacts (global memory)
 // ------------------------------------------------------------------------------------------------------------------
-struct GRef { float px, py, r, e, u; CBody b; int kind; };   // kind 0 cell, 1 dead, 2 wall
+struct GRef { float px, py, e, u; CBody b; int kind; };   // kind 0 cell, 1 dead, 2 wall
 __device__ __forceinline__ void gload(const SapioWorld &w, uint32_t id, int NC, int ND, GRef &g) {
     if ((int)id < NC) {
         g.kind = 0;
         float2 p = reinterpret_cast<const float2 *>(w.c_pos)[id], v = reinterpret_cast<const float2 *>(w.c_vel)[id], vb = reinterpret_cast<const float2 *>(w.c_vbias)[id];
-        float m = w.c_mass[id]; g.r = w.c_size[id] * 0.5f;
+        float m = w.c_mass[id]; g.b.r = w.c_size[id] * 0.5f;
         g.px = p.x; g.py = p.y; g.e = w.c_elast[id]; g.u = w.c_fric[id];
-        g.b.vx = v.x; g.b.vy = v.y; g.b.w = w.c_angvel[id]; g.b.vbx = vb.x; g.b.vby = vb.y; g.b.wb = w.c_wbias[id];
-        g.b.minv = 1.0f / m; g.b.iinv = 1.0f / (0.5f * m * g.r * g.r);
+        g.b.vx = v.x; g.b.vy = v.y; g.b.w = w.c_angvel[id]; g.b.vbx = vb.x; g.b.vby = vb.y;
+        g.b.minv = 1.0f / m; g.b.iinv = 1.0f / (0.5f * m * g.b.r * g.b.r);
     } else if ((int)id < NC + ND) {
         g.kind = 1;
         int d = (int)id - NC;
         float2 p = reinterpret_cast<const float2 *>(w.d_pos)[d], v = reinterpret_cast<const float2 *>(w.d_vel)[d], vb = reinterpret_cast<const float2 *>(w.d_vbias)[d];
-        g.r = w.d_size[d] * 0.5f;
+        g.b.r = w.d_size[d] * 0.5f;
         g.px = p.x; g.py = p.y; g.e = w.d_elast[d]; g.u = w.d_fric[d];
-        g.b.vx = v.x; g.b.vy = v.y; g.b.w = w.d_angvel[d]; g.b.vbx = vb.x; g.b.vby = vb.y; g.b.wb = w.d_wbias[d];
-        g.b.minv = 1.0f / w.d_mass[d]; g.b.iinv = 1.0f / (0.5f * w.d_mass0[d] * g.r * g.r);
+        g.b.vx = v.x; g.b.vy = v.y; g.b.w = w.d_angvel[d]; g.b.vbx = vb.x; g.b.vby = vb.y;
+        g.b.minv = 1.0f / w.d_mass[d]; g.b.iinv = 1.0f / (0.5f * w.d_mass0[d] * g.b.r * g.b.r);
     } else {
-        g.kind = 2; g.px = g.py = 0.f; g.r = w.p.frame_width; g.e = w.p.wall_elast; g.u = w.p.wall_fric;
-        g.b = CBody{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        g.kind = 2; g.px = g.py = 0.f; g.e = w.p.wall_elast; g.u = w.p.wall_fric;
+        g.b = CBody{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, w.p.frame_width};
     }
 }
 __device__ __forceinline__ void gstore(const SapioWorld &w, uint32_t id, int NC, const GRef &g) {
     if (g.kind == 0) {
         reinterpret_cast<float2 *>(w.c_vel)[id] = make_float2(g.b.vx, g.b.vy); w.c_angvel[id] = g.b.w;
-        reinterpret_cast<float2 *>(w.c_vbias)[id] = make_float2(g.b.vbx, g.b.vby); w.c_wbias[id] = g.b.wb;
+        reinterpret_cast<float2 *>(w.c_vbias)[id] = make_float2(g.b.vbx, g.b.vby);
     } else if (g.kind == 1) {
         int d = (int)id - NC;
         reinterpret_cast<float2 *>(w.d_vel)[d] = make_float2(g.b.vx, g.b.vy); w.d_angvel[d] = g.b.w;
-        reinterpret_cast<float2 *>(w.d_vbias)[d] = make_float2(g.b.vbx, g.b.vby); w.d_wbias[d] = g.b.wb;
+        reinterpret_cast<float2 *>(w.d_vbias)[d] = make_float2(g.b.vbx, g.b.vby);
     }
 }
-__device__ __forceinline__ void cross_geo(const SapioWorld &w, const GRef &A, const GRef &B, uint32_t idb, int WALL0, float bias_coef, CGeo &g) {
-    const float inv_dt = 1.0f / w.p.dt_phys;
-    if (B.kind == 2) {
-        WallHit h; circle_wall(w.p, (int)idb - WALL0, A.px, A.py, A.r, &h);
-        geo_wall(A.px, A.py, A.r, h, w.p.frame_width, A.b.minv, A.b.iinv, w.p.collision_slop, bias_coef, inv_dt, g);
-    } else geo_circles(A.px, A.py, A.r, B.px, B.py, B.r, A.b.minv, A.b.iinv, B.b.minv, B.b.iinv, w.p.collision_slop, bias_coef, inv_dt, g);
-}
-
 __device__ __forceinline__ bool body_fresh(const SapioWorld &w, uint32_t id, int NC, int ND, int32_t tick) {
     if ((int)id < NC) return w.org_birth_tick[id >> 6] == tick;
     if ((int)id < NC + ND) return w.d_state[id - NC] == 2;
     return false;
 }
 
-// per body: predecessor links of its contacts in canonical order (its adjacency order), contact index by construction
+// per body: predecessor links of its contacts in canonical order (its adjacency order); contact index by construction
 __global__ void __launch_bounds__(128) k_cross_links(WORLD_ARG, Workspace W) {
     const int NC = w.p.n_org * MAXC, NB = NC + w.p.n_dead;
     const int nx = W.flags[FL_NX];
@@ -299,21 +275,28 @@ __global__ void __launch_bounds__(128) k_cross_links(WORLD_ARG, Workspace W) {
     }
 }
 
-// per new cross contact: persistent-arbiter match (jnAcc/jtAcc of the previous step), bounce from pre-warm-start
-// velocities (cpArbiterPreStep), coupling marks
-__global__ void __launch_bounds__(128) k_cross_prestep(WORLD_ARG, Workspace W) {
+// per new cross contact: persistent-arbiter match (jnAcc/jtAcc of the previous step), normal and bias (double, once),
+// bounce from pre-warm-start velocities (cpArbiterPreStep), coupling marks
+__global__ void __launch_bounds__(128) k_cross_prestep(WORLD_ARG, Workspace W, StepK K) {
     const SapioParams &p = w.p;
     const int NC = p.n_org * MAXC, ND = p.n_dead, WALL0 = NC + ND;
     const int nx = W.flags[FL_NX];
     const int32_t tick = (int32_t)w.g_tick[0];
-    const float bc = bias_coef_of(p.collision_bias, p.dt_phys);
     const int pn = w.g_x_n[0];
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nx; c += gridDim.x * blockDim.x) {
         uint64_t key = W.nx_key[c];
         uint32_t a = (uint32_t)(key >> 32), b = (uint32_t)key;
         GRef A, B; gload(w, a, NC, ND, A); gload(w, b, NC, ND, B);
-        CGeo g; cross_geo(w, A, B, b, WALL0, bc, g);
-        W.nx_bounce[c] = contact_bounce(A.b, B.b, g, A.e * B.e);
+        float nxn, nyn; double d;
+        if (B.kind == 2) { WallHit h; circle_wall(p, (int)b - WALL0, A.px, A.py, A.b.r, &h); nxn = h.nx; nyn = h.ny; d = h.d; }
+        else {
+            double dx = (double)B.px - (double)A.px, dy = (double)B.py - (double)A.py;
+            d = sqrt(dx * dx + dy * dy);
+            if (d != 0.0) { nxn = (float)(dx / d); nyn = (float)(dy / d); } else { nxn = 1.f; nyn = 0.f; }
+        }
+        W.nx_n[c] = make_float2(nxn, nyn);
+        W.nx_bias[c] = contact_bias(d, A.b.r, B.b.r, p, K);
+        W.nx_bounce[c] = contact_vrn(A.b, B.b, nxn, nyn) * (A.e * B.e);
         W.nx_jbias[c] = 0.f;
         float jn = 0.f, jt = 0.f;
         if (pn > 0 && !body_fresh(w, a, NC, ND, tick) && !body_fresh(w, b, NC, ND, tick)) {
@@ -328,90 +311,118 @@ __global__ void __launch_bounds__(128) k_cross_prestep(WORLD_ARG, Workspace W) {
     }
 }
 
+// organisms -> coupled list or size class list (order inside a list is irrelevant: organisms are independent there)
+__global__ void k_classify(WORLD_ARG, Workspace W) {
+    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < w.p.n_org; o += gridDim.x * blockDim.x) {
+        if (w.org_state[o] != 1) continue;
+        if (W.org_coupled[o]) { W.coupled_list[atomicAdd(&W.flags[FL_NCOUPLED], 1)] = o; continue; }
+        int nc = w.org_ncells[o];
+        int cls = nc <= 16 ? 0 : (nc <= 32 ? 1 : (nc <= 48 ? 2 : 3));
+        W.cls_list[(size_t)cls * w.p.n_org + atomicAdd(&W.flags[FL_CLS0 + cls], 1)] = o;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
-// organism solver: one warp per organism, state in shared memory
+// organism solver: one warp per organism, state in shared memory, templated on the tile (cell rows) it can hold
 // ------------------------------------------------------------------------------------------------------------------
+template <int CM>
 struct OrgS {
-    float px[MAXC], py[MAXC], vx[MAXC], vy[MAXC], av[MAXC], vbx[MAXC], vby[MAXC], wb[MAXC];
-    float minv[MAXC], iinv[MAXC], rad[MAXC], el[MAXC], fr[MAXC], relx[MAXC], rely[MAXC];
-    float spx[MAXC], spy[MAXC], svx[MAXC], svy[MAXC], sjn[MAXC];
-    float jn[SAPIO_NPAIR];
-    float cb[SAPIO_ICAP], cjn[SAPIO_ICAP], cjt[SAPIO_ICAP], cjb[SAPIO_ICAP];
-    uint16_t ccode[SAPIO_ICAP];
-    uint8_t clev[SAPIO_ICAP];
-    uint8_t last[MAXC];
+    static constexpr int NP = CM * (CM - 1) / 2, IC = 3 * CM;
+    float4 pair[NP];                 // nx, ny, bias, jnAcc of pin (i,j)
+    float2 p[CM], v[CM], vb[CM], rel[CM], sp[CM], sv[CM];
+    float w[CM], minv[CM], iinv[CM], rad[CM], el[CM], fr[CM], sjn[CM];
+    float cnx[IC], cny[IC], cbias[IC], cb[IC], cjn[IC], cjt[IC], cjb[IC];
+    uint16_t ccode[IC];
+    uint8_t clev[IC];
+    uint8_t last[CM];
     int nic, nlev;
 };
 
+template <int CM>
 struct OrgCtx {
-    OrgS &s; const SapioWorld &w; int o, nc, lane;
+    typedef OrgS<CM> S;
+    static constexpr int H = (CM + 31) / 32;
+    S &s; const SapioWorld &w; const StepK &K; int o, nc, lane;
     uint64_t alive, sens;
-    float bc_contact, bc_joint, inv_dt;
-    __device__ OrgCtx(OrgS &s_, const SapioWorld &w_, int o_) : s(s_), w(w_), o(o_), lane(lane_id()) {
-        nc = w.org_ncells[o];
-        bc_contact = bias_coef_of(w.p.collision_bias, w.p.dt_phys);
-        bc_joint = bias_coef_of(w.p.joint_error_bias, w.p.dt_phys);
-        inv_dt = 1.0f / w.p.dt_phys;
-    }
+    __device__ OrgCtx(S &s_, const SapioWorld &w_, const StepK &K_, int o_) : s(s_), w(w_), K(K_), o(o_), lane(lane_id()) { nc = min(w.org_ncells[o], CM); }
     __device__ bool is_alive(int k) const { return (alive >> k) & 1ull; }
+    __device__ static int lp(int i, int j) { return i * (2 * CM - i - 1) / 2 + (j - i - 1); }
 
-    // cells + sensor bodies + joint impulses -> shared memory
     __device__ void load() {
         uint32_t am[2] = {0, 0}, sm[2] = {0, 0};
-        for (int h = 0; h < 2; h++) {
+#pragma unroll
+        for (int h = 0; h < H; h++) {
             int k = lane + 32 * h, row = o * MAXC + k;
             bool a = k < nc && w.c_alive[row] == SAPIO_CELL_ALIVE, sn = false;
             if (a) {
-                float2 p = reinterpret_cast<const float2 *>(w.c_pos)[row], v = reinterpret_cast<const float2 *>(w.c_vel)[row];
-                float2 vb = reinterpret_cast<const float2 *>(w.c_vbias)[row], rel = reinterpret_cast<const float2 *>(w.c_rel)[row];
                 float m = w.c_mass[row], r = w.c_size[row] * 0.5f;
-                s.px[k] = p.x; s.py[k] = p.y; s.vx[k] = v.x; s.vy[k] = v.y; s.av[k] = w.c_angvel[row];
-                s.vbx[k] = vb.x; s.vby[k] = vb.y; s.wb[k] = w.c_wbias[row];
+                s.p[k] = reinterpret_cast<const float2 *>(w.c_pos)[row]; s.v[k] = reinterpret_cast<const float2 *>(w.c_vel)[row];
+                s.vb[k] = reinterpret_cast<const float2 *>(w.c_vbias)[row]; s.rel[k] = reinterpret_cast<const float2 *>(w.c_rel)[row];
+                s.w[k] = w.c_angvel[row];
                 s.minv[k] = 1.0f / m; s.iinv[k] = 1.0f / (0.5f * m * r * r); s.rad[k] = r;
-                s.el[k] = w.c_elast[row]; s.fr[k] = w.c_fric[row]; s.relx[k] = rel.x; s.rely[k] = rel.y;
+                s.el[k] = w.c_elast[row]; s.fr[k] = w.c_fric[row];
                 sn = is_sensor_type(w.c_type[row]);
-                if (sn) {
-                    float2 sp = reinterpret_cast<const float2 *>(w.c_spos)[row], sv = reinterpret_cast<const float2 *>(w.c_svel)[row];
-                    s.spx[k] = sp.x; s.spy[k] = sp.y; s.svx[k] = sv.x; s.svy[k] = sv.y; s.sjn[k] = w.c_spin_jn[row];
-                }
+                if (sn) { s.sp[k] = reinterpret_cast<const float2 *>(w.c_spos)[row]; s.sv[k] = reinterpret_cast<const float2 *>(w.c_svel)[row]; s.sjn[k] = w.c_spin_jn[row]; }
             }
             am[h] = __ballot_sync(FULL, a); sm[h] = __ballot_sync(FULL, sn);
         }
         alive = ((uint64_t)am[1] << 32) | am[0]; sens = ((uint64_t)sm[1] << 32) | sm[0];
-        const float *gj = w.j_jn + (size_t)o * SAPIO_NPAIR;
-        for (int i = 0; i + 1 < nc; i++) {
-            int base = pair_index(i, i + 1);
-            for (int j = i + 1 + lane; j < nc; j += 32) s.jn[base + (j - i - 1)] = gj[base + (j - i - 1)];
-        }
         __syncwarp();
     }
 
-    // cpCollision: intra-organism cell/cell pairs and cell/wall pairs, in canonical (sorted code) order
-    __device__ void detect() {
-        int nic = 0;
-        bool over = false;
+    // One pass over all pairs (i<j) of living cells: pin-joint prestep (cpPinJoint.c preStep: n, bias; impulses from the
+    // previous step) and intra-organism collision detection (cpCollision.c CircleToCircle) share the same separation,
+    // computed once in double from the fp32 positions. Cell/wall contacts follow each row. Contacts come out in
+    // canonical order (sorted code i*128+j).
+    __device__ void prestep_pairs() {
+        int nic = 0; bool over = false;
+        const float *gj = w.j_jn + (size_t)o * SAPIO_NPAIR;
         for (int i = 0; i < nc; i++) {
             if (!is_alive(i)) continue;
-            float xi = s.px[i], yi = s.py[i], ri = s.rad[i];
-            for (int base = 0; base < nc; base += 32) {
+            float2 pi = s.p[i], ri = s.rel[i]; float radi = s.rad[i];
+            for (int base = i + 1; base < nc; base += 32) {
                 int j = base + lane;
-                bool hit = false;
-                if (j > i && j < nc && is_alive(j)) { double d2; hit = circles_overlap(xi, yi, ri, s.px[j], s.py[j], s.rad[j], &d2); }
+                bool hit = false; float nxf = 0.f, nyf = 0.f; double d = 0.0;
+                if (j < nc && is_alive(j)) {
+                    float2 pj = s.p[j], rj = s.rel[j];
+                    double dx = __dsub_rn((double)pj.x, (double)pi.x), dy = __dsub_rn((double)pj.y, (double)pi.y);
+                    double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                    d = sqrt(d2);
+                    if (d != 0.0) { double inv = 1.0 / d; nxf = (float)(dx * inv); nyf = (float)(dy * inv); }
+                    double lx = (double)rj.x - (double)ri.x, ly = (double)rj.y - (double)ri.y;
+                    double rest = sqrt(lx * lx + ly * ly);                 // |relative_pos_i - relative_pos_j| (connectTo at spawn)
+                    float bias = (float)(-K.bc_joint * (d - rest) / K.dt);
+                    s.pair[lp(i, j)] = make_float4(nxf, nyf, bias, gj[pair_index(i, j)]);
+                    double md = __dadd_rn((double)radi, (double)s.rad[j]);
+                    hit = d2 < __dmul_rn(md, md);
+                }
                 uint32_t m = __ballot_sync(FULL, hit);
-                if (hit) { int slot = nic + __popc(m & ((1u << lane) - 1)); if (slot < SAPIO_ICAP) s.ccode[slot] = (uint16_t)(i * 128 + j); else over = true; }
+                if (hit) {
+                    int slot = nic + __popc(m & ((1u << lane) - 1));
+                    if (slot < S::IC) {
+                        s.ccode[slot] = (uint16_t)(i * 128 + j);
+                        if (d == 0.0) { nxf = 1.f; nyf = 0.f; }                 // coincident centres: cpv(1, 0)
+                        s.cnx[slot] = nxf; s.cny[slot] = nyf; s.cbias[slot] = contact_bias(d, radi, s.rad[j], w.p, K);
+                    } else over = true;
+                }
                 nic += __popc(m);
             }
-            // walls: cheap reject first (a cell farther than r + 2*frame from every border cannot touch)
-            float fw2 = 2.0f * w.p.frame_width + ri + 1.0f;
-            if (xi < fw2 || yi < fw2 || xi > w.p.width - fw2 || yi > w.p.height - fw2) {
-                bool hit = false;
-                if (lane < SAPIO_NWALL) { WallHit h; hit = circle_wall(w.p, lane, xi, yi, ri, &h); }
+            float fw2 = 2.0f * w.p.frame_width + radi + 1.0f;                    // cheap reject: not near any border
+            if (pi.x < fw2 || pi.y < fw2 || pi.x > w.p.width - fw2 || pi.y > w.p.height - fw2) {
+                bool hit = false; WallHit h;
+                if (lane < SAPIO_NWALL) hit = circle_wall(w.p, lane, pi.x, pi.y, radi, &h);
                 uint32_t m = __ballot_sync(FULL, hit);
-                if (hit) { int slot = nic + __popc(m & ((1u << lane) - 1)); if (slot < SAPIO_ICAP) s.ccode[slot] = (uint16_t)(i * 128 + MAXC + lane); else over = true; }
+                if (hit) {
+                    int slot = nic + __popc(m & ((1u << lane) - 1));
+                    if (slot < S::IC) {
+                        s.ccode[slot] = (uint16_t)(i * 128 + MAXC + lane);
+                        s.cnx[slot] = h.nx; s.cny[slot] = h.ny; s.cbias[slot] = contact_bias(h.d, radi, w.p.frame_width, w.p, K);
+                    } else over = true;
+                }
                 nic += __popc(m);
             }
         }
-        if (__any_sync(FULL, over) || nic > SAPIO_ICAP) { nic = SAPIO_ICAP; if (lane == 0) w.g_stats[SAPIO_STAT_OVERFLOW] = 1; }
+        if (__any_sync(FULL, over) || nic > S::IC) { nic = S::IC; if (lane == 0) w.g_stats[SAPIO_STAT_OVERFLOW] = 1; }
         if (lane == 0) s.nic = nic;
         __syncwarp();
     }
@@ -432,9 +443,9 @@ struct OrgCtx {
         __syncwarp();
     }
 
-    // dependency levels: contact c runs after every earlier contact (list order) that shares a body with it
+    // dependency levels: contact c runs after every earlier contact (list order) that shares a cell with it
     __device__ void levels() {
-        for (int k = lane; k < MAXC; k += 32) s.last[k] = 0;
+        for (int k = lane; k < CM; k += 32) s.last[k] = 0;
         __syncwarp();
         if (lane == 0) {
             int mx = 0;
@@ -452,27 +463,19 @@ struct OrgCtx {
         __syncwarp();
     }
 
-    __device__ void cbody(int k, CBody &b) const { b.vx = s.vx[k]; b.vy = s.vy[k]; b.w = s.av[k]; b.vbx = s.vbx[k]; b.vby = s.vby[k]; b.wb = s.wb[k]; b.minv = s.minv[k]; b.iinv = s.iinv[k]; }
-    __device__ void cstore(int k, const CBody &b) { s.vx[k] = b.vx; s.vy[k] = b.vy; s.av[k] = b.w; s.vbx[k] = b.vbx; s.vby[k] = b.vby; s.wb[k] = b.wb; }
-    __device__ void geo(int c, int &i, int &j, CGeo &g, float &e, float &mu) const {
-        i = s.ccode[c] >> 7; j = s.ccode[c] & 127;
-        if (j < MAXC) {
-            geo_circles(s.px[i], s.py[i], s.rad[i], s.px[j], s.py[j], s.rad[j], s.minv[i], s.iinv[i], s.minv[j], s.iinv[j], w.p.collision_slop, bc_contact, inv_dt, g);
-            e = s.el[i] * s.el[j]; mu = s.fr[i] * s.fr[j];
-        } else {
-            WallHit h; circle_wall(w.p, j - MAXC, s.px[i], s.py[i], s.rad[i], &h);
-            geo_wall(s.px[i], s.py[i], s.rad[i], h, w.p.frame_width, s.minv[i], s.iinv[i], w.p.collision_slop, bc_contact, inv_dt, g);
-            e = s.el[i] * w.p.wall_elast; mu = s.fr[i] * w.p.wall_fric;
-        }
-    }
+    __device__ void cbody(int k, CBody &b) const { float2 v = s.v[k], vb = s.vb[k]; b.vx = v.x; b.vy = v.y; b.w = s.w[k]; b.vbx = vb.x; b.vby = vb.y; b.minv = s.minv[k]; b.iinv = s.iinv[k]; b.r = s.rad[k]; }
+    __device__ void cstore(int k, const CBody &b) { s.v[k] = make_float2(b.vx, b.vy); s.w[k] = b.w; s.vb[k] = make_float2(b.vbx, b.vby); }
+    __device__ CBody wall_body() const { return CBody{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, w.p.frame_width}; }
+
     // cpArbiterPreStep: bounce from the velocities before any cached impulse is applied
     __device__ void prestep_contacts() {
         for (int c = lane; c < s.nic; c += 32) {
-            int i, j; CGeo g; float e, mu;
-            geo(c, i, j, g, e, mu);
-            CBody A, B = CBody{0, 0, 0, 0, 0, 0, 0, 0};
-            cbody(i, A); if (j < MAXC) cbody(j, B);
-            s.cb[c] = contact_bounce(A, B, g, e);
+            int i = s.ccode[c] >> 7, j = s.ccode[c] & 127;
+            CBody A, B = wall_body();
+            cbody(i, A);
+            float e = s.el[i] * w.p.wall_elast;
+            if (j < MAXC) { cbody(j, B); e = s.el[i] * s.el[j]; }
+            s.cb[c] = contact_vrn(A, B, s.cnx[c], s.cny[c]) * e;
         }
         __syncwarp();
     }
@@ -482,12 +485,13 @@ struct OrgCtx {
         for (int L = 1; L <= s.nlev; L++) {
             for (int c = lane; c < s.nic; c += 32) {
                 if (s.clev[c] != L) continue;
-                int i, j; CGeo g; float e, mu;
-                geo(c, i, j, g, e, mu);
-                CBody A, B = CBody{0, 0, 0, 0, 0, 0, 0, 0};
-                cbody(i, A); if (j < MAXC) cbody(j, B);
-                if (WARM) contact_warm(A, B, g, s.cjn[c], s.cjt[c], dt_coef);
-                else contact_apply(A, B, g, s.cb[c], mu, s.cjn[c], s.cjt[c], s.cjb[c]);
+                int i = s.ccode[c] >> 7, j = s.ccode[c] & 127;
+                CBody A, B = wall_body();
+                cbody(i, A);
+                float mu = s.fr[i] * w.p.wall_fric;
+                if (j < MAXC) { cbody(j, B); mu = s.fr[i] * s.fr[j]; }
+                if (WARM) contact_warm(A, B, s.cnx[c], s.cny[c], s.cjn[c], s.cjt[c], dt_coef);
+                else contact_apply(A, B, s.cnx[c], s.cny[c], s.cbias[c], s.cb[c], mu, s.cjn[c], s.cjt[c], s.cjb[c]);
                 cstore(i, A); if (j < MAXC) cstore(j, B);
             }
             __syncwarp();
@@ -497,23 +501,24 @@ struct OrgCtx {
     // lexicographic order evaluated as anti-diagonals t = i + j (pairs of one diagonal share no body)
     template <bool WARM>
     __device__ void joints_pass(float dt_coef) {
-        for (int h = 0; h < 2; h++) {
+#pragma unroll
+        for (int h = 0; h < H; h++) {
             int k = lane + 32 * h;
             if (k < nc && ((sens >> k) & 1ull)) {
-                float dx = s.px[k] - s.spx[k], dy = s.py[k] - s.spy[k];
+                float2 pc = s.p[k], ps = s.sp[k], vc = s.v[k], vs = s.sv[k];
+                float dx = pc.x - ps.x, dy = pc.y - ps.y;
                 float d = sqrtf(dx * dx + dy * dy);
                 float inv = d != 0.f ? 1.0f / d : 0.f, nx = dx * inv, ny = dy * inv;
-                float mb = s.minv[k], nMass = 1.0f / (1.0f + mb);
-                float jnv;
+                float mb = s.minv[k], jnv;
                 if (WARM) jnv = s.sjn[k] * dt_coef;
                 else {
-                    float bias = -bc_joint * (d - 0.f) * inv_dt;
-                    float vrn = (s.vx[k] - s.svx[k]) * nx + (s.vy[k] - s.svy[k]) * ny;
-                    jnv = (bias - vrn) * nMass;
+                    float bias = (float)(-K.bc_joint * (double)d / K.dt);
+                    float vrn = (vc.x - vs.x) * nx + (vc.y - vs.y) * ny;
+                    jnv = (bias - vrn) * (1.0f / (1.0f + mb));
                     s.sjn[k] += jnv;
                 }
-                s.svx[k] -= nx * jnv; s.svy[k] -= ny * jnv;           // sensor body: mass 1
-                s.vx[k] += nx * jnv * mb; s.vy[k] += ny * jnv * mb;
+                s.sv[k] = make_float2(vs.x - nx * jnv, vs.y - ny * jnv);          // sensor body: mass 1 (sprites.py:303)
+                s.v[k] = make_float2(vc.x + nx * jnv * mb, vc.y + ny * jnv * mb);
             }
         }
         __syncwarp();
@@ -521,42 +526,38 @@ struct OrgCtx {
             int imin = max(0, t - (nc - 1)), imax = (t - 1) >> 1;
             int i = imin + lane, j = t - i;
             if (i <= imax && is_alive(i) && is_alive(j)) {
-                float dx = s.px[j] - s.px[i], dy = s.py[j] - s.py[i];
-                float d = sqrtf(dx * dx + dy * dy);
-                float inv = d != 0.f ? 1.0f / d : 0.f, nx = dx * inv, ny = dy * inv;
-                float ma = s.minv[i], mb = s.minv[j];
-                int q = pair_index(i, j);
-                float jnv;
-                if (WARM) jnv = s.jn[q] * dt_coef;
+                int q = lp(i, j);
+                float4 pr = s.pair[q];
+                float2 vi = s.v[i], vj = s.v[j];
+                float ma = s.minv[i], mb = s.minv[j], jnv;
+                if (WARM) jnv = pr.w * dt_coef;
                 else {
-                    float lx = s.relx[j] - s.relx[i], ly = s.rely[j] - s.rely[i];
-                    float rest = sqrtf(lx * lx + ly * ly);
-                    float bias = -bc_joint * (d - rest) * inv_dt;
-                    float vrn = (s.vx[j] - s.vx[i]) * nx + (s.vy[j] - s.vy[i]) * ny;
-                    jnv = (bias - vrn) * (1.0f / (ma + mb));
-                    s.jn[q] += jnv;
+                    float vrn = (vj.x - vi.x) * pr.x + (vj.y - vi.y) * pr.y;
+                    jnv = (pr.z - vrn) * (1.0f / (ma + mb));
+                    s.pair[q].w = pr.w + jnv;
                 }
-                float jx = nx * jnv, jy = ny * jnv;
-                s.vx[i] -= jx * ma; s.vy[i] -= jy * ma;
-                s.vx[j] += jx * mb; s.vy[j] += jy * mb;
+                float jx = pr.x * jnv, jy = pr.y * jnv;
+                s.v[i] = make_float2(vi.x - jx * ma, vi.y - jy * ma);
+                s.v[j] = make_float2(vj.x + jx * mb, vj.y + jy * mb);
             }
             __syncwarp();
         }
     }
 
     __device__ void store_vel() {
-        for (int h = 0; h < 2; h++) {
+#pragma unroll
+        for (int h = 0; h < H; h++) {
             int k = lane + 32 * h, row = o * MAXC + k;
             if (k < nc && is_alive(k)) {
-                reinterpret_cast<float2 *>(w.c_vel)[row] = make_float2(s.vx[k], s.vy[k]); w.c_angvel[row] = s.av[k];
-                reinterpret_cast<float2 *>(w.c_vbias)[row] = make_float2(s.vbx[k], s.vby[k]); w.c_wbias[row] = s.wb[k];
-                if ((sens >> k) & 1ull) { reinterpret_cast<float2 *>(w.c_svel)[row] = make_float2(s.svx[k], s.svy[k]); w.c_spin_jn[row] = s.sjn[k]; }
+                reinterpret_cast<float2 *>(w.c_vel)[row] = s.v[k]; w.c_angvel[row] = s.w[k];
+                reinterpret_cast<float2 *>(w.c_vbias)[row] = s.vb[k];
+                if ((sens >> k) & 1ull) { reinterpret_cast<float2 *>(w.c_svel)[row] = s.sv[k]; w.c_spin_jn[row] = s.sjn[k]; }
             }
         }
         float *gj = w.j_jn + (size_t)o * SAPIO_NPAIR;
         for (int i = 0; i + 1 < nc; i++) {
-            int base = pair_index(i, i + 1);
-            for (int j = i + 1 + lane; j < nc; j += 32) gj[base + (j - i - 1)] = s.jn[base + (j - i - 1)];
+            if (!is_alive(i)) continue;
+            for (int j = i + 1 + lane; j < nc; j += 32) if (is_alive(j)) gj[pair_index(i, j)] = s.pair[lp(i, j)].w;
         }
     }
     __device__ void store_contacts(float *ws_bounce, float *ws_jbias) {
@@ -567,36 +568,40 @@ struct OrgCtx {
         }
         if (lane == 0) w.org_ic_n[o] = s.nic;
     }
-    __device__ void load_contacts(const float *ws_bounce, const float *ws_jbias) {
-        int n = w.org_ic_n[o];
-        for (int c = lane; c < n; c += 32) {
+    // coupled path resume: the contact list was just re-detected (same positions => same list); fetch its impulses
+    __device__ void load_contact_state(const float *ws_bounce, const float *ws_jbias) {
+        for (int c = lane; c < s.nic; c += 32) {
             size_t g = (size_t)o * SAPIO_ICAP + c;
-            s.ccode[c] = w.ic_code[g]; s.cjn[c] = w.ic_jn[g]; s.cjt[c] = w.ic_jt[g];
-            s.cb[c] = ws_bounce[g]; s.cjb[c] = ws_jbias[g];
+            s.cjn[c] = w.ic_jn[g]; s.cjt[c] = w.ic_jt[g]; s.cb[c] = ws_bounce[g]; s.cjb[c] = ws_jbias[g];
         }
-        if (lane == 0) s.nic = n;
         __syncwarp();
     }
 };
 
 // organisms with no cross contact: the whole solve in one launch, everything on chip
-#define ORG_WARPS 4
-__global__ void __launch_bounds__(ORG_WARPS * 32) k_org_solve(WORLD_ARG, Workspace W) {
+template <int CM> struct OrgCfg { static constexpr int WARPS = CM <= 16 ? 8 : 4; };
+
+template <int CM>
+__global__ void __launch_bounds__(OrgCfg<CM>::WARPS * 32) k_org_solve(WORLD_ARG, Workspace W, StepK K, int cls) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    OrgS &s = reinterpret_cast<OrgS *>(smem_raw)[threadIdx.x >> 5];
-    const int warps = gridDim.x * ORG_WARPS;
+    OrgS<CM> &s = reinterpret_cast<OrgS<CM> *>(smem_raw)[threadIdx.x >> 5];
+    const int n = W.flags[FL_CLS0 + cls];
+    const int *list = W.cls_list + (size_t)cls * w.p.n_org;
     const float dt_coef = w.g_stepped[0] ? 1.0f : 0.0f;   // prev_dt == 0 on the very first step
     int nic_sum = 0;
-    for (int o = blockIdx.x * ORG_WARPS + (threadIdx.x >> 5); o < w.p.n_org; o += warps) {
-        if (w.org_state[o] != 1 || W.org_coupled[o]) continue;
-        OrgCtx c(s, w, o);
+    for (;;) {
+        int q = 0;
+        if (lane_id() == 0) q = atomicAdd(&W.flags[FL_WORK0 + cls], 1);     // dynamic scheduling: organisms differ in cost
+        q = __shfl_sync(FULL, q, 0);
+        if (q >= n) break;
+        OrgCtx<CM> c(s, w, K, list[q]);
         c.load();
-        c.detect();
+        c.prestep_pairs();
         c.match_prev();
         c.levels();
         c.prestep_contacts();
-        if (dt_coef != 0.f) { c.contacts_pass<true>(dt_coef); c.joints_pass<true>(dt_coef); }
-        for (int it = 0; it < w.p.iterations; it++) { c.contacts_pass<false>(0.f); c.joints_pass<false>(0.f); }
+        if (dt_coef != 0.f) { c.template contacts_pass<true>(dt_coef); c.template joints_pass<true>(dt_coef); }
+        for (int it = 0; it < w.p.iterations; it++) { c.template contacts_pass<false>(0.f); c.template joints_pass<false>(0.f); }
         c.store_vel();
         c.store_contacts(nullptr, nullptr);
         nic_sum += s.nic;
@@ -608,31 +613,30 @@ __global__ void __launch_bounds__(ORG_WARPS * 32) k_org_solve(WORLD_ARG, Workspa
 // ------------------------------------------------------------------------------------------------------------------
 // coupled path: cooperative kernel
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void k_coupled_list(WORLD_ARG, Workspace W) {
-    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < w.p.n_org; o += gridDim.x * blockDim.x)
-        if (w.org_state[o] == 1 && W.org_coupled[o]) W.coupled_list[atomicAdd(&W.flags[FL_NCOUPLED], 1)] = o;
-}
-
 template <bool WARM>
 __device__ __forceinline__ void cross_level_pass(const SapioWorld &w, const Workspace &W, int L, int nx, float dt_coef, int gtid, int gthreads) {
-    const int NC = w.p.n_org * MAXC, ND = w.p.n_dead, WALL0 = NC + ND;
-    const float bc = bias_coef_of(w.p.collision_bias, w.p.dt_phys);
+    const int NC = w.p.n_org * MAXC, ND = w.p.n_dead;
     for (int c = gtid; c < nx; c += gthreads) {
         if (W.nx_level[c] != L) continue;
         uint64_t key = W.nx_key[c];
         uint32_t a = (uint32_t)(key >> 32), b = (uint32_t)key;
         GRef A, B; gload(w, a, NC, ND, A); gload(w, b, NC, ND, B);
-        CGeo g; cross_geo(w, A, B, b, WALL0, bc, g);
-        if (WARM) contact_warm(A.b, B.b, g, W.nx_jn[c], W.nx_jt[c], dt_coef);
-        else { float jn = W.nx_jn[c], jt = W.nx_jt[c], jb = W.nx_jbias[c]; contact_apply(A.b, B.b, g, W.nx_bounce[c], A.u * B.u, jn, jt, jb); W.nx_jn[c] = jn; W.nx_jt[c] = jt; W.nx_jbias[c] = jb; }
+        float2 n = W.nx_n[c];
+        if (WARM) contact_warm(A.b, B.b, n.x, n.y, W.nx_jn[c], W.nx_jt[c], dt_coef);
+        else {
+            float jn = W.nx_jn[c], jt = W.nx_jt[c], jb = W.nx_jbias[c];
+            contact_apply(A.b, B.b, n.x, n.y, W.nx_bias[c], W.nx_bounce[c], A.u * B.u, jn, jt, jb);
+            W.nx_jn[c] = jn; W.nx_jt[c] = jt; W.nx_jbias[c] = jb;
+        }
         gstore(w, a, NC, A); gstore(w, b, NC, B);
     }
 }
 
-__global__ void __launch_bounds__(ORG_WARPS * 32) k_coupled(WORLD_ARG, Workspace W) {
+#define COUPLED_WARPS 4
+__global__ void __launch_bounds__(COUPLED_WARPS * 32) k_coupled(WORLD_ARG, Workspace W, StepK K) {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    OrgS &s = reinterpret_cast<OrgS *>(smem_raw)[threadIdx.x >> 5];
+    OrgS<MAXC> &s = reinterpret_cast<OrgS<MAXC> *>(smem_raw)[threadIdx.x >> 5];
     const int nx = W.flags[FL_NX];
     if (nx == 0) return;                                       // uniform over the grid: no barrier has been entered
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
@@ -658,20 +662,20 @@ __global__ void __launch_bounds__(ORG_WARPS * 32) k_coupled(WORLD_ARG, Workspace
     const int maxL = max(W.flags[FL_MAXLEVEL], 1);
     // stage A: coupled organisms detect their intra contacts and take their bounce before any velocity changes
     for (int q = gwarp; q < ncoupled; q += gwarps) {
-        OrgCtx c(s, w, W.coupled_list[q]);
-        c.load(); c.detect(); c.match_prev(); c.prestep_contacts();
+        OrgCtx<MAXC> c(s, w, K, W.coupled_list[q]);
+        c.load(); c.prestep_pairs(); c.match_prev(); c.prestep_contacts();
         c.store_contacts(W.ic_bounce, W.ic_jbias);
         if (lane_id() == 0) atomicAdd(&W.flags[FL_NIC], s.nic);
         __syncwarp();
     }
     grid.sync();
-    // stage B/C: cached impulses -- cross contacts by level, then each coupled organism's own arbiters and constraints
+    // cached impulses: cross contacts by level, then each coupled organism's own arbiters and constraints
     if (dt_coef != 0.f) {
         for (int L = 1; L <= maxL; L++) { cross_level_pass<true>(w, W, L, nx, dt_coef, gtid, gthreads); grid.sync(); }
         for (int q = gwarp; q < ncoupled; q += gwarps) {
-            OrgCtx c(s, w, W.coupled_list[q]);
-            c.load(); c.load_contacts(W.ic_bounce, W.ic_jbias); c.levels();
-            c.contacts_pass<true>(dt_coef); c.joints_pass<true>(dt_coef);
+            OrgCtx<MAXC> c(s, w, K, W.coupled_list[q]);
+            c.load(); c.prestep_pairs(); c.load_contact_state(W.ic_bounce, W.ic_jbias); c.levels();
+            c.template contacts_pass<true>(dt_coef); c.template joints_pass<true>(dt_coef);
             c.store_vel();
             __syncwarp();
         }
@@ -680,9 +684,9 @@ __global__ void __launch_bounds__(ORG_WARPS * 32) k_coupled(WORLD_ARG, Workspace
     for (int it = 0; it < w.p.iterations; it++) {
         for (int L = 1; L <= maxL; L++) { cross_level_pass<false>(w, W, L, nx, 0.f, gtid, gthreads); grid.sync(); }
         for (int q = gwarp; q < ncoupled; q += gwarps) {
-            OrgCtx c(s, w, W.coupled_list[q]);
-            c.load(); c.load_contacts(W.ic_bounce, W.ic_jbias); c.levels();
-            c.contacts_pass<false>(0.f); c.joints_pass<false>(0.f);
+            OrgCtx<MAXC> c(s, w, K, W.coupled_list[q]);
+            c.load(); c.prestep_pairs(); c.load_contact_state(W.ic_bounce, W.ic_jbias); c.levels();
+            c.template contacts_pass<false>(0.f); c.template joints_pass<false>(0.f);
             c.store_vel(); c.store_contacts(W.ic_bounce, W.ic_jbias);
             __syncwarp();
         }
@@ -710,24 +714,52 @@ __global__ void __launch_bounds__(256) k_step_finish(WORLD_ARG, Workspace W) {
 // ------------------------------------------------------------------------------------------------------------------
 // host-side launch sequence
 // ------------------------------------------------------------------------------------------------------------------
-static int g_coop_blocks = 0;
+struct StepPlan { bool ready; int sms; int coop_blocks; int org_blocks[4]; size_t org_smem[4]; size_t coop_smem; };
+static StepPlan g_plan = {false, 148, 0, {0, 0, 0, 0}, {0, 0, 0, 0}, 0};
+
+template <int CM>
+static cudaError_t plan_org(int cls) {
+    size_t smem = sizeof(OrgS<CM>) * OrgCfg<CM>::WARPS;
+    cudaError_t e = cudaFuncSetAttribute(k_org_solve<CM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_org_solve<CM>, OrgCfg<CM>::WARPS * 32, smem);
+    if (e != cudaSuccess) return e;
+    g_plan.org_smem[cls] = smem;
+    g_plan.org_blocks[cls] = (per_sm > 0 ? per_sm : 1) * g_plan.sms;     // persistent: every SM full, work pulled dynamically
+    return cudaSuccess;
+}
 
 static int launch_space_step(const SapioWorld &w, const Workspace &W, cudaStream_t st, char *err, size_t errlen) {
 #define STEP_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { snprintf(err, errlen, #expr ": %s", cudaGetErrorString(e_)); return SAPIO_E_CUDA; } } while (0)
     const SapioParams &p = w.p;
     const int NC = p.n_org * MAXC, NB = NC + p.n_dead, NG = p.grid_nx * p.grid_ny;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (!g_plan.ready) {
+        int dev = 0;
+        STEP_TRY(cudaGetDevice(&dev));
+        STEP_TRY(cudaDeviceGetAttribute(&g_plan.sms, cudaDevAttrMultiProcessorCount, dev));
+        STEP_TRY(plan_org<16>(0)); STEP_TRY(plan_org<32>(1)); STEP_TRY(plan_org<48>(2)); STEP_TRY(plan_org<64>(3));
+        g_plan.coop_smem = sizeof(OrgS<MAXC>) * COUPLED_WARPS;
+        STEP_TRY(cudaFuncSetAttribute(k_coupled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_plan.coop_smem));
+        int per_sm = 0;
+        STEP_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_coupled, COUPLED_WARPS * 32, g_plan.coop_smem));
+        g_plan.coop_blocks = per_sm * g_plan.sms;
+        if (g_plan.coop_blocks < 1) { snprintf(err, errlen, "k_coupled does not fit on an SM"); return SAPIO_E_CUDA; }
+        g_plan.ready = true;
+    }
+    const int sms = g_plan.sms;
     auto sgrid = [&](long items, int threads) { long want = (items + threads - 1) / threads, wave = (long)sms * 8; return (int)(want < 1 ? 1 : (want > wave ? wave : want)); };
+    StepK K;
+    K.dt = (double)p.dt_phys;
+    K.bc_contact = 1.0 - pow((double)p.collision_bias, K.dt);        // cpSpaceStep: biasCoef = 1 - collisionBias^dt
+    K.bc_joint = 1.0 - pow((double)p.joint_error_bias, K.dt);        // bias_coef(errorBias, dt)
+    K.dt_coef_unused = 0.f;
 
     STEP_TRY(cudaMemsetAsync(W.flags, 0, 256, st));
     STEP_TRY(cudaMemsetAsync(W.org_coupled, 0, (size_t)p.n_org, st));
     k_integrate<<<sgrid(NB, 256), 256, 0, st>>>(w, W.gkey, W.gval);
-    int bits = 1; while ((1ll << bits) < (long long)NG + 1 && bits < 32) bits++;
     size_t tmp = W.cub_bytes;
-    // inactive slots carry key ~0: with end_bit = bits they sort by their low bits only, so mask them out by sorting all 32
     STEP_TRY(cub::DeviceRadixSort::SortPairs(W.cub_tmp, tmp, W.gkey, W.skey, W.gval, W.sval, NB, 0, 32, st));
-    (void)bits;
     STEP_TRY(cudaMemsetAsync(W.cell_start, 0, (size_t)NG * 4, st));
     STEP_TRY(cudaMemsetAsync(W.cell_end, 0, (size_t)NG * 4, st));
     k_cell_bounds<<<sgrid(NB, 256), 256, 0, st>>>(W.skey, NB, NG, W.cell_start, W.cell_end);
@@ -741,33 +773,19 @@ static int launch_space_step(const SapioWorld &w, const Workspace &W, cudaStream
     STEP_TRY(cudaMemsetAsync(W.nx_prev_a, 0xFF, (size_t)p.x_cap * 4, st));
     STEP_TRY(cudaMemsetAsync(W.nx_prev_b, 0xFF, (size_t)p.x_cap * 4, st));
     k_cross_links<<<sgrid(NB, 128), 128, 0, st>>>(w, W);
-    k_cross_prestep<<<sgrid(p.x_cap, 128), 128, 0, st>>>(w, W);
-    k_coupled_list<<<sgrid(p.n_org, 256), 256, 0, st>>>(w, W);
-
-    const size_t smem = sizeof(OrgS) * ORG_WARPS;
-    static bool attr_done = false;
-    if (!attr_done) {
-        STEP_TRY(cudaFuncSetAttribute(k_org_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        STEP_TRY(cudaFuncSetAttribute(k_coupled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = 0;
-        STEP_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_coupled, ORG_WARPS * 32, smem));
-        g_coop_blocks = per_sm * sms;
-        attr_done = true;
-    }
-    {   // one warp per organism; a whole number of CTAs per SM
-        int per_sm = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_org_solve, ORG_WARPS * 32, smem);
-        long want = ((long)p.n_org + ORG_WARPS - 1) / ORG_WARPS, wave = (long)sms * (per_sm > 0 ? per_sm : 1);
-        long waves = (want + wave - 1) / wave;
-        int blocks = (int)(want <= wave ? want : wave * (waves > 8 ? 8 : waves));
-        if (blocks < 1) blocks = 1;
-        k_org_solve<<<blocks, ORG_WARPS * 32, smem, st>>>(w, W);
+    k_cross_prestep<<<sgrid(p.x_cap, 128), 128, 0, st>>>(w, W, K);
+    k_classify<<<sgrid(p.n_org, 256), 256, 0, st>>>(w, W);
+    {   // one warp per organism, persistent CTAs pulling organisms of their size class
+        auto blocks = [&](int cls, int warps) { long want = ((long)p.n_org + warps - 1) / warps; return (int)(want < g_plan.org_blocks[cls] ? want : g_plan.org_blocks[cls]); };
+        k_org_solve<16><<<blocks(0, OrgCfg<16>::WARPS), OrgCfg<16>::WARPS * 32, g_plan.org_smem[0], st>>>(w, W, K, 0);
+        k_org_solve<32><<<blocks(1, OrgCfg<32>::WARPS), OrgCfg<32>::WARPS * 32, g_plan.org_smem[1], st>>>(w, W, K, 1);
+        k_org_solve<48><<<blocks(2, OrgCfg<48>::WARPS), OrgCfg<48>::WARPS * 32, g_plan.org_smem[2], st>>>(w, W, K, 2);
+        k_org_solve<64><<<blocks(3, OrgCfg<64>::WARPS), OrgCfg<64>::WARPS * 32, g_plan.org_smem[3], st>>>(w, W, K, 3);
     }
     {
-        if (g_coop_blocks < 1) { snprintf(err, errlen, "k_coupled does not fit on an SM"); return SAPIO_E_CUDA; }
-        SapioWorld wc = w; Workspace Wc = W;
-        void *args[] = { (void *)&wc, (void *)&Wc };
-        STEP_TRY(cudaLaunchCooperativeKernel((void *)k_coupled, dim3(g_coop_blocks), dim3(ORG_WARPS * 32), args, smem, st));
+        SapioWorld wc = w; Workspace Wc = W; StepK Kc = K;
+        void *args[] = { (void *)&wc, (void *)&Wc, (void *)&Kc };
+        STEP_TRY(cudaLaunchCooperativeKernel((void *)k_coupled, dim3(g_plan.coop_blocks), dim3(COUPLED_WARPS * 32), args, g_plan.coop_smem, st));
     }
     k_step_finish<<<sgrid(NB + 1, 256), 256, 0, st>>>(w, W);
     STEP_TRY(cudaGetLastError());
