@@ -144,6 +144,10 @@ int oracle_inputs(const SapioWorld *w, int o, const double *energy, const uint8_
     return n;
 }
 
+/* pinning hook: the five uniforms (boredom gate, 4 for randn) the reference was fed, instead of the Philox draws */
+static const float *g_think_override = NULL;
+void oracle_set_think_uniforms(const float *u5) { g_think_override = u5; }
+
 /* neural.activate. History/STM are rings indexed by a running count (slot = count % capacity). */
 int oracle_think(SapioWorld *w, int o, const double *health, const double *energy, const uint8_t *alive, double rotation_deg) {
     (void)health;
@@ -163,8 +167,10 @@ int oracle_think(SapioWorld *w, int o, const double *health, const double *energ
     int32_t T = (int32_t)w->g_tick[0];
     uint32_t r[4];
     sapio_rng4(p->seed, w->org_uid[o], T, SAPIO_RNG_BOREDOM, 0, r);
-    if ((double)sapio_u01(r[0]) <= (double)w->org_boredom[o]) {                       /* neural.py:294-295 */
+    double gate_u = g_think_override ? (double)g_think_override[0] : (double)sapio_u01(r[0]);
+    if (gate_u <= (double)w->org_boredom[o]) {                                        /* neural.py:294-295 */
         sapio_rng4(p->seed, w->org_uid[o], T, SAPIO_RNG_RANDN, 0, r);
+        if (g_think_override) for (int q = 0; q < 4; q++) r[q] = (uint32_t)lrint((double)g_think_override[1 + q] * 16777216.0) << 8;
         for (int h = 0; h < 2; h++) {                                                  /* Box-Muller on (0,1] x [0,1) */
             double u1 = ((double)(r[2 * h] >> 8) + 1.0) / 16777216.0, u2 = (double)sapio_u01(r[2 * h + 1]);
             double rad = sqrt(-2.0 * log(u1)), th = 2.0 * M_PI * u2;

@@ -53,6 +53,9 @@ def lib():
         L.oracle_key1.argtypes = [dbl]; L.oracle_key1.restype = i32
         L.oracle_forward.argtypes = [fp, ctypes.POINTER(ctypes.c_int32), i32, fp, fp, fp]; L.oracle_forward.restype = None
         L.oracle_train_one.argtypes = [vp, i32]; L.oracle_train_one.restype = i32
+        L.oracle_think_now.argtypes = [vp, i32]; L.oracle_think_now.restype = i32
+        L.oracle_set_think_uniforms.argtypes = [ctypes.c_void_p]; L.oracle_set_think_uniforms.restype = None
+        L.oracle_rotation.argtypes = [vp, i32]; L.oracle_rotation.restype = dbl
         L.oracle_think.argtypes = [vp, i32, dp, dp, ctypes.POINTER(ctypes.c_uint8), dbl]; L.oracle_think.restype = i32
         L.oracle_inputs.argtypes = [vp, i32, dp, ctypes.POINTER(ctypes.c_uint8), dbl, dp]; L.oracle_inputs.restype = i32
         L.oracle_sensor_view.argtypes = [vp, i32, i32, ctypes.POINTER(ctypes.c_uint32), i32]; L.oracle_sensor_view.restype = i32
@@ -135,6 +138,17 @@ def forward(brain, ldim, x):
 
 
 def train_one(world, org) -> int: return lib().oracle_train_one(_ref(world), org)
+def think_now(world, org, uniforms=None) -> int:
+    """neural.activate for one organism; `uniforms` = (gate, 4 x randn) replaces the Philox draws (pinning tests)."""
+    if uniforms is None:
+        return lib().oracle_think_now(_ref(world), org)
+    a = np.ascontiguousarray(uniforms, dtype=np.float32)
+    lib().oracle_set_think_uniforms(a.ctypes.data)
+    try:
+        return lib().oracle_think_now(_ref(world), org)
+    finally:
+        lib().oracle_set_think_uniforms(None)
+def rotation(world, org) -> float: return lib().oracle_rotation(_ref(world), org)
 
 
 def inputs(world, org, rotation_deg=None):

@@ -368,3 +368,13 @@ int oracle_post(SapioWorld *w) {
     w->g_population[0] = pop;
     return 0;
 }
+
+/* test hook: neural.activate for organism o on the world's current state (dopamine/pain as stored) */
+int oracle_think_now(SapioWorld *w, int o) {
+    Org g; org_load(w, o, &g);
+    return oracle_think(w, o, g.health, g.energy, g.alive, org_rotation(w, &g));
+}
+double oracle_rotation(const SapioWorld *w, int o) {
+    Org g; org_load(w, o, &g);
+    return org_rotation(w, &g);
+}

@@ -23,7 +23,7 @@ def f32(x):
     return float(np.float32(x))
 
 
-def gen_rules(n_cases=10, seed=23):
+def gen_rules(n_cases=15, seed=23):
     ns = refshim.load()
     out = {"meta": np.asarray([n_cases, seed, N_TICKS], dtype=np.int32)}
     none = lambda: refshim.UniformFeed([], "none")
@@ -64,10 +64,10 @@ def gen_rules(n_cases=10, seed=23):
             elif mode == 1:    # nearly full: saturating add_energy, reproduction-gate halving
                 e, h = ci_["energy_storage"] * rng.uniform(0.985, 1.0), ci_["max_health"] * rng.uniform(0.5, 1.0)
             elif mode == 2:    # starving
-                e, h = ci_["energy_storage"] * rng.uniform(0.0, 0.05), ci_["max_health"] * rng.uniform(0.05, 0.4)
+                e, h = ci_["energy_storage"] * rng.uniform(0.0, 0.05), ci_["max_health"] * rng.uniform(0.0, 0.12)
             elif mode == 3:    # some cells about to die -> cascades, break damage, dead bodies
                 e, h = ci_["energy_storage"] * rng.uniform(0.1, 0.9), ci_["max_health"] * rng.uniform(0.2, 1.0)
-                if k > 0 and rng.random() < 0.25:
+                if k > 0 and rng.random() < 0.4:
                     h = -1.0 if rng.random() < 0.5 else 0.0
             else:
                 e, h = ci_["energy_storage"] * rng.uniform(0.0, 1.0), ci_["max_health"] * rng.uniform(0.0, 1.0)
