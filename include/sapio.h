@@ -128,44 +128,13 @@ size_t sapio_workspace_bytes(const SapioParams *p);
 int sapio_tick(const SapioWorld *w, void *ws, size_t ws_bytes, uint32_t phases, int n_ticks, void *stream);
 
 /* Stages, callable on their own (parity tests drive these one by one):                               */
-/* sprites.update_organisms: per-organism rules incl. think (neural.activate)          sprites.py:1809 */
-int sapio_rules(const SapioWorld *w, void *ws, size_t ws_bytes, uint32_t phases, void *stream);
-/* neural.train_network for every organism whose training is due                       neural.py:369   */
-int sapio_train(const SapioWorld *w, void *ws, size_t ws_bytes, void *stream);
-/* carnivore damage/eating gather, death -> dead bodies, gradual_dispersion, bounds    sprites.py:1326,1752,1849 */
-int sapio_settle(const SapioWorld *w, void *ws, size_t ws_bytes, void *stream);
-/* Organism.reproduce / DNA.mutate / get_new_organism_position / build_body            sprites.py:1441,1068,194,1698 */
-int sapio_reproduce(const SapioWorld *w, void *ws, size_t ws_bytes, void *stream);
 /* pymunk.Space.step(dt_phys)                                                          physics.py:432  */
 int sapio_space_step(const SapioWorld *w, void *ws, size_t ws_bytes, void *stream);
 /* Sprite.updateSprite for every solid sprite                                          physics.py:250  */
 int sapio_friction(const SapioWorld *w, void *stream);
 /* updateUI's simulation-relevant part: gas clamps, population recount                 Sapiogenesis.py:57-65 */
 int sapio_post(const SapioWorld *w, void *ws, size_t ws_bytes, void *stream);
-
-/* Host-buffer variant used for the end-to-end figure and by a GUI host: uploads the per-tick control
- * block (the values Sapiogenesis.py:82-85 re-reads from widgets each tick), runs n_ticks, downloads
- * the render state the reference pushes to Qt (Sprite.setPos/setRotation, physics.py:253-272) and the
- * UI counters (Sapiogenesis.py:62-69). Host pointers must be page-locked for async copies. */
-typedef struct SapioControl {
-    int32_t population_limit, offspring_amount, weight_persistence, repro_ticks;
-    float mutation_severity, brain_mutation_severity, learning_rate, pad;
-} SapioControl;
-typedef struct SapioFrameHeader {
-    double co2, o2; int64_t tick; int32_t population, n_dead_active; int64_t stats[16];
-} SapioFrameHeader;
-int sapio_tick_host(SapioWorld *w_device_resident_params, void *ws, size_t ws_bytes, uint32_t phases, int n_ticks,
-                    const SapioControl *h_control,      /* host, in  */
-                    SapioFrameHeader *h_header,         /* host, out */
-                    float *h_cell_pose,                 /* host, out: n_org*MAXC*4 floats (x, y, angle, alive) */
-                    float *h_dead_pose,                 /* host, out: n_dead*4 floats (x, y, angle, mass) */
-                    void *stream);
-
-/* Islands: pack/unpack one genome (cells table + growth tree + hidden widths + hidden weights) into a
- * flat record for NCCL send/recv == pickle of sprites.DNA (Sapiogenesis.py:243-254,413-424). */
-size_t sapio_genome_record_floats(const SapioParams *p);
-int sapio_pack_genomes(const SapioWorld *w, const int32_t *d_org_idx, int n, float *d_records, void *stream);
-int sapio_unpack_genomes(const SapioWorld *w, void *ws, size_t ws_bytes, const float *d_records, int n, void *stream);
+/*@STAGES@*/
 
 #ifdef __cplusplus
 }
