@@ -134,7 +134,19 @@ int sapio_space_step(const SapioWorld *w, void *ws, size_t ws_bytes, void *strea
 int sapio_friction(const SapioWorld *w, void *stream);
 /* updateUI's simulation-relevant part: gas clamps, population recount                 Sapiogenesis.py:57-65 */
 int sapio_post(const SapioWorld *w, void *ws, size_t ws_bytes, void *stream);
-/*@STAGES@*/
+/* sprites.update_organisms: per-organism rules incl. neural.activate when SAPIO_PH_THINK is set          sprites.py:1809, neural.py:91 */
+int sapio_rules(const SapioWorld *w, void *ws, size_t ws_bytes, uint32_t phases, void *stream);
+/* neural.train_network for every organism sapio_rules marked as due (org_req & SAPIO_REQ_TRAIN)           neural.py:369 */
+int sapio_train(const SapioWorld *w, void *ws, size_t ws_bytes, void *stream);
+/* deferred carnivore damage / eating, dying cells -> dead bodies, gradual_dispersion, bounds              sprites.py:1326,1497,1752,1849 */
+int sapio_settle(const SapioWorld *w, void *ws, size_t ws_bytes, void *stream);
+/* Organism.reproduce / DNA.mutate / get_new_organism_position / build_body for org_req & SAPIO_REQ_REPRODUCE  sprites.py:1441,1068,194,1698 */
+int sapio_reproduce(const SapioWorld *w, void *ws, size_t ws_bytes, void *stream);
+/* add_creature_clicked: DNA().randomize(spawn ranges) + Organism + build_body into the given free slots at the given
+ * positions (device arrays: n slots, 2n doubles); uids are g_next_uid, g_next_uid + 1, ...               Sapiogenesis.py:297-323 */
+int sapio_spawn(const SapioWorld *w, void *ws, size_t ws_bytes, const int32_t *d_slots, const double *d_pos, int n, void *stream);
+/* parity probe: sprite.info["view"] of one eye / olfactory cell as ascending body ids (device out, count may exceed cap) sprites.py:221-236 */
+int sapio_sensor_view(const SapioWorld *w, void *ws, size_t ws_bytes, int org, int cell, uint32_t *d_out, int cap, int32_t *d_count, void *stream);
 
 #ifdef __cplusplus
 }

@@ -42,8 +42,8 @@ def load() -> ctypes.CDLL:
     for name in ("sapio_train", "sapio_settle", "sapio_reproduce"):
         if hasattr(L, name):
             getattr(L, name).argtypes = [wp, vp, sz, vp]; getattr(L, name).restype = i32
-    if hasattr(L, "sapio_spawn"):
-        L.sapio_spawn.argtypes = [wp, vp, sz, ctypes.c_void_p, i32, vp]; L.sapio_spawn.restype = i32
+    L.sapio_spawn.argtypes = [wp, vp, sz, vp, vp, i32, vp]; L.sapio_spawn.restype = i32
+    L.sapio_sensor_view.argtypes = [wp, vp, sz, i32, i32, vp, i32, vp, vp]; L.sapio_sensor_view.restype = i32
     if L.sapio_abi_version() != 1:
         raise SapioError("libsapio_b200.so ABI version mismatch")
     _lib = L

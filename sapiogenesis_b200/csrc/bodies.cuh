@@ -6,6 +6,7 @@
 // cpBodyUpdatePosition (Chipmunk cpBody.c; SURVEY A-2 step 1) for every dynamic body: living cells, their sensor
 // bodies (sprites.py:300-323) and free dead cells. p = fma(v + v_bias, dt, p): the single fp32 op sequence the oracle mirrors.
 // Also writes the broadphase key of every solid body (grid cell index, or ~0 for "no body in this slot").
+template <bool INTEGRATE>
 __global__ void __launch_bounds__(256) k_integrate(WORLD_ARG, uint32_t *__restrict__ grid_key, uint32_t *__restrict__ grid_val) {
     const SapioParams &p = w.p;
     const int NC = p.n_org * MAXC, NB = NC + p.n_dead;
@@ -18,13 +19,16 @@ __global__ void __launch_bounds__(256) k_integrate(WORLD_ARG, uint32_t *__restri
             int o = b >> 6;
             if (w.org_state[o] == 1 && (b & 63) < w.org_ncells[o] && w.c_alive[b] == SAPIO_CELL_ALIVE) {
                 float2 *P = reinterpret_cast<float2 *>(w.c_pos), *V = reinterpret_cast<float2 *>(w.c_vel), *VB = reinterpret_cast<float2 *>(w.c_vbias);
-                pos = P[b]; float2 v = V[b], vb = VB[b];
+                pos = P[b];
+                if (INTEGRATE) {
+                float2 v = V[b], vb = VB[b];
                 pos.x = __fmaf_rn(__fadd_rn(v.x, vb.x), dt, pos.x);
                 pos.y = __fmaf_rn(__fadd_rn(v.y, vb.y), dt, pos.y);
                 P[b] = pos; VB[b] = make_float2(0.f, 0.f);
                 w.c_ang[b] = __fmaf_rn(__fadd_rn(w.c_angvel[b], w.c_wbias[b]), dt, w.c_ang[b]);
                 w.c_wbias[b] = 0.f;
-                if (is_sensor_type(w.c_type[b])) {
+                }
+                if (INTEGRATE && is_sensor_type(w.c_type[b])) {
                     float2 *SP = reinterpret_cast<float2 *>(w.c_spos), *SV = reinterpret_cast<float2 *>(w.c_svel), *SVB = reinterpret_cast<float2 *>(w.c_svbias);
                     float2 sp = SP[b], sv = SV[b], svb = SVB[b];
                     sp.x = __fmaf_rn(__fadd_rn(sv.x, svb.x), dt, sp.x);
@@ -37,12 +41,15 @@ __global__ void __launch_bounds__(256) k_integrate(WORLD_ARG, uint32_t *__restri
             int d = b - NC;
             if (w.d_state[d]) {
                 float2 *P = reinterpret_cast<float2 *>(w.d_pos), *V = reinterpret_cast<float2 *>(w.d_vel), *VB = reinterpret_cast<float2 *>(w.d_vbias);
-                pos = P[d]; float2 v = V[d], vb = VB[d];
+                pos = P[d];
+                if (INTEGRATE) {
+                float2 v = V[d], vb = VB[d];
                 pos.x = __fmaf_rn(__fadd_rn(v.x, vb.x), dt, pos.x);
                 pos.y = __fmaf_rn(__fadd_rn(v.y, vb.y), dt, pos.y);
                 P[d] = pos; VB[d] = make_float2(0.f, 0.f);
                 w.d_ang[d] = __fmaf_rn(__fadd_rn(w.d_angvel[d], w.d_wbias[d]), dt, w.d_ang[d]);
                 w.d_wbias[d] = 0.f;
+                }
                 solid = true;
             }
         }

@@ -1,12 +1,17 @@
 // sapio_abi.cu -- the C-ABI of libsapio_b200.so (include/sapio.h). Thin: argument checks, workspace carve-up,
 // kernel launches on the caller's stream. No allocation, no torch types, no CPU fallback: without a device every
 // compute entry point returns SAPIO_E_NODEVICE.
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <cub/cub.cuh>
 #include "common.cuh"
 #include "bodies.cuh"
 #include "step.cuh"
+#include "rules.cuh"
+#include "think.cuh"
+#include "train.cuh"
+#include "repro.cuh"
 
 static thread_local char g_err[512] = "";
 static int fail(int code, const char *fmt, const char *a = "") {
@@ -25,13 +30,179 @@ static int sm_count() {
     }
     return g_sms;
 }
-// streaming kernels: a whole number of waves over the SMs (148 on B200), 8 CTAs of 256 threads resident per SM
+// streaming kernels: a whole number of waves over the SMs (148 on B200), 8 CTAs resident per SM
 static int stream_grid(long items, int threads = 256) {
     int sms = sm_count() > 0 ? sm_count() : 148;
     long want = (items + threads - 1) / threads;
     long wave = (long)sms * 8;
     if (want <= wave) return (int)(want > 0 ? want : 1);
     return (int)wave;
+}
+
+static size_t cub_need(const SapioParams &p) {
+    size_t a = 0, b = 0, c = 0, d = 0;
+    cub::DeviceScan::InclusiveScan(nullptr, a, (Aff *)nullptr, (Aff *)nullptr, AffCompose(), p.n_org);
+    cub::DeviceReduce::Sum(nullptr, b, (double *)nullptr, (double *)nullptr, p.n_org);
+    cub::DeviceReduce::Reduce(nullptr, c, (double *)nullptr, (double *)nullptr, p.n_dead, MulD(), 1.0);
+    cub::DeviceScan::ExclusiveSum(nullptr, d, (int *)nullptr, (int *)nullptr, (p.n_org > p.n_dead ? p.n_org : p.n_dead) + 1);
+    size_t m = a > b ? a : b; m = m > c ? m : c; m = m > d ? m : d;
+    return m;
+}
+
+struct AllWs { Workspace step; RulesWs rules; TrainWs train; ReproWs repro; int train_ctas; int *probe; };
+
+static size_t carve_all(const SapioParams &p, char *base, AllWs *A) {
+    size_t off = carve_workspace(p, base, &A->step);
+    auto take = [&](size_t bytes) -> char * { char *r = base ? base + off : nullptr; off += (bytes + 255) & ~size_t(255); return r; };
+    const size_t NO = (size_t)p.n_org, ND = (size_t)p.n_dead;
+    RulesWs &R = A->rules;
+    R.gas_map = (Aff *)take(NO * sizeof(Aff)); R.gas_scan = (Aff *)take(NO * sizeof(Aff));
+    R.think_list = (int *)take(NO * 4); R.train_list = (int *)take(NO * 4); R.repro_list = (int *)take(NO * 4);
+    R.counters = (int *)take(256);
+    R.refund_sum = (double *)take(256);
+    R.dying_cnt = (int *)take((NO + 1) * 4); R.dying_off = (int *)take((NO + 1) * 4);
+    R.free_flag = (int *)take((ND + 1) * 4); R.free_off = (int *)take((ND + 1) * 4); R.free_list = (int *)take(ND * 4);
+    R.disp_factor = (double *)take(ND * 8); R.disp_prod = (double *)take(256);
+    A->train_ctas = 2 * 148;
+    TrainWs &T = A->train;
+    T.dz0 = (float *)take((size_t)A->train_ctas * SAPIO_MEMROWS * TRAIN_MAXW * 4);
+    T.hl = (float *)take((size_t)A->train_ctas * SAPIO_MEMROWS * TRAIN_MAXW * 4);
+    T.dO = (float *)take((size_t)A->train_ctas * SAPIO_MEMROWS * 4 * 4);
+    ReproWs &Q = A->repro;
+    Q.birth_cap = (int)(NO < 4096 ? NO : 4096);
+    Q.births = (Birth *)take((size_t)Q.birth_cap * sizeof(Birth));
+    Q.req_flag = (int *)take((NO + 1) * 4); Q.req_off = (int *)take((NO + 1) * 4);
+    Q.free_flag = (int *)take((NO + 1) * 4); Q.free_off = (int *)take((NO + 1) * 4);
+    Q.req_list = (int *)take(NO * 4); Q.free_list = (int *)take(NO * 4);
+    Q.accepted = (int *)take((size_t)Q.birth_cap * 4);
+    Q.counters = (int *)take(256);
+    A->probe = (int *)take(256);
+    // cub temp storage is shared by every scan / reduction / sort: one region sized for the largest user
+    size_t need = cub_need(p);
+    if (need > A->step.cub_bytes) { A->step.cub_tmp = take(need); A->step.cub_bytes = need; }
+    return off;
+}
+
+static bool g_tables_ready = false;
+static int ensure_tables() {
+    if (g_tables_ready) return 0;
+    double c[360], s[360];
+    for (int b = 0; b < 360; b++) { double rad = b * (M_PI / 180.0); c[b] = cos(rad); s[b] = sin(rad); }   // math.radians / math.cos
+    CUDA_TRY(cudaMemcpyToSymbol(C_COS, c, sizeof(c)));
+    CUDA_TRY(cudaMemcpyToSymbol(C_SIN, s, sizeof(s)));
+    g_tables_ready = true;
+    return 0;
+}
+
+static int check(const SapioWorld *w, void *ws, size_t ws_bytes, AllWs *out) {
+    if (!w) return fail(SAPIO_E_ARG, "null world%s");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); return fail(SAPIO_E_NODEVICE, "no CUDA device: libsapio_b200 has no CPU path%s"); }
+    if (w->p.width_cap > TRAIN_MAXW) return fail(SAPIO_E_ARG, "width_cap above the compiled maximum (128)%s");
+    if (out) {
+        size_t need = carve_all(w->p, (char *)ws, out);
+        if (!ws || ws_bytes < need) return fail(SAPIO_E_WORKSPACE, "workspace too small%s");
+    }
+    return ensure_tables();
+}
+
+// ---- stage launchers ----------------------------------------------------------------------------------------------
+static int launch_grid_only(const SapioWorld &w, const Workspace &W, cudaStream_t st) {
+    const int NC = w.p.n_org * MAXC, NB = NC + w.p.n_dead, NG = w.p.grid_nx * w.p.grid_ny;
+    k_integrate<false><<<stream_grid(NB), 256, 0, st>>>(w, W.gkey, W.gval);
+    size_t tmp = W.cub_bytes;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(W.cub_tmp, tmp, W.gkey, W.skey, W.gval, W.sval, NB, 0, 32, st));
+    CUDA_TRY(cudaMemsetAsync(W.cell_start, 0, (size_t)NG * 4, st));
+    CUDA_TRY(cudaMemsetAsync(W.cell_end, 0, (size_t)NG * 4, st));
+    k_cell_bounds<<<stream_grid(NB), 256, 0, st>>>(W.skey, NB, NG, W.cell_start, W.cell_end);
+    return 0;
+}
+
+static int launch_rules(const SapioWorld &w, AllWs &A, uint32_t phases, cudaStream_t st) {
+    const SapioParams &p = w.p;
+    RulesWs &R = A.rules;
+    CUDA_TRY(cudaMemsetAsync(R.counters, 0, 256, st));
+    const int org_grid = stream_grid((long)p.n_org * 32, RULES_WARPS * 32);
+    k_rules_begin<<<org_grid, RULES_WARPS * 32, 0, st>>>(w, R, phases);
+    size_t tmp = A.step.cub_bytes;
+    CUDA_TRY(cub::DeviceScan::InclusiveScan(A.step.cub_tmp, tmp, R.gas_map, R.gas_scan, AffCompose(), p.n_org, st));
+    if (phases & SAPIO_PH_THINK) {
+        int rc = launch_grid_only(w, A.step, st); if (rc) return rc;
+        size_t smem = (size_t)THINK_WARPS * (p.in_cap + 2 * (p.width_cap > 4 ? p.width_cap : 4)) * sizeof(float);
+        static size_t smem_set = 0;
+        if (smem > smem_set) { CUDA_TRY(cudaFuncSetAttribute(k_think, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_set = smem; }
+        k_think<<<stream_grid((long)p.n_org * 32 / 4 + 1, THINK_WARPS * 32), THINK_WARPS * 32, smem, st>>>(w, A.step, R);
+    }
+    k_rules_main<<<org_grid, RULES_WARPS * 32, 0, st>>>(w, R, phases);
+    tmp = A.step.cub_bytes;
+    CUDA_TRY(cub::DeviceReduce::Sum(A.step.cub_tmp, tmp, w.org_gas_refund, R.refund_sum, p.n_org, st));
+    k_rules_finish<<<1, 1, 0, st>>>(w, R);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+static int launch_train(const SapioWorld &w, AllWs &A, cudaStream_t st) {
+    const SapioParams &p = w.p;
+    size_t smem = (size_t)(SAPIO_STM + SAPIO_MEMROWS) * p.in_cap * sizeof(int16_t);
+    static size_t smem_set = 0;
+    if (smem > smem_set) { CUDA_TRY(cudaFuncSetAttribute(k_train, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_set = smem; }
+    int ctas = p.n_org < A.train_ctas ? p.n_org : A.train_ctas;
+    k_train<<<ctas, TRAIN_THREADS, smem, st>>>(w, A.rules, A.train);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+static int launch_settle(const SapioWorld &w, AllWs &A, cudaStream_t st) {
+    const SapioParams &p = w.p;
+    RulesWs &R = A.rules;
+    const long NB = (long)p.n_org * MAXC + p.n_dead;
+    k_settle_gather<<<stream_grid(NB), 256, 0, st>>>(w);
+    k_settle_count<<<stream_grid((p.n_org > p.n_dead ? p.n_org : p.n_dead) + 1), 256, 0, st>>>(w, R);
+    size_t tmp = A.step.cub_bytes;
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(A.step.cub_tmp, tmp, R.dying_cnt, R.dying_off, p.n_org + 1, st));
+    tmp = A.step.cub_bytes;
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(A.step.cub_tmp, tmp, R.free_flag, R.free_off, p.n_dead + 1, st));
+    k_settle_freelist<<<stream_grid(p.n_dead), 256, 0, st>>>(w, R);
+    k_settle_deaths<<<stream_grid(p.n_org), 256, 0, st>>>(w, R);
+    k_settle_disperse<<<stream_grid(NB), 256, 0, st>>>(w, R);
+    tmp = A.step.cub_bytes;
+    CUDA_TRY(cub::DeviceReduce::Reduce(A.step.cub_tmp, tmp, R.disp_factor, R.disp_prod, p.n_dead, MulD(), 1.0, st));
+    k_settle_gas<<<1, 1, 0, st>>>(w, R);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+static int launch_reproduce(const SapioWorld &w, AllWs &A, cudaStream_t st) {
+    const SapioParams &p = w.p;
+    ReproWs &Q = A.repro;
+    k_org_rects<<<stream_grid(p.n_org), 256, 0, st>>>(w);
+    for (int sib = 0; sib < p.offspring_amount; sib++) {
+        k_repro_flags<<<stream_grid(p.n_org + 1), 256, 0, st>>>(w, Q);
+        size_t tmp = A.step.cub_bytes;
+        CUDA_TRY(cub::DeviceScan::ExclusiveSum(A.step.cub_tmp, tmp, Q.req_flag, Q.req_off, p.n_org + 1, st));
+        tmp = A.step.cub_bytes;
+        CUDA_TRY(cub::DeviceScan::ExclusiveSum(A.step.cub_tmp, tmp, Q.free_flag, Q.free_off, p.n_org + 1, st));
+        k_repro_lists<<<stream_grid(p.n_org), 256, 0, st>>>(w, Q);
+        int blocks = (Q.birth_cap + REPRO_WARPS - 1) / REPRO_WARPS;
+        int cap = (sm_count() > 0 ? sm_count() : 148) * 8;
+        if (blocks > cap) blocks = cap;
+        k_repro_prepare<<<blocks, REPRO_WARPS * 32, 0, st>>>(w, Q, sib);
+        k_repro_resolve<<<1, 32, 0, st>>>(w, Q, sib);
+        k_repro_finish<<<blocks, REPRO_WARPS * 32, 0, st>>>(w, Q, sib);
+        if (sib + 1 < p.offspring_amount) k_repro_next_sibling<<<stream_grid(Q.birth_cap), 256, 0, st>>>(w, Q);
+    }
+    LAUNCH_CHECK();
+    return 0;
+}
+
+static int launch_post(const SapioWorld &w, AllWs &A, cudaStream_t st, int do_post, int advance) {
+    if (do_post) {
+        CUDA_TRY(cudaMemsetAsync(A.step.pop, 0, sizeof(int), st));
+        k_post_count<<<stream_grid(w.p.n_org), 256, 0, st>>>(w, A.step.pop);
+    }
+    k_post_finish<<<1, 1, 0, st>>>(w, A.step.pop, do_post, advance);
+    LAUNCH_CHECK();
+    return 0;
 }
 
 extern "C" {
@@ -46,18 +217,8 @@ int sapio_device_count(void) {
 
 size_t sapio_workspace_bytes(const SapioParams *p) {
     if (!p) return 0;
-    Workspace ws;
-    return carve_workspace(*p, nullptr, &ws);
-}
-
-static int check(const SapioWorld *w, void *ws, size_t ws_bytes, Workspace *out) {
-    if (!w) return fail(SAPIO_E_ARG, "null world%s");
-    if (sapio_device_count() <= 0) return fail(SAPIO_E_NODEVICE, "no CUDA device: libsapio_b200 has no CPU path%s");
-    if (out) {
-        size_t need = carve_workspace(w->p, (char *)ws, out);
-        if (!ws || ws_bytes < need) return fail(SAPIO_E_WORKSPACE, "workspace too small%s");
-    }
-    return 0;
+    AllWs A;
+    return carve_all(*p, nullptr, &A);
 }
 
 int sapio_friction(const SapioWorld *w, void *stream) {
@@ -67,35 +228,64 @@ int sapio_friction(const SapioWorld *w, void *stream) {
     LAUNCH_CHECK();
     return 0;
 }
-
 int sapio_post(const SapioWorld *w, void *ws, size_t ws_bytes, void *stream) {
-    Workspace W; int rc = check(w, ws, ws_bytes, &W); if (rc) return rc;
+    AllWs A; int rc = check(w, ws, ws_bytes, &A); if (rc) return rc;
+    return launch_post(*w, A, (cudaStream_t)stream, 1, 0);
+}
+int sapio_space_step(const SapioWorld *w, void *ws, size_t ws_bytes, void *stream) {
+    AllWs A; int rc = check(w, ws, ws_bytes, &A); if (rc) return rc;
+    return launch_space_step(*w, A.step, (cudaStream_t)stream, g_err, sizeof(g_err));
+}
+int sapio_rules(const SapioWorld *w, void *ws, size_t ws_bytes, uint32_t phases, void *stream) {
+    AllWs A; int rc = check(w, ws, ws_bytes, &A); if (rc) return rc;
+    return launch_rules(*w, A, phases, (cudaStream_t)stream);
+}
+int sapio_train(const SapioWorld *w, void *ws, size_t ws_bytes, void *stream) {
+    AllWs A; int rc = check(w, ws, ws_bytes, &A); if (rc) return rc;
+    return launch_train(*w, A, (cudaStream_t)stream);
+}
+int sapio_settle(const SapioWorld *w, void *ws, size_t ws_bytes, void *stream) {
+    AllWs A; int rc = check(w, ws, ws_bytes, &A); if (rc) return rc;
+    return launch_settle(*w, A, (cudaStream_t)stream);
+}
+int sapio_reproduce(const SapioWorld *w, void *ws, size_t ws_bytes, void *stream) {
+    AllWs A; int rc = check(w, ws, ws_bytes, &A); if (rc) return rc;
+    return launch_reproduce(*w, A, (cudaStream_t)stream);
+}
+int sapio_spawn(const SapioWorld *w, void *ws, size_t ws_bytes, const int32_t *d_slots, const double *d_pos, int n, void *stream) {
+    AllWs A; int rc = check(w, ws, ws_bytes, &A); if (rc) return rc;
+    if (n <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    CUDA_TRY(cudaMemsetAsync(W.pop, 0, sizeof(int), st));
-    k_post_count<<<stream_grid(w->p.n_org), 256, 0, st>>>(*w, W.pop);
-    k_post_finish<<<1, 1, 0, st>>>(*w, W.pop, 1, 0);
+    int blocks = (n + REPRO_WARPS - 1) / REPRO_WARPS, cap = (sm_count() > 0 ? sm_count() : 148) * 8;
+    if (blocks > cap) blocks = cap;
+    k_spawn<<<blocks, REPRO_WARPS * 32, 0, st>>>(*w, d_slots, d_pos, n);
+    k_spawn_finish<<<1, 1, 0, st>>>(*w, n);
+    LAUNCH_CHECK();
+    return 0;
+}
+int sapio_sensor_view(const SapioWorld *w, void *ws, size_t ws_bytes, int org, int cell, uint32_t *d_out, int cap, int32_t *d_count, void *stream) {
+    AllWs A; int rc = check(w, ws, ws_bytes, &A); if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = launch_grid_only(*w, A.step, st); if (rc) return rc;
+    k_sensor_view<<<1, 32, 0, st>>>(*w, A.step, org, cell, d_out, cap, d_count);
     LAUNCH_CHECK();
     return 0;
 }
 
-int sapio_space_step(const SapioWorld *w, void *ws, size_t ws_bytes, void *stream) {
-    Workspace W; int rc = check(w, ws, ws_bytes, &W); if (rc) return rc;
-    return launch_space_step(*w, W, (cudaStream_t)stream, g_err, sizeof(g_err));
-}
-
 int sapio_tick(const SapioWorld *w, void *ws, size_t ws_bytes, uint32_t phases, int n_ticks, void *stream) {
-    Workspace W; int rc = check(w, ws, ws_bytes, &W); if (rc) return rc;
+    AllWs A; int rc = check(w, ws, ws_bytes, &A); if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     long nb = (long)w->p.n_org * MAXC + w->p.n_dead;
     for (int t = 0; t < n_ticks; t++) {
-        if (phases & SAPIO_PH_STEP) { rc = launch_space_step(*w, W, st, g_err, sizeof(g_err)); if (rc) return rc; }
-        if (phases & SAPIO_PH_FRICTION) k_friction<<<stream_grid(nb), 256, 0, st>>>(*w);
-        if (phases & SAPIO_PH_POST) {
-            CUDA_TRY(cudaMemsetAsync(W.pop, 0, sizeof(int), st));
-            k_post_count<<<stream_grid(w->p.n_org), 256, 0, st>>>(*w, W.pop);
+        if (phases & SAPIO_PH_RULES) {
+            if ((rc = launch_rules(*w, A, phases, st))) return rc;
+            if (phases & SAPIO_PH_TRAIN) if ((rc = launch_train(*w, A, st))) return rc;
+            if ((rc = launch_settle(*w, A, st))) return rc;
+            if (phases & SAPIO_PH_REPRODUCE) if ((rc = launch_reproduce(*w, A, st))) return rc;
         }
-        k_post_finish<<<1, 1, 0, st>>>(*w, W.pop, (phases & SAPIO_PH_POST) ? 1 : 0, 1);
-        LAUNCH_CHECK();
+        if (phases & SAPIO_PH_STEP) { rc = launch_space_step(*w, A.step, st, g_err, sizeof(g_err)); if (rc) return rc; }
+        if (phases & SAPIO_PH_FRICTION) k_friction<<<stream_grid(nb), 256, 0, st>>>(*w);
+        if ((rc = launch_post(*w, A, st, (phases & SAPIO_PH_POST) ? 1 : 0, 1))) return rc;
     }
     return 0;
 }

@@ -757,7 +757,7 @@ static int launch_space_step(const SapioWorld &w, const Workspace &W, cudaStream
 
     STEP_TRY(cudaMemsetAsync(W.flags, 0, 256, st));
     STEP_TRY(cudaMemsetAsync(W.org_coupled, 0, (size_t)p.n_org, st));
-    k_integrate<<<sgrid(NB, 256), 256, 0, st>>>(w, W.gkey, W.gval);
+    k_integrate<true><<<sgrid(NB, 256), 256, 0, st>>>(w, W.gkey, W.gval);
     size_t tmp = W.cub_bytes;
     STEP_TRY(cub::DeviceRadixSort::SortPairs(W.cub_tmp, tmp, W.gkey, W.skey, W.gval, W.sval, NB, 0, 32, st));
     STEP_TRY(cudaMemsetAsync(W.cell_start, 0, (size_t)NG * 4, st));

@@ -1,0 +1,246 @@
+// think.cuh -- neural.activate (neural.py:91-366) for every organism whose brain is due: one warp per organism.
+//   sensors  : each eye / olfactory cell's `view` is the set of solid bodies of other organisms whose disc overlaps the
+//              sensor disc (centre: the sensor BODY, sprites.py:300-323); members are found through the broadphase grid,
+//              lanes striding over the grid cells the disc covers, exact double predicate (contract C3)
+//   encoding : 8-sector eye (neural.py:123-196), olfactory (neural.py:197-218), speed/x/y, energy (neural.py:227-244)
+//   forward  : networks.Network.forward (networks.py:301-308), warp-level FMA over the ragged layer chain (batch of one
+//              per organism: a GEMV chain, bound by reading the weights once)
+//   after    : 3-decimal rounding, boredom gate + randn (Philox), history / short-term memory rings, movement clamp,
+//              calculateStimulation + boredom (neural.py:60-75, 351-366)
+#pragma once
+#include "common.cuh"
+#include "rng.cuh"
+#include "rules.cuh"
+
+__device__ __forceinline__ double warp_max(double v) { for (int s = 16; s; s >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, s)); return v; }
+__device__ __forceinline__ double warp_sum_d(double v) { for (int s = 16; s; s >>= 1) v += __shfl_xor_sync(FULL, v, s); return v; }
+
+struct SenseOut { double eye[8]; double smell; int hits; };
+
+// Enumerates the view of the sensor at (sx, sy) radius R of organism o; encodes relative to the cell at (px, py).
+template <bool EYE>
+__device__ __forceinline__ void sense(const SapioWorld &w, const Workspace &W, int o, int64_t uid, float sx, float sy, float R, float px, float py, double rot, SenseOut &out) {
+    const SapioParams &p = w.p;
+    const int NC = p.n_org * MAXC, lane = lane_id();
+    const float gc = p.grid_cell, reach = R + 0.5f * gc;            // grid_cell >= 2 * largest solid radius
+    int cx0 = (int)floorf((sx - reach) / gc) + 1, cx1 = (int)floorf((sx + reach) / gc) + 1;
+    int cy0 = (int)floorf((sy - reach) / gc) + 1, cy1 = (int)floorf((sy + reach) / gc) + 1;
+    cx0 = max(cx0, 0); cy0 = max(cy0, 0); cx1 = min(cx1, p.grid_nx - 1); cy1 = min(cy1, p.grid_ny - 1);
+    const int nbx = cx1 - cx0 + 1, nby = cy1 - cy0 + 1;
+    double eye[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
+    double smell = 0.; int hits = 0;
+    if (nbx > 0 && nby > 0) {
+        for (int idx = lane; idx < nbx * nby; idx += 32) {
+            int c = (cy0 + idx / nbx) * p.grid_nx + cx0 + idx % nbx;
+            for (int i = W.cell_start[c], e = W.cell_end[c]; i < e; i++) {
+                int j = (int)W.sval[i];
+                float x, y, r; bool dead;
+                if (j < NC) {
+                    if ((j >> 6) == o || w.c_alive[j] == 0) continue;
+                    float2 q = reinterpret_cast<const float2 *>(w.c_pos)[j]; x = q.x; y = q.y; r = w.c_size[j] * 0.5f; dead = false;
+                } else {
+                    int d = j - NC;
+                    if (!w.d_state[d] || w.d_owner[d] == uid) continue;            // own dead cells are invisible (sprites.py:233)
+                    float2 q = reinterpret_cast<const float2 *>(w.d_pos)[d]; x = q.x; y = q.y; r = w.d_size[d] * 0.5f; dead = true;
+                }
+                double d2;
+                if (!circles_overlap(sx, sy, R, x, y, r, &d2)) continue;
+                hits++;
+                // encoding in double like the reference's Python floats: the values are rounded to 3 decimals next, and a
+                // 1e-7 fp32 error would flip a digit at every tie; this path runs once per think, not per tick
+                double ddx = (double)x - (double)px, ddy = (double)y - (double)py;
+                double dist = sqrt(ddx * ddx + ddy * ddy);
+                double val = fabs(((double)R - (dist + (double)r)) / (double)R);
+                if (EYE) {
+                    double ang = atan2(ddy, ddx) - rot;
+                    double dx = cos(ang), dy = sin(ang);
+                    int s;
+                    if (dx >= 0.0) { if (dy < 0.0) s = dx < .707 ? 0 : 1; else s = dx >= .707 ? 2 : 3; }
+                    else { if (dy >= 0.0) s = dy >= .707 ? 4 : 5; else s = dx < -.707 ? 6 : 7; }
+#pragma unroll
+                    for (int q = 0; q < 8; q++) if (q == s) eye[q] = fmax(eye[q], val);
+                } else if (dead) smell = fmax(smell, val);
+            }
+        }
+    }
+    if (EYE) {
+#pragma unroll
+        for (int q = 0; q < 8; q++) out.eye[q] = warp_max(eye[q]);
+    } else out.smell = warp_max(smell);
+    for (int s = 16; s; s >>= 1) hits += __shfl_xor_sync(FULL, hits, s);
+    out.hits = hits;
+}
+
+#define THINK_WARPS 4
+// dynamic shared memory per warp: in_cap + 2 * width_cap floats
+__global__ void __launch_bounds__(THINK_WARPS * 32) k_think(WORLD_ARG, Workspace W, RulesWs R) {
+    extern __shared__ float think_smem[];
+    const SapioParams &p = w.p;
+    const int IN = p.in_cap, lane = lane_id();
+    float *x = think_smem + (size_t)(threadIdx.x >> 5) * (IN + 2 * max(p.width_cap, 4));
+    float *act0 = x + IN, *act1 = act0 + max(p.width_cap, 4);
+    const int n_think = R.counters[RC_NTHINK];
+    const int32_t T = (int32_t)w.g_tick[0];
+    const int warps = gridDim.x * THINK_WARPS;
+    for (int q = blockIdx.x * THINK_WARPS + (threadIdx.x >> 5); q < n_think; q += warps) {
+        const int o = R.think_list[q];
+        const int nc = w.org_ncells[o], nl = w.org_nlayers[o];
+        const int32_t *ldim = w.org_ldim + o * 16;
+        const int I = ldim[0];
+        const int64_t uid = w.org_uid[o];
+        // Organism.rotation (sprites.py:1179-1201) as an angle
+        uint32_t a0 = __ballot_sync(FULL, lane < nc && w.c_alive[o * MAXC + lane] == SAPIO_CELL_ALIVE);
+        uint32_t a1 = __ballot_sync(FULL, lane + 32 < nc && w.c_alive[o * MAXC + lane + 32] == SAPIO_CELL_ALIVE);
+        uint64_t alive = ((uint64_t)a1 << 32) | a0;
+        double rot = 0.0;
+        {
+            uint64_t am = alive & ~1ull;
+            if (am) {
+                int rel = __ffsll((long long)am) - 1, r0 = o * MAXC, rr = r0 + rel;
+                double deg = (atan2((double)w.c_pos[2 * rr + 1] - (double)w.c_pos[2 * r0 + 1], (double)w.c_pos[2 * rr] - (double)w.c_pos[2 * r0])
+                              - atan2((double)w.c_rel[2 * rr + 1], (double)w.c_rel[2 * rr])) * (180.0 / 3.14159265358979323846);
+                deg = fmod(deg, 360.0); if (deg < 0.0) deg += 360.0;                   // math.degrees(angleDiff) % 360
+                rot = deg * (3.14159265358979323846 / 180.0);                           // math.radians
+            }
+        }
+        int n = 0;
+        for (int qi = 0; qi < w.org_nincell[o]; qi++) {
+            int k = w.org_incell[o * MAXC + qi], row = o * MAXC + k, t = w.c_type[row];
+            bool live = (alive >> k) & 1ull;
+            float2 cp = reinterpret_cast<const float2 *>(w.c_pos)[row], sp = reinterpret_cast<const float2 *>(w.c_spos)[row];
+            SenseOut so;
+            if (t == SAPIO_T_EYE) {
+#pragma unroll
+                for (int s = 0; s < 8; s++) so.eye[s] = 0.;
+                if (live) sense<true>(w, W, o, uid, sp.x, sp.y, w.c_size[row] * p.eyesight_mult, cp.x, cp.y, rot, so);
+                if (lane < 8) { double v = 0.;
+#pragma unroll
+                    for (int s = 0; s < 8; s++) if (s == lane) v = so.eye[s];
+                    x[n + lane] = (float)v; }
+                n += 8;
+            } else {
+                so.smell = 0.;
+                if (live) sense<false>(w, W, o, uid, sp.x, sp.y, w.c_size[row] * p.olfactory_mult, cp.x, cp.y, rot, so);
+                if (lane == 0) x[n] = (float)so.smell;
+                n += 1;
+            }
+        }
+        {   // speed, x_direction, y_direction (last commanded), energy fraction (neural.py:227-244)
+            double cur = 0., mx = 0.;
+            for (int k = lane; k < nc; k += 32) { int row = o * MAXC + k; if ((alive >> k) & 1ull) cur += (double)w.c_energy[row]; mx += (double)w.c_storage[row]; }
+            cur = warp_sum_d(cur); mx = warp_sum_d(mx);
+            if (lane == 0) { x[n] = w.org_move[4 * o + 1]; x[n + 1] = w.org_move[4 * o + 2]; x[n + 2] = w.org_move[4 * o + 3]; x[n + 3] = (float)((cur / mx * 100.0) / 100.); }
+            n += 4;
+        }
+        __syncwarp();
+        for (int i = lane; i < I; i += 32) x[i] = rintf(x[i] * 1000.0f) / 1000.0f;                 // neural.py:285 (round half to even)
+        __syncwarp();
+        // Network.forward: sigmoid after the first layer only
+        const float *brain = w.org_brain + (size_t)o * p.brain_cap;
+        const float *cur = x; float *dst = act0;
+        float out4[4] = {0.f, 0.f, 0.f, 0.f};
+        int off = 0;
+        for (int l = 0; l < nl; l++) {
+            const int fin = ldim[l], fout = ldim[l + 1];
+            const float *Wm = brain + off, *b = Wm + fout * fin;
+            for (int r = 0; r < fout; r++) {
+                float s = 0.f;
+                for (int c = lane; c < fin; c += 32) s += Wm[r * fin + c] * cur[c];
+                s = warp_sum(s) + b[r];
+                if (l == 0) s = 1.0f / (1.0f + expf(-s));
+                if (l == nl - 1) {
+#pragma unroll
+                    for (int z = 0; z < 4; z++) if (z == r) out4[z] = s;
+                } else if (lane == 0) dst[r] = s;
+            }
+            __syncwarp();
+            cur = dst; dst = (dst == act0) ? act1 : act0;
+            off += fout * fin + fout;
+        }
+        if (lane < 4) { float v = 0.f;
+#pragma unroll
+            for (int z = 0; z < 4; z++) if (z == lane) v = out4[z];
+            w.org_out_raw[4 * o + lane] = v; }
+        float outv[4];
+#pragma unroll
+        for (int z = 0; z < 4; z++) outv[z] = rintf(out4[z] * 1000.0f) / 1000.0f;                  // neural.py:292
+        uint32_t rr4[4];
+        rng4(p.seed, uid, T, RNG_BOREDOM, 0, rr4);
+        if (u01(rr4[0]) <= w.org_boredom[o]) {                                                     // neural.py:294-295
+            rng4(p.seed, uid, T, RNG_RANDN, 0, rr4);
+#pragma unroll
+            for (int h = 0; h < 2; h++) {                                                          // Box-Muller on (0,1] x [0,1)
+                float u1 = ((float)(rr4[2 * h] >> 8) + 1.0f) * (1.0f / 16777216.0f), u2 = u01(rr4[2 * h + 1]);
+                float rad = sqrtf(-2.0f * logf(u1)), th = 6.283185307179586f * u2;
+                outv[2 * h] = rad * cosf(th); outv[2 * h + 1] = rad * sinf(th);
+            }
+        }
+        // history rings (slot = running count % capacity), short-term memory (neural.py:301-318)
+        const int cnt = w.org_hist_n[o], nv = min(cnt, SAPIO_HIST);
+        float *hin = w.org_hist_in + (size_t)o * SAPIO_HIST * IN, *hout = w.org_hist_out + o * 40, *hdo = w.org_hist_dopa + o * 10;
+        const float dopamine = w.org_dopamine[o], pain = w.org_pain[o];
+        if ((fabsf(dopamine) > 0.1f || fabsf(pain) > 0.1f) && nv + 1 > 3) {
+            const int s4 = (cnt - 3) % SAPIO_HIST, sc = w.org_stm_n[o], slot = sc % SAPIO_STM;
+            float *sin_ = w.org_stm_in + ((size_t)o * SAPIO_STM + slot) * IN;
+            for (int i = lane; i < I; i += 32) sin_[i] = hin[(size_t)s4 * IN + i];
+            if (lane < 4) w.org_stm_out[(o * SAPIO_STM + slot) * 4 + lane] = hout[s4 * 4 + lane];
+            if (lane == 0) {
+                double d2 = hdo[(cnt - 2) % SAPIO_HIST], d1 = hdo[(cnt - 1) % SAPIO_HIST];
+                w.org_stm_rew[o * SAPIO_STM + slot] = (float)((((0.0 + d2) + d1) + (double)dopamine) / 3);
+                w.org_stm_n[o] = sc + 1;
+            }
+        }
+        __syncwarp();
+        const int slot = cnt % SAPIO_HIST;
+        for (int i = lane; i < I; i += 32) hin[(size_t)slot * IN + i] = x[i];
+        if (lane < 4) {
+            float v = 0.f;
+#pragma unroll
+            for (int z = 0; z < 4; z++) if (z == lane) v = outv[z];
+            hout[slot * 4 + lane] = v;
+            w.org_move[4 * o + lane] = fminf(fmaxf(v, -1.0f), 1.0f);                               // neural.py:320-349
+        }
+        if (lane == 0) { hdo[slot] = dopamine; w.org_hist_n[o] = cnt + 1; }
+        __syncwarp();
+        // calculateStimulation (neural.py:60-75): fp32, oldest entry first
+        const int nn = min(cnt + 1, SAPIO_HIST);
+        float part = 0.f;
+        for (int i = lane; i < I; i += 32) {
+            float s = 0.f;
+            for (int e = 0; e < nn; e++) { int sl = (cnt + 1 - nn + e) % SAPIO_HIST; s = s + (sl == slot ? x[i] : hin[(size_t)sl * IN + i]); }
+            part += fabsf(s / (float)nn);
+        }
+        const float new_stim = warp_sum(part) / (float)I;
+        if (lane == 0) {
+            float *sh = w.org_stim_hist + 10 * o;                                                  // neural.py:354-366
+            double avg = 0.0;
+            for (int i = 0; i < 9; i++) { float v = sh[i + 1]; sh[i] = v; avg += (double)v; }
+            sh[9] = new_stim; avg = (avg + (double)new_stim) / 10;
+            double stimulation = fabs((double)new_stim - avg), cu = w.org_curiosity[o];
+            w.org_stimulation[o] = (float)stimulation;
+            w.org_boredom[o] = (float)((stimulation != 0.0 && cu != 0.0) ? (1.0 - stimulation) * cu : 0.0);
+        }
+        __syncwarp();
+    }
+}
+
+// parity probe: the view of one sensor cell as a sorted id list (tests only: "sensor hit indices bit-exact")
+__global__ void k_sensor_view(WORLD_ARG, Workspace W, int o, int k, uint32_t *out, int cap, int *out_n) {
+    const SapioParams &p = w.p;
+    const int NC = p.n_org * MAXC, row = o * MAXC + k;
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float sx = w.c_spos[2 * row], sy = w.c_spos[2 * row + 1];
+    float R = w.c_size[row] * (w.c_type[row] == SAPIO_T_EYE ? p.eyesight_mult : p.olfactory_mult);
+    int n = 0;
+    for (int c = 0; c < p.grid_nx * p.grid_ny; c++)
+        for (int i = W.cell_start[c]; i < W.cell_end[c]; i++) {
+            int j = (int)W.sval[i];
+            float x, y, r;
+            if (j < NC) { if ((j >> 6) == o || w.c_alive[j] == 0) continue; x = w.c_pos[2 * j]; y = w.c_pos[2 * j + 1]; r = w.c_size[j] * 0.5f; }
+            else { int d = j - NC; if (!w.d_state[d] || w.d_owner[d] == w.org_uid[o]) continue; x = w.d_pos[2 * d]; y = w.d_pos[2 * d + 1]; r = w.d_size[d] * 0.5f; }
+            double d2;
+            if (circles_overlap(sx, sy, R, x, y, r, &d2)) { if (n < cap) out[n] = (uint32_t)j; n++; }
+        }
+    for (int i = 1; i < min(n, cap); i++) { uint32_t v = out[i]; int j = i - 1; while (j >= 0 && out[j] > v) { out[j + 1] = out[j]; j--; } out[j + 1] = v; }
+    *out_n = n;
+}

@@ -74,5 +74,29 @@ class Engine:
         with torch.cuda.device(self.world.device):
             _lib.check(self.lib.sapio_reproduce(self._ref(), *self._ws, self._stream_ptr()), "sapio_reproduce")
 
+    def spawn(self, slots, positions):
+        """add_creature_clicked (Sapiogenesis.py:297-323) for a batch: random genomes (DNA.randomize with the spawn ranges of
+        the params) materialised into free organism `slots` at `positions` [n, 2]."""
+        dev = self.world.device
+        slots_t = torch.as_tensor(slots, dtype=torch.int32, device=dev).contiguous()
+        pos_t = torch.as_tensor(positions, dtype=torch.float64, device=dev).contiguous().view(-1)
+        n = int(slots_t.numel())
+        assert pos_t.numel() == 2 * n
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.sapio_spawn(self._ref(), *self._ws, ctypes.c_void_p(slots_t.data_ptr()), ctypes.c_void_p(pos_t.data_ptr()), n,
+                                            self._stream_ptr()), "sapio_spawn")
+        self._keep = (slots_t, pos_t)
+
+    def sensor_view(self, org: int, cell: int, cap: int = 4096):
+        """sprite.info["view"] of one eye / olfactory cell as ascending body ids (parity probe)."""
+        dev = self.world.device
+        out = torch.zeros(cap, dtype=torch.int32, device=dev)
+        cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.sapio_sensor_view(self._ref(), *self._ws, org, cell, ctypes.c_void_p(out.data_ptr()), cap,
+                                                  ctypes.c_void_p(cnt.data_ptr()), self._stream_ptr()), "sapio_sensor_view")
+        n = int(cnt.item())
+        return out[:min(n, cap)].cpu().numpy().astype("uint32")
+
     def synchronize(self):
         torch.cuda.synchronize(self.world.device)

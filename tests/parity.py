@@ -1,0 +1,179 @@
+"""Field-by-field comparison of a GPU world against the oracle's world after the same stage(s) from identical state.
+
+Bit-exact (north star): every integer / index / flag field -- living-cell sets, contact-pair sets (cross list, adjacency,
+per-organism intra lists), decisions (requests, deaths, births, slots, uids, genome tables), memory counters.
+fp32 fields: |gpu - oracle| <= tol * max(rms(field), floor), tol = 1e-5 unless stated per field below."""
+from __future__ import annotations
+
+import numpy as np
+
+from sapiogenesis_b200.world import FIELDS, HIST, ICAP, MAXC, MEMROWS, NPAIR, STM
+
+TOL = 1e-5
+SKIP = {"org_gas_a", "org_gas_b", "c_dmg", "d_eaten", "org_rect", "g_stats", "org_out_raw"}
+# fields whose meaningful extent depends on counters / rings: handled explicitly
+SPECIAL = {"org_brain", "org_adam_m", "org_adam_v", "org_hist_in", "org_hist_out", "org_hist_dopa", "org_stm_in", "org_stm_out",
+           "org_stm_rew", "org_mem_in", "org_mem_out", "org_mem_rew", "org_incell", "org_ldim", "ic_code", "ic_jn", "ic_jt", "j_jn",
+           "x_key", "x_jn", "x_jt", "xa_off", "xa_other", "c_spos", "c_svel", "c_svbias", "c_spin_jn", "c_wbias", "d_wbias"}
+# dopamine / pain = (percent now - percent at the last snapshot) / dt with percents O(100) held in fp32 and dt >= 0.09 s: the
+# subtraction carries 100 * 6e-8 / 0.09 ~ 7e-5 of absolute noise whatever the size of the result, so these signals are compared
+# on the scale of the percent-per-second they are made of (floor 10), like every other fp32 field at 1e-5.
+DOPA_FLOOR = 10.0
+FLOORS = {"c_wbias": 1.0, "d_wbias": 1.0, "c_vbias": 1e-2, "d_vbias": 1e-2, "org_energy_diff": DOPA_FLOOR, "org_dopamine": DOPA_FLOOR,
+          "org_pain": DOPA_FLOOR}
+# The rotate actuator adds max_rot * command to omega every tick (sprites.py:1547, not scaled by dt) against 1.8 %/tick of
+# friction: cells of the test worlds spin at hundreds of rad/s, and ten Gauss-Seidel sweeps of friction impulses on top of
+# that accumulate a few fp32 ulps of omega itself. 3e-5 of the field's rms for angular velocities, 1e-5 everywhere else.
+TOLS = {"c_angvel": 3e-5, "d_angvel": 3e-5,
+        # co2 refund = overflow of add_energy = (energy + share) - storage with energy ~ storage ~ 1e3 in fp32: the difference
+        # carries the operands' 1e-7, i.e. ~1e-4 of its own size; its effect on the global co2 (~3e4, checked at 1e-5) is 1e-9
+        "org_gas_refund": 2e-4}
+
+
+def field_err(got, ref, floor=1e-3):
+    got = np.asarray(got, dtype=np.float64); ref = np.asarray(ref, dtype=np.float64)
+    if ref.size == 0:
+        return 0.0
+    scale = max(float(np.sqrt(np.mean(ref * ref))), floor)
+    return float(np.max(np.abs(got - ref)) / scale)
+
+
+class Report:
+    def __init__(self, tag):
+        self.tag, self.errs, self.bad = tag, {}, []
+
+    def exact(self, name, got, ref):
+        got, ref = np.asarray(got), np.asarray(ref)
+        if got.shape != ref.shape or not np.array_equal(got, ref):
+            n = int(np.sum(got != ref)) if got.shape == ref.shape else -1
+            where = np.argwhere(got != ref)[:5].tolist() if got.shape == ref.shape else []
+            self.bad.append(f"{name}: {n} of {ref.size} entries differ, first at {where}")
+
+    def close(self, name, got, ref, tol=None, floor=None):
+        e = field_err(got, ref, FLOORS.get(name, 1e-3) if floor is None else floor)
+        self.errs[name] = e
+        if not e <= (TOLS.get(name, TOL) if tol is None else tol):
+            self.bad.append(f"{name}: {e:.3e}")
+
+    def finish(self, verbose=True):
+        if verbose:
+            worst = sorted(self.errs.items(), key=lambda kv: -kv[1])[:8]
+            print(f"{self.tag}: worst " + " ".join(f"{k}={v:.1e}" for k, v in worst))
+        assert not self.bad, f"{self.tag}: " + "; ".join(self.bad[:12])
+
+
+def compare_worlds(wg, w, tag, brain_tol=TOL, check_brain=True, skip=(), verbose=True):
+    """wg: GPU world after the stage(s); w: oracle world after the same stage(s)."""
+    rep = Report(tag)
+    p = w.p
+    G = {f.name: wg.np(f.name) for f in FIELDS}
+    O = {f.name: w.np(f.name) for f in FIELDS}
+    rep.exact("org_state", G["org_state"], O["org_state"])
+    orgs = np.nonzero(O["org_state"] == 1)[0]
+    org_rows = np.zeros(p.n_org * MAXC, dtype=bool)
+    for o in orgs:
+        org_rows[o * MAXC: o * MAXC + int(O["org_ncells"][o])] = True
+    rep.exact("c_alive", G["c_alive"][org_rows], O["c_alive"][org_rows])
+    live = org_rows & (O["c_alive"] == 1)
+    rep.exact("d_state", G["d_state"] > 0, O["d_state"] > 0)
+    dead = O["d_state"] > 0
+    sens = live & np.isin(O["c_type"], (2, 3))
+    for f in FIELDS:
+        name = f.name
+        if name in SKIP or name in SPECIAL or name in skip or name in ("org_state", "c_alive", "d_state"):
+            continue
+        g, o = G[name], O[name]
+        if f.scope == "ORG":
+            g, o = g[orgs], o[orgs]
+        elif f.scope == "CELL":
+            m = org_rows if name in ("c_type", "c_parent", "c_mirror", "c_gorder", "c_id", "c_size", "c_mass", "c_elast", "c_fric", "c_rel",
+                                     "c_grow", "c_maxhealth", "c_use_idle", "c_use_act", "c_storage", "c_damage") else live
+            g, o = g[m], o[m]
+        elif f.scope == "DEAD":
+            g, o = g[dead], o[dead]
+        elif f.scope == "GLOB":
+            pass
+        else:
+            continue
+        if f.ctype in ("float", "double"):
+            if name in ("c_angvel", "d_angvel"):
+                # omega * radius is a rim speed: the error of an angular velocity is measured on the scale of the linear
+                # velocities over a typical cell radius (10 px)
+                vel = O["c_vel"][live] if name == "c_angvel" else O["d_vel"][dead]
+                rep.close(name, g, o, tol=TOLS[name], floor=max(1e-3, (float(np.sqrt(np.mean(vel.astype(np.float64) ** 2))) if vel.size else 0.0) / 10.0))
+            else:
+                rep.close(name, g, o)
+        else:
+            rep.exact(name, g, o)
+    # sensors
+    for name in ("c_spos",):
+        rep.exact(name, G[name][sens], O[name][sens])
+    for name in ("c_svel", "c_spin_jn"):
+        rep.close(name, G[name][sens], O[name][sens])
+    rep.close("c_wbias", G["c_wbias"][live], O["c_wbias"][live]); rep.close("d_wbias", G["d_wbias"][dead], O["d_wbias"][dead])
+    # contacts
+    nx = int(O["g_x_n"][0])
+    rep.exact("x_key", G["x_key"][:nx], O["x_key"][:nx])
+    # friction impulses are bounded by mu * jn: their error is measured on the scale of the normal impulses
+    rms = lambda a: float(np.sqrt(np.mean(np.asarray(a, dtype=np.float64) ** 2))) if len(a) else 0.0
+    rep.close("x_jn", G["x_jn"][:nx], O["x_jn"][:nx]); rep.close("x_jt", G["x_jt"][:nx], O["x_jt"][:nx], floor=max(1e-3, rms(O["x_jn"][:nx])))
+    rep.exact("xa_off", G["xa_off"], O["xa_off"])
+    na = int(O["xa_off"][-1])
+    rep.exact("xa_other", G["xa_other"].reshape(-1)[:na], O["xa_other"].reshape(-1)[:na])
+    icm = np.zeros(p.n_org * ICAP, dtype=bool)
+    jm = np.zeros(p.n_org * NPAIR, dtype=bool)
+    for o in orgs:
+        icm[o * ICAP: o * ICAP + int(O["org_ic_n"][o])] = True
+        nc = int(O["org_ncells"][o]); al = O["c_alive"][o * MAXC: o * MAXC + nc] == 1
+        for i in np.nonzero(al)[0]:
+            js = np.nonzero(al[i + 1:])[0] + i + 1
+            jm[o * NPAIR + i * (2 * MAXC - i - 1) // 2 + (js - i - 1)] = True
+    rep.exact("ic_code", G["ic_code"][icm], O["ic_code"][icm])
+    rep.close("ic_jn", G["ic_jn"][icm], O["ic_jn"][icm]); rep.close("ic_jt", G["ic_jt"][icm], O["ic_jt"][icm], floor=max(1e-3, rms(O["ic_jn"][icm])))
+    rep.close("j_jn", G["j_jn"][jm], O["j_jn"][jm])
+    # brains and memories
+    IN = p.in_cap
+    for o in orgs:
+        nl = int(O["org_nlayers"][o]); ld = O["org_ldim"][o]
+        rep.exact(f"org_ldim[{o}]", G["org_ldim"][o][: nl + 1], ld[: nl + 1])
+        nin = int(O["org_nincell"][o])
+        rep.exact(f"org_incell[{o}]", G["org_incell"][o][:nin], O["org_incell"][o][:nin])
+        if G["org_nlayers"][o] != nl:
+            continue
+        I = int(ld[0])
+        P = sum(int(ld[l + 1]) * int(ld[l]) + int(ld[l + 1]) for l in range(nl))
+        if check_brain:
+            gb, ob = G["org_brain"][o][:P].astype(np.float64), O["org_brain"][o][:P].astype(np.float64)
+            scale = np.maximum(np.abs(ob), np.sqrt(np.mean(ob ** 2)) if P else 1.0)
+            rel = np.abs(gb - ob) / scale
+            # Trained weights. Adam moves each weight by lr * m_hat / (sqrt(v_hat) + 1e-8): on the first steps that is
+            # lr * g / (|g| + 1e-8), ill-conditioned in the gradient's own fp32 noise wherever |g| is within a few orders of
+            # 1e-8 (common right after birth, when the batch holds one or two samples). The well-conditioned quantities are the
+            # gradient moments themselves: they must agree to 1e-5 of their scale. For the weights: >= 90 % of an organism's
+            # parameters within 1e-5 of the weight scale, none further than 1 % of one Adam step (lr = 0.02).
+            if P and (np.mean(rel <= brain_tol) < 0.90 or np.max(np.abs(gb - ob)) > 1e-2 * 0.02):
+                rep.bad.append(f"org_brain[{o}]: {np.mean(rel <= brain_tol):.4f} within {brain_tol}, max abs {np.max(np.abs(gb - ob)):.2e}")
+            if int(O["org_adam_t"][o]) > 0:
+                h0, hl = int(ld[1]), int(ld[nl - 1])
+                npar = h0 * I + h0 + 4 * hl + 4
+                # the gradient is built on (output - target) where the target is an earlier, 3-decimal-rounded output of the
+                # same network: |output - target| <= 5e-4, so the fp32 forward's 1e-7 is 1e-3 of it. The moments are therefore
+                # compared on the scale of the outputs (O(1)), not of their own (tiny) magnitude.
+                rep.close("org_adam_m", G["org_adam_m"][o][:npar], O["org_adam_m"][o][:npar], tol=1e-4, floor=1e-3)
+                rep.close("org_adam_v", G["org_adam_v"][o][:npar], O["org_adam_v"][o][:npar], tol=1e-4, floor=1e-6)
+            rep.errs["org_brain"] = max(rep.errs.get("org_brain", 0.0), float(np.max(rel)) if P else 0.0)
+        hn = min(int(O["org_hist_n"][o]), HIST)
+        rep.exact(f"org_hist_in[{o}]", G["org_hist_in"][o].reshape(HIST, IN)[:hn, :I], O["org_hist_in"][o].reshape(HIST, IN)[:hn, :I])
+        rep.close("org_hist_out", G["org_hist_out"][o][: hn * 4], O["org_hist_out"][o][: hn * 4], tol=1.5e-3, floor=1.0)
+        rep.close("org_hist_dopa", G["org_hist_dopa"][o][:hn], O["org_hist_dopa"][o][:hn], floor=DOPA_FLOOR)
+        sn = min(int(O["org_stm_n"][o]), STM)
+        rep.exact(f"org_stm_in[{o}]", G["org_stm_in"][o].reshape(STM, IN)[:sn, :I], O["org_stm_in"][o].reshape(STM, IN)[:sn, :I])
+        rep.close("org_stm_out", G["org_stm_out"][o][: sn * 4], O["org_stm_out"][o][: sn * 4], tol=1.5e-3, floor=1.0)
+        rep.close("org_stm_rew", G["org_stm_rew"][o][:sn], O["org_stm_rew"][o][:sn], floor=DOPA_FLOOR)
+        M = int(O["org_mem_n"][o])
+        if int(G["org_mem_n"][o]) == M and M:
+            rep.exact(f"org_mem_in[{o}]", G["org_mem_in"][o].reshape(MEMROWS, IN)[:M, :I], O["org_mem_in"][o].reshape(MEMROWS, IN)[:M, :I])
+            rep.close("org_mem_out", G["org_mem_out"][o][: M * 4], O["org_mem_out"][o][: M * 4], tol=1.5e-3, floor=1.0)
+            rep.close("org_mem_rew", G["org_mem_rew"][o][:M], O["org_mem_rew"][o][:M], floor=DOPA_FLOOR)
+    rep.finish(verbose)
+    return rep

@@ -1,0 +1,110 @@
+"""GPU parity of the whole world tick and of each stage (rules incl. think, train, settle, reproduce, spawn) against the
+oracle, always from identical state: the GPU world is re-created from the oracle's world before every compared call, so
+every tick of a real trajectory is a single-tick parity check (trajectories themselves are chaotic).
+All calls go through the C-ABI (sapio_* via sapiogenesis_b200.engine.Engine)."""
+import numpy as np
+import pytest
+import torch
+
+from parity import compare_worlds
+from sapiogenesis_b200.world import MAXC, PH_ALL, World, default_params
+from worlds import make_world
+
+pytestmark = pytest.mark.gpu
+
+
+def fast_world(oracle, n_org, seed, crowd, food, extra=24):
+    """A busy little world: brains think/train every 3 ticks, reproduction allowed every 8, plenty of free slots."""
+    w = make_world(oracle, n_org=n_org, seed=seed, n_food=food, crowd=crowd, kick=30.0, extra_slots=extra, n_dead_cap=64 * (n_org + extra))
+    w.p.think_ticks, w.p.train_ticks, w.p.repro_ticks = 3, 3, 8
+    w.p.population_limit = n_org + extra
+    return w
+
+
+def engine_for(w):
+    from sapiogenesis_b200.engine import Engine
+    wg = w.to("cuda")
+    return wg, Engine(wg)
+
+
+def test_spawn_matches_oracle(oracle):
+    p = default_params(n_org=40, n_dead=16, seed=5)
+    w = World(p)
+    rng = np.random.default_rng(3)
+    slots = [3, 0, 7, 12, 13, 20, 21, 22, 30, 39, 5, 6]
+    pos = rng.uniform(300, 1500, (len(slots), 2))
+    wg, eng = engine_for(w)
+    eng.spawn(slots, pos); eng.post(); eng.synchronize()
+    for s, (x, y) in zip(slots, pos):
+        assert oracle.spawn(w, s, float(x), float(y)) == 0
+    oracle.post(w)
+    assert wg.stats()["birth_fail_caps"] == 0
+    compare_worlds(wg, w, "spawn", brain_tol=0.0)
+    for s in slots:     # nn.Linear init + tempNet hidden weights: same uniforms, same double formula -> identical floats
+        np.testing.assert_array_equal(wg.np("org_brain")[s], w.np("org_brain")[s])
+
+
+@pytest.mark.parametrize("n_org,crowd,food,seed", [(16, 0.45, 40, 11), (40, 0.4, 120, 12)])
+def test_every_stage_matches_oracle_along_a_trajectory(oracle, n_org, crowd, food, seed):
+    w = fast_world(oracle, n_org, seed, crowd, food)
+    assert oracle.tick(w, PH_ALL, 6) == 0                 # warm up: contacts, adjacency, first thinks and memories exist
+    seen = dict(thinks=0, trains=0, births=0, cell_deaths=0, deaths=0)
+    for t in range(30):
+        if t == 8:                                         # provoke deaths (cascades, dead bodies) and births
+            alive = np.nonzero(w.np("c_alive") == 1)[0]
+            kill = alive[(alive % MAXC != 0)][::7]
+            w.t["c_health"][torch.from_numpy(kill)] = -1.0
+        if t in (10, 18):
+            w.t["c_energy"][:] = w.t["c_storage"]          # everybody full: reproduction gate opens, co2 refunds saturate
+        before = w.stats()
+        wg, eng = engine_for(w)
+        tag = f"n={n_org} tick={w.tick}"
+        eng.rules(PH_ALL); eng.synchronize(); assert oracle.rules(w, PH_ALL) == 0
+        compare_worlds(wg, w, tag + " rules", verbose=False)
+        eng.train(); eng.synchronize(); assert oracle.train(w) == 0
+        compare_worlds(wg, w, tag + " train", verbose=False)
+        eng.settle(); eng.synchronize(); assert oracle.settle(w) == 0
+        compare_worlds(wg, w, tag + " settle", verbose=False)
+        eng.reproduce(); eng.synchronize(); assert oracle.reproduce(w) == 0
+        compare_worlds(wg, w, tag + " reproduce", verbose=False)
+        eng.space_step(); eng.friction(); eng.post(); eng.synchronize()
+        assert oracle.space_step(w) == 0; oracle.friction(w); oracle.post(w)
+        compare_worlds(wg, w, tag + " step", verbose=(t % 10 == 0))
+        assert wg.stats()["overflow"] == 0
+        w.t["g_tick"] += 1
+        after = w.stats()
+        for k in seen:
+            seen[k] += after[k] - before[k]
+    print("events along the trajectory:", seen)
+    assert seen["thinks"] > 0 and seen["trains"] > 0 and seen["cell_deaths"] > 0 and seen["births"] > 0
+
+
+def test_full_tick_call_matches_oracle(oracle):
+    w = fast_world(oracle, 24, 21, 0.5, 60)
+    assert oracle.tick(w, PH_ALL, 5) == 0
+    for t in range(12):
+        if t == 4:
+            w.t["c_energy"][:] = w.t["c_storage"]
+        wg, eng = engine_for(w)
+        eng.tick(1, PH_ALL); eng.synchronize()
+        assert oracle.tick(w, PH_ALL, 1) == 0
+        assert wg.tick == w.tick
+        compare_worlds(wg, w, f"tick {w.tick}", verbose=(t % 4 == 0))
+
+
+def test_sensor_views_match_oracle(oracle):
+    w = fast_world(oracle, 30, 31, 0.4, 80)
+    assert oracle.tick(w, PH_ALL, 3) == 0
+    wg, eng = engine_for(w)
+    checked = members = 0
+    for o in np.nonzero(w.np("org_state") == 1)[0]:
+        for q in range(int(w.np("org_nincell")[o])):
+            k = int(w.np("org_incell")[o][q])
+            if w.np("c_alive")[o * MAXC + k] != 1:
+                continue
+            ref = np.sort(oracle.sensor_view(w, int(o), k))
+            got = eng.sensor_view(int(o), k)
+            np.testing.assert_array_equal(got, ref, err_msg=f"view of organism {o} cell {k}")
+            checked += 1; members += len(ref)
+    print(f"{checked} sensors, {members} viewed bodies, all hit lists identical")
+    assert checked > 20 and members > 100
