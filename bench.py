@@ -1,0 +1,279 @@
+#!/usr/bin/env python
+"""Benchmark of the per-tick world step (BASELINE.json: organism-ticks/s at 100k organisms, + HBM roofline fraction).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--organisms M] [--impl ours|reference]
+
+A step is one whole world tick (rules incl. think + dopamine training + reproduction/mutation, Space.step, friction,
+post) over one synthetic world of M organisms per GPU (population islands: weak scaling; SURVEY.md section 8(d, e)).
+`value` is device-timed with CUDA events, state resident in HBM; `e2e` goes through sapio_tick_host with pinned HOST buffers
+(event block up, counters + packed sprite poses down, copies inside the timed region).
+`--impl reference` times the CPU restatement of the reference (oracle/, kind "port": pymunk is not installable here, see
+DESIGN.md) on a bounded sample of the same workload, single-threaded like the reference.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "organism_ticks_per_sec"
+UNIT = "organism-ticks/s"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz, self._stop, self.index = [], set(), None, threading.Event(), index
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0])); self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if "Active" in v and "Not" not in v:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self.thread.start(); return self
+
+    def __exit__(self, *a):
+        self._stop.set(); self.thread.join(timeout=3)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def cpu_world(orc, n_org, seed):
+    """The same synthetic recipe as sapiogenesis_b200.synth.build_world, built on the host for the CPU arm."""
+    import math
+    import numpy as np
+    import torch
+    from sapiogenesis_b200.synth import REF_AREA
+    from sapiogenesis_b200.world import World, default_params
+    side = math.sqrt(n_org * REF_AREA)
+    n_slots = int(math.ceil(n_org * 1.25 / 64.0) * 64)
+    p = default_params(n_org=n_slots, n_dead=max(1024, 8 * n_org), width=side, height=side, seed=seed, population_limit=n_slots,
+                       x_cap=max(4096, 4 * n_org))
+    w = World(p)
+    rng = np.random.default_rng(seed)
+    cols = int(math.ceil(math.sqrt(n_org)))
+    pitch = (side - 200.0) / cols
+    w.t["g_co2"][0] = 30000.0 * n_org / 12.0
+    for i in range(n_org):
+        j = rng.uniform(-0.12, 0.12, 2) * pitch
+        assert orc.spawn(w, i, 100.0 + (i % cols + 0.5) * pitch + j[0], 100.0 + (i // cols + 0.5) * pitch + j[1]) == 0
+    nf = n_org // 4
+    t = w.t
+    t["d_state"][:nf] = 1
+    t["d_pos"][:nf] = torch.from_numpy(rng.uniform(60.0, side - 60.0, (nf, 2)).astype("float32"))
+    t["d_size"][:nf] = 30.0; t["d_mass"][:nf] = 12.0; t["d_mass0"][:nf] = 12.0; t["d_elast"][:nf] = .5; t["d_fric"][:nf] = .5; t["d_owner"][:nf] = -1
+    o = torch.arange(n_org, dtype=torch.int32)
+    t["org_think_tick"][:n_org] = -(o % p.think_ticks); t["org_dopa_tick"][:n_org] = -(o % p.think_ticks) - 1
+    t["org_train_tick"][:n_org] = -((o + 7) % p.train_ticks); t["org_lastbirth_tick"][:n_org] = -(o % p.repro_ticks)
+    orc.post(w)
+    return w
+
+
+def cpu_baseline(n_org=1000, ticks=24, seed=0):
+    """The restated reference on one host core (the reference is single-threaded Python + single-threaded Chipmunk)."""
+    from oracle import oracle as orc
+    orc.build()
+    w = cpu_world(orc, n_org, seed)
+    orc.tick(w, 127, 3)                                   # warm-up: contacts and adjacency exist
+    before = w.stats()["org_ticks"]
+    t0 = time.perf_counter()
+    orc.tick(w, 127, ticks)
+    dt = time.perf_counter() - t0
+    done = w.stats()["org_ticks"] - before
+    return {"value": done / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{n_org} organisms x {ticks} ticks of the same synthetic recipe, full tick, oracle/ (C restatement), {dt:.1f} s",
+            "host_cores_available": os.cpu_count()}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_org, ticks = args.ref_organisms, args.ref_ticks or 1
+    from oracle import oracle as orc
+    orc.build()
+    w = cpu_world(orc, n_org, 0)
+    orc.tick(w, 127, max(args.warmup, 3))
+    total_t, total_units = 0.0, 0
+    for _ in range(args.steps):
+        before = w.stats()["org_ticks"]
+        t0 = time.perf_counter()
+        orc.tick(w, 127, ticks)
+        total_t += time.perf_counter() - t0
+        total_units += w.stats()["org_ticks"] - before
+    v = total_units / total_t
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total_t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"full world tick, {n_org} organisms x {ticks} ticks per step (bounded sample of the 100k-organism workload)",
+                   "organisms": n_org},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": f"{n_org} organisms x {ticks} ticks per step, oracle/ C restatement of the reference (pymunk/Chipmunk not installable: DESIGN.md)"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from sapiogenesis_b200.synth import build_world, world_stats
+    from sapiogenesis_b200.world import PH_ALL
+
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the world step has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    M = args.organisms
+    w, eng = build_world(M, device=dev, seed=rank)
+    for _ in range(max(args.warmup, 3)):
+        eng.tick(1, PH_ALL)
+    eng.synchronize()
+    stats0 = world_stats(w)
+
+    # ---- device-resident throughput -------------------------------------------------------------------------------------
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = eng.launch_count()
+    ticks0 = w.stats()["org_ticks"]
+    eng.profile(True)
+    barrier()
+    with ClockSampler(local_rank) as clk:
+        ev0.record()
+        eng.tick(args.steps, PH_ALL)
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    prof = eng.profile_read(reset=True)
+    eng.profile(False)
+    units = w.stats()["org_ticks"] - ticks0
+    launches = eng.launch_count() - launches0
+    t = torch.tensor([ms, float(units)], dtype=torch.float64, device=dev)
+    if world_size > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, units = float(tmax[0]), float(tsum[1])
+    value = units / (ms / 1e3)
+
+    # ---- end to end through the C-ABI with host buffers ---------------------------------------------------------------------
+    e2e_steps = max(3, min(args.steps, 20))
+    eng.tick_host(1, PH_ALL)
+    ticks1 = w.stats()["org_ticks"]
+    h2d = d2h = 0
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        hdr, cells, dead, (bi, bo) = eng.tick_host(1, PH_ALL)
+        h2d += bi; d2h += bo
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    e2e_units = w.stats()["org_ticks"] - ticks1
+    t = torch.tensor([e2e_s, float(e2e_units)], dtype=torch.float64, device=dev)
+    if world_size > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        e2e_s, e2e_units = float(tmax[0]), float(tsum[1])
+    e2e_value = e2e_units / e2e_s
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel (algorithmic bytes: DESIGN.md "Kernels") -----------------------------------
+        s = world_stats(w)
+        peak, peak_src = peaks()
+        stage_ms = {k: v[0] / max(v[1], 1) for k, v in prof.items() if v[1] > 0}
+        dom = max(stage_ms, key=stage_ms.get) if stage_ms else "org_solve"
+        alg = {  # bytes per launch group, every array touched once
+            "org_solve": 74 * s["cells"] + 32 * s["sensors"] + 8 * s["pairs"] + 20 * s["intra_contacts"],
+        }
+        roof = None
+        if "org_solve" in stage_ms:
+            ach = alg["org_solve"] / (stage_ms["org_solve"] / 1e3) / 1e9
+            roof = {"bound": "hbm", "kernel": "k_org_solve<16|32|48|64> (organism solver: intra contacts + pin joints, 10 iterations on chip)",
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": alg["org_solve"], "avg_ms": stage_ms["org_solve"],
+                    "share_of_step": stage_ms["org_solve"] / (ms / args.steps), "dominant_stage": dom}
+        cpu = cpu_baseline(args.ref_organisms, args.ref_ticks or 40) if not args.no_cpu else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"full world tick (rules + think + dopamine training + reproduction/mutation + Space.step + friction), "
+                                   f"{M} organisms per GPU island (BASELINE configs[2]); state {w.nbytes() / 2**30:.1f} GiB per GPU, far larger than L2",
+                       "organisms_per_gpu": M, "living_after": s["organisms"], "cells": s["cells"], "pin_joints": s["pairs"],
+                       "dead_cells": s["dead"], "cross_contacts": s["cross_contacts"], "intra_contacts": s["intra_contacts"],
+                       "l2_policy": "inputs larger than L2"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps,
+                    "steps": e2e_steps, "api": "sapio_tick_host (pinned host buffers, event block up, counters + packed sprite poses down)"},
+            "gpu_launches": int(launches),
+            "stage_ms": {k: round(v, 4) for k, v in sorted(stage_ms.items(), key=lambda kv: -kv[1])},
+            "clocks": clk.summary(),
+            "births": w.stats()["births"], "cell_deaths": w.stats()["cell_deaths"],
+        }
+        if roof:
+            line["roofline"] = roof
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--organisms", type=int, default=100_000, help="organisms per GPU (island)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-organisms", type=int, default=2000, help="organisms of the CPU arm's bounded sample")
+    ap.add_argument("--ref-ticks", type=int, default=0, help="ticks per CPU step (default: 40 for cpu_baseline, 1 per step for --impl reference)")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

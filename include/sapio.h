@@ -148,6 +148,32 @@ int sapio_spawn(const SapioWorld *w, void *ws, size_t ws_bytes, const int32_t *d
 /* parity probe: sprite.info["view"] of one eye / olfactory cell as ascending body ids (device out, count may exceed cap) sprites.py:221-236 */
 int sapio_sensor_view(const SapioWorld *w, void *ws, size_t ws_bytes, int org, int cell, uint32_t *d_out, int cap, int32_t *d_count, void *stream);
 
+/* ---- end-to-end path for a GUI host (host buffers; the copies are inside the call) --------------------------------
+ * Uploads the per-tick event block updateUI applies (Sapiogenesis.py:37-47), runs n_ticks ticks, then downloads what the
+ * reference pushes to Qt every frame: the UI counters (Sapiogenesis.py:62-69) and the pose of every solid sprite
+ * (Sprite.setPos / setRotation, physics.py:253-272), packed. Host pointers should be page-locked. Synchronises `stream`. */
+typedef struct SapioControl { float drought, poison; int32_t pad[2]; } SapioControl;   /* amounts per tick = severity * uDiff */
+typedef struct SapioFrameHeader {
+    double co2, o2; int64_t tick; int32_t population, n_cells, n_dead, pad; int64_t stats[16];
+} SapioFrameHeader;
+int sapio_tick_host(const SapioWorld *w, void *ws, size_t ws_bytes, uint32_t phases, int n_ticks,
+                    const SapioControl *h_control,      /* host, in  */
+                    SapioFrameHeader *h_header,         /* host, out */
+                    float *h_cells, int cell_cap,       /* host, out: n_cells x (x, y, angle, organism slot) */
+                    float *h_dead, int dead_cap,        /* host, out: n_dead  x (x, y, angle, mass)          */
+                    void *stream);
+/* the same events as a stage (applied after the step, before sapio_post) */
+int sapio_events(const SapioWorld *w, void *ws, size_t ws_bytes, float drought, float poison, void *stream);
+
+/* ---- measurement hooks ------------------------------------------------------------------------------------------- */
+/* per-stage device time (CUDA events on the launching stream); names: sapio_profile_name(i), i < sapio_profile_stages() */
+int sapio_profile(int enable);
+int sapio_profile_stages(void);
+const char *sapio_profile_name(int i);
+int sapio_profile_read(double *ms_out, int64_t *count_out, int reset);
+/* number of kernels of this library launched so far in this process */
+uint64_t sapio_launch_count(void);
+
 #ifdef __cplusplus
 }
 #endif

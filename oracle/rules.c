@@ -378,3 +378,15 @@ double oracle_rotation(const SapioWorld *w, int o) {
     Org g; org_load(w, o, &g);
     return org_rotation(w, &g);
 }
+
+/* updateUI world events (Sapiogenesis.py:37-47): drought takes `drought` from both gases, poison takes 5 * `poison` health
+ * from every cell of every organism; amounts are severity * uDiff, computed by the host */
+int oracle_events(SapioWorld *w, double drought, double poison) {
+    if (poison != 0)
+        for (int o = 0; o < w->p.n_org; o++) {
+            if (w->org_state[o] != 1) continue;
+            for (int k = 0; k < w->org_ncells[o]; k++) w->c_health[o * MAXC + k] = (float)((double)w->c_health[o * MAXC + k] - poison * 5.0);
+        }
+    if (drought != 0) { w->g_o2[0] -= drought; w->g_co2[0] -= drought; }
+    return 0;
+}

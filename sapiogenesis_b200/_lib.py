@@ -44,6 +44,14 @@ def load() -> ctypes.CDLL:
             getattr(L, name).argtypes = [wp, vp, sz, vp]; getattr(L, name).restype = i32
     L.sapio_spawn.argtypes = [wp, vp, sz, vp, vp, i32, vp]; L.sapio_spawn.restype = i32
     L.sapio_sensor_view.argtypes = [wp, vp, sz, i32, i32, vp, i32, vp, vp]; L.sapio_sensor_view.restype = i32
+    f32 = ctypes.c_float
+    L.sapio_events.argtypes = [wp, vp, sz, f32, f32, vp]; L.sapio_events.restype = i32
+    L.sapio_tick_host.argtypes = [wp, vp, sz, u32, i32, vp, vp, vp, i32, vp, i32, vp]; L.sapio_tick_host.restype = i32
+    L.sapio_profile.argtypes = [i32]; L.sapio_profile.restype = i32
+    L.sapio_profile_stages.restype = i32
+    L.sapio_profile_name.argtypes = [i32]; L.sapio_profile_name.restype = ctypes.c_char_p
+    L.sapio_profile_read.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64), i32]; L.sapio_profile_read.restype = i32
+    L.sapio_launch_count.restype = ctypes.c_uint64
     if L.sapio_abi_version() != 1:
         raise SapioError("libsapio_b200.so ABI version mismatch")
     _lib = L

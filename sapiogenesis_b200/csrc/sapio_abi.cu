@@ -12,6 +12,7 @@
 #include "think.cuh"
 #include "train.cuh"
 #include "repro.cuh"
+#include "frame.cuh"
 
 static thread_local char g_err[512] = "";
 static int fail(int code, const char *fmt, const char *a = "") {
@@ -49,7 +50,7 @@ static size_t cub_need(const SapioParams &p) {
     return m;
 }
 
-struct AllWs { Workspace step; RulesWs rules; TrainWs train; ReproWs repro; int train_ctas; int *probe; };
+struct AllWs { Workspace step; RulesWs rules; TrainWs train; ReproWs repro; FrameWs frame; int train_ctas; int *probe; };
 
 static size_t carve_all(const SapioParams &p, char *base, AllWs *A) {
     size_t off = carve_workspace(p, base, &A->step);
@@ -77,6 +78,9 @@ static size_t carve_all(const SapioParams &p, char *base, AllWs *A) {
     Q.accepted = (int *)take((size_t)Q.birth_cap * 4);
     Q.counters = (int *)take(256);
     A->probe = (int *)take(256);
+    FrameWs &F = A->frame;
+    F.control = (SapioControl *)take(256); F.header = (SapioFrameHeader *)take(512); F.counts = (int *)take(256);
+    F.cells = (float4 *)take(NO * MAXC * sizeof(float4)); F.dead = (float4 *)take(ND * sizeof(float4));
     // cub temp storage is shared by every scan / reduction / sort: one region sized for the largest user
     size_t need = cub_need(p);
     if (need > A->step.cub_bytes) { A->step.cub_tmp = take(need); A->step.cub_bytes = need; }
@@ -121,22 +125,30 @@ static int launch_grid_only(const SapioWorld &w, const Workspace &W, cudaStream_
 static int launch_rules(const SapioWorld &w, AllWs &A, uint32_t phases, cudaStream_t st) {
     const SapioParams &p = w.p;
     RulesWs &R = A.rules;
+    prof_mark(st, PT_RULES_BEGIN);
     CUDA_TRY(cudaMemsetAsync(R.counters, 0, 256, st));
     const int org_grid = stream_grid((long)p.n_org * 32, RULES_WARPS * 32);
     k_rules_begin<<<org_grid, RULES_WARPS * 32, 0, st>>>(w, R, phases);
+    prof_mark(st, PT_GAS_SCAN);
     size_t tmp = A.step.cub_bytes;
     CUDA_TRY(cub::DeviceScan::InclusiveScan(A.step.cub_tmp, tmp, R.gas_map, R.gas_scan, AffCompose(), p.n_org, st));
     if (phases & SAPIO_PH_THINK) {
+        prof_mark(st, PT_GRID);
         int rc = launch_grid_only(w, A.step, st); if (rc) return rc;
+        prof_mark(st, PT_THINK);
         size_t smem = (size_t)THINK_WARPS * (p.in_cap + 2 * (p.width_cap > 4 ? p.width_cap : 4)) * sizeof(float);
         static size_t smem_set = 0;
         if (smem > smem_set) { CUDA_TRY(cudaFuncSetAttribute(k_think, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_set = smem; }
         k_think<<<stream_grid((long)p.n_org * 32 / 4 + 1, THINK_WARPS * 32), THINK_WARPS * 32, smem, st>>>(w, A.step, R);
+        LAUNCHES(3);
     }
+    prof_mark(st, PT_RULES_MAIN);
     k_rules_main<<<org_grid, RULES_WARPS * 32, 0, st>>>(w, R, phases);
     tmp = A.step.cub_bytes;
     CUDA_TRY(cub::DeviceReduce::Sum(A.step.cub_tmp, tmp, w.org_gas_refund, R.refund_sum, p.n_org, st));
     k_rules_finish<<<1, 1, 0, st>>>(w, R);
+    LAUNCHES(3);
+    prof_mark(st, PT_END);
     LAUNCH_CHECK();
     return 0;
 }
@@ -147,7 +159,10 @@ static int launch_train(const SapioWorld &w, AllWs &A, cudaStream_t st) {
     static size_t smem_set = 0;
     if (smem > smem_set) { CUDA_TRY(cudaFuncSetAttribute(k_train, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_set = smem; }
     int ctas = p.n_org < A.train_ctas ? p.n_org : A.train_ctas;
+    prof_mark(st, PT_TRAIN);
     k_train<<<ctas, TRAIN_THREADS, smem, st>>>(w, A.rules, A.train);
+    LAUNCHES(1);
+    prof_mark(st, PT_END);
     LAUNCH_CHECK();
     return 0;
 }
@@ -156,6 +171,7 @@ static int launch_settle(const SapioWorld &w, AllWs &A, cudaStream_t st) {
     const SapioParams &p = w.p;
     RulesWs &R = A.rules;
     const long NB = (long)p.n_org * MAXC + p.n_dead;
+    prof_mark(st, PT_SETTLE);
     k_settle_gather<<<stream_grid(NB), 256, 0, st>>>(w);
     k_settle_count<<<stream_grid((p.n_org > p.n_dead ? p.n_org : p.n_dead) + 1), 256, 0, st>>>(w, R);
     size_t tmp = A.step.cub_bytes;
@@ -168,6 +184,8 @@ static int launch_settle(const SapioWorld &w, AllWs &A, cudaStream_t st) {
     tmp = A.step.cub_bytes;
     CUDA_TRY(cub::DeviceReduce::Reduce(A.step.cub_tmp, tmp, R.disp_factor, R.disp_prod, p.n_dead, MulD(), 1.0, st));
     k_settle_gas<<<1, 1, 0, st>>>(w, R);
+    LAUNCHES(6);
+    prof_mark(st, PT_END);
     LAUNCH_CHECK();
     return 0;
 }
@@ -175,7 +193,9 @@ static int launch_settle(const SapioWorld &w, AllWs &A, cudaStream_t st) {
 static int launch_reproduce(const SapioWorld &w, AllWs &A, cudaStream_t st) {
     const SapioParams &p = w.p;
     ReproWs &Q = A.repro;
+    prof_mark(st, PT_REPRODUCE);
     k_org_rects<<<stream_grid(p.n_org), 256, 0, st>>>(w);
+    LAUNCHES(1);
     for (int sib = 0; sib < p.offspring_amount; sib++) {
         k_repro_flags<<<stream_grid(p.n_org + 1), 256, 0, st>>>(w, Q);
         size_t tmp = A.step.cub_bytes;
@@ -190,19 +210,39 @@ static int launch_reproduce(const SapioWorld &w, AllWs &A, cudaStream_t st) {
         k_repro_resolve<<<1, 32, 0, st>>>(w, Q, sib);
         k_repro_finish<<<blocks, REPRO_WARPS * 32, 0, st>>>(w, Q, sib);
         if (sib + 1 < p.offspring_amount) k_repro_next_sibling<<<stream_grid(Q.birth_cap), 256, 0, st>>>(w, Q);
+        LAUNCHES(5);
     }
+    prof_mark(st, PT_END);
     LAUNCH_CHECK();
     return 0;
 }
 
 static int launch_post(const SapioWorld &w, AllWs &A, cudaStream_t st, int do_post, int advance) {
+    prof_mark(st, PT_POST);
+    LAUNCHES(do_post ? 2 : 1);
     if (do_post) {
         CUDA_TRY(cudaMemsetAsync(A.step.pop, 0, sizeof(int), st));
         k_post_count<<<stream_grid(w.p.n_org), 256, 0, st>>>(w, A.step.pop);
     }
     k_post_finish<<<1, 1, 0, st>>>(w, A.step.pop, do_post, advance);
+    prof_mark(st, PT_END);
     LAUNCH_CHECK();
     return 0;
+}
+
+static int launch_tick(const SapioWorld &w, AllWs &A, uint32_t phases, const SapioControl *d_control, cudaStream_t st) {
+    int rc;
+    const long nb = (long)w.p.n_org * MAXC + w.p.n_dead;
+    if (phases & SAPIO_PH_RULES) {
+        if ((rc = launch_rules(w, A, phases, st))) return rc;
+        if (phases & SAPIO_PH_TRAIN) if ((rc = launch_train(w, A, st))) return rc;
+        if ((rc = launch_settle(w, A, st))) return rc;
+        if (phases & SAPIO_PH_REPRODUCE) if ((rc = launch_reproduce(w, A, st))) return rc;
+    }
+    if (phases & SAPIO_PH_STEP) { rc = launch_space_step(w, A.step, st, g_err, sizeof(g_err)); if (rc) return rc; }
+    if (phases & SAPIO_PH_FRICTION) { prof_mark(st, PT_FRICTION); k_friction<<<stream_grid(nb), 256, 0, st>>>(w); LAUNCHES(1); }
+    if (d_control) { k_events<<<stream_grid(nb), 256, 0, st>>>(w, d_control); LAUNCHES(1); }
+    return launch_post(w, A, st, (phases & SAPIO_PH_POST) ? 1 : 0, 1);
 }
 
 extern "C" {
@@ -274,20 +314,56 @@ int sapio_sensor_view(const SapioWorld *w, void *ws, size_t ws_bytes, int org, i
 
 int sapio_tick(const SapioWorld *w, void *ws, size_t ws_bytes, uint32_t phases, int n_ticks, void *stream) {
     AllWs A; int rc = check(w, ws, ws_bytes, &A); if (rc) return rc;
-    cudaStream_t st = (cudaStream_t)stream;
-    long nb = (long)w->p.n_org * MAXC + w->p.n_dead;
-    for (int t = 0; t < n_ticks; t++) {
-        if (phases & SAPIO_PH_RULES) {
-            if ((rc = launch_rules(*w, A, phases, st))) return rc;
-            if (phases & SAPIO_PH_TRAIN) if ((rc = launch_train(*w, A, st))) return rc;
-            if ((rc = launch_settle(*w, A, st))) return rc;
-            if (phases & SAPIO_PH_REPRODUCE) if ((rc = launch_reproduce(*w, A, st))) return rc;
-        }
-        if (phases & SAPIO_PH_STEP) { rc = launch_space_step(*w, A.step, st, g_err, sizeof(g_err)); if (rc) return rc; }
-        if (phases & SAPIO_PH_FRICTION) k_friction<<<stream_grid(nb), 256, 0, st>>>(*w);
-        if ((rc = launch_post(*w, A, st, (phases & SAPIO_PH_POST) ? 1 : 0, 1))) return rc;
-    }
+    for (int t = 0; t < n_ticks; t++) if ((rc = launch_tick(*w, A, phases, nullptr, (cudaStream_t)stream))) return rc;
     return 0;
 }
+
+int sapio_events(const SapioWorld *w, void *ws, size_t ws_bytes, float drought, float poison, void *stream) {
+    AllWs A; int rc = check(w, ws, ws_bytes, &A); if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    SapioControl c = {drought, poison, {0, 0}};
+    CUDA_TRY(cudaMemcpyAsync(A.frame.control, &c, sizeof(c), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));                       // `c` lives on this stack frame
+    k_events<<<stream_grid((long)w->p.n_org * MAXC), 256, 0, st>>>(*w, A.frame.control);
+    LAUNCHES(1);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int sapio_tick_host(const SapioWorld *w, void *ws, size_t ws_bytes, uint32_t phases, int n_ticks, const SapioControl *h_control,
+                    SapioFrameHeader *h_header, float *h_cells, int cell_cap, float *h_dead, int dead_cap, void *stream) {
+    AllWs A; int rc = check(w, ws, ws_bytes, &A); if (rc) return rc;
+    if (!h_control || !h_header) return fail(SAPIO_E_ARG, "null host buffer%s");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long nb = (long)w->p.n_org * MAXC + w->p.n_dead;
+    const int ccap = h_cells ? (cell_cap < w->p.n_org * MAXC ? cell_cap : w->p.n_org * MAXC) : 0;
+    const int dcap = h_dead ? (dead_cap < w->p.n_dead ? dead_cap : w->p.n_dead) : 0;
+    CUDA_TRY(cudaMemcpyAsync(A.frame.control, h_control, sizeof(SapioControl), cudaMemcpyHostToDevice, st));
+    for (int t = 0; t < n_ticks; t++) if ((rc = launch_tick(*w, A, phases, A.frame.control, st))) return rc;
+    prof_mark(st, PT_FRAME);
+    CUDA_TRY(cudaMemsetAsync(A.frame.counts, 0, 256, st));
+    k_pack_frame<<<stream_grid(nb), 256, 0, st>>>(*w, A.frame, ccap, dcap);
+    k_frame_header<<<1, 1, 0, st>>>(*w, A.frame);
+    LAUNCHES(2);
+    CUDA_TRY(cudaMemcpyAsync(h_header, A.frame.header, sizeof(SapioFrameHeader), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    int nc = h_header->n_cells < ccap ? h_header->n_cells : ccap, nd = h_header->n_dead < dcap ? h_header->n_dead : dcap;
+    if (nc > 0) CUDA_TRY(cudaMemcpyAsync(h_cells, A.frame.cells, (size_t)nc * sizeof(float4), cudaMemcpyDeviceToHost, st));
+    if (nd > 0) CUDA_TRY(cudaMemcpyAsync(h_dead, A.frame.dead, (size_t)nd * sizeof(float4), cudaMemcpyDeviceToHost, st));
+    prof_mark(st, PT_END);
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int sapio_profile(int enable) { if (!enable && g_prof.on) prof_collect(); g_prof.on = enable != 0; return 0; }
+int sapio_profile_stages(void) { return PT_COUNT - 1; }
+const char *sapio_profile_name(int i) { return (i >= 0 && i < PT_COUNT) ? PROF_NAMES[i] : ""; }
+int sapio_profile_read(double *ms_out, int64_t *count_out, int reset) {
+    prof_collect();
+    for (int i = 0; i < PT_COUNT - 1; i++) { if (ms_out) ms_out[i] = g_prof.ms[i]; if (count_out) count_out[i] = g_prof.count[i]; }
+    if (reset) for (int i = 0; i < PT_COUNT; i++) { g_prof.ms[i] = 0; g_prof.count[i] = 0; }
+    return 0;
+}
+uint64_t sapio_launch_count(void) { return g_prof.launches; }
 
 }  // extern "C"

@@ -22,6 +22,7 @@
 #include <cub/cub.cuh>
 #include "common.cuh"
 #include "bodies.cuh"
+#include "prof.cuh"
 namespace cg = cooperative_groups;
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -755,6 +756,7 @@ static int launch_space_step(const SapioWorld &w, const Workspace &W, cudaStream
     K.bc_joint = 1.0 - pow((double)p.joint_error_bias, K.dt);        // bias_coef(errorBias, dt)
     K.dt_coef_unused = 0.f;
 
+    prof_mark(st, PT_BROADPHASE);
     STEP_TRY(cudaMemsetAsync(W.flags, 0, 256, st));
     STEP_TRY(cudaMemsetAsync(W.org_coupled, 0, (size_t)p.n_org, st));
     k_integrate<true><<<sgrid(NB, 256), 256, 0, st>>>(w, W.gkey, W.gval);
@@ -763,6 +765,7 @@ static int launch_space_step(const SapioWorld &w, const Workspace &W, cudaStream
     STEP_TRY(cudaMemsetAsync(W.cell_start, 0, (size_t)NG * 4, st));
     STEP_TRY(cudaMemsetAsync(W.cell_end, 0, (size_t)NG * 4, st));
     k_cell_bounds<<<sgrid(NB, 256), 256, 0, st>>>(W.skey, NB, NG, W.cell_start, W.cell_end);
+    prof_mark(st, PT_NARROW);
     k_narrow<false><<<sgrid(NB + 1, 128), 128, 0, st>>>(w, W);
     tmp = W.cub_bytes;
     STEP_TRY(cub::DeviceScan::ExclusiveSum(W.cub_tmp, tmp, W.cnt_up, W.off_up, NB + 1, st));
@@ -775,6 +778,8 @@ static int launch_space_step(const SapioWorld &w, const Workspace &W, cudaStream
     k_cross_links<<<sgrid(NB, 128), 128, 0, st>>>(w, W);
     k_cross_prestep<<<sgrid(p.x_cap, 128), 128, 0, st>>>(w, W, K);
     k_classify<<<sgrid(p.n_org, 256), 256, 0, st>>>(w, W);
+    LAUNCHES(9);
+    prof_mark(st, PT_ORG_SOLVE);
     {   // one warp per organism, persistent CTAs pulling organisms of their size class
         auto blocks = [&](int cls, int warps) { long want = ((long)p.n_org + warps - 1) / warps; return (int)(want < g_plan.org_blocks[cls] ? want : g_plan.org_blocks[cls]); };
         k_org_solve<16><<<blocks(0, OrgCfg<16>::WARPS), OrgCfg<16>::WARPS * 32, g_plan.org_smem[0], st>>>(w, W, K, 0);
@@ -782,12 +787,17 @@ static int launch_space_step(const SapioWorld &w, const Workspace &W, cudaStream
         k_org_solve<48><<<blocks(2, OrgCfg<48>::WARPS), OrgCfg<48>::WARPS * 32, g_plan.org_smem[2], st>>>(w, W, K, 2);
         k_org_solve<64><<<blocks(3, OrgCfg<64>::WARPS), OrgCfg<64>::WARPS * 32, g_plan.org_smem[3], st>>>(w, W, K, 3);
     }
+    LAUNCHES(4);
+    prof_mark(st, PT_COUPLED);
     {
         SapioWorld wc = w; Workspace Wc = W; StepK Kc = K;
         void *args[] = { (void *)&wc, (void *)&Wc, (void *)&Kc };
         STEP_TRY(cudaLaunchCooperativeKernel((void *)k_coupled, dim3(g_plan.coop_blocks), dim3(COUPLED_WARPS * 32), args, g_plan.coop_smem, st));
     }
+    prof_mark(st, PT_STEP_FINISH);
     k_step_finish<<<sgrid(NB + 1, 256), 256, 0, st>>>(w, W);
+    LAUNCHES(2);
+    prof_mark(st, PT_END);
     STEP_TRY(cudaGetLastError());
     return 0;
 #undef STEP_TRY

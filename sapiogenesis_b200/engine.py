@@ -98,5 +98,53 @@ class Engine:
         n = int(cnt.item())
         return out[:min(n, cap)].cpu().numpy().astype("uint32")
 
+    def events(self, drought: float = 0.0, poison: float = 0.0):
+        """updateUI's world events (Sapiogenesis.py:37-47), amounts = severity * uDiff."""
+        with torch.cuda.device(self.world.device):
+            _lib.check(self.lib.sapio_events(self._ref(), *self._ws, drought, poison, self._stream_ptr()), "sapio_events")
+
+    # -- end-to-end path: host buffers in, host buffers out (what a GUI host does every frame) ------------------
+    def _host_buffers(self):
+        if getattr(self, "_hb", None) is None:
+            from .world import MAXC
+            p = self.world.p
+            self._hb = dict(
+                control=torch.zeros(4, dtype=torch.float32).pin_memory(),
+                header=torch.zeros(24, dtype=torch.int64).pin_memory(),                 # SapioFrameHeader = 168 bytes
+                cells=torch.zeros(p.n_org * MAXC, 4, dtype=torch.float32).pin_memory(),
+                dead=torch.zeros(p.n_dead, 4, dtype=torch.float32).pin_memory())
+        return self._hb
+
+    def tick_host(self, n: int = 1, phases: int = PH_ALL, drought: float = 0.0, poison: float = 0.0):
+        """n ticks through sapio_tick_host: uploads the event block from pinned host memory, downloads the frame
+        (counters + packed sprite poses) into pinned host memory. Returns (header dict, cells [n,4], dead [m,4], bytes)."""
+        hb = self._host_buffers()
+        hb["control"][0], hb["control"][1] = drought, poison
+        with torch.cuda.device(self.world.device):
+            _lib.check(self.lib.sapio_tick_host(
+                self._ref(), *self._ws, phases, n, ctypes.c_void_p(hb["control"].data_ptr()), ctypes.c_void_p(hb["header"].data_ptr()),
+                ctypes.c_void_p(hb["cells"].data_ptr()), hb["cells"].shape[0], ctypes.c_void_p(hb["dead"].data_ptr()), hb["dead"].shape[0],
+                self._stream_ptr()), "sapio_tick_host")
+        raw = hb["header"].numpy()
+        hdr = dict(co2=float(raw[:1].view("float64")[0]), o2=float(raw[1:2].view("float64")[0]), tick=int(raw[2]),
+                   population=int(raw[3:4].view("int32")[0]), n_cells=int(raw[3:4].view("int32")[1]), n_dead=int(raw[4:5].view("int32")[0]),
+                   stats=[int(v) for v in raw[5:21]])
+        h2d = 16
+        d2h = 168 + 16 * (hdr["n_cells"] + hdr["n_dead"])
+        return hdr, hb["cells"][:hdr["n_cells"]], hb["dead"][:hdr["n_dead"]], (h2d, d2h)
+
+    # -- measurement hooks ---------------------------------------------------------------------------------------
+    def profile(self, enable: bool):
+        self.lib.sapio_profile(1 if enable else 0)
+
+    def profile_read(self, reset: bool = True):
+        n = self.lib.sapio_profile_stages()
+        ms = (ctypes.c_double * n)(); cnt = (ctypes.c_int64 * n)()
+        self.lib.sapio_profile_read(ms, cnt, 1 if reset else 0)
+        return {self.lib.sapio_profile_name(i).decode(): (ms[i], cnt[i]) for i in range(n)}
+
+    def launch_count(self) -> int:
+        return int(self.lib.sapio_launch_count())
+
     def synchronize(self):
         torch.cuda.synchronize(self.world.device)
