@@ -84,7 +84,7 @@ def cpu_world(orc, n_org, seed):
     rng = np.random.default_rng(seed)
     cols = int(math.ceil(math.sqrt(n_org)))
     pitch = (side - 200.0) / cols
-    w.t["g_co2"][0] = 30000.0 * n_org / 12.0
+    w.t["g_co2"][0] = 30000.0 * (2.0 * side) / (3180.0 + 1800.0)
     for i in range(n_org):
         j = rng.uniform(-0.12, 0.12, 2) * pitch
         assert orc.spawn(w, i, 100.0 + (i % cols + 0.5) * pitch + j[0], 100.0 + (i // cols + 0.5) * pitch + j[1]) == 0

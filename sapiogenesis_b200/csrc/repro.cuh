@@ -82,12 +82,13 @@ __global__ void __launch_bounds__(REPRO_WARPS * 32) k_repro_prepare(WORLD_ARG, R
     const SapioParams &p = w.p;
     const int lane = lane_id(), n_req = Q.counters[0];
     const int32_t T = (int32_t)w.g_tick[0];
+    __shared__ DGenome sg[REPRO_WARPS];
     for (int r = blockIdx.x * REPRO_WARPS + (threadIdx.x >> 5); r < n_req; r += gridDim.x * REPRO_WARPS) {
         Birth &B = Q.births[r];
         const int parent = Q.req_list[r];
+        DGenome &g = sg[threadIdx.x >> 5];                    // the dict-walking logic runs on shared memory, not on global
         if (lane == 0) {
             B.parent = parent; B.accepted = 0; B.slot = -1; B.ok = 0;
-            DGenome &g = B.g;
             g_from_world(w, parent, g);
             double prect[2]; g_get_size(g, prect);                                  // old_organism.dna.get_size()
             RngStream u(p.seed, w.org_uid[parent], T, RNG_GENOME, (uint32_t)sibling << 20);
@@ -105,6 +106,11 @@ __global__ void __launch_bounds__(REPRO_WARPS * 32) k_repro_prepare(WORLD_ARG, R
                 g_get_rect(g, B.rect);
                 B.ok = 1;
             }
+        }
+        __syncwarp();
+        {   // publish the child genome for the later phases
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(&g); uint32_t *dst = reinterpret_cast<uint32_t *>(&B.g);
+            for (int e = lane; e < (int)(sizeof(DGenome) / 4); e += 32) dst[e] = src[e];
         }
         __syncwarp();
         uint32_t mask[12];
@@ -163,16 +169,19 @@ __global__ void __launch_bounds__(REPRO_WARPS * 32) k_repro_prepare(WORLD_ARG, R
 }
 
 // Organism.__init__ + build_body rows (sprites.py:1089-1125, 1698-1729, build_sprite :255-325); whole warp
-__device__ __forceinline__ void write_rows(const SapioWorld &w, int slot, const DGenome &g, const uint8_t *order, double px, double py, int64_t uid, int32_t tick) {
+// g, order and row_of live in shared memory
+__device__ __forceinline__ void write_rows(const SapioWorld &w, int slot, const DGenome &g, const uint8_t *order, uint8_t *row_of, double px, double py, int64_t uid, int32_t tick) {
     const int lane = lane_id(), nc = g.n;
     float sum_h = 0.f, sum_mh = 0.f, sum_e = 0.f, sum_st = 0.f;
+    for (int k = lane; k < nc; k += 32) row_of[order[k]] = (uint8_t)k;
+    __syncwarp();
     for (int k = lane; k < MAXC; k += 32) {
         int row = slot * MAXC + k;
         if (k >= nc) { w.c_alive[row] = 0; continue; }
         int j = order[k];
         int prow = -1, mrow = -1;
-        if (!g.first[j]) { int pj = g_index_of(g, g.parent_id[j]); for (int q = 0; q < nc; q++) if (order[q] == pj) prow = q; }
-        if (g.mirror_id[j]) { int mj = g_index_of(g, g.mirror_id[j]); if (mj >= 0) for (int q = 0; q < nc; q++) if (order[q] == mj) mrow = q; }
+        if (!g.first[j]) { int pj = g_index_of(g, g.parent_id[j]); if (pj >= 0) prow = row_of[pj]; }
+        if (g.mirror_id[j]) { int mj = g_index_of(g, g.mirror_id[j]); if (mj >= 0) mrow = row_of[mj]; }
         w.c_alive[row] = SAPIO_CELL_ALIVE; w.c_type[row] = (uint8_t)g.type[j]; w.c_inuse[row] = 0;
         w.c_parent[row] = (int8_t)prow; w.c_mirror[row] = (int8_t)mrow; w.c_gorder[row] = (uint8_t)j; w.c_id[row] = g.id[j];
         float x = (float)(px + g.relx[j]), y = (float)(py + g.rely[j]);
@@ -208,7 +217,7 @@ __device__ __forceinline__ void write_rows(const SapioWorld &w, int slot, const 
         // neural.setup_network wiring (neural.py:436-467): eyes then olfactory cells, each in dna.cells order
         int nin = 0;
         for (int pass = 0; pass < 2; pass++)
-            for (int j = 0; j < nc; j++) if (g.type[j] == (pass == 0 ? SAPIO_T_EYE : SAPIO_T_OLFACTORY)) { for (int q = 0; q < nc; q++) if (order[q] == j) w.org_incell[slot * MAXC + nin] = (uint8_t)q; nin++; }
+            for (int j = 0; j < nc; j++) if (g.type[j] == (pass == 0 ? SAPIO_T_EYE : SAPIO_T_OLFACTORY)) w.org_incell[slot * MAXC + nin++] = row_of[j];
         w.org_nincell[slot] = nin;
         int32_t *ldim = w.org_ldim + slot * 16;
         for (int i = 0; i < 16; i++) ldim[i] = 0;
@@ -256,20 +265,25 @@ __global__ void __launch_bounds__(32) k_repro_resolve(WORLD_ARG, ReproWs Q, int 
             if (n_acc >= n_free || n_acc >= Q.birth_cap) { overflow = true; break; }
             const int slot = Q.free_list[n_acc];
             const int64_t uid = w.g_next_uid[0];
-            write_rows(w, slot, B.g, B.order, x, y, uid, T);
+            // the newborn's Organism.get_rect (sprites.py:1211-1232) from the positions its cells will get: the first cell's
+            // centre widened by every cell's disc, all positions as the fp32 the world holds -- for the births still to be placed
+            const DGenome &cg = B.g;
+            const double hx = (double)(float)x, hy = (double)(float)y;     // first cell: relative_pos (0, 0)
+            double minx = hx, maxx = hx, miny = hy, maxy = hy;
+            for (int j = lane; j < cg.n; j += 32) {
+                double cx = (double)(float)(x + cg.relx[j]), cy = (double)(float)(y + cg.rely[j]), rad = (double)(float)cg.size[j] / 2.0;
+                minx = fmin(minx, cx - rad); maxx = fmax(maxx, cx + rad); miny = fmin(miny, cy - rad); maxy = fmax(maxy, cy + rad);
+            }
+            for (int s = 16; s; s >>= 1) {
+                minx = fmin(minx, __shfl_xor_sync(FULL, minx, s)); maxx = fmax(maxx, __shfl_xor_sync(FULL, maxx, s));
+                miny = fmin(miny, __shfl_xor_sync(FULL, miny, s)); maxy = fmax(maxy, __shfl_xor_sync(FULL, maxy, s));
+            }
             if (lane == 0) {
                 w.g_next_uid[0] = uid + 1;
                 B.accepted = 1; B.slot = slot; B.uid = uid; B.px = x; B.py = y;
                 Q.accepted[n_acc] = slot;
-                // the newborn's Organism.get_rect, for the births still to be placed this tick
-                int r0 = slot * MAXC;
-                double minx = w.c_pos[2 * r0], maxx = minx, miny = w.c_pos[2 * r0 + 1], maxy = miny;
-                for (int k = 0; k < B.g.n; k++) {
-                    double cx = w.c_pos[2 * (r0 + k)], cy = w.c_pos[2 * (r0 + k) + 1], rad = (double)w.c_size[r0 + k] / 2.0;
-                    if (cx - rad < minx) minx = cx - rad; if (cx + rad > maxx) maxx = cx + rad;
-                    if (cy - rad < miny) miny = cy - rad; if (cy + rad > maxy) maxy = cy + rad;
-                }
                 w.org_rect[4 * slot] = minx; w.org_rect[4 * slot + 1] = miny; w.org_rect[4 * slot + 2] = maxx; w.org_rect[4 * slot + 3] = maxy;
+                w.org_state[slot] = 1;                                   // rows follow in k_repro_finish
                 stat_add(w, SAPIO_STAT_BIRTHS, 1);
             }
             __syncwarp();
@@ -364,9 +378,19 @@ __global__ void __launch_bounds__(REPRO_WARPS * 32) k_repro_finish(WORLD_ARG, Re
     const SapioParams &p = w.p;
     const int lane = lane_id(), n_req = Q.counters[0];
     const int32_t T = (int32_t)w.g_tick[0];
+    __shared__ DGenome sg[REPRO_WARPS];
+    __shared__ uint8_t sorder[REPRO_WARPS][MAXC], srow_of[REPRO_WARPS][MAXC];
     for (int r = blockIdx.x * REPRO_WARPS + (threadIdx.x >> 5); r < n_req; r += gridDim.x * REPRO_WARPS) {
         Birth &B = Q.births[r];
-        if (!B.accepted) { if (lane == 0 && B.ok == 0) {} continue; }
+        if (!B.accepted) continue;
+        DGenome &g = sg[threadIdx.x >> 5];
+        {
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(&B.g); uint32_t *dst = reinterpret_cast<uint32_t *>(&g);
+            for (int e = lane; e < (int)(sizeof(DGenome) / 4); e += 32) dst[e] = src[e];
+            for (int k = lane; k < MAXC; k += 32) sorder[threadIdx.x >> 5][k] = B.order[k];
+        }
+        __syncwarp();
+        write_rows(w, B.slot, g, sorder[threadIdx.x >> 5], srow_of[threadIdx.x >> 5], B.px, B.py, B.uid, T);
         build_brain(w, B.slot, B.uid, T, 1, B.parent, w.org_uid[B.parent], sibling, B.brain_changed != 0, B.old_h, B.old_n);
         const double d0 = B.rect[0] + B.px, d1 = B.rect[1] + B.py, d2 = B.rect[2] + B.px, d3 = B.rect[3] + B.py;
         int removed = 0;
@@ -396,6 +420,7 @@ __global__ void __launch_bounds__(REPRO_WARPS * 32) k_spawn(WORLD_ARG, const int
     __shared__ DGenome sg[REPRO_WARPS];
     __shared__ uint8_t sorder[REPRO_WARPS][MAXC];
     __shared__ int sok[REPRO_WARPS];
+    __shared__ uint8_t srow_of[REPRO_WARPS][MAXC];
     DGenome &g = sg[threadIdx.x >> 5];
     uint8_t *order = sorder[threadIdx.x >> 5];
     for (int i = blockIdx.x * REPRO_WARPS + (threadIdx.x >> 5); i < n; i += gridDim.x * REPRO_WARPS) {
@@ -411,7 +436,7 @@ __global__ void __launch_bounds__(REPRO_WARPS * 32) k_spawn(WORLD_ARG, const int
         }
         __syncwarp();
         if (sok[threadIdx.x >> 5]) {
-            write_rows(w, slots[i], g, order, pos[2 * i], pos[2 * i + 1], uid, T);
+            write_rows(w, slots[i], g, order, srow_of[threadIdx.x >> 5], pos[2 * i], pos[2 * i + 1], uid, T);
             build_brain(w, slots[i], uid, T, 0, -1, 0, 0, false, nullptr, 0);
         } else if (lane == 0) stat_add(w, SAPIO_STAT_BIRTH_FAIL_CAPS, 1);
         __syncwarp();

@@ -6,7 +6,7 @@ population limit is 12; worlds of 10k..1M organisms are generated here with the 
   - square world, side sqrt(N * area_per_org); default area = 3180 * 1800 / 12 px^2 (the reference's density at its limit)
   - one organism per cell of a jittered grid; no two spawn boxes overlap (grid pitch > largest genome extent)
   - food: N/4 dead cells of the add_dead_clicked recipe (Sapiogenesis.py:490-507), uniformly placed
-  - gases: co2 = 30000 * N / 12, oxygen = 0 (same availability per organism as the default world)
+  - gases: co2 = 30000 * (W + H) / 4980, oxygen = 0: the same co2 intake per co2C cell and tick as in the default world
   - brain / training / reproduction clocks staggered over their periods, so every tick sees 1/17 of the brains
     (the reference staggers them by spawn time)
 """
@@ -42,7 +42,9 @@ def build_world(n_organisms: int, device="cuda", seed: int = 0, area_per_org: fl
     idx = np.arange(n_organisms)
     jitter = rng.uniform(-0.12, 0.12, (n_organisms, 2)) * pitch
     pos = np.stack([100.0 + (idx % cols + 0.5) * pitch, 100.0 + (idx // cols + 0.5) * pitch], axis=1) + jitter
-    w.t["g_co2"][0] = 30000.0 * n_organisms / 12.0
+    # gases: a co2C cell converts size / (W + H) * dt of the world's co2 per tick (sprites.py:1413-1416), so the reservoir is
+    # scaled with (W + H) to give every cell the default world's intake at t = 0 (30000 at W + H = 4980)
+    w.t["g_co2"][0] = 30000.0 * (2.0 * side) / (3180.0 + 1800.0)
     eng.spawn(np.arange(n_organisms, dtype=np.int32), pos)
     t = w.t
     if n_food:
