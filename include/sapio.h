@@ -145,6 +145,11 @@ int sapio_reproduce(const SapioWorld *w, void *ws, size_t ws_bytes, void *stream
 /* add_creature_clicked: DNA().randomize(spawn ranges) + Organism + build_body into the given free slots at the given
  * positions (device arrays: n slots, 2n doubles); uids are g_next_uid, g_next_uid + 1, ...               Sapiogenesis.py:297-323 */
 int sapio_spawn(const SapioWorld *w, void *ws, size_t ws_bytes, const int32_t *d_slots, const double *d_pos, int n, void *stream);
+/* neural.activate(network, environment, organism, uDiff) for n given organisms now (device array of slots): sensors,
+ * forward pass, boredom gate, history / short-term memory, movement outputs, stimulation -- outside the think cadence   neural.py:91-366 */
+int sapio_activate(const SapioWorld *w, void *ws, size_t ws_bytes, const int32_t *d_orgs, int n, void *stream);
+/* neural.train_network(organism, epochs=1) for n given organisms now: memory curation + one Adam epoch                neural.py:369-423 */
+int sapio_train_network(const SapioWorld *w, void *ws, size_t ws_bytes, const int32_t *d_orgs, int n, void *stream);
 /* parity probe: sprite.info["view"] of one eye / olfactory cell as ascending body ids (device out, count may exceed cap) sprites.py:221-236 */
 int sapio_sensor_view(const SapioWorld *w, void *ws, size_t ws_bytes, int org, int cell, uint32_t *d_out, int cap, int32_t *d_count, void *stream);
 

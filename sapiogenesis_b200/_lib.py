@@ -44,6 +44,8 @@ def load() -> ctypes.CDLL:
             getattr(L, name).argtypes = [wp, vp, sz, vp]; getattr(L, name).restype = i32
     L.sapio_spawn.argtypes = [wp, vp, sz, vp, vp, i32, vp]; L.sapio_spawn.restype = i32
     L.sapio_sensor_view.argtypes = [wp, vp, sz, i32, i32, vp, i32, vp, vp]; L.sapio_sensor_view.restype = i32
+    for name in ("sapio_activate", "sapio_train_network"):
+        getattr(L, name).argtypes = [wp, vp, sz, vp, i32, vp]; getattr(L, name).restype = i32
     f32 = ctypes.c_float
     L.sapio_events.argtypes = [wp, vp, sz, f32, f32, vp]; L.sapio_events.restype = i32
     L.sapio_tick_host.argtypes = [wp, vp, sz, u32, i32, vp, vp, vp, i32, vp, i32, vp]; L.sapio_tick_host.restype = i32

@@ -288,6 +288,39 @@ int sapio_settle(const SapioWorld *w, void *ws, size_t ws_bytes, void *stream) {
     AllWs A; int rc = check(w, ws, ws_bytes, &A); if (rc) return rc;
     return launch_settle(*w, A, (cudaStream_t)stream);
 }
+__global__ void k_fill_list(int *list, int *counter, const int32_t *src, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) list[i] = src[i];
+    if (i == 0) *counter = n;
+}
+static int check_list(const SapioWorld *w, const int32_t *d_orgs, int n) {
+    if (n < 0 || n > w->p.n_org || (n && !d_orgs)) { snprintf(g_err, sizeof(g_err), "bad organism list (n = %d)", n); return SAPIO_E_ARG; }
+    return 0;
+}
+int sapio_activate(const SapioWorld *w, void *ws, size_t ws_bytes, const int32_t *d_orgs, int n, void *stream) {
+    AllWs A; int rc = check(w, ws, ws_bytes, &A); if (rc) return rc;
+    if ((rc = check_list(w, d_orgs, n))) return rc;
+    if (n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const SapioParams &p = w->p;
+    k_fill_list<<<(n + 255) / 256, 256, 0, st>>>(A.rules.think_list, A.rules.counters + RC_NTHINK, d_orgs, n);
+    if ((rc = launch_grid_only(*w, A.step, st))) return rc;
+    size_t smem = (size_t)THINK_WARPS * (p.in_cap + 2 * (p.width_cap > 4 ? p.width_cap : 4)) * sizeof(float);
+    CUDA_TRY(cudaFuncSetAttribute(k_think, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_think<<<stream_grid((long)n * 32, THINK_WARPS * 32), THINK_WARPS * 32, smem, st>>>(*w, A.step, A.rules);
+    LAUNCHES(4);
+    LAUNCH_CHECK();
+    return 0;
+}
+int sapio_train_network(const SapioWorld *w, void *ws, size_t ws_bytes, const int32_t *d_orgs, int n, void *stream) {
+    AllWs A; int rc = check(w, ws, ws_bytes, &A); if (rc) return rc;
+    if ((rc = check_list(w, d_orgs, n))) return rc;
+    if (n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    k_fill_list<<<(n + 255) / 256, 256, 0, st>>>(A.rules.train_list, A.rules.counters + RC_NTRAIN, d_orgs, n);
+    LAUNCHES(1);
+    return launch_train(*w, A, st);
+}
 int sapio_reproduce(const SapioWorld *w, void *ws, size_t ws_bytes, void *stream) {
     AllWs A; int rc = check(w, ws, ws_bytes, &A); if (rc) return rc;
     return launch_reproduce(*w, A, (cudaStream_t)stream);

@@ -87,6 +87,25 @@ class Engine:
                                             self._stream_ptr()), "sapio_spawn")
         self._keep = (slots_t, pos_t)
 
+    def _org_list(self, orgs):
+        return torch.as_tensor(orgs, dtype=torch.int32, device=self.world.device).contiguous().view(-1)
+
+    def activate(self, orgs):
+        """neural.activate (neural.py:91-366) for the given organism slots, now."""
+        lst = self._org_list(orgs)
+        with torch.cuda.device(self.world.device):
+            _lib.check(self.lib.sapio_activate(self._ref(), *self._ws, ctypes.c_void_p(lst.data_ptr()), int(lst.numel()),
+                                               self._stream_ptr()), "sapio_activate")
+        self._keep = (lst,)
+
+    def train_network(self, orgs):
+        """neural.train_network (neural.py:369-423) for the given organism slots, now."""
+        lst = self._org_list(orgs)
+        with torch.cuda.device(self.world.device):
+            _lib.check(self.lib.sapio_train_network(self._ref(), *self._ws, ctypes.c_void_p(lst.data_ptr()), int(lst.numel()),
+                                                    self._stream_ptr()), "sapio_train_network")
+        self._keep = (lst,)
+
     def sensor_view(self, org: int, cell: int, cap: int = 4096):
         """sprite.info["view"] of one eye / olfactory cell as ascending body ids (parity probe)."""
         dev = self.world.device

@@ -1,0 +1,116 @@
+"""The reference-named host side (sapiogenesis_b200.physics / sprites / neural): surface on CPU, behaviour on the GPU.
+
+The expected names and parameter lists below were read off the reference (physics.py:279-471, sprites.py:37-65,1809,
+neural.py:91,369,426) and are written out here: nothing in the tests reads /root/reference."""
+import inspect
+
+import numpy as np
+import pytest
+import torch
+
+from parity import compare_worlds
+from sapiogenesis_b200.world import MAXC, PH_ALL
+from worlds import make_world
+
+
+def test_reference_entry_points_exist_with_the_reference_parameters():
+    from sapiogenesis_b200 import neural, physics, sprites
+    params = lambda f: list(inspect.signature(f).parameters)
+    assert params(physics.Environment.__init__)[:8] == ["self", "worldView", "scene", "width", "height", "friction", "gravity", "frameWidth"]
+    assert params(physics.Environment.update) == ["self", "event"]
+    for name in ("preUpdateEvent", "postUpdateEvent", "pause_world", "resume_world", "removeSprite", "add_ball_sprite", "stop"):
+        assert callable(getattr(physics.Environment, name))
+    assert params(physics.Environment.add_ball_sprite)[:7] == ["self", "xy", "width", "height", "mass", "friction", "elasticity"]
+    assert params(physics.setupEnvironment)[:4] == ["worldView", "scene", "friction", "gravity"]
+    for name in ("getPos", "getCenter", "getWidth", "getHeight", "bump", "updateSprite"):
+        assert callable(getattr(physics.Sprite, name))
+    assert params(sprites.update_organisms) == ["environment"]
+    assert params(sprites.disperse_all_dead) == ["environment"]
+    knobs = dict(co2_conversion_ratio=3, cell_dispersion_rate=6, reproduction_limit=6, offspring_amount=1, heal_rate=4, mass_cutoff=1,
+                 break_damage=5, starvation_rate=6, neural_update_delay=.5, learning_update_delay=.5, training_epochs=1,
+                 max_push_speed=250, max_rotation_speed=6, age_limit=200, eyesight_multiplier=10, olfactory_multiplier=15)
+    for k, v in knobs.items():
+        assert getattr(sprites, k) == v, k
+    for name in ("alive", "kill", "total_energy", "max_energy", "health_percent", "energy_percent"):
+        assert callable(getattr(sprites.Organism, name))
+    assert params(neural.activate) == ["network", "environment", "organism", "uDiff"]
+    assert params(neural.train_network) == ["organism", "epochs"]
+    assert params(neural.setup_network) == ["dna", "learning_rate", "rnn", "hiddenSize"]
+
+
+def test_environment_refuses_to_run_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from sapiogenesis_b200 import physics
+    from sapiogenesis_b200._lib import SapioError
+    with pytest.raises((SapioError, RuntimeError, AssertionError)):
+        physics.Environment(None, None, 3180, 1800, device="cuda")
+    with pytest.raises(SapioError):
+        physics.Environment(None, None, 3180, 1800, device="cpu")
+
+
+def _env_from(w):
+    """An Environment wrapped around an existing world (state identical to `w`)."""
+    from sapiogenesis_b200 import physics
+    from sapiogenesis_b200.engine import Engine
+    env = physics.Environment.__new__(physics.Environment)
+    physics.Environment.__init__(env, None, None, w.p.width, w.p.height, capacity=w.p.n_org, dead_capacity=w.p.n_dead)
+    env.world = w.to("cuda")
+    env.engine = Engine(env.world)
+    return env
+
+
+@pytest.mark.gpu
+def test_update_loop_is_the_fused_tick(oracle):
+    """env.preUpdateEvent = update_organisms; env.update() per timer event (Sapiogenesis.py:687, physics.py:425) is
+    bit-identical to sapio_tick on the same state, and tracks the oracle."""
+    from sapiogenesis_b200 import sprites
+    from sapiogenesis_b200.engine import Engine
+    w = make_world(oracle, n_org=24, seed=21, n_food=60, crowd=0.45, kick=30.0, extra_slots=8, n_dead_cap=64 * 32)
+    w.p.think_ticks, w.p.train_ticks, w.p.repro_ticks = 3, 3, 8
+    saved = (sprites.neural_update_delay, sprites.learning_update_delay, sprites.reproduction_limit)
+    sprites.neural_update_delay, sprites.learning_update_delay, sprites.reproduction_limit = 3 * 0.03, 3 * 0.03, 8 * 0.03
+    try:
+        env = _env_from(w)
+        env.preUpdateEvent = lambda: sprites.update_organisms(env)
+        wf = w.to("cuda"); ef = Engine(wf)
+        for _ in range(12):
+            env.update(None)
+        ef.tick(12); ef.synchronize(); env.engine.synchronize()
+        assert (env.world.p.think_ticks, env.world.p.repro_ticks) == (3, 8)
+        for name in wf.t:
+            a, b = env.world.t[name], wf.t[name]
+            assert torch.equal(a, b) or torch.equal(torch.nan_to_num(a.double()), torch.nan_to_num(b.double())), name
+        assert env.world.tick == w.tick + 12
+        assert env.info["population"] == int((wf.t["org_state"] == 1).sum())
+        assert len(env.info["organism_list"]) == env.info["population"]
+        org = env.info["organism_list"][0]
+        assert org.alive() and 0.0 <= org.energy_percent() <= 100.0 and len(org.cells) == int((wf.t["c_alive"][org.slot * MAXC:(org.slot + 1) * MAXC] == 1).sum())
+        env.pause_world(); t0 = env.world.tick; env.update(None); assert env.world.tick == t0
+    finally:
+        sprites.neural_update_delay, sprites.learning_update_delay, sprites.reproduction_limit = saved
+
+
+@pytest.mark.gpu
+def test_activate_and_train_network_on_demand(oracle):
+    """neural.activate / neural.train_network for one organism outside the cadence == the oracle's."""
+    from sapiogenesis_b200 import neural
+    w = make_world(oracle, n_org=12, seed=8, n_food=40, crowd=0.45, kick=30.0)
+    w.p.think_ticks, w.p.train_ticks = 3, 3
+    assert oracle.tick(w, PH_ALL, 40) == 0
+    env = _env_from(w)
+    orgs = [o for o in env.info["organism_list"]][:4]
+    for org in orgs:
+        out = neural.activate(org.brain, env, org, 0.03)
+        assert oracle.think_now(w, org.slot) == 0
+        np.testing.assert_allclose(out, w.np("org_move")[org.slot], rtol=0, atol=2e-3)
+    env.engine.synchronize()
+    compare_worlds(env.world, w, "activate on demand", verbose=False)
+    for org in orgs:
+        neural.train_network(org, epochs=1)
+        assert oracle.train_one(w, org.slot) == 0
+    env.engine.synchronize()
+    compare_worlds(env.world, w, "train_network on demand", verbose=False)
+    net = orgs[0].brain
+    dims = net.structure
+    assert [tuple(W.shape) for W, _ in net.layers()] == [(dims[i + 1], dims[i]) for i in range(len(dims) - 1)]
