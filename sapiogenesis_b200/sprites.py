@@ -36,7 +36,7 @@ cell_types = list(CELL_TYPES[:8])                      # sprites.py:22
 
 def _ticks(seconds: float, dt: float) -> int:
     """Virtual-clock form of `time.time() - t0 >= seconds` with one tick == dt seconds."""
-    return max(1, math.ceil(seconds / dt - 1e-9))
+    return max(1, math.ceil(seconds / dt - 1e-4))          # dt is stored as fp32
 
 
 def _sync_knobs(environment) -> None:
