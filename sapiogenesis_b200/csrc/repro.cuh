@@ -17,11 +17,13 @@
 
 __constant__ double C_COS[360], C_SIN[360];      // cos/sin of the integer bearings, filled by the host's libm (== the oracle's)
 
+#define REPRO_NEAR_CAP 64                          // organisms within reach of one birth's candidates; beyond: full scan
 struct Birth {
     DGenome g;
     int parent, ok, accepted, slot, brain_changed, old_n; int old_h[16];
-    int64_t uid; double px, py, rect[4], dist[2];
+    int64_t uid; double px, py, rect[4], dist[2], box[4];
     uint32_t viable[12];
+    int near_n, near[REPRO_NEAR_CAP];
     uint8_t order[MAXC];
 };
 struct ReproWs {
@@ -42,7 +44,8 @@ __device__ __forceinline__ bool rects_block(const double d[4], const double r[4]
 }
 
 // Organism.get_rect (sprites.py:1211-1232): seeded with the first cell's centre, widened by living cells' discs
-__global__ void __launch_bounds__(256) k_org_rects(WORLD_ARG) {
+__global__ void __launch_bounds__(256) k_org_rects(WORLD_ARG, const int *n_req) {
+    if (n_req && *n_req == 0) return;
     for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < w.p.n_org; o += gridDim.x * blockDim.x) {
         if (w.org_state[o] != 1) continue;
         int r0 = o * MAXC;
@@ -113,6 +116,58 @@ __global__ void __launch_bounds__(REPRO_WARPS * 32) k_repro_prepare(WORLD_ARG, R
             for (int e = lane; e < (int)(sizeof(DGenome) / 4); e += 32) dst[e] = src[e];
         }
         __syncwarp();
+        if (lane == 0) {
+            B.near_n = 0;
+            if (B.ok) {   // reach box of all 360 candidates: organisms outside cannot block any of them
+                const double ppx = w.org_pos[2 * parent], ppy = w.org_pos[2 * parent + 1];
+                B.box[0] = ppx - B.dist[0] + B.rect[0]; B.box[1] = ppy - B.dist[1] + B.rect[1];
+                B.box[2] = ppx + B.dist[0] + B.rect[2]; B.box[3] = ppy + B.dist[1] + B.rect[3];
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// phase 1b: thread per living organism, all requests from shared-memory tiles: who lies within reach of which birth
+#define NEAR_TILE 128
+__global__ void __launch_bounds__(256) k_repro_near(WORLD_ARG, ReproWs Q) {
+    const int n_req = Q.counters[0];
+    if (n_req == 0) return;
+    __shared__ double box[NEAR_TILE][4];
+    __shared__ uint8_t okv[NEAR_TILE];
+    const int n = w.p.n_org;
+    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const int o = base + threadIdx.x;
+        const bool live = o < n && w.org_state[o] == 1;
+        double q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+        if (live) { q0 = w.org_rect[4 * o]; q1 = w.org_rect[4 * o + 1]; q2 = w.org_rect[4 * o + 2]; q3 = w.org_rect[4 * o + 3]; }
+        for (int t0 = 0; t0 < n_req; t0 += NEAR_TILE) {
+            __syncthreads();
+            for (int e = threadIdx.x; e < NEAR_TILE; e += blockDim.x) {
+                int r = t0 + e; bool ok = r < n_req && Q.births[r].ok;
+                okv[e] = ok;
+                if (ok) { box[e][0] = Q.births[r].box[0]; box[e][1] = Q.births[r].box[1]; box[e][2] = Q.births[r].box[2]; box[e][3] = Q.births[r].box[3]; }
+            }
+            __syncthreads();
+            if (!live) continue;
+            const int cnt = min(NEAR_TILE, n_req - t0);
+            for (int e = 0; e < cnt; e++) {
+                if (!okv[e]) continue;
+                if (q2 < box[e][0] || q0 > box[e][2] || q3 < box[e][1] || q1 > box[e][3]) continue;
+                int k = atomicAdd(&Q.births[t0 + e].near_n, 1);
+                if (k < REPRO_NEAR_CAP) Q.births[t0 + e].near[k] = o;
+            }
+        }
+    }
+}
+
+// phase 1c: one warp per request: all 360 bearings against the world bounds and the organisms within reach
+__global__ void __launch_bounds__(REPRO_WARPS * 32) k_repro_place(WORLD_ARG, ReproWs Q) {
+    const SapioParams &p = w.p;
+    const int lane = lane_id(), n_req = Q.counters[0];
+    for (int r = blockIdx.x * REPRO_WARPS + (threadIdx.x >> 5); r < n_req; r += gridDim.x * REPRO_WARPS) {
+        Birth &B = Q.births[r];
+        const int parent = B.parent;
         uint32_t mask[12];
 #pragma unroll
         for (int t = 0; t < 12; t++) mask[t] = 0;
@@ -128,15 +183,18 @@ __global__ void __launch_bounds__(REPRO_WARPS * 32) k_repro_prepare(WORLD_ARG, R
                 double x = ppx + C_COS[b] * dx, y = ppy + C_SIN[b] * dy;
                 if (!(r0 + x < 0 || r2 + x > (double)p.width || r1 + y < 0 || r3 + y > (double)p.height)) mine |= 1u << t;
             }
-            // reach box of all candidates: skip organisms that cannot touch any of them
-            const double bx0 = ppx - dx + r0, bx1 = ppx + dx + r2, by0 = ppy - dy + r1, by1 = ppy + dy + r3;
-            for (int base = 0; base < p.n_org; base += 32) {
-                int o = base + lane;
+            const int nn = B.near_n;
+            const bool listed = nn <= REPRO_NEAR_CAP;
+            const int total = listed ? nn : p.n_org;
+            for (int base = 0; base < total; base += 32) {
+                const int e = base + lane;
+                int o = -1;
+                if (e < total) o = listed ? B.near[e] : e;
                 bool near = false;
                 double q[4] = {0, 0, 0, 0};
-                if (o < p.n_org && w.org_state[o] == 1) {
+                if (o >= 0 && w.org_state[o] == 1) {
                     q[0] = w.org_rect[4 * o]; q[1] = w.org_rect[4 * o + 1]; q[2] = w.org_rect[4 * o + 2]; q[3] = w.org_rect[4 * o + 3];
-                    near = !(q[2] < bx0 || q[0] > bx1 || q[3] < by0 || q[1] > by1);
+                    near = !(q[2] < B.box[0] || q[0] > B.box[2] || q[3] < B.box[1] || q[1] > B.box[3]);
                 }
                 uint32_t m = __ballot_sync(FULL, near);
                 while (m) {
@@ -375,7 +433,6 @@ __device__ void build_brain(const SapioWorld &w, int slot, int64_t uid, int32_t 
 
 // phase 3: brains + footprint (dead cells whose centre lies strictly inside the newborn's rect are deleted, sprites.py:184-217)
 __global__ void __launch_bounds__(REPRO_WARPS * 32) k_repro_finish(WORLD_ARG, ReproWs Q, int sibling) {
-    const SapioParams &p = w.p;
     const int lane = lane_id(), n_req = Q.counters[0];
     const int32_t T = (int32_t)w.g_tick[0];
     __shared__ DGenome sg[REPRO_WARPS];
@@ -392,16 +449,42 @@ __global__ void __launch_bounds__(REPRO_WARPS * 32) k_repro_finish(WORLD_ARG, Re
         __syncwarp();
         write_rows(w, B.slot, g, sorder[threadIdx.x >> 5], srow_of[threadIdx.x >> 5], B.px, B.py, B.uid, T);
         build_brain(w, B.slot, B.uid, T, 1, B.parent, w.org_uid[B.parent], sibling, B.brain_changed != 0, B.old_h, B.old_n);
-        const double d0 = B.rect[0] + B.px, d1 = B.rect[1] + B.py, d2 = B.rect[2] + B.px, d3 = B.rect[3] + B.py;
-        int removed = 0;
-        for (int d = lane; d < p.n_dead; d += 32) {
-            if (!w.d_state[d]) continue;
-            double x = w.d_pos[2 * d], y = w.d_pos[2 * d + 1];
-            if (x > d0 && x < d2 && y > d1 && y < d3) { w.d_state[d] = 0; removed++; }
-        }
-        for (int s = 16; s; s >>= 1) removed += __shfl_xor_sync(FULL, removed, s);
-        if (lane == 0) stat_add(w, SAPIO_STAT_DEAD_REMOVED, removed);
     }
+}
+// build_body's footprint clearing (sprites.py:1707-1713): a dead cell whose centre lies strictly inside the newborn's DNA rect
+// is deleted. Thread per dead cell against the accepted births of this round (shared-memory tiles).
+__global__ void __launch_bounds__(256) k_repro_clear(WORLD_ARG, ReproWs Q) {
+    const int n_req = Q.counters[0];
+    if (Q.counters[2] == 0) return;
+    __shared__ double fp[NEAR_TILE][4];
+    __shared__ uint8_t acc[NEAR_TILE];
+    __shared__ int s_removed;
+    if (threadIdx.x == 0) s_removed = 0;
+    const int n = w.p.n_dead;
+    int removed = 0;
+    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const int d = base + threadIdx.x;
+        const bool live = d < n && w.d_state[d] != 0;
+        double x = 0, y = 0;
+        if (live) { x = w.d_pos[2 * d]; y = w.d_pos[2 * d + 1]; }
+        bool hit = false;
+        for (int t0 = 0; t0 < n_req; t0 += NEAR_TILE) {
+            __syncthreads();
+            for (int e = threadIdx.x; e < NEAR_TILE; e += blockDim.x) {
+                int r = t0 + e; bool a = r < n_req && Q.births[r].accepted;
+                acc[e] = a;
+                if (a) { const Birth &B = Q.births[r]; fp[e][0] = B.rect[0] + B.px; fp[e][1] = B.rect[1] + B.py; fp[e][2] = B.rect[2] + B.px; fp[e][3] = B.rect[3] + B.py; }
+            }
+            __syncthreads();
+            if (!live || hit) continue;
+            const int cnt = min(NEAR_TILE, n_req - t0);
+            for (int e = 0; e < cnt && !hit; e++) hit = acc[e] && x > fp[e][0] && x < fp[e][2] && y > fp[e][1] && y < fp[e][3];
+        }
+        if (hit) { w.d_state[d] = 0; removed++; }
+    }
+    if (removed) atomicAdd(&s_removed, removed);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_removed) stat_add(w, SAPIO_STAT_DEAD_REMOVED, s_removed);
 }
 // siblings: a parent whose offspring i was not born stops reproducing this tick (sprites.py:1456-1459)
 __global__ void k_repro_next_sibling(WORLD_ARG, ReproWs Q) {

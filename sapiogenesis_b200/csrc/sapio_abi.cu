@@ -1,6 +1,7 @@
 // sapio_abi.cu -- the C-ABI of libsapio_b200.so (include/sapio.h). Thin: argument checks, workspace carve-up,
 // kernel launches on the caller's stream. No allocation, no torch types, no CPU fallback: without a device every
 // compute entry point returns SAPIO_E_NODEVICE.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -64,11 +65,10 @@ static size_t carve_all(const SapioParams &p, char *base, AllWs *A) {
     R.dying_cnt = (int *)take((NO + 1) * 4); R.dying_off = (int *)take((NO + 1) * 4);
     R.free_flag = (int *)take((ND + 1) * 4); R.free_off = (int *)take((ND + 1) * 4); R.free_list = (int *)take(ND * 4);
     R.disp_factor = (double *)take(ND * 8); R.disp_prod = (double *)take(256);
-    A->train_ctas = 2 * 148;
+    A->train_ctas = (int)std::min<long>(8 * 148, std::max<long>(8, NO / 8));      // 8 CTAs of 256 threads per SM; ~1/17 of the organisms train per tick
     TrainWs &T = A->train;
-    T.dz0 = (float *)take((size_t)A->train_ctas * SAPIO_MEMROWS * TRAIN_MAXW * 4);
-    T.hl = (float *)take((size_t)A->train_ctas * SAPIO_MEMROWS * TRAIN_MAXW * 4);
-    T.dO = (float *)take((size_t)A->train_ctas * SAPIO_MEMROWS * 4 * 4);
+    T.per_cta = (size_t)(p.in_cap + 4 * TRAIN_MAXW + 4) * SAPIO_MEMROWS;
+    T.buf = (float *)take((size_t)A->train_ctas * T.per_cta * 4);
     ReproWs &Q = A->repro;
     Q.birth_cap = (int)(NO < 4096 ? NO : 4096);
     Q.births = (Birth *)take((size_t)Q.birth_cap * sizeof(Birth));
@@ -155,12 +155,9 @@ static int launch_rules(const SapioWorld &w, AllWs &A, uint32_t phases, cudaStre
 
 static int launch_train(const SapioWorld &w, AllWs &A, cudaStream_t st) {
     const SapioParams &p = w.p;
-    size_t smem = (size_t)(SAPIO_STM + SAPIO_MEMROWS) * p.in_cap * sizeof(int16_t);
-    static size_t smem_set = 0;
-    if (smem > smem_set) { CUDA_TRY(cudaFuncSetAttribute(k_train, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_set = smem; }
     int ctas = p.n_org < A.train_ctas ? p.n_org : A.train_ctas;
     prof_mark(st, PT_TRAIN);
-    k_train<<<ctas, TRAIN_THREADS, smem, st>>>(w, A.rules, A.train);
+    k_train<<<ctas, TRAIN_THREADS, 0, st>>>(w, A.rules, A.train);
     LAUNCHES(1);
     prof_mark(st, PT_END);
     LAUNCH_CHECK();
@@ -194,8 +191,6 @@ static int launch_reproduce(const SapioWorld &w, AllWs &A, cudaStream_t st) {
     const SapioParams &p = w.p;
     ReproWs &Q = A.repro;
     prof_mark(st, PT_REPRODUCE);
-    k_org_rects<<<stream_grid(p.n_org), 256, 0, st>>>(w);
-    LAUNCHES(1);
     for (int sib = 0; sib < p.offspring_amount; sib++) {
         k_repro_flags<<<stream_grid(p.n_org + 1), 256, 0, st>>>(w, Q);
         size_t tmp = A.step.cub_bytes;
@@ -206,11 +201,15 @@ static int launch_reproduce(const SapioWorld &w, AllWs &A, cudaStream_t st) {
         int blocks = (Q.birth_cap + REPRO_WARPS - 1) / REPRO_WARPS;
         int cap = (sm_count() > 0 ? sm_count() : 148) * 8;
         if (blocks > cap) blocks = cap;
+        if (sib == 0) k_org_rects<<<stream_grid(p.n_org), 256, 0, st>>>(w, Q.counters);
         k_repro_prepare<<<blocks, REPRO_WARPS * 32, 0, st>>>(w, Q, sib);
+        k_repro_near<<<stream_grid(p.n_org), 256, 0, st>>>(w, Q);
+        k_repro_place<<<blocks, REPRO_WARPS * 32, 0, st>>>(w, Q);
         k_repro_resolve<<<1, 32, 0, st>>>(w, Q, sib);
         k_repro_finish<<<blocks, REPRO_WARPS * 32, 0, st>>>(w, Q, sib);
+        k_repro_clear<<<stream_grid(p.n_dead), 256, 0, st>>>(w, Q);
         if (sib + 1 < p.offspring_amount) k_repro_next_sibling<<<stream_grid(Q.birth_cap), 256, 0, st>>>(w, Q);
-        LAUNCHES(5);
+        LAUNCHES(sib == 0 ? 11 : 10);
     }
     prof_mark(st, PT_END);
     LAUNCH_CHECK();

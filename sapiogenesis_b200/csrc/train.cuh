@@ -1,5 +1,10 @@
 // train.cuh -- neural.train_network (neural.py:369-423): the "dopamine RL update". One CTA per organism whose training
-// is due.
+// is due. Layout of the work:
+//   hash     : every short-term row and every stored row gets a 128-bit hash of its 1-decimal key vector (warp per row)
+//   curate   : one warp walks the short-term rows chronologically on hashes, rewards and row indices only (no data moves)
+//   apply    : the surviving row moves are materialised in parallel (sources and destinations are disjoint, see below)
+//   epoch    : batch forward / backward with activations stored transposed [unit][sample] in the CTA's scratch (sample index
+//              fastest: coalesced), one thread per (unit, sample); then one thread per optimizer parameter
 //   curation : for every short-term memory (chronological), the best-rewarded action among short-term memories with the same
 //              1-decimal input key replaces / joins the curated memory (first match by key; replaced when its reward is not
 //              greater); then trim to memory_limit dropping the lowest reward first. Keys are Python round(x, 1) semantics on
@@ -32,147 +37,187 @@ __device__ __forceinline__ int py_round1_x10(double v) {
 __device__ __forceinline__ int key_stm(float x) { return py_round1_x10((double)x); }                 // float(tensor element)
 __device__ __forceinline__ int key_mem(float x) { return py_round1_x10(rint((double)x * 1000.0) / 1000.0); }   // round(x, 3) first
 
-struct TrainWs { float *dz0, *hl, *dO; };          // per CTA: [MEMROWS x TRAIN_MAXW], [MEMROWS x TRAIN_MAXW], [MEMROWS x 4]
+struct TrainWs { float *buf; size_t per_cta; };   // per CTA: (in_cap + 4 * TRAIN_MAXW + 4) * MEMROWS floats
+#define TR_S SAPIO_MEMROWS                          // column stride of the transposed activation buffers
 
-__global__ void __launch_bounds__(TRAIN_THREADS) k_train(WORLD_ARG, RulesWs R, TrainWs TW) {
-    extern __shared__ int16_t train_keys[];        // [STM][IN] short-term keys, then [MEMROWS][IN] memory keys
-    __shared__ float red_f[TRAIN_THREADS];
-    __shared__ int red_i[TRAIN_THREADS];
-    __shared__ int sh_best, sh_found, sh_dst, sh_add, sh_M;
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {          // splitmix64 finaliser
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31);
+}
+// key-vector hash: sum over positions of two independent mixes of (key, position). Rows are equal iff their key vectors are equal,
+// up to a 2^-128 collision probability per comparison.
+__device__ __forceinline__ void key_hash_add(int key, int c, unsigned long long &a, unsigned long long &b) {
+    unsigned long long v = ((unsigned long long)(unsigned)c << 32) | (unsigned)(key & 0xffff);
+    a += mix64(v + 0x9E3779B97F4A7C15ull); b += mix64(v * 0xD6E8FEB86659FD93ull + 0x2545F4914F6CDD1Dull);
+}
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+    for (int s = 16; s; s >>= 1) v += __shfl_xor_sync(FULL, v, s);
+    return v;
+}
+
+__global__ void __launch_bounds__(TRAIN_THREADS, 4) k_train(WORLD_ARG, RulesWs R, TrainWs TW) {
+    __shared__ unsigned long long hs[2][SAPIO_STM], hm[2][SAPIO_STM], hmem[2][SAPIO_MEMROWS];
+    __shared__ float rew_s[SAPIO_MEMROWS], red_f[TRAIN_THREADS];
+    __shared__ int16_t rowsrc[SAPIO_MEMROWS];      // -1 row untouched | 0..231 content of original row | 256 + i short-term row i
+    __shared__ uint8_t bestof[SAPIO_STM];
+    __shared__ int sh_M;
     const SapioParams &p = w.p;
-    const int IN = p.in_cap, tid = threadIdx.x;
-    int16_t *kstm = train_keys, *kmem = train_keys + SAPIO_STM * IN;
-    float *dz0 = TW.dz0 + (size_t)blockIdx.x * SAPIO_MEMROWS * TRAIN_MAXW, *hlast = TW.hl + (size_t)blockIdx.x * SAPIO_MEMROWS * TRAIN_MAXW;
-    float *dOut = TW.dO + (size_t)blockIdx.x * SAPIO_MEMROWS * 4;
+    const int IN = p.in_cap, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    float *XT = TW.buf + (size_t)blockIdx.x * TW.per_cta, *H0T = XT + (size_t)IN * TR_S, *P = H0T + TRAIN_MAXW * TR_S, *Q = P + TRAIN_MAXW * TR_S,
+          *D = Q + TRAIN_MAXW * TR_S, *dOT = D + TRAIN_MAXW * TR_S;
     const int n_train = R.counters[RC_NTRAIN];
     for (int q = blockIdx.x; q < n_train; q += gridDim.x) {
         const int o = R.train_list[q];
         const int32_t *ldim = w.org_ldim + o * 16;
         const int nl = w.org_nlayers[o], I = ldim[0];
-        const int sc = w.org_stm_n[o], sn = min(sc, SAPIO_STM);
+        const int sc = w.org_stm_n[o], sn = min(sc, SAPIO_STM), M0 = w.org_mem_n[o];
         float *min_ = w.org_mem_in + (size_t)o * SAPIO_MEMROWS * IN, *mout = w.org_mem_out + (size_t)o * SAPIO_MEMROWS * 4, *mrew = w.org_mem_rew + (size_t)o * SAPIO_MEMROWS;
         const float *sin_ = w.org_stm_in + (size_t)o * SAPIO_STM * IN, *sout = w.org_stm_out + o * SAPIO_STM * 4, *srew = w.org_stm_rew + o * SAPIO_STM;
-        if (tid == 0) sh_M = w.org_mem_n[o];
-        for (int e = tid; e < sn * I; e += TRAIN_THREADS) { int r = e / I, c = e % I; int slot = (sc - sn + r) % SAPIO_STM; kstm[r * IN + c] = (int16_t)key_stm(sin_[(size_t)slot * IN + c]); }
-        __syncthreads();
-        for (int e = tid; e < sh_M * I; e += TRAIN_THREADS) { int r = e / I, c = e % I; kmem[r * IN + c] = (int16_t)key_mem(min_[(size_t)r * IN + c]); }
-        __syncthreads();
-        for (int i = 0; i < sn; i++) {                                             // chronological (neural.py:374)
-            const int si = (sc - sn + i) % SAPIO_STM;
-            // (a) sorted(allActions, key=reward)[-1]: highest reward, the LAST of equal maxima
-            float br = -INFINITY; int bj = -1;
-            if (tid < sn) {
-                bool same = true;
-                for (int c = 0; c < I && same; c++) same = kstm[tid * IN + c] == kstm[i * IN + c];
-                if (same) { br = srew[(sc - sn + tid) % SAPIO_STM]; bj = tid; }
+#define STM_SLOT(i) ((sc - sn + (i)) % SAPIO_STM)
+        // ---- hash: short-term rows under both key rules (as a probe: float(x); as a stored row: round(x, 3)), stored rows ----
+        for (int r = wid; r < sn + M0; r += TRAIN_THREADS / 32) {
+            unsigned long long a = 0, b = 0, a2 = 0, b2 = 0;
+            if (r < sn) {
+                const float *x = sin_ + (size_t)STM_SLOT(r) * IN;
+                for (int c = lane; c < I; c += 32) { float v = x[c]; key_hash_add(key_stm(v), c, a, b); key_hash_add(key_mem(v), c, a2, b2); }
+                a = warp_sum_u64(a); b = warp_sum_u64(b); a2 = warp_sum_u64(a2); b2 = warp_sum_u64(b2);
+                if (lane == 0) { hs[0][r] = a; hs[1][r] = b; hm[0][r] = a2; hm[1][r] = b2; }
+            } else {
+                const int m = r - sn;
+                const float *x = min_ + (size_t)m * IN;
+                for (int c = lane; c < I; c += 32) key_hash_add(key_mem(x[c]), c, a, b);
+                a = warp_sum_u64(a); b = warp_sum_u64(b);
+                if (lane == 0) { hmem[0][m] = a; hmem[1][m] = b; }
             }
-            red_f[tid] = br; red_i[tid] = bj;
-            __syncthreads();
-            for (int s = TRAIN_THREADS / 2; s; s >>= 1) {
-                if (tid < s) { float r2 = red_f[tid + s]; int j2 = red_i[tid + s]; if (j2 >= 0 && (red_i[tid] < 0 || r2 > red_f[tid] || (r2 == red_f[tid] && j2 > red_i[tid]))) { red_f[tid] = r2; red_i[tid] = j2; } }
-                __syncthreads();
-            }
-            const float best_r = red_f[0]; const int best = (sc - sn + red_i[0]) % SAPIO_STM;
-            __syncthreads();
-            // (b) rounded_training_data.index(key): first stored row with the same key
-            int found = 1 << 30;
-            for (int m = tid; m < sh_M; m += TRAIN_THREADS) {
-                bool same = true;
-                for (int c = 0; c < I && same; c++) same = kmem[m * IN + c] == kstm[i * IN + c];
-                if (same) { found = m; break; }
-            }
-            red_i[tid] = found;
-            __syncthreads();
-            for (int s = TRAIN_THREADS / 2; s; s >>= 1) { if (tid < s) red_i[tid] = min(red_i[tid], red_i[tid + s]); __syncthreads(); }
-            if (tid == 0) {
-                int f = red_i[0], add = 1, dst = sh_M;
-                if (f < (1 << 30)) { if (mrew[f] > best_r) add = 0; else dst = f; }
-                if (add && dst == sh_M) { if (sh_M >= SAPIO_MEMROWS) add = 0; else sh_M++; }
-                sh_add = add; sh_dst = dst;
-            }
-            __syncthreads();
-            if (sh_add) {
-                const int dst = sh_dst;
-                for (int c = tid; c < I; c += TRAIN_THREADS) { float v = sin_[(size_t)si * IN + c]; min_[(size_t)dst * IN + c] = v; kmem[dst * IN + c] = (int16_t)key_mem(v); }
-                if (tid < 4) mout[dst * 4 + tid] = sout[best * 4 + tid];
-                if (tid == 0) mrew[dst] = srew[si];                                                // sic: mem[2], not bestReward (neural.py:395)
-            }
-            __syncthreads();
         }
-        // trim (neural.py:399-404)
-        while (sh_M > p.memory_limit && (w.org_flags[o] & SAPIO_F_FINITE_MEMORY)) {
-            const int M = sh_M;
-            float lr = INFINITY; int li = 1 << 30;
-            for (int m = tid; m < M; m += TRAIN_THREADS) { float r = mrew[m]; if (r < lr) { lr = r; li = m; } }
-            red_f[tid] = lr; red_i[tid] = li;
-            __syncthreads();
-            for (int s = TRAIN_THREADS / 2; s; s >>= 1) {
-                if (tid < s) { float r2 = red_f[tid + s]; int j2 = red_i[tid + s]; if (r2 < red_f[tid] || (r2 == red_f[tid] && j2 < red_i[tid])) { red_f[tid] = r2; red_i[tid] = j2; } }
-                __syncthreads();
-            }
-            const int lo = red_i[0], last = M - 1;
-            __syncthreads();
-            if (lo != last) {
-                for (int c = tid; c < I; c += TRAIN_THREADS) { min_[(size_t)lo * IN + c] = min_[(size_t)last * IN + c]; kmem[lo * IN + c] = kmem[last * IN + c]; }
-                if (tid < 4) mout[lo * 4 + tid] = mout[last * 4 + tid];
-                if (tid == 0) mrew[lo] = mrew[last];
-            }
-            if (tid == 0) sh_M = last;
-            __syncthreads();
+        for (int m = tid; m < SAPIO_MEMROWS; m += TRAIN_THREADS) { rowsrc[m] = -1; rew_s[m] = m < M0 ? mrew[m] : 0.f; }
+        __syncthreads();
+        // (a) sorted(allActions, key=reward)[-1] among the short-term rows with the same key: highest reward, the LAST of equal maxima
+        if (tid < sn) {
+            float br = -INFINITY; int bj = tid;
+            for (int j = 0; j < sn; j++)
+                if (hs[0][j] == hs[0][tid] && hs[1][j] == hs[1][tid]) { float r = srew[STM_SLOT(j)]; if (r >= br) { br = r; bj = j; } }
+            bestof[tid] = (uint8_t)bj;
         }
+        __syncthreads();
+        // ---- curate (neural.py:374-404): one warp, chronological, bookkeeping only ----
+        if (wid == 0) {
+            int M = M0;
+            for (int i = 0; i < sn; i++) {
+                const unsigned long long a = hs[0][i], b = hs[1][i];
+                int found = -1;                                   // (b) rounded_training_data.index(key): first stored row with the key
+                for (int base = 0; base < M; base += 32) {
+                    int m = base + lane;
+                    unsigned bal = __ballot_sync(FULL, m < M && hmem[0][m] == a && hmem[1][m] == b);
+                    if (bal) { found = base + __ffs(bal) - 1; break; }
+                }
+                const float best_r = srew[STM_SLOT(bestof[i])];
+                int add = 1, dst = M;
+                if (found >= 0) { if (rew_s[found] > best_r) add = 0; else dst = found; }
+                if (add && dst == M) { if (M >= SAPIO_MEMROWS) add = 0; else M++; }
+                __syncwarp();
+                if (add && lane == 0) {                           // input of THIS memory, action of the best one, reward of this one (sic, neural.py:395)
+                    rowsrc[dst] = (int16_t)(256 + i); rew_s[dst] = srew[STM_SLOT(i)]; hmem[0][dst] = hm[0][i]; hmem[1][dst] = hm[1][i];
+                }
+                __syncwarp();
+            }
+            // trim (neural.py:399-404): drop the lowest reward (first of equal minima), the last row fills the hole
+            while (M > p.memory_limit && (w.org_flags[o] & SAPIO_F_FINITE_MEMORY)) {
+                float lr = INFINITY; int li = 1 << 30;
+                for (int m = lane; m < M; m += 32) { float r = rew_s[m]; if (r < lr) { lr = r; li = m; } }
+                for (int s = 16; s; s >>= 1) {
+                    float r2 = __shfl_xor_sync(FULL, lr, s); int j2 = __shfl_xor_sync(FULL, li, s);
+                    if (r2 < lr || (r2 == lr && j2 < li)) { lr = r2; li = j2; }
+                }
+                const int last = M - 1, lo = li < M ? li : last;
+                __syncwarp();
+                if (lo != last && lane == 0) { rowsrc[lo] = rowsrc[last] < 0 ? (int16_t)last : rowsrc[last]; rew_s[lo] = rew_s[last]; }
+                M = last;
+                __syncwarp();
+            }
+            if (lane == 0) sh_M = M;
+        }
+        __syncthreads();
         const int M = sh_M;
+        // ---- apply: a row only ever moves when it is the last one, so every original source row lies at or beyond M and every
+        //      destination below M: the copies are independent ----
+        for (int m = wid; m < M; m += TRAIN_THREADS / 32) {
+            const int src = rowsrc[m];
+            if (src < 0) continue;
+            const float *x, *y;
+            if (src >= 256) { x = sin_ + (size_t)STM_SLOT(src - 256) * IN; y = sout + STM_SLOT(bestof[src - 256]) * 4; }
+            else { x = min_ + (size_t)src * IN; y = mout + src * 4; }
+            for (int c = lane; c < I; c += 32) min_[(size_t)m * IN + c] = x[c];
+            if (lane < 4) mout[m * 4 + lane] = y[lane];
+            if (lane == 0) mrew[m] = rew_s[m];
+        }
         if (tid == 0) w.org_mem_n[o] = M;
+        __syncthreads();
         if (M > 0) {
             float *brain = w.org_brain + (size_t)o * p.brain_cap;
             const int h0 = ldim[1], hl = ldim[nl - 1];
             int off_out = 0;
             for (int l = 0; l < nl - 1; l++) off_out += ldim[l + 1] * ldim[l] + ldim[l + 1];
             float *Win = brain, *bin = brain + h0 * I, *Wout = brain + off_out, *bout = Wout + 4 * hl;
-            // phase 1: one thread per sample -- forward, loss, backward down to the first layer's pre-activation
+            // ---- epoch, forward: X^T, then layer by layer; thread = (unit r, sample m), m fastest ----
+            for (int e = tid; e < M * I; e += TRAIN_THREADS) { int m = e / I, c = e - m * I; XT[c * TR_S + m] = min_[(size_t)m * IN + c]; }
+            __syncthreads();
+            const float *cur = XT, *hlastT = XT;
+            int off = 0;
+            for (int l = 0; l < nl; l++) {
+                const int fin = ldim[l], fout = ldim[l + 1];
+                const float *Wm = brain + off, *b = Wm + fout * fin;
+                float *dst = (l == nl - 1) ? dOT : (l == 0) ? H0T : (cur == P ? Q : P);
+                for (int e = tid; e < fout * M; e += TRAIN_THREADS) {
+                    const int r = e / M, m = e - r * M;
+                    float s = 0.f;
+                    for (int c = 0; c < fin; c++) s += Wm[r * fin + c] * cur[c * TR_S + m];
+                    s += b[r];
+                    if (l == 0) s = 1.0f / (1.0f + expf(-s));
+                    dst[r * TR_S + m] = s;
+                }
+                __syncthreads();
+                if (l == nl - 2) hlastT = dst;
+                cur = dst; off += fout * fin + fout;
+            }
+            // MSELoss(mean) and its gradient at the outputs (one thread per sample: M <= 232 < TRAIN_THREADS)
             float lsum = 0.f;
-            for (int m = tid; m < M; m += TRAIN_THREADS) {
-                const float *x = min_ + (size_t)m * IN, *y = mout + m * 4;
-                float a[2][TRAIN_MAXW];
-                float *h0v = dz0 + (size_t)m * TRAIN_MAXW;           // holds H0 first, dz0 afterwards
-                const float *cur = x; int off = 0, pp = 0;
-                for (int l = 0; l < nl; l++) {
-                    const int fin = ldim[l], fout = ldim[l + 1];
-                    const float *Wm = brain + off, *b = Wm + fout * fin;
-                    for (int r = 0; r < fout; r++) {
-                        float s = 0.f;
-                        for (int c = 0; c < fin; c++) s += Wm[r * fin + c] * cur[c];
-                        s += b[r];
-                        if (l == 0) { s = 1.0f / (1.0f + expf(-s)); h0v[r] = s; }
-                        a[pp][r] = s;
-                    }
-                    if (l == nl - 2 || (nl == 1)) for (int r = 0; r < fout; r++) hlast[(size_t)m * TRAIN_MAXW + r] = a[pp][r];
-                    cur = a[pp]; pp ^= 1; off += fout * fin + fout;
-                }
-                float dO[4];
+            if (tid < M) {
+                const float *y = mout + tid * 4;
 #pragma unroll
-                for (int z = 0; z < 4; z++) { float e = cur[z] - y[z]; lsum += e * e; dO[z] = 2.0f * e / (float)(M * 4); dOut[m * 4 + z] = dO[z]; }
-                float *d = a[0], *d2 = a[1];
-                for (int c = 0; c < hl; c++) { float s = 0.f;
-#pragma unroll
-                    for (int z = 0; z < 4; z++) s += dO[z] * Wout[z * hl + c];
-                    d[c] = s; }
-                for (int l = nl - 2; l >= 1; l--) {
-                    const int fin = ldim[l], fout = ldim[l + 1];
-                    int offl = 0;
-                    for (int t = 0; t < l; t++) offl += ldim[t + 1] * ldim[t] + ldim[t + 1];
-                    const float *Wm = brain + offl;
-                    for (int c = 0; c < fin; c++) { float s = 0.f; for (int r = 0; r < fout; r++) s += d[r] * Wm[r * fin + c]; d2[c] = s; }
-                    float *t2 = d; d = d2; d2 = t2;
-                }
-                for (int r = 0; r < h0; r++) { float hv = h0v[r]; h0v[r] = d[r] * hv * (1.0f - hv); }
+                for (int z = 0; z < 4; z++) { float e = dOT[z * TR_S + tid] - y[z]; lsum += e * e; dOT[z * TR_S + tid] = 2.0f * e / (float)(M * 4); }
             }
             red_f[tid] = lsum;
             __syncthreads();
             for (int s = TRAIN_THREADS / 2; s; s >>= 1) { if (tid < s) red_f[tid] += red_f[tid + s]; __syncthreads(); }
             if (tid == 0) w.org_loss[o] = red_f[0] / (float)(M * 4);
-            __threadfence_block();
+            // ---- backward down to the first layer's pre-activation (hidden layers have no activation) ----
+            float *d = D, *d2 = (hlastT == P) ? Q : P;
+            for (int e = tid; e < hl * M; e += TRAIN_THREADS) {
+                const int c = e / M, m = e - c * M;
+                float s = 0.f;
+#pragma unroll
+                for (int z = 0; z < 4; z++) s += dOT[z * TR_S + m] * Wout[z * hl + c];
+                d[c * TR_S + m] = s;
+            }
             __syncthreads();
-            // phase 2: one thread per optimizer parameter -- gradient (samples in ascending order) and the Adam step
+            for (int l = nl - 2; l >= 1; l--) {
+                const int fin = ldim[l], fout = ldim[l + 1];
+                int offl = 0;
+                for (int t = 0; t < l; t++) offl += ldim[t + 1] * ldim[t] + ldim[t + 1];
+                const float *Wm = brain + offl;
+                for (int e = tid; e < fin * M; e += TRAIN_THREADS) {
+                    const int c = e / M, m = e - c * M;
+                    float s = 0.f;
+                    for (int r = 0; r < fout; r++) s += d[r * TR_S + m] * Wm[r * fin + c];
+                    d2[c * TR_S + m] = s;
+                }
+                __syncthreads();
+                float *t2 = d; d = d2; d2 = t2;
+            }
+            float *dz0T = d2;
+            for (int e = tid; e < h0 * M; e += TRAIN_THREADS) { const int r = e / M, m = e - r * M; float hv = H0T[r * TR_S + m]; dz0T[r * TR_S + m] = d[r * TR_S + m] * hv * (1.0f - hv); }
+            __syncthreads();
+            // ---- one thread per optimizer parameter: gradient (samples in ascending order) and the Adam step ----
             const int t = w.org_adam_t[o] + 1;
             const float lr = p.learning_rate, b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
             const double bc1 = 1.0 - pow((double)b1, (double)t), bc2 = 1.0 - pow((double)b2, (double)t);
@@ -183,10 +228,10 @@ __global__ void __launch_bounds__(TRAIN_THREADS) k_train(WORLD_ARG, RulesWs R, T
                 // Adam divides by |g| + 1e-8: gradients are summed over the batch in double so that their own rounding noise does not
                 // decide the update of near-zero components
                 double gd = 0.0; float *prm;
-                if (e < h0 * I) { int r = e / I, c = e % I; for (int m = 0; m < M; m++) gd += (double)__fmul_rn(dz0[(size_t)m * TRAIN_MAXW + r], min_[(size_t)m * IN + c]); prm = &Win[e]; }
-                else if (e < np_in) { int r = e - h0 * I; for (int m = 0; m < M; m++) gd += (double)dz0[(size_t)m * TRAIN_MAXW + r]; prm = &bin[r]; }
-                else if (e < np_in + 4 * hl) { int z = (e - np_in) / hl, c = (e - np_in) % hl; for (int m = 0; m < M; m++) gd += (double)__fmul_rn(dOut[m * 4 + z], hlast[(size_t)m * TRAIN_MAXW + c]); prm = &Wout[e - np_in]; }
-                else { int z = e - np_in - 4 * hl; for (int m = 0; m < M; m++) gd += (double)dOut[m * 4 + z]; prm = &bout[z]; }
+                if (e < h0 * I) { int r = e / I, c = e % I; for (int m = 0; m < M; m++) gd += (double)__fmul_rn(dz0T[r * TR_S + m], min_[(size_t)m * IN + c]); prm = &Win[e]; }
+                else if (e < np_in) { int r = e - h0 * I; for (int m = 0; m < M; m++) gd += (double)dz0T[r * TR_S + m]; prm = &bin[r]; }
+                else if (e < np_in + 4 * hl) { int z = (e - np_in) / hl, c = (e - np_in) % hl; for (int m = 0; m < M; m++) gd += (double)__fmul_rn(dOT[z * TR_S + m], hlastT[c * TR_S + m]); prm = &Wout[e - np_in]; }
+                else { int z = e - np_in - 4 * hl; for (int m = 0; m < M; m++) gd += (double)dOT[z * TR_S + m]; prm = &bout[z]; }
                 const float g = (float)gd;
                 float m1 = b1 * am[e] + (1.0f - b1) * g, v1 = b2 * av[e] + (1.0f - b2) * g * g;
                 am[e] = m1; av[e] = v1;
@@ -198,5 +243,6 @@ __global__ void __launch_bounds__(TRAIN_THREADS) k_train(WORLD_ARG, RulesWs R, T
         }
         if (tid == 0) { w.org_train_tick[o] = (int32_t)w.g_tick[0]; stat_add(w, SAPIO_STAT_TRAINS, 1); }
         __syncthreads();
+#undef STM_SLOT
     }
 }
