@@ -1,0 +1,447 @@
+// orgsolve.cuh -- the per-organism part of Space.step: intra-organism contacts, sensor pins and the all-pairs pin joints of
+// one organism, 10 Gauss-Seidel sweeps entirely in shared memory.
+//
+// Shape of the work (what bounds this kernel): per sweep an organism of n living cells has n(n-1)/2 pin joints that must be
+// applied in lexicographic order. Pairs on one anti-diagonal t = i + j share no body and all their predecessors lie on
+// earlier diagonals, so the order is kept exactly by walking 2n-3 wavefronts of at most n/2 pairs: a dependent chain of
+// ~11 * (2n + contact levels) short steps per organism and tick. The kernel is therefore bound by the latency of that chain
+// and by how many organisms are in flight per SM, not by memory:
+//   * G = 4/8/16/32 lanes per organism (32/G organisms per warp, organisms of one warp have near-equal n)
+//   * living cells are compacted (rank space): no liveness tests in the sweeps
+//   * pair constants live in wavefront-major order: a wavefront reads one contiguous run of float4
+//   * contacts are sorted by dependency level once per tick; a level is one step
+//   * eight size classes (8..64 rows) so that the shared-memory footprint, which sets the occupancy, follows the size
+#pragma once
+#include "common.cuh"
+
+template <int CM>
+struct alignas(16) OrgS {
+    static constexpr int NP = CM * (CM - 1) / 2;
+    static constexpr int IC = 2 * CM < 16 ? 16 : 2 * CM;          // intra contacts kept on chip (global cap SAPIO_ICAP = 192)
+    float4 pair[NP];                 // wavefront-major: nx, ny, bias, jnAcc of a pin joint
+    float4 vm[CM];                   // vx, vy, w, 1/m                       (index = rank among the living cells)
+    float4 bb[CM];                   // bias velocity x, y, r/I, r
+    float4 spin[CM];                 // sensor pin: nx, ny, bias, jnAcc
+    float2 sv[CM];                   // sensor body velocity
+    float2 p[CM], rel[CM];
+    float cnx[IC], cny[IC], cbias[IC], cbo[IC], cjn[IC], cjt[IC], cjb[IC], cnm[IC], ctm[IC], cmu[IC];
+    uint16_t ccode[IC];              // canonical key: row_i * 128 + row_j (walls: 64 + wall)
+    uint8_t ca[IC], cbk[IC];         // ranks of the two cells (255: wall)
+    uint8_t corder[IC], clev[IC], sstart[IC + 2], lcnt[IC + 2];
+    uint8_t row_of[CM], last[CM], issens[CM];
+    int n, nic, nsteps;
+};
+
+__device__ __forceinline__ int tri_f(int m) { return ((m + 1) >> 1) * ((m >> 1) + 1); }       // sum_{u=1..m} ceil(u/2)
+// first slot of wavefront t (pairs i + j == t) for n cells
+__device__ __forceinline__ int wf_off(int t, int n) { return t <= n ? tri_f(t - 1) : n * (n - 1) / 2 - tri_f(2 * n - 2 - t); }
+
+template <int CM, int G>
+struct OrgCtx {
+    typedef OrgS<CM> S;
+    static constexpr int KC = (S::IC + G - 1) / G;                  // contacts per lane when all are touched
+    static constexpr uint32_t GM = G == 32 ? 0xFFFFFFFFu : ((1u << G) - 1u);
+    S &s; const SapioWorld &w; const StepK &K;
+    int o, nc, n, lane, sl, gshift;
+    uint64_t sens;
+    __device__ OrgCtx(S &s_, const SapioWorld &w_, const StepK &K_, int o_) : s(s_), w(w_), K(K_), o(o_) {
+        lane = lane_id(); sl = lane % G; gshift = lane - sl;
+        nc = o >= 0 ? min(w.org_ncells[o], CM) : 0; n = 0; sens = 0;
+    }
+    __device__ uint32_t gballot(bool pred) const { return (__ballot_sync(FULL, pred) >> gshift) & GM; }
+    __device__ static int wmax(int v) { for (int s_ = 16; s_; s_ >>= 1) v = max(v, __shfl_xor_sync(FULL, v, s_)); return v; }
+
+    __device__ void load() {
+        uint32_t am[2];
+        bool a[2], sn[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            int k = sl + G * h, row = o * MAXC + k;
+            a[h] = k < nc && w.c_alive[row] == SAPIO_CELL_ALIVE;
+            sn[h] = a[h] && is_sensor_type(w.c_type[row]);
+            am[h] = gballot(a[h]);
+        }
+        n = __popc(am[0]) + __popc(am[1]);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            if (!a[h]) continue;
+            const int k = sl + G * h, row = o * MAXC + k;
+            const int r = (h ? __popc(am[0]) : 0) + __popc(am[h] & ((1u << sl) - 1u));
+            const float m = w.c_mass[row], rad = w.c_size[row] * 0.5f;
+            const float2 pc = reinterpret_cast<const float2 *>(w.c_pos)[row], v = reinterpret_cast<const float2 *>(w.c_vel)[row];
+            const float2 vb = reinterpret_cast<const float2 *>(w.c_vbias)[row];
+            const float minv = 1.0f / m, iinv = 1.0f / (0.5f * m * rad * rad);
+            s.p[r] = pc; s.rel[r] = reinterpret_cast<const float2 *>(w.c_rel)[row];
+            s.vm[r] = make_float4(v.x, v.y, w.c_angvel[row], minv);
+            s.bb[r] = make_float4(vb.x, vb.y, iinv * rad, rad);
+            s.row_of[r] = (uint8_t)k; s.issens[r] = sn[h];
+            if (sn[h]) {   // cpPinJoint preStep of the sensor pin (sensor body -> cell, anchors at the centres, rest length 0)
+                const float2 ps = reinterpret_cast<const float2 *>(w.c_spos)[row];
+                float dx = pc.x - ps.x, dy = pc.y - ps.y;
+                float d = sqrtf(dx * dx + dy * dy);
+                float inv = d != 0.f ? 1.0f / d : 0.f;
+                s.spin[r] = make_float4(dx * inv, dy * inv, (float)(-K.bc_joint * (double)d / K.dt), w.c_spin_jn[row]);
+                s.sv[r] = reinterpret_cast<const float2 *>(w.c_svel)[row];
+            }
+        }
+        if (sl == 0) s.n = n;
+        __syncwarp();
+        uint32_t s0 = gballot(sl < n && s.issens[sl]), s1 = gballot(sl + G < n && s.issens[min(sl + G, CM - 1)]);
+        sens = ((uint64_t)s1 << G) | s0;
+    }
+
+    // One pass over all pairs (i<j) of living cells in lexicographic order, a full group of lanes at a time: pin-joint
+    // prestep (cpPinJoint.c preStep: n, bias; impulse of the previous step) and intra-organism collision detection
+    // (cpCollision.c CircleToCircle) share the same separation, computed once in double from the fp32 positions.
+    // Cell/wall contacts follow; the list is brought into canonical order (sorted code) when there are any.
+    __device__ void prestep_pairs() {
+        const int NPn = n * (n - 1) / 2, NPmax = wmax(NPn);
+        int nic = 0; bool over = false;
+        const float *gj = w.j_jn + (size_t)max(o, 0) * SAPIO_NPAIR;
+        for (int base = 0; base < NPmax; base += G) {
+            const int pidx = base + sl;
+            bool hit = false; float nxf = 0.f, nyf = 0.f, bias_c = 0.f; int i = 0, j = 0;
+            if (pidx < NPn) {
+                const int tn = 2 * n - 1;
+                i = (int)(((float)tn - sqrtf((float)(tn * tn - 8 * pidx))) * 0.5f);
+                while (i > 0 && i * (tn - i) / 2 > pidx) i--;
+                while ((i + 1) * (tn - i - 1) / 2 <= pidx) i++;
+                j = pidx - i * (tn - i) / 2 + i + 1;
+                const float2 pi = s.p[i], pj = s.p[j], ri = s.rel[i], rj = s.rel[j];
+                const float radi = s.bb[i].w, radj = s.bb[j].w;
+                double dx = __dsub_rn((double)pj.x, (double)pi.x), dy = __dsub_rn((double)pj.y, (double)pi.y);
+                double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                double d = sqrt(d2);
+                if (d != 0.0) { double inv = 1.0 / d; nxf = (float)(dx * inv); nyf = (float)(dy * inv); }
+                double lx = (double)rj.x - (double)ri.x, ly = (double)rj.y - (double)ri.y;
+                double rest = sqrt(lx * lx + ly * ly);                 // |relative_pos_i - relative_pos_j| (connectTo at spawn)
+                float bias = (float)(-K.bc_joint * (d - rest) / K.dt);
+                const int t = i + j;
+                s.pair[wf_off(t, n) + i - max(0, t - (n - 1))] = make_float4(nxf, nyf, bias, gj[pair_index(s.row_of[i], s.row_of[j])]);
+                double md = __dadd_rn((double)radi, (double)radj);
+                hit = d2 < __dmul_rn(md, md);
+                if (hit) { if (d == 0.0) { nxf = 1.f; nyf = 0.f; } bias_c = contact_bias(d, radi, radj, w.p, K); }   // coincident centres: cpv(1, 0)
+            }
+            const uint32_t m = gballot(hit);
+            if (hit) {
+                int slot = nic + __popc(m & ((1u << sl) - 1u));
+                if (slot < S::IC) {
+                    s.ccode[slot] = (uint16_t)(s.row_of[i] * 128 + s.row_of[j]); s.ca[slot] = (uint8_t)i; s.cbk[slot] = (uint8_t)j;
+                    s.cnx[slot] = nxf; s.cny[slot] = nyf; s.cbias[slot] = bias_c;
+                } else over = true;
+            }
+            nic += __popc(m);
+        }
+        // walls
+        bool anywall = false;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int r = sl + G * h;
+            bool near = false; float2 pi = make_float2(0.f, 0.f); float radi = 0.f;
+            if (r < n) {
+                pi = s.p[r]; radi = s.bb[r].w;
+                float fw2 = 2.0f * w.p.frame_width + radi + 1.0f;                    // cheap reject: not near any border
+                near = pi.x < fw2 || pi.y < fw2 || pi.x > w.p.width - fw2 || pi.y > w.p.height - fw2;
+            }
+            if (!__any_sync(FULL, near)) continue;
+            for (int wl = 0; wl < SAPIO_NWALL; wl++) {
+                WallHit hw; bool hit = near && circle_wall(w.p, wl, pi.x, pi.y, radi, &hw);
+                const uint32_t m = gballot(hit);
+                if (hit) {
+                    int slot = nic + __popc(m & ((1u << sl) - 1u));
+                    if (slot < S::IC) {
+                        s.ccode[slot] = (uint16_t)(s.row_of[r] * 128 + MAXC + wl); s.ca[slot] = (uint8_t)r; s.cbk[slot] = 255;
+                        s.cnx[slot] = hw.nx; s.cny[slot] = hw.ny; s.cbias[slot] = contact_bias(hw.d, radi, w.p.frame_width, w.p, K);
+                    } else over = true;
+                    anywall = true;
+                }
+                nic += __popc(m);
+            }
+        }
+        if (gballot(over) || nic > S::IC) { nic = S::IC; if (sl == 0) w.g_stats[SAPIO_STAT_OVERFLOW] = 1; }
+        if (sl == 0) s.nic = nic;
+        __syncwarp();
+        if (__any_sync(FULL, anywall)) {       // merge the wall contacts into canonical order: rank = number of smaller codes
+            uint16_t code[KC]; uint8_t a_[KC], b_[KC]; float x_[KC], y_[KC], bi_[KC]; int rk[KC];
+#pragma unroll
+            for (int q = 0; q < KC; q++) {
+                const int c = sl + G * q;
+                rk[q] = -1;
+                if (c < nic) {
+                    code[q] = s.ccode[c]; a_[q] = s.ca[c]; b_[q] = s.cbk[c]; x_[q] = s.cnx[c]; y_[q] = s.cny[c]; bi_[q] = s.cbias[c];
+                    int r = 0;
+                    for (int e = 0; e < nic; e++) r += s.ccode[e] < code[q];
+                    rk[q] = r;
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < KC; q++)
+                if (rk[q] >= 0) { const int r = rk[q]; s.ccode[r] = code[q]; s.ca[r] = a_[q]; s.cbk[r] = b_[q]; s.cnx[r] = x_[q]; s.cny[r] = y_[q]; s.cbias[r] = bi_[q]; }
+            __syncwarp();
+        }
+    }
+
+    // persistent arbiters: jnAcc/jtAcc of the previous step's intra list (sorted by code)
+    __device__ void match_prev() {
+        const int pn = o >= 0 ? w.org_ic_n[o] : 0;
+        const uint16_t *pc = w.ic_code + (size_t)max(o, 0) * SAPIO_ICAP;
+        for (int c = sl; c < s.nic; c += G) {
+            uint16_t code = s.ccode[c];
+            int lo = 0, hi = pn;
+            while (lo < hi) { int mid = (lo + hi) >> 1; if (pc[mid] < code) lo = mid + 1; else hi = mid; }
+            bool f = lo < pn && pc[lo] == code;
+            s.cjn[c] = f ? w.ic_jn[(size_t)o * SAPIO_ICAP + lo] : 0.f;
+            s.cjt[c] = f ? w.ic_jt[(size_t)o * SAPIO_ICAP + lo] : 0.f;
+            s.cjb[c] = 0.f;
+        }
+        __syncwarp();
+    }
+
+    // dependency levels: contact c runs after every earlier contact (list order) that shares a cell with it. The contacts are
+    // then ordered by level (stable) and cut into steps of at most G contacts of one level.
+    __device__ void schedule() {
+        if (sl == 0) {
+            const int nic = s.nic;
+            for (int k = 0; k < n; k++) s.last[k] = 0;
+            for (int L = 0; L <= nic + 1 && L < S::IC + 2; L++) s.lcnt[L] = 0;
+            int mx = 0;
+            for (int c = 0; c < nic; c++) {
+                const int a = s.ca[c], b = s.cbk[c];
+                int L = s.last[a];
+                if (b != 255 && s.last[b] > L) L = s.last[b];
+                L++;
+                s.clev[c] = (uint8_t)L; s.last[a] = (uint8_t)L;
+                if (b != 255) s.last[b] = (uint8_t)L;
+                s.lcnt[L]++;
+                mx = max(mx, L);
+            }
+            int ns = 0, pos = 0;
+            for (int L = 1; L <= mx; L++) {                     // lcnt[L] becomes the write cursor of level L
+                const int cnt = s.lcnt[L];
+                for (int k = 0; k < cnt; k += G) s.sstart[ns++] = (uint8_t)(pos + k);
+                s.lcnt[L] = (uint8_t)pos; pos += cnt;
+            }
+            s.sstart[ns] = (uint8_t)nic;
+            for (int c = 0; c < nic; c++) s.corder[s.lcnt[s.clev[c]]++] = (uint8_t)c;
+            s.nsteps = ns;
+        }
+        __syncwarp();
+    }
+
+    // cpArbiterPreStep: effective masses, friction, and (BOUNCE) the bounce from the velocities before any cached impulse
+    template <bool BOUNCE>
+    __device__ void prestep_contacts() {
+        for (int c = sl; c < s.nic; c += G) {
+            const int a = s.ca[c], b = s.cbk[c];
+            const int rowa = o * MAXC + s.row_of[a];
+            const float4 va = s.vm[a], ba = s.bb[a];
+            float4 vb = make_float4(0.f, 0.f, 0.f, 0.f), bbv = make_float4(0.f, 0.f, 0.f, w.p.frame_width);
+            float e = w.c_elast[rowa] * w.p.wall_elast, mu = w.c_fric[rowa] * w.p.wall_fric;
+            if (b != 255) { const int rowb = o * MAXC + s.row_of[b]; vb = s.vm[b]; bbv = s.bb[b]; e = w.c_elast[rowa] * w.c_elast[rowb]; mu = w.c_fric[rowa] * w.c_fric[rowb]; }
+            s.cnm[c] = 1.0f / (va.w + vb.w);
+            s.ctm[c] = 1.0f / (va.w + vb.w + ba.z * ba.w + bbv.z * bbv.w);
+            s.cmu[c] = mu;
+            if (BOUNCE) s.cbo[c] = ((vb.x - va.x) * s.cnx[c] + (vb.y - va.y) * s.cny[c]) * e;
+        }
+        __syncwarp();
+    }
+
+    // one sweep over the intra contacts in canonical order (level steps); WARM: cached impulses instead of the solver step
+    template <bool WARM>
+    __device__ void contacts_pass(float dt_coef, int nsteps_max) {
+        for (int st = 0; st < nsteps_max; st++) {
+            if (st < s.nsteps) {
+                const int pos = s.sstart[st] + sl;
+                if (pos < s.sstart[st + 1]) {
+                    const int c = s.corder[pos], a = s.ca[c], b = s.cbk[c];
+                    float4 va = s.vm[a], ba = s.bb[a];
+                    float4 vb = make_float4(0.f, 0.f, 0.f, 0.f), bbv = make_float4(0.f, 0.f, 0.f, w.p.frame_width);
+                    if (b != 255) { vb = s.vm[b]; bbv = s.bb[b]; }
+                    const float nx = s.cnx[c], ny = s.cny[c];
+                    if (WARM) {   // cpArbiterApplyCachedImpulse
+                        const float jn = s.cjn[c] * dt_coef, jt = s.cjt[c] * dt_coef;
+                        const float jx = nx * jn - ny * jt, jy = nx * jt + ny * jn;
+                        va.x -= jx * va.w; va.y -= jy * va.w; va.z -= ba.z * jt;
+                        vb.x += jx * vb.w; vb.y += jy * vb.w; vb.z -= bbv.z * jt;
+                    } else {      // cpArbiterApplyImpulse (SURVEY A-5), circles: r x n = 0
+                        const float nMass = s.cnm[c], tMass = s.ctm[c];
+                        const float dvx = vb.x - va.x, dvy = vb.y - va.y;
+                        const float vbn = (bbv.x - ba.x) * nx + (bbv.y - ba.y) * ny;
+                        const float vrn = dvx * nx + dvy * ny;
+                        const float vrt = (dvy * nx - dvx * ny) - bbv.w * vb.z - ba.w * va.z;
+                        const float jbnOld = s.cjb[c], jBias = fmaxf(jbnOld + (s.cbias[c] - vbn) * nMass, 0.0f);
+                        const float jnOld = s.cjn[c], jnAcc = fmaxf(jnOld + -(s.cbo[c] + vrn) * nMass, 0.0f);
+                        const float jtMax = s.cmu[c] * jnAcc;
+                        const float jtOld = s.cjt[c], jtAcc = fminf(fmaxf(jtOld + -vrt * tMass, -jtMax), jtMax);
+                        s.cjb[c] = jBias; s.cjn[c] = jnAcc; s.cjt[c] = jtAcc;
+                        const float bj = jBias - jbnOld;
+                        ba.x -= nx * bj * va.w; ba.y -= ny * bj * va.w;
+                        bbv.x += nx * bj * vb.w; bbv.y += ny * bj * vb.w;
+                        const float dn = jnAcc - jnOld, dtg = jtAcc - jtOld;
+                        const float jx = nx * dn - ny * dtg, jy = nx * dtg + ny * dn;
+                        va.x -= jx * va.w; va.y -= jy * va.w; va.z -= ba.z * dtg;
+                        vb.x += jx * vb.w; vb.y += jy * vb.w; vb.z -= bbv.z * dtg;
+                        reinterpret_cast<float2 *>(&s.bb[a])[0] = make_float2(ba.x, ba.y);
+                        if (b != 255) reinterpret_cast<float2 *>(&s.bb[b])[0] = make_float2(bbv.x, bbv.y);
+                    }
+                    s.vm[a] = va;
+                    if (b != 255) s.vm[b] = vb;
+                }
+            }
+            __syncwarp();
+        }
+    }
+
+    // cpPinJoint.c with anchors at the centres: sensor pins (sensor body -> cell, rest 0), then all pairs (i<j) in
+    // lexicographic order evaluated as anti-diagonals t = i + j
+    template <bool WARM>
+    __device__ void joints_pass(float dt_coef, int tmax) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int k = sl + G * h;
+            if (k < n && ((sens >> k) & 1ull)) {
+                const float4 sp = s.spin[k], vc = s.vm[k]; const float2 vs = s.sv[k];
+                float jnv;
+                if (WARM) jnv = sp.w * dt_coef;
+                else {
+                    float vrn = (vc.x - vs.x) * sp.x + (vc.y - vs.y) * sp.y;
+                    jnv = (sp.z - vrn) * (1.0f / (1.0f + vc.w));
+                    s.spin[k].w = sp.w + jnv;
+                }
+                s.sv[k] = make_float2(vs.x - sp.x * jnv, vs.y - sp.y * jnv);          // sensor body: mass 1 (sprites.py:303)
+                reinterpret_cast<float2 *>(&s.vm[k])[0] = make_float2(vc.x + sp.x * jnv * vc.w, vc.y + sp.y * jnv * vc.w);
+            }
+        }
+        __syncwarp();
+        int off = 0;
+        for (int t = 1; t <= tmax; t++) {
+            const int imin = max(0, t - (n - 1)), imax = (t - 1) >> 1;
+            const int i = imin + sl;
+            if (i <= imax) {
+                const int j = t - i, q = off + sl;
+                const float4 pr = s.pair[q], vi = s.vm[i], vj = s.vm[j];
+                float jnv;
+                if (WARM) jnv = pr.w * dt_coef;
+                else {
+                    float vrn = (vj.x - vi.x) * pr.x + (vj.y - vi.y) * pr.y;
+                    jnv = (pr.z - vrn) * (1.0f / (vi.w + vj.w));
+                    s.pair[q].w = pr.w + jnv;
+                }
+                const float jx = pr.x * jnv, jy = pr.y * jnv;
+                reinterpret_cast<float2 *>(&s.vm[i])[0] = make_float2(vi.x - jx * vi.w, vi.y - jy * vi.w);
+                reinterpret_cast<float2 *>(&s.vm[j])[0] = make_float2(vj.x + jx * vj.w, vj.y + jy * vj.w);
+            }
+            off += max(imax - imin + 1, 0);
+            __syncwarp();
+        }
+    }
+
+    __device__ void store_vel() {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int r = sl + G * h;
+            if (r < n) {
+                const int row = o * MAXC + s.row_of[r];
+                const float4 v = s.vm[r], b = s.bb[r];
+                reinterpret_cast<float2 *>(w.c_vel)[row] = make_float2(v.x, v.y); w.c_angvel[row] = v.z;
+                reinterpret_cast<float2 *>(w.c_vbias)[row] = make_float2(b.x, b.y);
+                if ((sens >> r) & 1ull) { reinterpret_cast<float2 *>(w.c_svel)[row] = s.sv[r]; w.c_spin_jn[row] = s.spin[r].w; }
+            }
+        }
+        float *gj = w.j_jn + (size_t)max(o, 0) * SAPIO_NPAIR;
+        const int NPn = n * (n - 1) / 2, tn = 2 * n - 1;
+        for (int pidx = sl; pidx < NPn; pidx += G) {
+            int i = (int)(((float)tn - sqrtf((float)(tn * tn - 8 * pidx))) * 0.5f);
+            while (i > 0 && i * (tn - i) / 2 > pidx) i--;
+            while ((i + 1) * (tn - i - 1) / 2 <= pidx) i++;
+            const int j = pidx - i * (tn - i) / 2 + i + 1, t = i + j;
+            gj[pair_index(s.row_of[i], s.row_of[j])] = s.pair[wf_off(t, n) + i - max(0, t - (n - 1))].w;
+        }
+    }
+    __device__ void store_contacts(float *ws_bounce, float *ws_jbias) {
+        for (int c = sl; c < s.nic; c += G) {
+            size_t g = (size_t)o * SAPIO_ICAP + c;
+            w.ic_code[g] = s.ccode[c]; w.ic_jn[g] = s.cjn[c]; w.ic_jt[g] = s.cjt[c];
+            if (ws_bounce) { ws_bounce[g] = s.cbo[c]; ws_jbias[g] = s.cjb[c]; }
+        }
+        if (sl == 0 && o >= 0) w.org_ic_n[o] = s.nic;
+    }
+    // coupled path resume: the contact list was just re-detected (same positions => same list); fetch its impulses
+    __device__ void load_contact_state(const float *ws_bounce, const float *ws_jbias) {
+        for (int c = sl; c < s.nic; c += G) {
+            size_t g = (size_t)o * SAPIO_ICAP + c;
+            s.cjn[c] = w.ic_jn[g]; s.cjt[c] = w.ic_jt[g]; s.cbo[c] = ws_bounce[g]; s.cjb[c] = ws_jbias[g];
+        }
+        __syncwarp();
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// organisms with no cross contact: the whole solve in one launch, everything on chip
+// ------------------------------------------------------------------------------------------------------------------
+#define ORG_CLASSES 8
+template <int CM> struct OrgCfg {
+    static constexpr int G = CM <= 8 ? 4 : CM <= 16 ? 8 : CM <= 32 ? 16 : 32;          // lanes per organism
+    static constexpr int NG = 32 / G;                                                     // organisms per warp
+    static constexpr int WARP_BYTES = (int)sizeof(OrgS<CM>) * NG;
+    static constexpr int FIT = (227 * 1024 - 2048) / WARP_BYTES;                          // warps an SM can hold
+    static constexpr int WARPS = FIT <= 8 ? (FIT < 1 ? 1 : FIT) : (FIT <= 16 ? FIT / 2 : 8);
+};
+__host__ __device__ inline int org_class_of(int nc) { return nc <= 8 ? 0 : (nc - 1) >> 3; }      // rows 1..8 -> 0, 9..16 -> 1, ...
+
+template <int CM>
+__global__ void __launch_bounds__(OrgCfg<CM>::WARPS * 32) k_org_solve(WORLD_ARG, Workspace W, StepK K, int cls) {
+    constexpr int G = OrgCfg<CM>::G, NG = OrgCfg<CM>::NG;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = lane_id();
+    OrgS<CM> &s = reinterpret_cast<OrgS<CM> *>(smem_raw)[(threadIdx.x >> 5) * NG + lane / G];
+    const int start = W.flags[FL_CLS0 + cls], end = W.flags[FL_CLS0 + cls + 1];
+    const int n_items = (end - start + NG - 1) / NG;
+    const float dt_coef = w.g_stepped[0] ? 1.0f : 0.0f;   // prev_dt == 0 on the very first step
+    const int iterations = w.p.iterations;
+    int nic_sum = 0;
+    for (;;) {
+        int q = 0;
+        if (lane == 0) q = atomicAdd(&W.flags[FL_WORK0 + cls], 1);          // dynamic scheduling: organisms differ in cost
+        q = __shfl_sync(FULL, q, 0);
+        if (q >= n_items) break;
+        const int idx = end - 1 - (q * NG + lane / G);                        // largest organisms of the class first
+        OrgCtx<CM, G> c(s, w, K, idx >= start ? W.sorted_orgs[idx] : -1);
+        c.load();
+        c.prestep_pairs();
+        c.match_prev();
+        c.schedule();
+        c.template prestep_contacts<true>();
+        const int nsteps_max = OrgCtx<CM, G>::wmax(s.nsteps), tmax = 2 * OrgCtx<CM, G>::wmax(c.n) - 3;
+        if (dt_coef != 0.f) { c.template contacts_pass<true>(dt_coef, nsteps_max); c.template joints_pass<true>(dt_coef, tmax); }
+        for (int it = 0; it < iterations; it++) { c.template contacts_pass<false>(0.f, nsteps_max); c.template joints_pass<false>(0.f, tmax); }
+        if (c.o >= 0) { c.store_vel(); c.store_contacts(nullptr, nullptr); if (c.sl == 0) nic_sum += s.nic; }
+        __syncwarp();
+    }
+    if (nic_sum) atomicAdd(&W.flags[FL_NIC], nic_sum);
+}
+
+// organisms -> coupled list, or a list sorted by cell rows (counting sort: histogram, scan, scatter)
+__global__ void k_classify_count(WORLD_ARG, Workspace W) {
+    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < w.p.n_org; o += gridDim.x * blockDim.x) {
+        if (w.org_state[o] != 1) continue;
+        if (W.org_coupled[o]) { W.coupled_list[atomicAdd(&W.flags[FL_NCOUPLED], 1)] = o; continue; }
+        atomicAdd(&W.size_hist[min(max(w.org_ncells[o], 1), MAXC)], 1);
+    }
+}
+__global__ void k_classify_scan(Workspace W) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int acc = 0;
+    for (int nc = 1; nc <= MAXC; nc++) {
+        if (nc == 1 || ((nc - 1) & 7) == 0) W.flags[FL_CLS0 + org_class_of(nc)] = acc;       // first size of a class
+        int c = W.size_hist[nc]; W.size_hist[nc] = acc; acc += c;
+    }
+    W.flags[FL_CLS0 + ORG_CLASSES] = acc;
+}
+__global__ void k_classify_scatter(WORLD_ARG, Workspace W) {
+    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < w.p.n_org; o += gridDim.x * blockDim.x) {
+        if (w.org_state[o] != 1 || W.org_coupled[o]) continue;
+        W.sorted_orgs[atomicAdd(&W.size_hist[min(max(w.org_ncells[o], 1), MAXC)], 1)] = o;
+    }
+}

@@ -43,17 +43,20 @@ struct Workspace {
     uint32_t *adj_other;            // adjacency: partner body id per entry [2*x_cap]
     uint8_t *org_coupled;           // [n_org]
     int *coupled_list;              // [n_org]
-    int *cls_list;                  // [4][n_org] uncoupled organisms by size class (16/32/48/64 cell rows)
+    int *sorted_orgs;               // [n_org] uncoupled organisms sorted by cell rows
+    int *size_hist;                 // [MAXC + 1] inside the flags block: histogram, then scatter cursors
     float *ic_bounce, *ic_jbias;    // [n_org * ICAP] (coupled path only)
 };
-enum { FL_NX = 0, FL_NADJ = 1, FL_OVERFLOW = 2, FL_MAXLEVEL = 3, FL_CHANGED = 4, FL_NCOUPLED = 5, FL_NIC = 6, FL_CLS0 = 8 /* ..11 */, FL_WORK0 = 12 /* ..15 */ };
+enum { FL_NX = 0, FL_NADJ = 1, FL_OVERFLOW = 2, FL_MAXLEVEL = 3, FL_CHANGED = 4, FL_NCOUPLED = 5, FL_NIC = 6, FL_CLS0 = 8 /* ..16: class starts + end */,
+       FL_WORK0 = 20 /* ..27 */, FL_HIST = 32 /* ..96 */, FL_BYTES = 512 };
 
 static size_t carve_workspace(const SapioParams &p, char *base, Workspace *W) {
     size_t off = 0;
     auto take = [&](size_t bytes) -> char * { char *r = base ? base + off : nullptr; off += (bytes + 255) & ~size_t(255); return r; };
     const size_t NB = (size_t)p.n_org * MAXC + p.n_dead, XC = (size_t)p.x_cap, NG = (size_t)p.grid_nx * p.grid_ny;
     W->pop = (int *)take(256);
-    W->flags = (int *)take(256);
+    W->flags = (int *)take(FL_BYTES);
+    W->size_hist = W->flags ? W->flags + FL_HIST : nullptr;
     W->gkey = (uint32_t *)take(NB * 4); W->gval = (uint32_t *)take(NB * 4);
     W->skey = (uint32_t *)take(NB * 4); W->sval = (uint32_t *)take(NB * 4);
     size_t sort_bytes = 0, scan_bytes = 0;
@@ -72,7 +75,7 @@ static size_t carve_workspace(const SapioParams &p, char *base, Workspace *W) {
     W->adj_other = (uint32_t *)take(2 * XC * 4);
     W->org_coupled = (uint8_t *)take((size_t)p.n_org);
     W->coupled_list = (int *)take((size_t)p.n_org * 4);
-    W->cls_list = (int *)take((size_t)p.n_org * 4 * 4);
+    W->sorted_orgs = (int *)take((size_t)p.n_org * 4);
     W->ic_bounce = (float *)take((size_t)p.n_org * SAPIO_ICAP * 4);
     W->ic_jbias = (float *)take((size_t)p.n_org * SAPIO_ICAP * 4);
     return off;
@@ -312,304 +315,7 @@ __global__ void __launch_bounds__(128) k_cross_prestep(WORLD_ARG, Workspace W, S
     }
 }
 
-// organisms -> coupled list or size class list (order inside a list is irrelevant: organisms are independent there)
-__global__ void k_classify(WORLD_ARG, Workspace W) {
-    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < w.p.n_org; o += gridDim.x * blockDim.x) {
-        if (w.org_state[o] != 1) continue;
-        if (W.org_coupled[o]) { W.coupled_list[atomicAdd(&W.flags[FL_NCOUPLED], 1)] = o; continue; }
-        int nc = w.org_ncells[o];
-        int cls = nc <= 16 ? 0 : (nc <= 32 ? 1 : (nc <= 48 ? 2 : 3));
-        W.cls_list[(size_t)cls * w.p.n_org + atomicAdd(&W.flags[FL_CLS0 + cls], 1)] = o;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// organism solver: one warp per organism, state in shared memory, templated on the tile (cell rows) it can hold
-// ------------------------------------------------------------------------------------------------------------------
-template <int CM>
-struct OrgS {
-    static constexpr int NP = CM * (CM - 1) / 2, IC = 3 * CM;
-    float4 pair[NP];                 // nx, ny, bias, jnAcc of pin (i,j)
-    float2 p[CM], v[CM], vb[CM], rel[CM], sp[CM], sv[CM];
-    float w[CM], minv[CM], iinv[CM], rad[CM], el[CM], fr[CM], sjn[CM];
-    float cnx[IC], cny[IC], cbias[IC], cb[IC], cjn[IC], cjt[IC], cjb[IC];
-    uint16_t ccode[IC];
-    uint8_t clev[IC];
-    uint8_t last[CM];
-    int nic, nlev;
-};
-
-template <int CM>
-struct OrgCtx {
-    typedef OrgS<CM> S;
-    static constexpr int H = (CM + 31) / 32;
-    S &s; const SapioWorld &w; const StepK &K; int o, nc, lane;
-    uint64_t alive, sens;
-    __device__ OrgCtx(S &s_, const SapioWorld &w_, const StepK &K_, int o_) : s(s_), w(w_), K(K_), o(o_), lane(lane_id()) { nc = min(w.org_ncells[o], CM); }
-    __device__ bool is_alive(int k) const { return (alive >> k) & 1ull; }
-    __device__ static int lp(int i, int j) { return i * (2 * CM - i - 1) / 2 + (j - i - 1); }
-
-    __device__ void load() {
-        uint32_t am[2] = {0, 0}, sm[2] = {0, 0};
-#pragma unroll
-        for (int h = 0; h < H; h++) {
-            int k = lane + 32 * h, row = o * MAXC + k;
-            bool a = k < nc && w.c_alive[row] == SAPIO_CELL_ALIVE, sn = false;
-            if (a) {
-                float m = w.c_mass[row], r = w.c_size[row] * 0.5f;
-                s.p[k] = reinterpret_cast<const float2 *>(w.c_pos)[row]; s.v[k] = reinterpret_cast<const float2 *>(w.c_vel)[row];
-                s.vb[k] = reinterpret_cast<const float2 *>(w.c_vbias)[row]; s.rel[k] = reinterpret_cast<const float2 *>(w.c_rel)[row];
-                s.w[k] = w.c_angvel[row];
-                s.minv[k] = 1.0f / m; s.iinv[k] = 1.0f / (0.5f * m * r * r); s.rad[k] = r;
-                s.el[k] = w.c_elast[row]; s.fr[k] = w.c_fric[row];
-                sn = is_sensor_type(w.c_type[row]);
-                if (sn) { s.sp[k] = reinterpret_cast<const float2 *>(w.c_spos)[row]; s.sv[k] = reinterpret_cast<const float2 *>(w.c_svel)[row]; s.sjn[k] = w.c_spin_jn[row]; }
-            }
-            am[h] = __ballot_sync(FULL, a); sm[h] = __ballot_sync(FULL, sn);
-        }
-        alive = ((uint64_t)am[1] << 32) | am[0]; sens = ((uint64_t)sm[1] << 32) | sm[0];
-        __syncwarp();
-    }
-
-    // One pass over all pairs (i<j) of living cells: pin-joint prestep (cpPinJoint.c preStep: n, bias; impulses from the
-    // previous step) and intra-organism collision detection (cpCollision.c CircleToCircle) share the same separation,
-    // computed once in double from the fp32 positions. Cell/wall contacts follow each row. Contacts come out in
-    // canonical order (sorted code i*128+j).
-    __device__ void prestep_pairs() {
-        int nic = 0; bool over = false;
-        const float *gj = w.j_jn + (size_t)o * SAPIO_NPAIR;
-        for (int i = 0; i < nc; i++) {
-            if (!is_alive(i)) continue;
-            float2 pi = s.p[i], ri = s.rel[i]; float radi = s.rad[i];
-            for (int base = i + 1; base < nc; base += 32) {
-                int j = base + lane;
-                bool hit = false; float nxf = 0.f, nyf = 0.f; double d = 0.0;
-                if (j < nc && is_alive(j)) {
-                    float2 pj = s.p[j], rj = s.rel[j];
-                    double dx = __dsub_rn((double)pj.x, (double)pi.x), dy = __dsub_rn((double)pj.y, (double)pi.y);
-                    double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-                    d = sqrt(d2);
-                    if (d != 0.0) { double inv = 1.0 / d; nxf = (float)(dx * inv); nyf = (float)(dy * inv); }
-                    double lx = (double)rj.x - (double)ri.x, ly = (double)rj.y - (double)ri.y;
-                    double rest = sqrt(lx * lx + ly * ly);                 // |relative_pos_i - relative_pos_j| (connectTo at spawn)
-                    float bias = (float)(-K.bc_joint * (d - rest) / K.dt);
-                    s.pair[lp(i, j)] = make_float4(nxf, nyf, bias, gj[pair_index(i, j)]);
-                    double md = __dadd_rn((double)radi, (double)s.rad[j]);
-                    hit = d2 < __dmul_rn(md, md);
-                }
-                uint32_t m = __ballot_sync(FULL, hit);
-                if (hit) {
-                    int slot = nic + __popc(m & ((1u << lane) - 1));
-                    if (slot < S::IC) {
-                        s.ccode[slot] = (uint16_t)(i * 128 + j);
-                        if (d == 0.0) { nxf = 1.f; nyf = 0.f; }                 // coincident centres: cpv(1, 0)
-                        s.cnx[slot] = nxf; s.cny[slot] = nyf; s.cbias[slot] = contact_bias(d, radi, s.rad[j], w.p, K);
-                    } else over = true;
-                }
-                nic += __popc(m);
-            }
-            float fw2 = 2.0f * w.p.frame_width + radi + 1.0f;                    // cheap reject: not near any border
-            if (pi.x < fw2 || pi.y < fw2 || pi.x > w.p.width - fw2 || pi.y > w.p.height - fw2) {
-                bool hit = false; WallHit h;
-                if (lane < SAPIO_NWALL) hit = circle_wall(w.p, lane, pi.x, pi.y, radi, &h);
-                uint32_t m = __ballot_sync(FULL, hit);
-                if (hit) {
-                    int slot = nic + __popc(m & ((1u << lane) - 1));
-                    if (slot < S::IC) {
-                        s.ccode[slot] = (uint16_t)(i * 128 + MAXC + lane);
-                        s.cnx[slot] = h.nx; s.cny[slot] = h.ny; s.cbias[slot] = contact_bias(h.d, radi, w.p.frame_width, w.p, K);
-                    } else over = true;
-                }
-                nic += __popc(m);
-            }
-        }
-        if (__any_sync(FULL, over) || nic > S::IC) { nic = S::IC; if (lane == 0) w.g_stats[SAPIO_STAT_OVERFLOW] = 1; }
-        if (lane == 0) s.nic = nic;
-        __syncwarp();
-    }
-
-    // persistent arbiters: jnAcc/jtAcc of the previous step's intra list (sorted by code)
-    __device__ void match_prev() {
-        const int pn = w.org_ic_n[o];
-        const uint16_t *pc = w.ic_code + (size_t)o * SAPIO_ICAP;
-        for (int c = lane; c < s.nic; c += 32) {
-            uint16_t code = s.ccode[c];
-            int lo = 0, hi = pn;
-            while (lo < hi) { int mid = (lo + hi) >> 1; if (pc[mid] < code) lo = mid + 1; else hi = mid; }
-            bool f = lo < pn && pc[lo] == code;
-            s.cjn[c] = f ? w.ic_jn[(size_t)o * SAPIO_ICAP + lo] : 0.f;
-            s.cjt[c] = f ? w.ic_jt[(size_t)o * SAPIO_ICAP + lo] : 0.f;
-            s.cjb[c] = 0.f;
-        }
-        __syncwarp();
-    }
-
-    // dependency levels: contact c runs after every earlier contact (list order) that shares a cell with it
-    __device__ void levels() {
-        for (int k = lane; k < CM; k += 32) s.last[k] = 0;
-        __syncwarp();
-        if (lane == 0) {
-            int mx = 0;
-            for (int c = 0; c < s.nic; c++) {
-                int i = s.ccode[c] >> 7, j = s.ccode[c] & 127;
-                int L = s.last[i];
-                if (j < MAXC && s.last[j] > L) L = s.last[j];
-                L++;
-                s.clev[c] = (uint8_t)L; s.last[i] = (uint8_t)L;
-                if (j < MAXC) s.last[j] = (uint8_t)L;
-                mx = max(mx, L);
-            }
-            s.nlev = mx;
-        }
-        __syncwarp();
-    }
-
-    __device__ void cbody(int k, CBody &b) const { float2 v = s.v[k], vb = s.vb[k]; b.vx = v.x; b.vy = v.y; b.w = s.w[k]; b.vbx = vb.x; b.vby = vb.y; b.minv = s.minv[k]; b.iinv = s.iinv[k]; b.r = s.rad[k]; }
-    __device__ void cstore(int k, const CBody &b) { s.v[k] = make_float2(b.vx, b.vy); s.w[k] = b.w; s.vb[k] = make_float2(b.vbx, b.vby); }
-    __device__ CBody wall_body() const { return CBody{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, w.p.frame_width}; }
-
-    // cpArbiterPreStep: bounce from the velocities before any cached impulse is applied
-    __device__ void prestep_contacts() {
-        for (int c = lane; c < s.nic; c += 32) {
-            int i = s.ccode[c] >> 7, j = s.ccode[c] & 127;
-            CBody A, B = wall_body();
-            cbody(i, A);
-            float e = s.el[i] * w.p.wall_elast;
-            if (j < MAXC) { cbody(j, B); e = s.el[i] * s.el[j]; }
-            s.cb[c] = contact_vrn(A, B, s.cnx[c], s.cny[c]) * e;
-        }
-        __syncwarp();
-    }
-    // one sweep over the intra contacts in canonical order (levels); WARM: cached impulses instead of the solver step
-    template <bool WARM>
-    __device__ void contacts_pass(float dt_coef) {
-        for (int L = 1; L <= s.nlev; L++) {
-            for (int c = lane; c < s.nic; c += 32) {
-                if (s.clev[c] != L) continue;
-                int i = s.ccode[c] >> 7, j = s.ccode[c] & 127;
-                CBody A, B = wall_body();
-                cbody(i, A);
-                float mu = s.fr[i] * w.p.wall_fric;
-                if (j < MAXC) { cbody(j, B); mu = s.fr[i] * s.fr[j]; }
-                if (WARM) contact_warm(A, B, s.cnx[c], s.cny[c], s.cjn[c], s.cjt[c], dt_coef);
-                else contact_apply(A, B, s.cnx[c], s.cny[c], s.cbias[c], s.cb[c], mu, s.cjn[c], s.cjt[c], s.cjb[c]);
-                cstore(i, A); if (j < MAXC) cstore(j, B);
-            }
-            __syncwarp();
-        }
-    }
-    // cpPinJoint.c with anchors at the centres: sensor pins (sensor body -> cell, rest 0), then all pairs (i<j) in
-    // lexicographic order evaluated as anti-diagonals t = i + j (pairs of one diagonal share no body)
-    template <bool WARM>
-    __device__ void joints_pass(float dt_coef) {
-#pragma unroll
-        for (int h = 0; h < H; h++) {
-            int k = lane + 32 * h;
-            if (k < nc && ((sens >> k) & 1ull)) {
-                float2 pc = s.p[k], ps = s.sp[k], vc = s.v[k], vs = s.sv[k];
-                float dx = pc.x - ps.x, dy = pc.y - ps.y;
-                float d = sqrtf(dx * dx + dy * dy);
-                float inv = d != 0.f ? 1.0f / d : 0.f, nx = dx * inv, ny = dy * inv;
-                float mb = s.minv[k], jnv;
-                if (WARM) jnv = s.sjn[k] * dt_coef;
-                else {
-                    float bias = (float)(-K.bc_joint * (double)d / K.dt);
-                    float vrn = (vc.x - vs.x) * nx + (vc.y - vs.y) * ny;
-                    jnv = (bias - vrn) * (1.0f / (1.0f + mb));
-                    s.sjn[k] += jnv;
-                }
-                s.sv[k] = make_float2(vs.x - nx * jnv, vs.y - ny * jnv);          // sensor body: mass 1 (sprites.py:303)
-                s.v[k] = make_float2(vc.x + nx * jnv * mb, vc.y + ny * jnv * mb);
-            }
-        }
-        __syncwarp();
-        for (int t = 1; t <= 2 * nc - 3; t++) {
-            int imin = max(0, t - (nc - 1)), imax = (t - 1) >> 1;
-            int i = imin + lane, j = t - i;
-            if (i <= imax && is_alive(i) && is_alive(j)) {
-                int q = lp(i, j);
-                float4 pr = s.pair[q];
-                float2 vi = s.v[i], vj = s.v[j];
-                float ma = s.minv[i], mb = s.minv[j], jnv;
-                if (WARM) jnv = pr.w * dt_coef;
-                else {
-                    float vrn = (vj.x - vi.x) * pr.x + (vj.y - vi.y) * pr.y;
-                    jnv = (pr.z - vrn) * (1.0f / (ma + mb));
-                    s.pair[q].w = pr.w + jnv;
-                }
-                float jx = pr.x * jnv, jy = pr.y * jnv;
-                s.v[i] = make_float2(vi.x - jx * ma, vi.y - jy * ma);
-                s.v[j] = make_float2(vj.x + jx * mb, vj.y + jy * mb);
-            }
-            __syncwarp();
-        }
-    }
-
-    __device__ void store_vel() {
-#pragma unroll
-        for (int h = 0; h < H; h++) {
-            int k = lane + 32 * h, row = o * MAXC + k;
-            if (k < nc && is_alive(k)) {
-                reinterpret_cast<float2 *>(w.c_vel)[row] = s.v[k]; w.c_angvel[row] = s.w[k];
-                reinterpret_cast<float2 *>(w.c_vbias)[row] = s.vb[k];
-                if ((sens >> k) & 1ull) { reinterpret_cast<float2 *>(w.c_svel)[row] = s.sv[k]; w.c_spin_jn[row] = s.sjn[k]; }
-            }
-        }
-        float *gj = w.j_jn + (size_t)o * SAPIO_NPAIR;
-        for (int i = 0; i + 1 < nc; i++) {
-            if (!is_alive(i)) continue;
-            for (int j = i + 1 + lane; j < nc; j += 32) if (is_alive(j)) gj[pair_index(i, j)] = s.pair[lp(i, j)].w;
-        }
-    }
-    __device__ void store_contacts(float *ws_bounce, float *ws_jbias) {
-        for (int c = lane; c < s.nic; c += 32) {
-            size_t g = (size_t)o * SAPIO_ICAP + c;
-            w.ic_code[g] = s.ccode[c]; w.ic_jn[g] = s.cjn[c]; w.ic_jt[g] = s.cjt[c];
-            if (ws_bounce) { ws_bounce[g] = s.cb[c]; ws_jbias[g] = s.cjb[c]; }
-        }
-        if (lane == 0) w.org_ic_n[o] = s.nic;
-    }
-    // coupled path resume: the contact list was just re-detected (same positions => same list); fetch its impulses
-    __device__ void load_contact_state(const float *ws_bounce, const float *ws_jbias) {
-        for (int c = lane; c < s.nic; c += 32) {
-            size_t g = (size_t)o * SAPIO_ICAP + c;
-            s.cjn[c] = w.ic_jn[g]; s.cjt[c] = w.ic_jt[g]; s.cb[c] = ws_bounce[g]; s.cjb[c] = ws_jbias[g];
-        }
-        __syncwarp();
-    }
-};
-
-// organisms with no cross contact: the whole solve in one launch, everything on chip
-template <int CM> struct OrgCfg { static constexpr int WARPS = CM <= 16 ? 8 : 4; };
-
-template <int CM>
-__global__ void __launch_bounds__(OrgCfg<CM>::WARPS * 32) k_org_solve(WORLD_ARG, Workspace W, StepK K, int cls) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    OrgS<CM> &s = reinterpret_cast<OrgS<CM> *>(smem_raw)[threadIdx.x >> 5];
-    const int n = W.flags[FL_CLS0 + cls];
-    const int *list = W.cls_list + (size_t)cls * w.p.n_org;
-    const float dt_coef = w.g_stepped[0] ? 1.0f : 0.0f;   // prev_dt == 0 on the very first step
-    int nic_sum = 0;
-    for (;;) {
-        int q = 0;
-        if (lane_id() == 0) q = atomicAdd(&W.flags[FL_WORK0 + cls], 1);     // dynamic scheduling: organisms differ in cost
-        q = __shfl_sync(FULL, q, 0);
-        if (q >= n) break;
-        OrgCtx<CM> c(s, w, K, list[q]);
-        c.load();
-        c.prestep_pairs();
-        c.match_prev();
-        c.levels();
-        c.prestep_contacts();
-        if (dt_coef != 0.f) { c.template contacts_pass<true>(dt_coef); c.template joints_pass<true>(dt_coef); }
-        for (int it = 0; it < w.p.iterations; it++) { c.template contacts_pass<false>(0.f); c.template joints_pass<false>(0.f); }
-        c.store_vel();
-        c.store_contacts(nullptr, nullptr);
-        nic_sum += s.nic;
-        __syncwarp();
-    }
-    if (lane_id() == 0 && nic_sum) atomicAdd(&W.flags[FL_NIC], nic_sum);
-}
+#include "orgsolve.cuh"
 
 // ------------------------------------------------------------------------------------------------------------------
 // coupled path: cooperative kernel
@@ -638,6 +344,7 @@ __global__ void __launch_bounds__(COUPLED_WARPS * 32) k_coupled(WORLD_ARG, Works
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     OrgS<MAXC> &s = reinterpret_cast<OrgS<MAXC> *>(smem_raw)[threadIdx.x >> 5];
+    typedef OrgCtx<MAXC, 32> Ctx;
     const int nx = W.flags[FL_NX];
     if (nx == 0) return;                                       // uniform over the grid: no barrier has been entered
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
@@ -663,8 +370,8 @@ __global__ void __launch_bounds__(COUPLED_WARPS * 32) k_coupled(WORLD_ARG, Works
     const int maxL = max(W.flags[FL_MAXLEVEL], 1);
     // stage A: coupled organisms detect their intra contacts and take their bounce before any velocity changes
     for (int q = gwarp; q < ncoupled; q += gwarps) {
-        OrgCtx<MAXC> c(s, w, K, W.coupled_list[q]);
-        c.load(); c.prestep_pairs(); c.match_prev(); c.prestep_contacts();
+        Ctx c(s, w, K, W.coupled_list[q]);
+        c.load(); c.prestep_pairs(); c.match_prev(); c.template prestep_contacts<true>();
         c.store_contacts(W.ic_bounce, W.ic_jbias);
         if (lane_id() == 0) atomicAdd(&W.flags[FL_NIC], s.nic);
         __syncwarp();
@@ -674,9 +381,9 @@ __global__ void __launch_bounds__(COUPLED_WARPS * 32) k_coupled(WORLD_ARG, Works
     if (dt_coef != 0.f) {
         for (int L = 1; L <= maxL; L++) { cross_level_pass<true>(w, W, L, nx, dt_coef, gtid, gthreads); grid.sync(); }
         for (int q = gwarp; q < ncoupled; q += gwarps) {
-            OrgCtx<MAXC> c(s, w, K, W.coupled_list[q]);
-            c.load(); c.prestep_pairs(); c.load_contact_state(W.ic_bounce, W.ic_jbias); c.levels();
-            c.template contacts_pass<true>(dt_coef); c.template joints_pass<true>(dt_coef);
+            Ctx c(s, w, K, W.coupled_list[q]);
+            c.load(); c.prestep_pairs(); c.load_contact_state(W.ic_bounce, W.ic_jbias); c.schedule(); c.template prestep_contacts<false>();
+            c.template contacts_pass<true>(dt_coef, s.nsteps); c.template joints_pass<true>(dt_coef, 2 * c.n - 3);
             c.store_vel();
             __syncwarp();
         }
@@ -685,9 +392,9 @@ __global__ void __launch_bounds__(COUPLED_WARPS * 32) k_coupled(WORLD_ARG, Works
     for (int it = 0; it < w.p.iterations; it++) {
         for (int L = 1; L <= maxL; L++) { cross_level_pass<false>(w, W, L, nx, 0.f, gtid, gthreads); grid.sync(); }
         for (int q = gwarp; q < ncoupled; q += gwarps) {
-            OrgCtx<MAXC> c(s, w, K, W.coupled_list[q]);
-            c.load(); c.prestep_pairs(); c.load_contact_state(W.ic_bounce, W.ic_jbias); c.levels();
-            c.template contacts_pass<false>(0.f); c.template joints_pass<false>(0.f);
+            Ctx c(s, w, K, W.coupled_list[q]);
+            c.load(); c.prestep_pairs(); c.load_contact_state(W.ic_bounce, W.ic_jbias); c.schedule(); c.template prestep_contacts<false>();
+            c.template contacts_pass<false>(0.f, s.nsteps); c.template joints_pass<false>(0.f, 2 * c.n - 3);
             c.store_vel(); c.store_contacts(W.ic_bounce, W.ic_jbias);
             __syncwarp();
         }
@@ -715,12 +422,12 @@ __global__ void __launch_bounds__(256) k_step_finish(WORLD_ARG, Workspace W) {
 // ------------------------------------------------------------------------------------------------------------------
 // host-side launch sequence
 // ------------------------------------------------------------------------------------------------------------------
-struct StepPlan { bool ready; int sms; int coop_blocks; int org_blocks[4]; size_t org_smem[4]; size_t coop_smem; };
-static StepPlan g_plan = {false, 148, 0, {0, 0, 0, 0}, {0, 0, 0, 0}, 0};
+struct StepPlan { bool ready; int sms; int coop_blocks; int org_blocks[ORG_CLASSES]; size_t org_smem[ORG_CLASSES]; size_t coop_smem; cudaStream_t side[ORG_CLASSES]; cudaEvent_t fork, join[ORG_CLASSES]; };
+static StepPlan g_plan = {};
 
 template <int CM>
 static cudaError_t plan_org(int cls) {
-    size_t smem = sizeof(OrgS<CM>) * OrgCfg<CM>::WARPS;
+    size_t smem = (size_t)OrgCfg<CM>::WARP_BYTES * OrgCfg<CM>::WARPS;
     cudaError_t e = cudaFuncSetAttribute(k_org_solve<CM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
@@ -739,7 +446,13 @@ static int launch_space_step(const SapioWorld &w, const Workspace &W, cudaStream
         int dev = 0;
         STEP_TRY(cudaGetDevice(&dev));
         STEP_TRY(cudaDeviceGetAttribute(&g_plan.sms, cudaDevAttrMultiProcessorCount, dev));
-        STEP_TRY(plan_org<16>(0)); STEP_TRY(plan_org<32>(1)); STEP_TRY(plan_org<48>(2)); STEP_TRY(plan_org<64>(3));
+        STEP_TRY(plan_org<8>(0)); STEP_TRY(plan_org<16>(1)); STEP_TRY(plan_org<24>(2)); STEP_TRY(plan_org<32>(3));
+        STEP_TRY(plan_org<40>(4)); STEP_TRY(plan_org<48>(5)); STEP_TRY(plan_org<56>(6)); STEP_TRY(plan_org<64>(7));
+        STEP_TRY(cudaEventCreateWithFlags(&g_plan.fork, cudaEventDisableTiming));
+        for (int c = 0; c < ORG_CLASSES; c++) {
+            STEP_TRY(cudaStreamCreateWithFlags(&g_plan.side[c], cudaStreamNonBlocking));
+            STEP_TRY(cudaEventCreateWithFlags(&g_plan.join[c], cudaEventDisableTiming));
+        }
         g_plan.coop_smem = sizeof(OrgS<MAXC>) * COUPLED_WARPS;
         STEP_TRY(cudaFuncSetAttribute(k_coupled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_plan.coop_smem));
         int per_sm = 0;
@@ -757,7 +470,7 @@ static int launch_space_step(const SapioWorld &w, const Workspace &W, cudaStream
     K.dt_coef_unused = 0.f;
 
     prof_mark(st, PT_BROADPHASE);
-    STEP_TRY(cudaMemsetAsync(W.flags, 0, 256, st));
+    STEP_TRY(cudaMemsetAsync(W.flags, 0, FL_BYTES, st));
     STEP_TRY(cudaMemsetAsync(W.org_coupled, 0, (size_t)p.n_org, st));
     k_integrate<true><<<sgrid(NB, 256), 256, 0, st>>>(w, W.gkey, W.gval);
     size_t tmp = W.cub_bytes;
@@ -777,17 +490,25 @@ static int launch_space_step(const SapioWorld &w, const Workspace &W, cudaStream
     STEP_TRY(cudaMemsetAsync(W.nx_prev_b, 0xFF, (size_t)p.x_cap * 4, st));
     k_cross_links<<<sgrid(NB, 128), 128, 0, st>>>(w, W);
     k_cross_prestep<<<sgrid(p.x_cap, 128), 128, 0, st>>>(w, W, K);
-    k_classify<<<sgrid(p.n_org, 256), 256, 0, st>>>(w, W);
-    LAUNCHES(9);
+    k_classify_count<<<sgrid(p.n_org, 256), 256, 0, st>>>(w, W);
+    k_classify_scan<<<1, 32, 0, st>>>(W);
+    k_classify_scatter<<<sgrid(p.n_org, 256), 256, 0, st>>>(w, W);
+    LAUNCHES(11);
     prof_mark(st, PT_ORG_SOLVE);
-    {   // one warp per organism, persistent CTAs pulling organisms of their size class
-        auto blocks = [&](int cls, int warps) { long want = ((long)p.n_org + warps - 1) / warps; return (int)(want < g_plan.org_blocks[cls] ? want : g_plan.org_blocks[cls]); };
-        k_org_solve<16><<<blocks(0, OrgCfg<16>::WARPS), OrgCfg<16>::WARPS * 32, g_plan.org_smem[0], st>>>(w, W, K, 0);
-        k_org_solve<32><<<blocks(1, OrgCfg<32>::WARPS), OrgCfg<32>::WARPS * 32, g_plan.org_smem[1], st>>>(w, W, K, 1);
-        k_org_solve<48><<<blocks(2, OrgCfg<48>::WARPS), OrgCfg<48>::WARPS * 32, g_plan.org_smem[2], st>>>(w, W, K, 2);
-        k_org_solve<64><<<blocks(3, OrgCfg<64>::WARPS), OrgCfg<64>::WARPS * 32, g_plan.org_smem[3], st>>>(w, W, K, 3);
+    {   // persistent CTAs per size class, largest class first; the classes run concurrently on side streams so that the tail of
+        // one class is filled by the next (organisms of different classes are independent)
+        STEP_TRY(cudaEventRecord(g_plan.fork, st));
+#define ORG_LAUNCH(CM, cls) do { \
+            cudaStream_t ss = g_plan.side[cls]; \
+            STEP_TRY(cudaStreamWaitEvent(ss, g_plan.fork, 0)); \
+            k_org_solve<CM><<<g_plan.org_blocks[cls], OrgCfg<CM>::WARPS * 32, g_plan.org_smem[cls], ss>>>(w, W, K, cls); \
+            STEP_TRY(cudaEventRecord(g_plan.join[cls], ss)); \
+            STEP_TRY(cudaStreamWaitEvent(st, g_plan.join[cls], 0)); } while (0)
+        ORG_LAUNCH(64, 7); ORG_LAUNCH(56, 6); ORG_LAUNCH(48, 5); ORG_LAUNCH(40, 4);
+        ORG_LAUNCH(32, 3); ORG_LAUNCH(24, 2); ORG_LAUNCH(16, 1); ORG_LAUNCH(8, 0);
+#undef ORG_LAUNCH
     }
-    LAUNCHES(4);
+    LAUNCHES(8);
     prof_mark(st, PT_COUPLED);
     {
         SapioWorld wc = w; Workspace Wc = W; StepK Kc = K;
