@@ -32,6 +32,7 @@ struct alignas(16) OrgS {
     int n, nic, nsteps;
 };
 
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ int tri_f(int m) { return ((m + 1) >> 1) * ((m >> 1) + 1); }       // sum_{u=1..m} ceil(u/2)
 // first slot of wavefront t (pairs i + j == t) for n cells
 __device__ __forceinline__ int wf_off(int t, int n) { return t <= n ? tri_f(t - 1) : n * (n - 1) / 2 - tri_f(2 * n - 2 - t); }
@@ -305,32 +306,33 @@ struct OrgCtx {
                 float jnv;
                 if (WARM) jnv = sp.w * dt_coef;
                 else {
-                    float vrn = (vc.x - vs.x) * sp.x + (vc.y - vs.y) * sp.y;
-                    jnv = (sp.z - vrn) * (1.0f / (1.0f + vc.w));
+                    jnv = fmaf(-(vc.x - vs.x), sp.x, fmaf(-(vc.y - vs.y), sp.y, sp.z)) * (1.0f / (1.0f + vc.w));      // (bias - v_rel.n) * k
                     s.spin[k].w = sp.w + jnv;
                 }
-                s.sv[k] = make_float2(vs.x - sp.x * jnv, vs.y - sp.y * jnv);          // sensor body: mass 1 (sprites.py:303)
-                reinterpret_cast<float2 *>(&s.vm[k])[0] = make_float2(vc.x + sp.x * jnv * vc.w, vc.y + sp.y * jnv * vc.w);
+                const float jx = sp.x * jnv, jy = sp.y * jnv;
+                s.sv[k] = make_float2(vs.x - jx, vs.y - jy);                                   // sensor body: mass 1 (sprites.py:303)
+                reinterpret_cast<float2 *>(&s.vm[k])[0] = make_float2(fmaf(jx, vc.w, vc.x), fmaf(jy, vc.w, vc.y));
             }
         }
         __syncwarp();
+        // Per wavefront: barrier -> pair constants and two velocity loads -> (bias - v_rel.n) with the cancellation kept exact by
+        // FMAs -> times the effective mass (hardware reciprocal: 1 ulp, multiplicative, so the error vanishes with the impulse) ->
+        // two stores -> barrier.
         int off = 0;
         for (int t = 1; t <= tmax; t++) {
-            const int imin = max(0, t - (n - 1)), imax = (t - 1) >> 1;
-            const int i = imin + sl;
+            const int imin = max(0, t - (n - 1)), imax = (t - 1) >> 1, i = imin + sl;
             if (i <= imax) {
                 const int j = t - i, q = off + sl;
                 const float4 pr = s.pair[q], vi = s.vm[i], vj = s.vm[j];
                 float jnv;
                 if (WARM) jnv = pr.w * dt_coef;
                 else {
-                    float vrn = (vj.x - vi.x) * pr.x + (vj.y - vi.y) * pr.y;
-                    jnv = (pr.z - vrn) * (1.0f / (vi.w + vj.w));
+                    jnv = fmaf(-(vj.x - vi.x), pr.x, fmaf(-(vj.y - vi.y), pr.y, pr.z)) * rcp_approx(vi.w + vj.w);
                     s.pair[q].w = pr.w + jnv;
                 }
                 const float jx = pr.x * jnv, jy = pr.y * jnv;
-                reinterpret_cast<float2 *>(&s.vm[i])[0] = make_float2(vi.x - jx * vi.w, vi.y - jy * vi.w);
-                reinterpret_cast<float2 *>(&s.vm[j])[0] = make_float2(vj.x + jx * vj.w, vj.y + jy * vj.w);
+                reinterpret_cast<float2 *>(&s.vm[i])[0] = make_float2(fmaf(-jx, vi.w, vi.x), fmaf(-jy, vi.w, vi.y));
+                reinterpret_cast<float2 *>(&s.vm[j])[0] = make_float2(fmaf(jx, vj.w, vj.x), fmaf(jy, vj.w, vj.y));
             }
             off += max(imax - imin + 1, 0);
             __syncwarp();

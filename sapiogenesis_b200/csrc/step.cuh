@@ -5,9 +5,9 @@
 //   k_integrate        position integration of every body + broadphase key                         (bodies.cuh)
 //   radix sort         bodies by grid cell (spatial hash over a dense uniform grid)
 //   k_cell_bounds      cell -> [start,end) in the sorted body list
-//   k_narrow<false>    per body: cross partners in the 3x3 neighbourhood (exact double predicate), counts
+//   k_narrow_find      per body (cell-sorted order): cross partners in the 3x3 neighbourhood (exact double predicate), parked in a scratch run
 //   exclusive scans    counts -> offsets: deterministic, globally sorted pair list without sorting pairs
-//   k_narrow<true>     per body: writes its sorted adjacency and its (a<b) contact keys
+//   k_narrow_fill      per body with partners: its sorted adjacency and its (a<b) contact keys at the scanned offsets
 //   k_cross_links      per body: contact index of every adjacency entry + predecessor links (Gauss-Seidel order)
 //   k_cross_prestep    per cross contact: warm-start match against the previous step's list, normal/bias/bounce, coupling flags
 //   k_classify         organisms -> coupled list, or one of four size classes (16/32/48/64 cell rows)
@@ -41,6 +41,8 @@ struct Workspace {
     float2 *nx_n;                   // contact normal (a -> b)
     int *nx_level, *nx_prev_a, *nx_prev_b;
     uint32_t *adj_other;            // adjacency: partner body id per entry [2*x_cap]
+    uint32_t *adj_tmp;              // partner runs in discovery order [2*x_cap]
+    int2 *hit_list;                 // (body, start of its run) [2*x_cap]
     uint8_t *org_coupled;           // [n_org]
     int *coupled_list;              // [n_org]
     int *sorted_orgs;               // [n_org] uncoupled organisms sorted by cell rows
@@ -48,7 +50,7 @@ struct Workspace {
     float *ic_bounce, *ic_jbias;    // [n_org * ICAP] (coupled path only)
 };
 enum { FL_NX = 0, FL_NADJ = 1, FL_OVERFLOW = 2, FL_MAXLEVEL = 3, FL_CHANGED = 4, FL_NCOUPLED = 5, FL_NIC = 6, FL_CLS0 = 8 /* ..16: class starts + end */,
-       FL_WORK0 = 20 /* ..27 */, FL_HIST = 32 /* ..96 */, FL_BYTES = 512 };
+       FL_WORK0 = 20 /* ..27 */, FL_TMPTOP = 28, FL_NHIT = 29, FL_HIST = 32 /* ..96 */, FL_BYTES = 512 };
 
 static size_t carve_workspace(const SapioParams &p, char *base, Workspace *W) {
     size_t off = 0;
@@ -73,6 +75,8 @@ static size_t carve_workspace(const SapioParams &p, char *base, Workspace *W) {
     W->nx_bias = (float *)take(XC * 4); W->nx_n = (float2 *)take(XC * 8);
     W->nx_level = (int *)take(XC * 4); W->nx_prev_a = (int *)take(XC * 4); W->nx_prev_b = (int *)take(XC * 4);
     W->adj_other = (uint32_t *)take(2 * XC * 4);
+    W->adj_tmp = (uint32_t *)take(2 * XC * 4);
+    W->hit_list = (int2 *)take(2 * XC * 8);
     W->org_coupled = (uint8_t *)take((size_t)p.n_org);
     W->coupled_list = (int *)take((size_t)p.n_org * 4);
     W->sorted_orgs = (int *)take((size_t)p.n_org * 4);
@@ -99,18 +103,17 @@ __device__ __forceinline__ void body_circle(const SapioWorld &w, int b, int NC, 
 }
 
 #define NARROW_LOCAL 48
-// One thread per body slot. Partners = solid bodies that are not living cells of the same organism (those pairs belong
-// to the organism kernel), found in the 3x3 grid cells around the body; dead cells also test the four walls.
-// FILL = false: counts. FILL = true: writes the adjacency (all partners, ascending id, walls last) and the contact keys
-// (partners with a larger id) at the scanned offsets -- both lists come out globally sorted without sorting pairs.
-template <bool FILL>
-__global__ void __launch_bounds__(128) k_narrow(WORLD_ARG, Workspace W) {
+// Pass 1, one thread per entry of the cell-sorted body list (neighbouring threads walk the same grid cells). Partners = solid
+// bodies that are not living cells of the same organism (those pairs belong to the organism kernel), found in the 3x3 grid
+// cells around the body; dead cells also test the four walls. A body with partners parks them (ascending id, walls last) in a
+// scratch run and registers itself in the hit list; almost every body has none.
+__global__ void __launch_bounds__(128) k_narrow_find(WORLD_ARG, Workspace W) {
     const SapioParams &p = w.p;
     const int NC = p.n_org * MAXC, NB = NC + p.n_dead, WALL0 = NB;
-    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b <= NB; b += gridDim.x * blockDim.x) {
-        if (b == NB) { if (!FILL) { W.cnt_up[b] = 0; W.cnt_all[b] = 0; } continue; }
-        uint32_t key = W.gkey[b];
-        if (key == 0xFFFFFFFFu) { if (!FILL) { W.cnt_up[b] = 0; W.cnt_all[b] = 0; } continue; }
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < NB; idx += gridDim.x * blockDim.x) {
+        const uint32_t key = W.skey[idx];
+        if (key == 0xFFFFFFFFu) continue;                    // empty slots sort to the end
+        const int b = (int)W.sval[idx];
         float mx, my, mr;
         body_circle(w, b, NC, mx, my, mr);
         const int my_org = b < NC ? (b >> 6) : -1;
@@ -132,7 +135,7 @@ __global__ void __launch_bounds__(128) k_narrow(WORLD_ARG, Workspace W) {
                     body_circle(w, j, NC, ox, oy, orad);
                     double d2;
                     if (!circles_overlap(mx, my, mr, ox, oy, orad, &d2)) continue;
-                    if (n < NARROW_LOCAL) { if (FILL) loc[n] = (uint32_t)j; n++; up += (j > b); } else over = true;
+                    if (n < NARROW_LOCAL) { loc[n] = (uint32_t)j; n++; up += (j > b); } else over = true;
                 }
             }
         }
@@ -140,19 +143,32 @@ __global__ void __launch_bounds__(128) k_narrow(WORLD_ARG, Workspace W) {
             for (int wi = 0; wi < SAPIO_NWALL; wi++) {
                 WallHit h;
                 if (!circle_wall(p, wi, mx, my, mr, &h)) continue;
-                if (n < NARROW_LOCAL) { if (FILL) loc[n] = (uint32_t)(WALL0 + wi); n++; up++; } else over = true;
+                if (n < NARROW_LOCAL) { loc[n] = (uint32_t)(WALL0 + wi); n++; up++; } else over = true;
             }
         }
         if (over) atomicOr(&W.flags[FL_OVERFLOW], 1);
-        if (!FILL) { W.cnt_all[b] = n; W.cnt_up[b] = up; }
-        else {
-            for (int i = 1; i < n; i++) { uint32_t v = loc[i]; int j = i - 1; while (j >= 0 && loc[j] > v) { loc[j + 1] = loc[j]; j--; } loc[j + 1] = v; }
-            int oa = W.off_all[b], ou = W.off_up[b];
-            const int xcap = p.x_cap;
-            for (int i = 0; i < n; i++) {
-                if (oa + i < 2 * xcap) W.adj_other[oa + i] = loc[i];
-                if (loc[i] > (uint32_t)b) { if (ou < xcap) W.nx_key[ou] = ((uint64_t)(uint32_t)b << 32) | loc[i]; ou++; }
-            }
+        if (n == 0) continue;
+        W.cnt_all[b] = n; W.cnt_up[b] = up;
+        for (int i = 1; i < n; i++) { uint32_t v = loc[i]; int j = i - 1; while (j >= 0 && loc[j] > v) { loc[j + 1] = loc[j]; j--; } loc[j + 1] = v; }
+        const int start = atomicAdd(&W.flags[FL_TMPTOP], n), h = atomicAdd(&W.flags[FL_NHIT], 1);
+        if (start + n > 2 * p.x_cap || h >= 2 * p.x_cap) { atomicOr(&W.flags[FL_OVERFLOW], 1); continue; }
+        W.hit_list[h] = make_int2(b, start);
+        for (int i = 0; i < n; i++) W.adj_tmp[start + i] = loc[i];
+    }
+}
+// Pass 2, after the scans of the per-body counts: every registered body copies its run to its place in the adjacency and emits
+// the contact keys (partners with a larger id) -- both lists come out globally sorted without sorting pairs.
+__global__ void __launch_bounds__(128) k_narrow_fill(WORLD_ARG, Workspace W) {
+    const int nh = min(W.flags[FL_NHIT], 2 * w.p.x_cap), xcap = w.p.x_cap;
+    for (int h = blockIdx.x * blockDim.x + threadIdx.x; h < nh; h += gridDim.x * blockDim.x) {
+        const int2 e = W.hit_list[h];
+        const int b = e.x, n = W.cnt_all[b];
+        const int oa = W.off_all[b];
+        int ou = W.off_up[b];
+        for (int i = 0; i < n; i++) {
+            const uint32_t v = W.adj_tmp[e.y + i];
+            if (oa + i < 2 * xcap) W.adj_other[oa + i] = v;
+            if (v > (uint32_t)b) { if (ou < xcap) W.nx_key[ou] = ((uint64_t)(uint32_t)b << 32) | v; ou++; }
         }
     }
 }
@@ -479,13 +495,15 @@ static int launch_space_step(const SapioWorld &w, const Workspace &W, cudaStream
     STEP_TRY(cudaMemsetAsync(W.cell_end, 0, (size_t)NG * 4, st));
     k_cell_bounds<<<sgrid(NB, 256), 256, 0, st>>>(W.skey, NB, NG, W.cell_start, W.cell_end);
     prof_mark(st, PT_NARROW);
-    k_narrow<false><<<sgrid(NB + 1, 128), 128, 0, st>>>(w, W);
+    STEP_TRY(cudaMemsetAsync(W.cnt_up, 0, (size_t)(NB + 1) * 4, st));
+    STEP_TRY(cudaMemsetAsync(W.cnt_all, 0, (size_t)(NB + 1) * 4, st));
+    k_narrow_find<<<sgrid(NB, 128), 128, 0, st>>>(w, W);
     tmp = W.cub_bytes;
     STEP_TRY(cub::DeviceScan::ExclusiveSum(W.cub_tmp, tmp, W.cnt_up, W.off_up, NB + 1, st));
     tmp = W.cub_bytes;
     STEP_TRY(cub::DeviceScan::ExclusiveSum(W.cub_tmp, tmp, W.cnt_all, W.off_all, NB + 1, st));
     k_narrow_totals<<<1, 1, 0, st>>>(w, W);
-    k_narrow<true><<<sgrid(NB + 1, 128), 128, 0, st>>>(w, W);
+    k_narrow_fill<<<sgrid(2 * (long)p.x_cap, 128), 128, 0, st>>>(w, W);
     STEP_TRY(cudaMemsetAsync(W.nx_prev_a, 0xFF, (size_t)p.x_cap * 4, st));
     STEP_TRY(cudaMemsetAsync(W.nx_prev_b, 0xFF, (size_t)p.x_cap * 4, st));
     k_cross_links<<<sgrid(NB, 128), 128, 0, st>>>(w, W);

@@ -25,6 +25,9 @@ FLOORS = {"c_wbias": 1.0, "d_wbias": 1.0, "c_vbias": 1e-2, "d_vbias": 1e-2, "org
 # friction: cells of the test worlds spin at hundreds of rad/s, and ten Gauss-Seidel sweeps of friction impulses on top of
 # that accumulate a few fp32 ulps of omega itself. 3e-5 of the field's rms for angular velocities, 1e-5 everywhere else.
 TOLS = {"c_angvel": 3e-5, "d_angvel": 3e-5,
+        # cached contact impulses are sums of ten clamped increments of a stiff Gauss-Seidel solve carried in fp32, each fed by
+        # the ~n^2/2 pin impulses of both organisms: 3e-5 of the field's rms; the velocities they produce are held to 1e-5
+        "x_jn": 3e-5, "ic_jn": 3e-5,
         # co2 refund = overflow of add_energy = (energy + share) - storage with energy ~ storage ~ 1e3 in fp32: the difference
         # carries the operands' 1e-7, i.e. ~1e-4 of its own size; its effect on the global co2 (~3e4, checked at 1e-5) is 1e-9
         "org_gas_refund": 2e-4}
