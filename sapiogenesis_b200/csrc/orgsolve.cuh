@@ -95,19 +95,35 @@ struct OrgCtx {
     // prestep (cpPinJoint.c preStep: n, bias; impulse of the previous step) and intra-organism collision detection
     // (cpCollision.c CircleToCircle) share the same separation, computed once in double from the fp32 positions.
     // Cell/wall contacts follow; the list is brought into canonical order (sorted code) when there are any.
+    __device__ static void pair_of(int pidx, int n, int &i, int &j) {          // lexicographic pair index -> (i, j)
+        const int tn = 2 * n - 1;
+        i = (int)(((float)tn - sqrtf((float)(tn * tn - 8 * pidx))) * 0.5f);
+        while (i > 0 && i * (tn - i) / 2 > pidx) i--;
+        while ((i + 1) * (tn - i - 1) / 2 <= pidx) i++;
+        j = pidx - i * (tn - i) / 2 + i + 1;
+    }
+    __device__ int slot_of(int i, int j) const { const int t = i + j; return wf_off(t, n) + i - max(0, t - (n - 1)); }
+
     __device__ void prestep_pairs() {
         const int NPn = n * (n - 1) / 2, NPmax = wmax(NPn);
         int nic = 0; bool over = false;
         const float *gj = w.j_jn + (size_t)max(o, 0) * SAPIO_NPAIR;
+        // cached impulses first: a pure gather with several loads in flight per lane
+        for (int base = 0; base < NPn; base += 4 * G) {
+            float v[4]; int q[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int pidx = base + sl + G * u; q[u] = -1; v[u] = 0.f;
+                if (pidx < NPn) { int i, j; pair_of(pidx, n, i, j); q[u] = slot_of(i, j); v[u] = gj[pair_index(s.row_of[i], s.row_of[j])]; }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) if (q[u] >= 0) s.pair[q[u]].w = v[u];
+        }
         for (int base = 0; base < NPmax; base += G) {
             const int pidx = base + sl;
             bool hit = false; float nxf = 0.f, nyf = 0.f, bias_c = 0.f; int i = 0, j = 0;
             if (pidx < NPn) {
-                const int tn = 2 * n - 1;
-                i = (int)(((float)tn - sqrtf((float)(tn * tn - 8 * pidx))) * 0.5f);
-                while (i > 0 && i * (tn - i) / 2 > pidx) i--;
-                while ((i + 1) * (tn - i - 1) / 2 <= pidx) i++;
-                j = pidx - i * (tn - i) / 2 + i + 1;
+                pair_of(pidx, n, i, j);
                 const float2 pi = s.p[i], pj = s.p[j], ri = s.rel[i], rj = s.rel[j];
                 const float radi = s.bb[i].w, radj = s.bb[j].w;
                 double dx = __dsub_rn((double)pj.x, (double)pi.x), dy = __dsub_rn((double)pj.y, (double)pi.y);
@@ -117,8 +133,8 @@ struct OrgCtx {
                 double lx = (double)rj.x - (double)ri.x, ly = (double)rj.y - (double)ri.y;
                 double rest = sqrt(lx * lx + ly * ly);                 // |relative_pos_i - relative_pos_j| (connectTo at spawn)
                 float bias = (float)(-K.bc_joint * (d - rest) / K.dt);
-                const int t = i + j;
-                s.pair[wf_off(t, n) + i - max(0, t - (n - 1))] = make_float4(nxf, nyf, bias, gj[pair_index(s.row_of[i], s.row_of[j])]);
+                float *pq = reinterpret_cast<float *>(&s.pair[slot_of(i, j)]);
+                pq[0] = nxf; pq[1] = nyf; pq[2] = bias;
                 double md = __dadd_rn((double)radi, (double)radj);
                 hit = d2 < __dmul_rn(md, md);
                 if (hit) { if (d == 0.0) { nxf = 1.f; nyf = 0.f; } bias_c = contact_bias(d, radi, radj, w.p, K); }   // coincident centres: cpv(1, 0)
@@ -352,13 +368,10 @@ struct OrgCtx {
             }
         }
         float *gj = w.j_jn + (size_t)max(o, 0) * SAPIO_NPAIR;
-        const int NPn = n * (n - 1) / 2, tn = 2 * n - 1;
+        const int NPn = n * (n - 1) / 2;
         for (int pidx = sl; pidx < NPn; pidx += G) {
-            int i = (int)(((float)tn - sqrtf((float)(tn * tn - 8 * pidx))) * 0.5f);
-            while (i > 0 && i * (tn - i) / 2 > pidx) i--;
-            while ((i + 1) * (tn - i - 1) / 2 <= pidx) i++;
-            const int j = pidx - i * (tn - i) / 2 + i + 1, t = i + j;
-            gj[pair_index(s.row_of[i], s.row_of[j])] = s.pair[wf_off(t, n) + i - max(0, t - (n - 1))].w;
+            int i, j; pair_of(pidx, n, i, j);
+            gj[pair_index(s.row_of[i], s.row_of[j])] = s.pair[slot_of(i, j)].w;
         }
     }
     __device__ void store_contacts(float *ws_bounce, float *ws_jbias) {
