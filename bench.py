@@ -168,8 +168,10 @@ def run_ours(args):
 
     M = args.organisms
     w, eng = build_world(M, device=dev, seed=rank)
-    for _ in range(max(args.warmup, 3)):
-        eng.tick(1, PH_ALL)
+    # N > 1: population islands with ring migration of whole organisms (the only exchange step of the path; NCCL p2p)
+    from sapiogenesis_b200.islands import Island
+    isl = Island(w, eng, every=args.migrate_every if world_size > 1 else 0, count=args.migrate_count, seed=1234)
+    isl.step(max(args.warmup, 3))
     eng.synchronize()
     stats0 = world_stats(w)
 
@@ -181,7 +183,7 @@ def run_ours(args):
     barrier()
     with ClockSampler(local_rank) as clk:
         ev0.record()
-        eng.tick(args.steps, PH_ALL)
+        isl.step(args.steps)
         ev1.record()
         barrier()
     ms = ev0.elapsed_time(ev1)
@@ -247,7 +249,9 @@ def run_ours(args):
                                    f"{M} organisms per GPU island (BASELINE configs[2]); state {w.nbytes() / 2**30:.1f} GiB per GPU, far larger than L2",
                        "organisms_per_gpu": M, "living_after": s["organisms"], "cells": s["cells"], "pin_joints": s["pairs"],
                        "dead_cells": s["dead"], "cross_contacts": s["cross_contacts"], "intra_contacts": s["intra_contacts"],
-                       "l2_policy": "inputs larger than L2"},
+                       "l2_policy": "inputs larger than L2",
+                       "parallelism": f"{world_size} island(s), one per GPU" + (f"; ring migration of {args.migrate_count} whole organisms every "
+                                      f"{args.migrate_every} ticks over NCCL p2p ({isl.migrated_out} sent by rank 0 in total)" if world_size > 1 and args.migrate_every else "")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps,
                     "steps": e2e_steps, "api": "sapio_tick_host (pinned host buffers, event block up, counters + packed sprite poses down)"},
             "gpu_launches": int(launches),
@@ -274,6 +278,8 @@ def main():
     ap.add_argument("--ref-organisms", type=int, default=2000, help="organisms of the CPU arm's bounded sample")
     ap.add_argument("--ref-ticks", type=int, default=0, help="ticks per CPU step (default: 40 for cpu_baseline, 1 per step for --impl reference)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--migrate-every", type=int, default=50, help="N > 1: ticks between ring migrations (0 = never)")
+    ap.add_argument("--migrate-count", type=int, default=64, help="organisms each island sends per migration")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

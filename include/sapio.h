@@ -153,6 +153,17 @@ int sapio_train_network(const SapioWorld *w, void *ws, size_t ws_bytes, const in
 /* parity probe: sprite.info["view"] of one eye / olfactory cell as ascending body ids (device out, count may exceed cap) sprites.py:221-236 */
 int sapio_sensor_view(const SapioWorld *w, void *ws, size_t ws_bytes, int org, int cell, uint32_t *d_out, int cap, int32_t *d_count, void *stream);
 
+/* ---- island migration (one world per GPU). The reference has one world; this is the exchange step of the
+ * multi-GPU extension: a record is every per-organism array (scopes ORG / CELL / PAIR / ICON of sapio_fields.def) of one
+ * organism, i.e. its DNA tables (sprites.py:329-408), cells, brain (networks.py:137-230), optimizer state and memories. */
+size_t sapio_organism_record_bytes(const SapioParams *p);
+/* gathers the organisms in d_slots into n consecutive records */
+int sapio_pack_organisms(const SapioWorld *w, const int32_t *d_slots, int n, void *d_buf, size_t buf_bytes, void *stream);
+/* scatters n records into the (free) slots d_slots; the arrivals get the uids g_next_uid, g_next_uid + 1, ... */
+int sapio_unpack_organisms(const SapioWorld *w, const int32_t *d_slots, int n, const void *d_buf, size_t buf_bytes, void *stream);
+/* frees the slots of organisms that left (no dead cells remain: they live on in another world) */
+int sapio_release_organisms(const SapioWorld *w, const int32_t *d_slots, int n, void *stream);
+
 /* ---- end-to-end path for a GUI host (host buffers; the copies are inside the call) --------------------------------
  * Uploads the per-tick event block updateUI applies (Sapiogenesis.py:37-47), runs n_ticks ticks, then downloads what the
  * reference pushes to Qt every frame: the UI counters (Sapiogenesis.py:62-69) and the pose of every solid sprite

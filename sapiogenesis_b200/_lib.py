@@ -46,6 +46,10 @@ def load() -> ctypes.CDLL:
     L.sapio_sensor_view.argtypes = [wp, vp, sz, i32, i32, vp, i32, vp, vp]; L.sapio_sensor_view.restype = i32
     for name in ("sapio_activate", "sapio_train_network"):
         getattr(L, name).argtypes = [wp, vp, sz, vp, i32, vp]; getattr(L, name).restype = i32
+    L.sapio_organism_record_bytes.argtypes = [vp]; L.sapio_organism_record_bytes.restype = sz
+    L.sapio_pack_organisms.argtypes = [wp, vp, i32, vp, sz, vp]; L.sapio_pack_organisms.restype = i32
+    L.sapio_unpack_organisms.argtypes = [wp, vp, i32, vp, sz, vp]; L.sapio_unpack_organisms.restype = i32
+    L.sapio_release_organisms.argtypes = [wp, vp, i32, vp]; L.sapio_release_organisms.restype = i32
     f32 = ctypes.c_float
     L.sapio_events.argtypes = [wp, vp, sz, f32, f32, vp]; L.sapio_events.restype = i32
     L.sapio_tick_host.argtypes = [wp, vp, sz, u32, i32, vp, vp, vp, i32, vp, i32, vp]; L.sapio_tick_host.restype = i32

@@ -14,6 +14,7 @@
 #include "train.cuh"
 #include "repro.cuh"
 #include "frame.cuh"
+#include "migrate.cuh"
 
 static thread_local char g_err[512] = "";
 static int fail(int code, const char *fmt, const char *a = "") {
@@ -384,6 +385,44 @@ int sapio_tick_host(const SapioWorld *w, void *ws, size_t ws_bytes, uint32_t pha
     if (nd > 0) CUDA_TRY(cudaMemcpyAsync(h_dead, A.frame.dead, (size_t)nd * sizeof(float4), cudaMemcpyDeviceToHost, st));
     prof_mark(st, PT_END);
     CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+size_t sapio_organism_record_bytes(const SapioParams *p) {
+    if (!p) return 0;
+    MigTable T; mig_table(*p, nullptr, T);
+    return T.record_bytes;
+}
+static int mig_check(const SapioWorld *w, const int32_t *d_slots, int n, const void *d_buf, size_t buf_bytes, MigTable &T) {
+    int rc = check(w, nullptr, 0, nullptr); if (rc) return rc;
+    if ((rc = check_list(w, d_slots, n))) return rc;
+    mig_table(w->p, w, T);
+    if (T.n > MIG_MAX_FIELDS) return fail(SAPIO_E_ARG, "field table overflow%s");
+    if (n && (!d_buf || buf_bytes < (size_t)n * T.record_bytes)) return fail(SAPIO_E_ARG, "record buffer too small%s");
+    return 0;
+}
+int sapio_pack_organisms(const SapioWorld *w, const int32_t *d_slots, int n, void *d_buf, size_t buf_bytes, void *stream) {
+    MigTable T; int rc = mig_check(w, d_slots, n, d_buf, buf_bytes, T); if (rc) return rc;
+    if (n == 0) return 0;
+    k_org_records<true><<<n < 1184 ? n : 1184, 256, 0, (cudaStream_t)stream>>>(T, d_slots, n, (char *)d_buf, w->g_next_uid);
+    LAUNCHES(1); LAUNCH_CHECK();
+    return 0;
+}
+int sapio_unpack_organisms(const SapioWorld *w, const int32_t *d_slots, int n, const void *d_buf, size_t buf_bytes, void *stream) {
+    MigTable T; int rc = mig_check(w, d_slots, n, d_buf, buf_bytes, T); if (rc) return rc;
+    if (n == 0) return 0;
+    k_org_records<false><<<n < 1184 ? n : 1184, 256, 0, (cudaStream_t)stream>>>(T, d_slots, n, (char *)const_cast<void *>(d_buf), w->g_next_uid);
+    k_uid_advance<<<1, 1, 0, (cudaStream_t)stream>>>(w->g_next_uid, n);
+    LAUNCHES(2); LAUNCH_CHECK();
+    return 0;
+}
+int sapio_release_organisms(const SapioWorld *w, const int32_t *d_slots, int n, void *stream) {
+    int rc = check(w, nullptr, 0, nullptr); if (rc) return rc;
+    if ((rc = check_list(w, d_slots, n))) return rc;
+    if (n == 0) return 0;
+    k_release_slots<<<n < 4096 ? n : 4096, MAXC, 0, (cudaStream_t)stream>>>(*w, d_slots, n);
+    k_release_contacts<<<stream_grid(w->p.x_cap), 256, 0, (cudaStream_t)stream>>>(*w);
+    LAUNCHES(2); LAUNCH_CHECK();
     return 0;
 }
 

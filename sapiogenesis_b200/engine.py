@@ -106,6 +106,39 @@ class Engine:
                                                     self._stream_ptr()), "sapio_train_network")
         self._keep = (lst,)
 
+    # -- island migration: whole-organism records (csrc/migrate.cuh) ---------------------------------------------------
+    def record_bytes(self) -> int:
+        return int(self.lib.sapio_organism_record_bytes(ctypes.byref(self.world.p)))
+
+    def pack_organisms(self, slots, out: torch.Tensor | None = None) -> torch.Tensor:
+        """Gathers the organisms in `slots` into a [n, record_bytes] uint8 tensor on the device."""
+        lst = self._org_list(slots)
+        n, rb = int(lst.numel()), self.record_bytes()
+        buf = out if out is not None else torch.empty((n, rb), dtype=torch.uint8, device=self.world.device)
+        assert buf.is_contiguous() and buf.numel() >= n * rb and buf.device == self.world.device
+        with torch.cuda.device(self.world.device):
+            _lib.check(self.lib.sapio_pack_organisms(self._ref(), ctypes.c_void_p(lst.data_ptr()), n, ctypes.c_void_p(buf.data_ptr()),
+                                                     buf.numel(), self._stream_ptr()), "sapio_pack_organisms")
+        self._keep = (lst, buf)
+        return buf
+
+    def unpack_organisms(self, slots, records: torch.Tensor):
+        """Scatters records into the free `slots`; the arrivals get fresh uids from this world."""
+        lst = self._org_list(slots)
+        n = int(lst.numel())
+        assert records.is_contiguous() and records.device == self.world.device and records.numel() >= n * self.record_bytes()
+        with torch.cuda.device(self.world.device):
+            _lib.check(self.lib.sapio_unpack_organisms(self._ref(), ctypes.c_void_p(lst.data_ptr()), n, ctypes.c_void_p(records.data_ptr()),
+                                                       records.numel(), self._stream_ptr()), "sapio_unpack_organisms")
+        self._keep = (lst, records)
+
+    def release_organisms(self, slots):
+        lst = self._org_list(slots)
+        with torch.cuda.device(self.world.device):
+            _lib.check(self.lib.sapio_release_organisms(self._ref(), ctypes.c_void_p(lst.data_ptr()), int(lst.numel()), self._stream_ptr()),
+                       "sapio_release_organisms")
+        self._keep = (lst,)
+
     def sensor_view(self, org: int, cell: int, cap: int = 4096):
         """sprite.info["view"] of one eye / olfactory cell as ascending body ids (parity probe)."""
         dev = self.world.device
