@@ -115,7 +115,7 @@ class Engine:
         lst = self._org_list(slots)
         n, rb = int(lst.numel()), self.record_bytes()
         buf = out if out is not None else torch.empty((n, rb), dtype=torch.uint8, device=self.world.device)
-        assert buf.is_contiguous() and buf.numel() >= n * rb and buf.device == self.world.device
+        assert buf.is_contiguous() and buf.numel() >= n * rb and buf.is_cuda
         with torch.cuda.device(self.world.device):
             _lib.check(self.lib.sapio_pack_organisms(self._ref(), ctypes.c_void_p(lst.data_ptr()), n, ctypes.c_void_p(buf.data_ptr()),
                                                      buf.numel(), self._stream_ptr()), "sapio_pack_organisms")
@@ -126,7 +126,7 @@ class Engine:
         """Scatters records into the free `slots`; the arrivals get fresh uids from this world."""
         lst = self._org_list(slots)
         n = int(lst.numel())
-        assert records.is_contiguous() and records.device == self.world.device and records.numel() >= n * self.record_bytes()
+        assert records.is_contiguous() and records.is_cuda and records.numel() >= n * self.record_bytes()
         with torch.cuda.device(self.world.device):
             _lib.check(self.lib.sapio_unpack_organisms(self._ref(), ctypes.c_void_p(lst.data_ptr()), n, ctypes.c_void_p(records.data_ptr()),
                                                        records.numel(), self._stream_ptr()), "sapio_unpack_organisms")
