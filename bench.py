@@ -172,6 +172,8 @@ def run_ours(args):
     from sapiogenesis_b200.islands import Island
     isl = Island(w, eng, every=args.migrate_every if world_size > 1 else 0, count=args.migrate_count, seed=1234)
     isl.step(max(args.warmup, 3))
+    if world_size > 1 and args.migrate_every:
+        isl.migrate()                                   # warm-up of the exchange step too (NCCL p2p channels are set up lazily)
     eng.synchronize()
     stats0 = world_stats(w)
 

@@ -62,7 +62,10 @@ enum {
 /* phase mask for sapio_tick */
 enum {
     SAPIO_PH_RULES = 1, SAPIO_PH_THINK = 2, SAPIO_PH_TRAIN = 4, SAPIO_PH_REPRODUCE = 8,
-    SAPIO_PH_STEP = 16, SAPIO_PH_FRICTION = 32, SAPIO_PH_POST = 64, SAPIO_PH_ALL = 127
+    SAPIO_PH_STEP = 16, SAPIO_PH_FRICTION = 32, SAPIO_PH_POST = 64, SAPIO_PH_ALL = 127,
+    /* caller's assertion: no body was added or moved since the last SAPIO_PH_STEP on this workspace, so the spatial grid that
+     * step built (positions after integration) is still the grid of the world and neural.activate's sensors may use it */
+    SAPIO_PH_REUSE_GRID = 128
 };
 
 enum { SAPIO_OK = 0, SAPIO_E_ARG = -1, SAPIO_E_CUDA = -2, SAPIO_E_WORKSPACE = -3, SAPIO_E_OVERFLOW = -4, SAPIO_E_NODEVICE = -5 };

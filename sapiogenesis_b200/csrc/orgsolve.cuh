@@ -355,7 +355,7 @@ struct OrgCtx {
         }
     }
 
-    __device__ void store_vel() {
+    __device__ void store_vel(bool pins = true) {
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const int r = sl + G * h;
@@ -367,6 +367,7 @@ struct OrgCtx {
                 if ((sens >> r) & 1ull) { reinterpret_cast<float2 *>(w.c_svel)[row] = s.sv[r]; w.c_spin_jn[row] = s.spin[r].w; }
             }
         }
+        if (!pins) return;
         float *gj = w.j_jn + (size_t)max(o, 0) * SAPIO_NPAIR;
         const int NPn = n * (n - 1) / 2;
         for (int pidx = sl; pidx < NPn; pidx += G) {
@@ -382,6 +383,34 @@ struct OrgCtx {
         }
         if (sl == 0 && o >= 0) w.org_ic_n[o] = s.nic;
     }
+    // coupled path: what prestep_pairs / schedule / prestep_contacts produced is parked in global memory (same struct layout) so
+    // that the passes between the grid barriers do not detect and pre-step again
+    __device__ void save_static(S *g) const {
+        const int NPn = n * (n - 1) / 2, nic = s.nic;
+        for (int q = sl; q < NPn; q += G) g->pair[q] = s.pair[q];
+        for (int c = sl; c < nic; c += G) {
+            g->cnx[c] = s.cnx[c]; g->cny[c] = s.cny[c]; g->cbias[c] = s.cbias[c]; g->cnm[c] = s.cnm[c]; g->ctm[c] = s.ctm[c]; g->cmu[c] = s.cmu[c];
+            g->ccode[c] = s.ccode[c]; g->ca[c] = s.ca[c]; g->cbk[c] = s.cbk[c]; g->corder[c] = s.corder[c];
+        }
+        for (int q = sl; q <= s.nsteps; q += G) g->sstart[q] = s.sstart[q];
+        if (sl == 0) { g->nic = nic; g->nsteps = s.nsteps; }
+    }
+    __device__ void restore_static(const S *g) {
+        const int NPn = n * (n - 1) / 2, nic = g->nic, ns = g->nsteps;
+        for (int q = sl; q < NPn; q += G) s.pair[q] = g->pair[q];
+        for (int c = sl; c < nic; c += G) {
+            s.cnx[c] = g->cnx[c]; s.cny[c] = g->cny[c]; s.cbias[c] = g->cbias[c]; s.cnm[c] = g->cnm[c]; s.ctm[c] = g->ctm[c]; s.cmu[c] = g->cmu[c];
+            s.ccode[c] = g->ccode[c]; s.ca[c] = g->ca[c]; s.cbk[c] = g->cbk[c]; s.corder[c] = g->corder[c];
+        }
+        for (int q = sl; q <= ns; q += G) s.sstart[q] = g->sstart[q];
+        if (sl == 0) { s.nic = nic; s.nsteps = ns; }
+        __syncwarp();
+    }
+    __device__ void save_pairs(S *g) const {
+        const int NPn = n * (n - 1) / 2;
+        for (int q = sl; q < NPn; q += G) g->pair[q].w = s.pair[q].w;
+    }
+
     // coupled path resume: the contact list was just re-detected (same positions => same list); fetch its impulses
     __device__ void load_contact_state(const float *ws_bounce, const float *ws_jbias) {
         for (int c = sl; c < s.nic; c += G) {

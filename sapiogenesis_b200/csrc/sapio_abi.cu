@@ -135,7 +135,7 @@ static int launch_rules(const SapioWorld &w, AllWs &A, uint32_t phases, cudaStre
     CUDA_TRY(cub::DeviceScan::InclusiveScan(A.step.cub_tmp, tmp, R.gas_map, R.gas_scan, AffCompose(), p.n_org, st));
     if (phases & SAPIO_PH_THINK) {
         prof_mark(st, PT_GRID);
-        int rc = launch_grid_only(w, A.step, st); if (rc) return rc;
+        if (!(phases & SAPIO_PH_REUSE_GRID)) { int rc = launch_grid_only(w, A.step, st); if (rc) return rc; }
         prof_mark(st, PT_THINK);
         size_t smem = (size_t)THINK_WARPS * (p.in_cap + 2 * (p.width_cap > 4 ? p.width_cap : 4)) * sizeof(float);
         static size_t smem_set = 0;
@@ -347,7 +347,10 @@ int sapio_sensor_view(const SapioWorld *w, void *ws, size_t ws_bytes, int org, i
 
 int sapio_tick(const SapioWorld *w, void *ws, size_t ws_bytes, uint32_t phases, int n_ticks, void *stream) {
     AllWs A; int rc = check(w, ws, ws_bytes, &A); if (rc) return rc;
-    for (int t = 0; t < n_ticks; t++) if ((rc = launch_tick(*w, A, phases, nullptr, (cudaStream_t)stream))) return rc;
+    for (int t = 0; t < n_ticks; t++) {       // inside one call nothing but the tick touches the world: ticks after the first reuse the step's grid
+        if ((rc = launch_tick(*w, A, phases, nullptr, (cudaStream_t)stream))) return rc;
+        if (phases & SAPIO_PH_STEP) phases |= SAPIO_PH_REUSE_GRID;
+    }
     return 0;
 }
 
@@ -372,7 +375,10 @@ int sapio_tick_host(const SapioWorld *w, void *ws, size_t ws_bytes, uint32_t pha
     const int ccap = h_cells ? (cell_cap < w->p.n_org * MAXC ? cell_cap : w->p.n_org * MAXC) : 0;
     const int dcap = h_dead ? (dead_cap < w->p.n_dead ? dead_cap : w->p.n_dead) : 0;
     CUDA_TRY(cudaMemcpyAsync(A.frame.control, h_control, sizeof(SapioControl), cudaMemcpyHostToDevice, st));
-    for (int t = 0; t < n_ticks; t++) if ((rc = launch_tick(*w, A, phases, A.frame.control, st))) return rc;
+    for (int t = 0; t < n_ticks; t++) {
+        if ((rc = launch_tick(*w, A, phases, A.frame.control, st))) return rc;
+        if (phases & SAPIO_PH_STEP) phases |= SAPIO_PH_REUSE_GRID;
+    }
     prof_mark(st, PT_FRAME);
     CUDA_TRY(cudaMemsetAsync(A.frame.counts, 0, 256, st));
     k_pack_frame<<<stream_grid(nb), 256, 0, st>>>(*w, A.frame, ccap, dcap);

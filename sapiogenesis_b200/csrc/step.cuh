@@ -48,10 +48,12 @@ struct Workspace {
     int *sorted_orgs;               // [n_org] uncoupled organisms sorted by cell rows
     int *size_hist;                 // [MAXC + 1] inside the flags block: histogram, then scatter cursors
     float *ic_bounce, *ic_jbias;    // [n_org * ICAP] (coupled path only)
+    char *cp_state; int cp_cap;     // parked solver state of the first cp_cap coupled organisms (sizeof(OrgS<MAXC>) each)
 };
 enum { FL_NX = 0, FL_NADJ = 1, FL_OVERFLOW = 2, FL_MAXLEVEL = 3, FL_CHANGED = 4, FL_NCOUPLED = 5, FL_NIC = 6, FL_CLS0 = 8 /* ..16: class starts + end */,
        FL_WORK0 = 20 /* ..27 */, FL_TMPTOP = 28, FL_NHIT = 29, FL_HIST = 32 /* ..96 */, FL_BYTES = 512 };
 
+#define COUPLED_STATE_BYTES 49152      /* >= sizeof(OrgS<MAXC>), checked where the struct is known */
 static size_t carve_workspace(const SapioParams &p, char *base, Workspace *W) {
     size_t off = 0;
     auto take = [&](size_t bytes) -> char * { char *r = base ? base + off : nullptr; off += (bytes + 255) & ~size_t(255); return r; };
@@ -82,6 +84,8 @@ static size_t carve_workspace(const SapioParams &p, char *base, Workspace *W) {
     W->sorted_orgs = (int *)take((size_t)p.n_org * 4);
     W->ic_bounce = (float *)take((size_t)p.n_org * SAPIO_ICAP * 4);
     W->ic_jbias = (float *)take((size_t)p.n_org * SAPIO_ICAP * 4);
+    W->cp_cap = p.n_org < 8192 ? p.n_org : 8192;
+    W->cp_state = take((size_t)W->cp_cap * COUPLED_STATE_BYTES);
     return off;
 }
 
@@ -385,35 +389,42 @@ __global__ void __launch_bounds__(COUPLED_WARPS * 32) k_coupled(WORLD_ARG, Works
     }
     const int maxL = max(W.flags[FL_MAXLEVEL], 1);
     // stage A: coupled organisms detect their intra contacts and take their bounce before any velocity changes
+    static_assert(sizeof(OrgS<MAXC>) <= COUPLED_STATE_BYTES, "COUPLED_STATE_BYTES too small");
+    auto parked = [&](int q) { return q < W.cp_cap ? reinterpret_cast<OrgS<MAXC> *>(W.cp_state + (size_t)q * COUPLED_STATE_BYTES) : nullptr; };
     for (int q = gwarp; q < ncoupled; q += gwarps) {
         Ctx c(s, w, K, W.coupled_list[q]);
-        c.load(); c.prestep_pairs(); c.match_prev(); c.template prestep_contacts<true>();
+        c.load(); c.prestep_pairs(); c.match_prev(); c.schedule(); c.template prestep_contacts<true>();
         c.store_contacts(W.ic_bounce, W.ic_jbias);
+        if (OrgS<MAXC> *g = parked(q)) c.save_static(g);
         if (lane_id() == 0) atomicAdd(&W.flags[FL_NIC], s.nic);
         __syncwarp();
     }
     grid.sync();
+    // one pass of a coupled organism's own arbiters and constraints between two rounds of cross contacts
+    auto org_pass = [&](int q, bool warm, bool last) {
+        Ctx c(s, w, K, W.coupled_list[q]);
+        c.load();
+        OrgS<MAXC> *g = parked(q);
+        if (g) c.restore_static(g);
+        else { c.prestep_pairs(); c.schedule(); c.template prestep_contacts<false>(); }
+        c.load_contact_state(W.ic_bounce, W.ic_jbias);
+        if (warm) { c.template contacts_pass<true>(dt_coef, s.nsteps); c.template joints_pass<true>(dt_coef, 2 * c.n - 3); }
+        else { c.template contacts_pass<false>(0.f, s.nsteps); c.template joints_pass<false>(0.f, 2 * c.n - 3); }
+        c.store_vel(!g || last);
+        if (g) c.save_pairs(g);
+        if (!warm) c.store_contacts(W.ic_bounce, W.ic_jbias);
+        __syncwarp();
+    };
     // cached impulses: cross contacts by level, then each coupled organism's own arbiters and constraints
     if (dt_coef != 0.f) {
         for (int L = 1; L <= maxL; L++) { cross_level_pass<true>(w, W, L, nx, dt_coef, gtid, gthreads); grid.sync(); }
-        for (int q = gwarp; q < ncoupled; q += gwarps) {
-            Ctx c(s, w, K, W.coupled_list[q]);
-            c.load(); c.prestep_pairs(); c.load_contact_state(W.ic_bounce, W.ic_jbias); c.schedule(); c.template prestep_contacts<false>();
-            c.template contacts_pass<true>(dt_coef, s.nsteps); c.template joints_pass<true>(dt_coef, 2 * c.n - 3);
-            c.store_vel();
-            __syncwarp();
-        }
+        for (int q = gwarp; q < ncoupled; q += gwarps) org_pass(q, true, false);
         grid.sync();
     }
-    for (int it = 0; it < w.p.iterations; it++) {
+    const int iterations = w.p.iterations;
+    for (int it = 0; it < iterations; it++) {
         for (int L = 1; L <= maxL; L++) { cross_level_pass<false>(w, W, L, nx, 0.f, gtid, gthreads); grid.sync(); }
-        for (int q = gwarp; q < ncoupled; q += gwarps) {
-            Ctx c(s, w, K, W.coupled_list[q]);
-            c.load(); c.prestep_pairs(); c.load_contact_state(W.ic_bounce, W.ic_jbias); c.schedule(); c.template prestep_contacts<false>();
-            c.template contacts_pass<false>(0.f, s.nsteps); c.template joints_pass<false>(0.f, 2 * c.n - 3);
-            c.store_vel(); c.store_contacts(W.ic_bounce, W.ic_jbias);
-            __syncwarp();
-        }
+        for (int q = gwarp; q < ncoupled; q += gwarps) org_pass(q, false, it == iterations - 1);
         grid.sync();
     }
 }

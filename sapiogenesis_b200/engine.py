@@ -11,7 +11,7 @@ import ctypes
 import torch
 
 from . import _lib
-from .world import PH_ALL, World
+from .world import PH_ALL, PH_REUSE_GRID, PH_STEP, PH_THINK, World
 
 
 class Engine:
@@ -28,6 +28,10 @@ class Engine:
         self.workspace = torch.zeros(nbytes, dtype=torch.uint8, device=world.device)
         self._ws = (ctypes.c_void_p(self.workspace.data_ptr()), ctypes.c_size_t(nbytes))
         self._struct = world.struct()
+        # Opt-in: the owner promises that bodies are only added or moved through this engine (tick / spawn / unpack), never by
+        # writing the world's tensors directly. The grid built by a tick's Space.step then serves the next tick's sensors.
+        self.exclusive = False
+        self._grid_valid = False
 
     def _stream_ptr(self):
         s = self.stream if self.stream is not None else torch.cuda.current_stream(self.world.device)
@@ -42,13 +46,16 @@ class Engine:
 
     # -- whole tick ------------------------------------------------------------------------------
     def tick(self, n: int = 1, phases: int = PH_ALL):
+        ph = phases | (PH_REUSE_GRID if (self.exclusive and self._grid_valid and (phases & PH_THINK)) else 0)
         with torch.cuda.device(self.world.device):
-            _lib.check(self.lib.sapio_tick(self._ref(), *self._ws, phases, n, self._stream_ptr()), "sapio_tick")
+            _lib.check(self.lib.sapio_tick(self._ref(), *self._ws, ph, n, self._stream_ptr()), "sapio_tick")
+        self._grid_valid = bool(phases & PH_STEP) if n > 0 else self._grid_valid
 
     # -- stages ----------------------------------------------------------------------------------
     def space_step(self):
         with torch.cuda.device(self.world.device):
             _lib.check(self.lib.sapio_space_step(self._ref(), *self._ws, self._stream_ptr()), "sapio_space_step")
+        self._grid_valid = True
 
     def friction(self):
         with torch.cuda.device(self.world.device):
@@ -69,10 +76,12 @@ class Engine:
     def settle(self):
         with torch.cuda.device(self.world.device):
             _lib.check(self.lib.sapio_settle(self._ref(), *self._ws, self._stream_ptr()), "sapio_settle")
+        self._grid_valid = False
 
     def reproduce(self):
         with torch.cuda.device(self.world.device):
             _lib.check(self.lib.sapio_reproduce(self._ref(), *self._ws, self._stream_ptr()), "sapio_reproduce")
+        self._grid_valid = False
 
     def spawn(self, slots, positions):
         """add_creature_clicked (Sapiogenesis.py:297-323) for a batch: random genomes (DNA.randomize with the spawn ranges of
@@ -86,6 +95,7 @@ class Engine:
             _lib.check(self.lib.sapio_spawn(self._ref(), *self._ws, ctypes.c_void_p(slots_t.data_ptr()), ctypes.c_void_p(pos_t.data_ptr()), n,
                                             self._stream_ptr()), "sapio_spawn")
         self._keep = (slots_t, pos_t)
+        self._grid_valid = False
 
     def _org_list(self, orgs):
         return torch.as_tensor(orgs, dtype=torch.int32, device=self.world.device).contiguous().view(-1)
@@ -131,6 +141,7 @@ class Engine:
             _lib.check(self.lib.sapio_unpack_organisms(self._ref(), ctypes.c_void_p(lst.data_ptr()), n, ctypes.c_void_p(records.data_ptr()),
                                                        records.numel(), self._stream_ptr()), "sapio_unpack_organisms")
         self._keep = (lst, records)
+        self._grid_valid = False
 
     def release_organisms(self, slots):
         lst = self._org_list(slots)
@@ -172,9 +183,11 @@ class Engine:
         (counters + packed sprite poses) into pinned host memory. Returns (header dict, cells [n,4], dead [m,4], bytes)."""
         hb = self._host_buffers()
         hb["control"][0], hb["control"][1] = drought, poison
+        ph = phases | (PH_REUSE_GRID if (self.exclusive and self._grid_valid and (phases & PH_THINK)) else 0)
+        self._grid_valid = bool(phases & PH_STEP) if n > 0 else self._grid_valid
         with torch.cuda.device(self.world.device):
             _lib.check(self.lib.sapio_tick_host(
-                self._ref(), *self._ws, phases, n, ctypes.c_void_p(hb["control"].data_ptr()), ctypes.c_void_p(hb["header"].data_ptr()),
+                self._ref(), *self._ws, ph, n, ctypes.c_void_p(hb["control"].data_ptr()), ctypes.c_void_p(hb["header"].data_ptr()),
                 ctypes.c_void_p(hb["cells"].data_ptr()), hb["cells"].shape[0], ctypes.c_void_p(hb["dead"].data_ptr()), hb["dead"].shape[0],
                 self._stream_ptr()), "sapio_tick_host")
         raw = hb["header"].numpy()

@@ -55,6 +55,7 @@ class Island:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.size = dist.get_world_size(group) if dist.is_initialized() else 1
         self._tick = int(world.tick)                       # host mirror of g_tick: no device read in the loop
+        engine.exclusive = True                            # bodies only change through the engine here: the step's grid serves the next think
         self.migrated_out = self.migrated_in = self.dropped = 0
         self._send = torch.zeros((self.count, engine.record_bytes()), dtype=torch.uint8, device=world.device) if self.count else None
 

@@ -40,6 +40,7 @@ F_IMMORTAL, F_MALADAPTIVE, F_FINITE_MEMORY, F_MIRROR_X, F_MIRROR_Y = 1, 2, 4, 8,
 
 PH_RULES, PH_THINK, PH_TRAIN, PH_REPRODUCE, PH_STEP, PH_FRICTION, PH_POST = 1, 2, 4, 8, 16, 32, 64
 PH_ALL = 127
+PH_REUSE_GRID = 128
 
 STAT_NAMES = ["births", "deaths", "cell_deaths", "dead_removed", "thinks", "trains", "xcontacts",
               "icontacts", "birth_fail_place", "birth_fail_caps", "overflow", "org_ticks", "levels",

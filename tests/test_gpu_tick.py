@@ -108,3 +108,24 @@ def test_sensor_views_match_oracle(oracle):
             checked += 1; members += len(ref)
     print(f"{checked} sensors, {members} viewed bodies, all hit lists identical")
     assert checked > 20 and members > 100
+
+
+def test_reusing_the_step_grid_for_the_next_think_changes_nothing(oracle):
+    """SAPIO_PH_REUSE_GRID (Engine.exclusive): tick by tick, with spawns in between, bit-identical to rebuilding the grid."""
+    import torch
+    w = fast_world(oracle, 24, 31, 0.45, 60)
+    assert oracle.tick(w, PH_ALL, 5) == 0
+    wa, ea = engine_for(w)
+    wb, eb = engine_for(w)
+    eb.exclusive = True
+    for t in range(24):
+        if t == 9:                                         # a body added through the engine invalidates the grid
+            free = torch.nonzero(wa.t["org_state"] == 0).view(-1)[:1].to(torch.int32)
+            ea.spawn(free, [[900.0, 700.0]]); eb.spawn(free.clone(), [[900.0, 700.0]])
+        ea.tick(1); eb.tick(1)
+    ea.tick(6); eb.tick(6)
+    ea.synchronize(); eb.synchronize()
+    assert wa.stats()["thinks"] > 0 and wa.stats() == wb.stats()
+    for name in wa.t:
+        a, b = wa.t[name], wb.t[name]
+        assert torch.equal(a, b) or torch.equal(torch.nan_to_num(a.double()), torch.nan_to_num(b.double())), name
