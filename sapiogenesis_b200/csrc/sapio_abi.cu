@@ -103,7 +103,7 @@ static int check(const SapioWorld *w, void *ws, size_t ws_bytes, AllWs *out) {
     if (!w) return fail(SAPIO_E_ARG, "null world%s");
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); return fail(SAPIO_E_NODEVICE, "no CUDA device: libsapio_b200 has no CPU path%s"); }
-    if (w->p.width_cap > TRAIN_MAXW) return fail(SAPIO_E_ARG, "width_cap above the compiled maximum (128)%s");
+    if (w->p.width_cap > TRAIN_MAXW || w->p.in_cap > 128) return fail(SAPIO_E_ARG, "width_cap / in_cap above the compiled maximum (128)%s");
     if (out) {
         size_t need = carve_all(w->p, (char *)ws, out);
         if (!ws || ws_bytes < need) return fail(SAPIO_E_WORKSPACE, "workspace too small%s");

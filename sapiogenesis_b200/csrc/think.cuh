@@ -143,15 +143,40 @@ __global__ void __launch_bounds__(THINK_WARPS * 32) k_think(WORLD_ARG, Workspace
         for (int l = 0; l < nl; l++) {
             const int fin = ldim[l], fout = ldim[l + 1];
             const float *Wm = brain + off, *b = Wm + fout * fin;
-            for (int r = 0; r < fout; r++) {
-                float s = 0.f;
-                for (int c = lane; c < fin; c += 32) s += Wm[r * fin + c] * cur[c];
-                s = warp_sum(s) + b[r];
-                if (l == 0) s = 1.0f / (1.0f + expf(-s));
-                if (l == nl - 1) {
+            // eight output rows at a time: their weights (cold, straight from HBM) are all requested before the first is used.
+            // Per row the summation order is unchanged: lane-strided partial sums in ascending column order, then the butterfly.
+            for (int r0 = 0; r0 < fout; r0 += 8) {
+                float acc[8], wv[8][4], bv[8];
 #pragma unroll
-                    for (int z = 0; z < 4; z++) if (z == r) out4[z] = s;
-                } else if (lane == 0) dst[r] = s;
+                for (int u = 0; u < 8; u++) {
+                    const int r = r0 + u;
+                    bv[u] = r < fout ? b[r] : 0.f;
+#pragma unroll
+                    for (int cc = 0; cc < 4; cc++) { const int c = lane + 32 * cc; wv[u][cc] = (r < fout && c < fin) ? Wm[r * fin + c] : 0.f; }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    float sacc = 0.f;
+#pragma unroll
+                    for (int cc = 0; cc < 4; cc++) { const int c = lane + 32 * cc; if (c < fin) sacc += wv[u][cc] * cur[c]; }
+                    acc[u] = sacc;
+                }
+#pragma unroll
+                for (int sh = 16; sh; sh >>= 1) {
+#pragma unroll
+                    for (int u = 0; u < 8; u++) acc[u] += __shfl_xor_sync(FULL, acc[u], sh);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int r = r0 + u;
+                    if (r >= fout) break;
+                    float sv = acc[u] + bv[u];
+                    if (l == 0) sv = 1.0f / (1.0f + expf(-sv));
+                    if (l == nl - 1) {
+#pragma unroll
+                        for (int z = 0; z < 4; z++) if (z == r) out4[z] = sv;
+                    } else if (lane == 0) dst[r] = sv;
+                }
             }
             __syncwarp();
             cur = dst; dst = (dst == act0) ? act1 : act0;

@@ -30,6 +30,7 @@ def main():
     secs = out.split('"Kernel Name",')[1:]
     tag = re.search(r'ILi(\d+)E', want)
     if tag: secs = [x for x in secs if '(int)%s>' % tag.group(1) in x.split('\n')[0]]
+    else: secs = [x for x in secs if (want + '(') in x.split('\n')[0]] or secs
     sec = secs[which]
     lines = sec.split('\n'); print(lines[0][:100])
     rdr = csv.reader(io.StringIO('\n'.join(lines[1:]))); hdr = next(rdr); ix = {h: i for i, h in enumerate(hdr)}
