@@ -29,7 +29,7 @@ def build_world(n_organisms: int, device="cuda", seed: int = 0, area_per_org: fl
     """Returns (world, engine) with n_organisms living organisms on `device`."""
     n_slots = int(math.ceil(n_organisms * slot_factor / 64.0) * 64)
     n_food = int(n_organisms * food_per_org)
-    n_dead = max(1024, int(n_organisms * 8))
+    n_dead = max(1024, int(n_organisms * 24))          # a starvation wave leaves ~20 dead cells per organism lying around for ~1400 ticks
     side = math.sqrt(n_organisms * area_per_org)
     p = default_params(n_org=n_slots, n_dead=n_dead, width=side, height=side, in_cap=in_cap, brain_cap=brain_cap, seed=seed,
                        population_limit=population_limit if population_limit is not None else n_slots,

@@ -62,9 +62,15 @@ def momentum_scale(world) -> float:
     return 0.5 * float(np.median(m)) * float(np.sqrt(np.mean(v * v))) if m.size else 0.0
 
 
+# outputs of the iterative solver: in a dense pile their fp32 error grows with the length of the contact chains; a test may
+# state a looser tolerance for them (phys_tol) while every other field keeps its own
+SOLVER_FIELDS = {"c_vel", "c_angvel", "c_vbias", "c_svel", "c_spin_jn", "c_wbias", "d_vel", "d_angvel", "d_vbias", "d_wbias",
+                 "x_jn", "x_jt", "ic_jn", "ic_jt", "j_jn"}
+
+
 class Report:
-    def __init__(self, tag):
-        self.tag, self.errs, self.bad = tag, {}, []
+    def __init__(self, tag, phys_tol=None):
+        self.tag, self.errs, self.bad, self.phys_tol = tag, {}, [], phys_tol
 
     def exact(self, name, got, ref):
         got, ref = np.asarray(got), np.asarray(ref)
@@ -76,7 +82,10 @@ class Report:
     def close(self, name, got, ref, tol=None, floor=None):
         e = field_err(got, ref, FLOORS.get(name, 1e-3) if floor is None else floor, elementwise=name in ELEMENTWISE)
         self.errs[name] = e
-        if not e <= (TOLS.get(name, TOL) if tol is None else tol):
+        lim = TOLS.get(name, TOL) if tol is None else tol
+        if self.phys_tol is not None and name in SOLVER_FIELDS:
+            lim = max(lim, self.phys_tol)
+        if not e <= lim:
             self.bad.append(f"{name}: {e:.3e}")
 
     def finish(self, verbose=True):
@@ -86,9 +95,9 @@ class Report:
         assert not self.bad, f"{self.tag}: " + "; ".join(self.bad[:12])
 
 
-def compare_worlds(wg, w, tag, brain_tol=TOL, check_brain=True, skip=(), verbose=True):
+def compare_worlds(wg, w, tag, brain_tol=TOL, check_brain=True, skip=(), verbose=True, phys_tol=None):
     """wg: GPU world after the stage(s); w: oracle world after the same stage(s)."""
-    rep = Report(tag)
+    rep = Report(tag, phys_tol)
     p = w.p
     G = {f.name: wg.np(f.name) for f in FIELDS}
     O = {f.name: w.np(f.name) for f in FIELDS}
