@@ -14,11 +14,15 @@
 #pragma once
 #include "common.cuh"
 
-template <int CM>
+// GC ("global constants"): the read-only part of a pin joint (nx, ny, bias) lives in a per-warp scratch in global memory (L2
+// resident: it is rewritten for every organism the warp takes) and is fetched three wavefronts ahead; shared memory keeps only
+// the accumulated impulse. 4 instead of 16 bytes per joint on chip: twice the organisms in flight for the large classes.
+template <int CM, bool GC = false>
 struct alignas(16) OrgS {
     static constexpr int NP = CM * (CM - 1) / 2;
     static constexpr int IC = 2 * CM < 16 ? 16 : 2 * CM;          // intra contacts kept on chip (global cap SAPIO_ICAP = 192)
-    float4 pair[NP];                 // wavefront-major: nx, ny, bias, jnAcc of a pin joint
+    float4 pair[GC ? 1 : NP];        // wavefront-major: nx, ny, bias, jnAcc of a pin joint
+    float jn[GC ? NP : 1];           // GC: jnAcc alone
     float4 vm[CM];                   // vx, vy, w, 1/m                       (index = rank among the living cells)
     float4 bb[CM];                   // bias velocity x, y, r/I, r
     float4 spin[CM];                 // sensor pin: nx, ny, bias, jnAcc
@@ -37,15 +41,16 @@ __device__ __forceinline__ int tri_f(int m) { return ((m + 1) >> 1) * ((m >> 1) 
 // first slot of wavefront t (pairs i + j == t) for n cells
 __device__ __forceinline__ int wf_off(int t, int n) { return t <= n ? tri_f(t - 1) : n * (n - 1) / 2 - tri_f(2 * n - 2 - t); }
 
-template <int CM, int G>
+template <int CM, int G, bool GC = false>
 struct OrgCtx {
-    typedef OrgS<CM> S;
+    typedef OrgS<CM, GC> S;
     static constexpr int KC = (S::IC + G - 1) / G;                  // contacts per lane when all are touched
     static constexpr uint32_t GM = G == 32 ? 0xFFFFFFFFu : ((1u << G) - 1u);
     S &s; const SapioWorld &w; const StepK &K;
     int o, nc, n, lane, sl, gshift;
     uint64_t sens;
-    __device__ OrgCtx(S &s_, const SapioWorld &w_, const StepK &K_, int o_) : s(s_), w(w_), K(K_), o(o_) {
+    float4 *cst;                                                    // GC: this warp's constants scratch
+    __device__ OrgCtx(S &s_, const SapioWorld &w_, const StepK &K_, int o_, float4 *cst_ = nullptr) : s(s_), w(w_), K(K_), o(o_), cst(cst_) {
         lane = lane_id(); sl = lane % G; gshift = lane - sl;
         nc = o >= 0 ? min(w.org_ncells[o], CM) : 0; n = 0; sens = 0;
     }
@@ -117,7 +122,7 @@ struct OrgCtx {
                 if (pidx < NPn) { int i, j; pair_of(pidx, n, i, j); q[u] = slot_of(i, j); v[u] = gj[pair_index(s.row_of[i], s.row_of[j])]; }
             }
 #pragma unroll
-            for (int u = 0; u < 4; u++) if (q[u] >= 0) s.pair[q[u]].w = v[u];
+            for (int u = 0; u < 4; u++) if (q[u] >= 0) { if (GC) s.jn[q[u]] = v[u]; else s.pair[q[u]].w = v[u]; }
         }
         for (int base = 0; base < NPmax; base += G) {
             const int pidx = base + sl;
@@ -133,8 +138,8 @@ struct OrgCtx {
                 double lx = (double)rj.x - (double)ri.x, ly = (double)rj.y - (double)ri.y;
                 double rest = sqrt(lx * lx + ly * ly);                 // |relative_pos_i - relative_pos_j| (connectTo at spawn)
                 float bias = (float)(-K.bc_joint * (d - rest) / K.dt);
-                float *pq = reinterpret_cast<float *>(&s.pair[slot_of(i, j)]);
-                pq[0] = nxf; pq[1] = nyf; pq[2] = bias;
+                if (GC) cst[slot_of(i, j)] = make_float4(nxf, nyf, bias, 0.f);
+                else { float *pq = reinterpret_cast<float *>(&s.pair[slot_of(i, j)]); pq[0] = nxf; pq[1] = nyf; pq[2] = bias; }
                 double md = __dadd_rn((double)radi, (double)radj);
                 hit = d2 < __dmul_rn(md, md);
                 if (hit) { if (d == 0.0) { nxf = 1.f; nyf = 0.f; } bias_c = contact_bias(d, radi, radj, w.p, K); }   // coincident centres: cpv(1, 0)
@@ -334,6 +339,7 @@ struct OrgCtx {
         // Per wavefront: barrier -> pair constants and two velocity loads -> (bias - v_rel.n) with the cancellation kept exact by
         // FMAs -> times the effective mass (hardware reciprocal: 1 ulp, multiplicative, so the error vanishes with the impulse) ->
         // two stores -> barrier.
+        if (GC) { joints_wavefronts_gc<WARM>(dt_coef, tmax); return; }
         int off = 0;
         for (int t = 1; t <= tmax; t++) {
             const int imin = max(0, t - (n - 1)), imax = (t - 1) >> 1, i = imin + sl;
@@ -355,6 +361,48 @@ struct OrgCtx {
         }
     }
 
+    // GC variant of the wavefront loop: the constants of wavefront t + 3 are requested (L2) while wavefront t runs
+    __device__ float4 fetch_cst(int &tp, int &offp) const {
+        const int imin = max(0, tp - (n - 1)), imax = (tp - 1) >> 1;
+        float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (imin + sl <= imax) c = __ldcg(&cst[offp + sl]);
+        offp += max(imax - imin + 1, 0); tp++;
+        return c;
+    }
+    template <bool WARM>
+    __device__ void wavefront_gc(const float4 pr, int t, int &off, float dt_coef) {
+        const int imin = max(0, t - (n - 1)), imax = (t - 1) >> 1, i = imin + sl;
+        if (i <= imax) {
+            const int j = t - i, q = off + sl;
+            const float4 vi = s.vm[i], vj = s.vm[j];
+            const float jold = s.jn[q];
+            float jnv;
+            if (WARM) jnv = jold * dt_coef;
+            else {
+                jnv = fmaf(-(vj.x - vi.x), pr.x, fmaf(-(vj.y - vi.y), pr.y, pr.z)) * rcp_approx(vi.w + vj.w);
+                s.jn[q] = jold + jnv;
+            }
+            const float jx = pr.x * jnv, jy = pr.y * jnv;
+            reinterpret_cast<float2 *>(&s.vm[i])[0] = make_float2(fmaf(-jx, vi.w, vi.x), fmaf(-jy, vi.w, vi.y));
+            reinterpret_cast<float2 *>(&s.vm[j])[0] = make_float2(fmaf(jx, vj.w, vj.x), fmaf(jy, vj.w, vj.y));
+        }
+        off += max(imax - imin + 1, 0);
+        __syncwarp();
+    }
+    template <bool WARM>
+    __device__ void joints_wavefronts_gc(float dt_coef, int tmax) {
+        constexpr int D = 8;                                   // prefetch distance in wavefronts (~100 cycles each) against L2 latency
+        int tp = 1, offp = 0, off = 0;
+        float4 c[D];
+#pragma unroll
+        for (int u = 0; u < D; u++) c[u] = fetch_cst(tp, offp);
+        for (int t = 1; t <= tmax; t += D) {
+#pragma unroll
+            for (int u = 0; u < D; u++)
+                if (t + u <= tmax) { wavefront_gc<WARM>(c[u], t + u, off, dt_coef); c[u] = fetch_cst(tp, offp); }
+        }
+    }
+
     __device__ void store_vel(bool pins = true) {
 #pragma unroll
         for (int h = 0; h < 2; h++) {
@@ -372,7 +420,7 @@ struct OrgCtx {
         const int NPn = n * (n - 1) / 2;
         for (int pidx = sl; pidx < NPn; pidx += G) {
             int i, j; pair_of(pidx, n, i, j);
-            gj[pair_index(s.row_of[i], s.row_of[j])] = s.pair[slot_of(i, j)].w;
+            gj[pair_index(s.row_of[i], s.row_of[j])] = GC ? s.jn[slot_of(i, j)] : s.pair[slot_of(i, j)].w;
         }
     }
     __device__ void store_contacts(float *ws_bounce, float *ws_jbias) {
@@ -425,10 +473,15 @@ struct OrgCtx {
 // organisms with no cross contact: the whole solve in one launch, everything on chip
 // ------------------------------------------------------------------------------------------------------------------
 #define ORG_CLASSES 8
+#ifndef ORG_GC
+#define ORG_GC 0          /* measured (profiles/r1c_org_solve.md): 15 instead of 8 warps per SM, same time -- kept as a switch */
+#endif
+#define ORG_GC_WARPS (148 * 32)             /* scratch slots per GC class: more than any grid of resident warps */
 template <int CM> struct OrgCfg {
     static constexpr int G = CM <= 8 ? 4 : CM <= 16 ? 8 : CM <= 32 ? 16 : 32;          // lanes per organism
     static constexpr int NG = 32 / G;                                                     // organisms per warp
-    static constexpr int WARP_BYTES = (int)sizeof(OrgS<CM>) * NG;
+    static constexpr bool GC = ORG_GC && CM > 32;                                         // pin constants in global scratch
+    static constexpr int WARP_BYTES = (int)sizeof(OrgS<CM, GC>) * NG;
     static constexpr int FIT = (227 * 1024 - 2048) / WARP_BYTES;                          // warps an SM can hold
     static constexpr int WARPS = FIT <= 8 ? (FIT < 1 ? 1 : FIT) : (FIT <= 16 ? FIT / 2 : 8);
 };
@@ -437,9 +490,11 @@ __host__ __device__ inline int org_class_of(int nc) { return nc <= 8 ? 0 : (nc -
 template <int CM>
 __global__ void __launch_bounds__(OrgCfg<CM>::WARPS * 32) k_org_solve(WORLD_ARG, Workspace W, StepK K, int cls) {
     constexpr int G = OrgCfg<CM>::G, NG = OrgCfg<CM>::NG;
+    constexpr bool GC = OrgCfg<CM>::GC;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = lane_id();
-    OrgS<CM> &s = reinterpret_cast<OrgS<CM> *>(smem_raw)[(threadIdx.x >> 5) * NG + lane / G];
+    OrgS<CM, GC> &s = reinterpret_cast<OrgS<CM, GC> *>(smem_raw)[(threadIdx.x >> 5) * NG + lane / G];
+    float4 *cst = GC ? W.pair_cst + ((size_t)(cls - 4) * ORG_GC_WARPS + (size_t)blockIdx.x * OrgCfg<CM>::WARPS + (threadIdx.x >> 5)) * SAPIO_NPAIR : nullptr;
     const int start = W.flags[FL_CLS0 + cls], end = W.flags[FL_CLS0 + cls + 1];
     const int n_items = (end - start + NG - 1) / NG;
     const float dt_coef = w.g_stepped[0] ? 1.0f : 0.0f;   // prev_dt == 0 on the very first step
@@ -451,13 +506,13 @@ __global__ void __launch_bounds__(OrgCfg<CM>::WARPS * 32) k_org_solve(WORLD_ARG,
         q = __shfl_sync(FULL, q, 0);
         if (q >= n_items) break;
         const int idx = end - 1 - (q * NG + lane / G);                        // largest organisms of the class first
-        OrgCtx<CM, G> c(s, w, K, idx >= start ? W.sorted_orgs[idx] : -1);
+        OrgCtx<CM, G, GC> c(s, w, K, idx >= start ? W.sorted_orgs[idx] : -1, cst);
         c.load();
         c.prestep_pairs();
         c.match_prev();
         c.schedule();
         c.template prestep_contacts<true>();
-        const int nsteps_max = OrgCtx<CM, G>::wmax(s.nsteps), tmax = 2 * OrgCtx<CM, G>::wmax(c.n) - 3;
+        const int nsteps_max = OrgCtx<CM, G, GC>::wmax(s.nsteps), tmax = 2 * OrgCtx<CM, G, GC>::wmax(c.n) - 3;
         if (dt_coef != 0.f) { c.template contacts_pass<true>(dt_coef, nsteps_max); c.template joints_pass<true>(dt_coef, tmax); }
         for (int it = 0; it < iterations; it++) { c.template contacts_pass<false>(0.f, nsteps_max); c.template joints_pass<false>(0.f, tmax); }
         if (c.o >= 0) { c.store_vel(); c.store_contacts(nullptr, nullptr); if (c.sl == 0) nic_sum += s.nic; }

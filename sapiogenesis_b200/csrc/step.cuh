@@ -48,6 +48,7 @@ struct Workspace {
     int *sorted_orgs;               // [n_org] uncoupled organisms sorted by cell rows
     int *size_hist;                 // [MAXC + 1] inside the flags block: histogram, then scatter cursors
     float *ic_bounce, *ic_jbias;    // [n_org * ICAP] (coupled path only)
+    float4 *pair_cst;               // [4 classes][ORG_GC_WARPS][NPAIR] pin constants of the organism a warp is solving (GC classes)
     char *cp_state; int cp_cap;     // parked solver state of the first cp_cap coupled organisms (sizeof(OrgS<MAXC>) each)
 };
 enum { FL_NX = 0, FL_NADJ = 1, FL_OVERFLOW = 2, FL_MAXLEVEL = 3, FL_CHANGED = 4, FL_NCOUPLED = 5, FL_NIC = 6, FL_CLS0 = 8 /* ..16: class starts + end */,
@@ -84,6 +85,7 @@ static size_t carve_workspace(const SapioParams &p, char *base, Workspace *W) {
     W->sorted_orgs = (int *)take((size_t)p.n_org * 4);
     W->ic_bounce = (float *)take((size_t)p.n_org * SAPIO_ICAP * 4);
     W->ic_jbias = (float *)take((size_t)p.n_org * SAPIO_ICAP * 4);
+    W->pair_cst = (float4 *)take((size_t)4 * (148 * 32) * SAPIO_NPAIR * sizeof(float4));
     W->cp_cap = p.n_org < 8192 ? p.n_org : 8192;
     W->cp_state = take((size_t)W->cp_cap * COUPLED_STATE_BYTES);
     return off;
