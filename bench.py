@@ -219,14 +219,20 @@ def run_ours(args):
 
     # ---- end to end through the C-ABI with host buffers ---------------------------------------------------------------------
     e2e_steps = max(3, min(args.steps, 20))
-    eng.tick_host(1, PH_ALL)
+    eng.tick_host(1, PH_ALL)                               # pinned buffers, copy stream and the size guess exist after these
+    eng.tick_host_begin(1, PH_ALL); eng.tick_host_end()
+    eng.tick_host_begin(1, PH_ALL); eng.tick_host_end()
     ticks1 = w.stats()["org_ticks"]
     h2d = d2h = 0
     barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        hdr, cells, dead, (bi, bo) = eng.tick_host(1, PH_ALL)
+    eng.tick_host_begin(1, PH_ALL)                         # frame k downloads (copy stream, pinned host memory) while tick k + 1 computes;
+    for _ in range(e2e_steps - 1):                         # every step uploads its event block and receives its own frame
+        eng.tick_host_begin(1, PH_ALL)
+        hdr, cells, dead, (bi, bo) = eng.tick_host_end()
         h2d += bi; d2h += bo
+    hdr, cells, dead, (bi, bo) = eng.tick_host_end()
+    h2d += bi; d2h += bo
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
     e2e_units = w.stats()["org_ticks"] - ticks1
@@ -272,7 +278,7 @@ def run_ours(args):
                        "parallelism": f"{world_size} island(s), one per GPU" + (f"; ring migration of {args.migrate_count} whole organisms every "
                                       f"{args.migrate_every} ticks over NCCL p2p ({isl.migrated_out} sent by rank 0 in total)" if world_size > 1 and args.migrate_every else "")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps,
-                    "steps": e2e_steps, "api": "sapio_tick_host (pinned host buffers, event block up, counters + packed sprite poses down)"},
+                    "steps": e2e_steps, "api": "sapio_tick_host_begin / _end (pinned host buffers; per tick: event block up, counters + packed sprite poses down; the download of frame k overlaps tick k + 1)"},
             "gpu_launches": int(launches),
             "stage_ms": {k: round(v, 4) for k, v in sorted(stage_ms.items(), key=lambda kv: -kv[1])},
             "clocks": clk.summary(),

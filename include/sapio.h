@@ -181,6 +181,14 @@ int sapio_tick_host(const SapioWorld *w, void *ws, size_t ws_bytes, uint32_t pha
                     float *h_cells, int cell_cap,       /* host, out: n_cells x (x, y, angle, organism slot) */
                     float *h_dead, int dead_cap,        /* host, out: n_dead  x (x, y, angle, mass)          */
                     void *stream);
+/* The same exchange, pipelined: _begin queues the ticks, the packing and -- on a copy stream of the library -- the download, and
+ * returns at once; _end waits for that download (and fetches a remainder if the world grew past the size guessed from the previous
+ * frame). A host that calls begin(k + 1) before end(k) with two sets of pinned buffers overlaps the download of frame k with the
+ * computation of tick k + 1. One frame in flight per device. */
+int sapio_tick_host_begin(const SapioWorld *w, void *ws, size_t ws_bytes, uint32_t phases, int n_ticks, const SapioControl *h_control,
+                          SapioFrameHeader *h_header, float *h_cells, int cell_cap, float *h_dead, int dead_cap, void *stream);
+int sapio_tick_host_end(void);
+
 /* the same events as a stage (applied after the step, before sapio_post) */
 int sapio_events(const SapioWorld *w, void *ws, size_t ws_bytes, float drought, float poison, void *stream);
 

@@ -53,6 +53,8 @@ def load() -> ctypes.CDLL:
     f32 = ctypes.c_float
     L.sapio_events.argtypes = [wp, vp, sz, f32, f32, vp]; L.sapio_events.restype = i32
     L.sapio_tick_host.argtypes = [wp, vp, sz, u32, i32, vp, vp, vp, i32, vp, i32, vp]; L.sapio_tick_host.restype = i32
+    L.sapio_tick_host_begin.argtypes = [wp, vp, sz, u32, i32, vp, vp, vp, i32, vp, i32, vp]; L.sapio_tick_host_begin.restype = i32
+    L.sapio_tick_host_end.argtypes = []; L.sapio_tick_host_end.restype = i32
     L.sapio_profile.argtypes = [i32]; L.sapio_profile.restype = i32
     L.sapio_profile_stages.restype = i32
     L.sapio_profile_name.argtypes = [i32]; L.sapio_profile_name.restype = ctypes.c_char_p

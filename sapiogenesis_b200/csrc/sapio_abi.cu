@@ -52,7 +52,7 @@ static size_t cub_need(const SapioParams &p) {
     return m;
 }
 
-struct AllWs { Workspace step; RulesWs rules; TrainWs train; ReproWs repro; FrameWs frame; int train_ctas; int *probe; };
+struct AllWs { Workspace step; RulesWs rules; TrainWs train; ReproWs repro; FrameWs frame, frame2; int train_ctas; int *probe; };
 
 static size_t carve_all(const SapioParams &p, char *base, AllWs *A) {
     size_t off = carve_workspace(p, base, &A->step);
@@ -82,6 +82,9 @@ static size_t carve_all(const SapioParams &p, char *base, AllWs *A) {
     FrameWs &F = A->frame;
     F.control = (SapioControl *)take(256); F.header = (SapioFrameHeader *)take(512); F.counts = (int *)take(256);
     F.cells = (float4 *)take(NO * MAXC * sizeof(float4)); F.dead = (float4 *)take(ND * sizeof(float4));
+    FrameWs &F2 = A->frame2;                               // second device frame: the pipelined exchange packs k + 1 while k downloads
+    F2.control = F.control; F2.header = (SapioFrameHeader *)take(512); F2.counts = (int *)take(256);
+    F2.cells = (float4 *)take(NO * MAXC * sizeof(float4)); F2.dead = (float4 *)take(ND * sizeof(float4));
     // cub temp storage is shared by every scan / reduction / sort: one region sized for the largest user
     size_t need = cub_need(p);
     if (need > A->step.cub_bytes) { A->step.cub_tmp = take(need); A->step.cub_bytes = need; }
@@ -429,6 +432,84 @@ int sapio_release_organisms(const SapioWorld *w, const int32_t *d_slots, int n, 
     k_release_slots<<<n < 4096 ? n : 4096, MAXC, 0, (cudaStream_t)stream>>>(*w, d_slots, n);
     k_release_contacts<<<stream_grid(w->p.x_cap), 256, 0, (cudaStream_t)stream>>>(*w);
     LAUNCHES(2); LAUNCH_CHECK();
+    return 0;
+}
+
+// ---- pipelined host exchange: the download of frame k runs on a copy stream while tick k + 1 computes --------------------
+struct HostFrame {
+    cudaEvent_t packed = nullptr, copied = nullptr;
+    int sent_cells = 0, sent_dead = 0;            // what the queued download covers
+    SapioFrameHeader *h_header = nullptr; float *h_cells = nullptr, *h_dead = nullptr; int ccap = 0, dcap = 0;
+    const float4 *d_cells = nullptr, *d_dead = nullptr;
+};
+struct HostPipe {
+    bool ready = false;
+    cudaStream_t copy = nullptr;
+    HostFrame fr[2];
+    int head = 0, count = 0;                      // ring of frames in flight (oldest first)
+    long seq = 0;                                 // frames begun: parity picks the device frame buffer
+    int last_cells = -1, last_dead = -1;          // counts of the last collected frame (host side)
+};
+static HostPipe g_pipe[64];
+
+int sapio_tick_host_begin(const SapioWorld *w, void *ws, size_t ws_bytes, uint32_t phases, int n_ticks, const SapioControl *h_control,
+                          SapioFrameHeader *h_header, float *h_cells, int cell_cap, float *h_dead, int dead_cap, void *stream) {
+    AllWs A; int rc = check(w, ws, ws_bytes, &A); if (rc) return rc;
+    if (!h_control || !h_header) return fail(SAPIO_E_ARG, "null host buffer%s");
+    int dev = 0; CUDA_TRY(cudaGetDevice(&dev));
+    HostPipe &P = g_pipe[dev & 63];
+    if (P.count == 2) return fail(SAPIO_E_ARG, "sapio_tick_host_begin: two frames are already in flight (collect one with sapio_tick_host_end)%s");
+    if (!P.ready) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&P.copy, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; k++) {
+            CUDA_TRY(cudaEventCreateWithFlags(&P.fr[k].packed, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&P.fr[k].copied, cudaEventDisableTiming));
+        }
+        P.ready = true;
+    }
+    HostFrame &H = P.fr[(P.head + P.count) & 1];
+    FrameWs &F = (P.seq & 1) ? A.frame2 : A.frame;                   // the frame before last used this buffer and has been collected
+    cudaStream_t st = (cudaStream_t)stream;
+    const long nb = (long)w->p.n_org * MAXC + w->p.n_dead;
+    const int ccap = h_cells ? (cell_cap < w->p.n_org * MAXC ? cell_cap : w->p.n_org * MAXC) : 0;
+    const int dcap = h_dead ? (dead_cap < w->p.n_dead ? dead_cap : w->p.n_dead) : 0;
+    CUDA_TRY(cudaMemcpyAsync(A.frame.control, h_control, sizeof(SapioControl), cudaMemcpyHostToDevice, st));
+    for (int t = 0; t < n_ticks; t++) {
+        if ((rc = launch_tick(*w, A, phases, A.frame.control, st))) return rc;
+        if (phases & SAPIO_PH_STEP) phases |= SAPIO_PH_REUSE_GRID;
+    }
+    prof_mark(st, PT_FRAME);
+    CUDA_TRY(cudaMemsetAsync(F.counts, 0, 256, st));
+    k_pack_frame<<<stream_grid(nb), 256, 0, st>>>(*w, F, ccap, dcap);
+    k_frame_header<<<1, 1, 0, st>>>(*w, F);
+    LAUNCHES(2);
+    prof_mark(st, PT_END);
+    CUDA_TRY(cudaEventRecord(H.packed, st));
+    CUDA_TRY(cudaStreamWaitEvent(P.copy, H.packed, 0));
+    // the counts are only known on the device: download what the last collected frame held plus a margin; _end fetches a rest
+    auto guess = [](int last, int cap) { if (last < 0) return cap; long g = (long)last + last / 16 + 8192; return (int)(g < cap ? g : cap); };
+    H.sent_cells = guess(P.last_cells, ccap); H.sent_dead = guess(P.last_dead, dcap);
+    CUDA_TRY(cudaMemcpyAsync(h_header, F.header, sizeof(SapioFrameHeader), cudaMemcpyDeviceToHost, P.copy));
+    if (H.sent_cells > 0) CUDA_TRY(cudaMemcpyAsync(h_cells, F.cells, (size_t)H.sent_cells * sizeof(float4), cudaMemcpyDeviceToHost, P.copy));
+    if (H.sent_dead > 0) CUDA_TRY(cudaMemcpyAsync(h_dead, F.dead, (size_t)H.sent_dead * sizeof(float4), cudaMemcpyDeviceToHost, P.copy));
+    CUDA_TRY(cudaEventRecord(H.copied, P.copy));
+    H.h_header = h_header; H.h_cells = h_cells; H.h_dead = h_dead; H.ccap = ccap; H.dcap = dcap; H.d_cells = F.cells; H.d_dead = F.dead;
+    P.count++; P.seq++;
+    return 0;
+}
+int sapio_tick_host_end(void) {
+    int dev = 0; CUDA_TRY(cudaGetDevice(&dev));
+    HostPipe &P = g_pipe[dev & 63];
+    if (P.count == 0) return fail(SAPIO_E_ARG, "sapio_tick_host_end without sapio_tick_host_begin%s");
+    HostFrame &H = P.fr[P.head];
+    CUDA_TRY(cudaEventSynchronize(H.copied));
+    const int nc = H.h_header->n_cells < H.ccap ? H.h_header->n_cells : H.ccap, nd = H.h_header->n_dead < H.dcap ? H.h_header->n_dead : H.dcap;
+    bool rest = false;
+    if (nc > H.sent_cells) { CUDA_TRY(cudaMemcpyAsync(H.h_cells + 4 * (size_t)H.sent_cells, H.d_cells + H.sent_cells, (size_t)(nc - H.sent_cells) * sizeof(float4), cudaMemcpyDeviceToHost, P.copy)); rest = true; }
+    if (nd > H.sent_dead) { CUDA_TRY(cudaMemcpyAsync(H.h_dead + 4 * (size_t)H.sent_dead, H.d_dead + H.sent_dead, (size_t)(nd - H.sent_dead) * sizeof(float4), cudaMemcpyDeviceToHost, P.copy)); rest = true; }
+    if (rest) CUDA_TRY(cudaStreamSynchronize(P.copy));
+    P.last_cells = nc; P.last_dead = nd;
+    P.head ^= 1; P.count--;
     return 0;
 }
 

@@ -167,16 +167,51 @@ class Engine:
             _lib.check(self.lib.sapio_events(self._ref(), *self._ws, drought, poison, self._stream_ptr()), "sapio_events")
 
     # -- end-to-end path: host buffers in, host buffers out (what a GUI host does every frame) ------------------
-    def _host_buffers(self):
-        if getattr(self, "_hb", None) is None:
-            from .world import MAXC
-            p = self.world.p
-            self._hb = dict(
-                control=torch.zeros(4, dtype=torch.float32).pin_memory(),
-                header=torch.zeros(24, dtype=torch.int64).pin_memory(),                 # SapioFrameHeader = 168 bytes
-                cells=torch.zeros(p.n_org * MAXC, 4, dtype=torch.float32).pin_memory(),
-                dead=torch.zeros(p.n_dead, 4, dtype=torch.float32).pin_memory())
-        return self._hb
+    def _new_host_buffers(self):
+        from .world import MAXC
+        p = self.world.p
+        return dict(control=torch.zeros(4, dtype=torch.float32).pin_memory(),
+                    header=torch.zeros(24, dtype=torch.int64).pin_memory(),                 # SapioFrameHeader = 168 bytes
+                    cells=torch.zeros(p.n_org * MAXC, 4, dtype=torch.float32).pin_memory(),
+                    dead=torch.zeros(p.n_dead, 4, dtype=torch.float32).pin_memory())
+
+    def _host_buffers(self, k: int = 0):
+        if getattr(self, "_hbs", None) is None:
+            self._hbs = {}
+        if k not in self._hbs:
+            self._hbs[k] = self._new_host_buffers()
+        return self._hbs[k]
+
+    @staticmethod
+    def _parse_frame(hb):
+        raw = hb["header"].numpy()
+        hdr = dict(co2=float(raw[:1].view("float64")[0]), o2=float(raw[1:2].view("float64")[0]), tick=int(raw[2]),
+                   population=int(raw[3:4].view("int32")[0]), n_cells=int(raw[3:4].view("int32")[1]), n_dead=int(raw[4:5].view("int32")[0]),
+                   stats=[int(v) for v in raw[5:21]])
+        return hdr, hb["cells"][:hdr["n_cells"]], hb["dead"][:hdr["n_dead"]], (16, 168 + 16 * (hdr["n_cells"] + hdr["n_dead"]))
+
+    # pipelined form: begin(k + 1) may be called before end(k); frames come back in order, each in its own pinned buffers
+    def tick_host_begin(self, n: int = 1, phases: int = PH_ALL, drought: float = 0.0, poison: float = 0.0):
+        self._seq = getattr(self, "_seq", 0)
+        self._inflight = getattr(self, "_inflight", [])
+        hb = self._host_buffers(self._seq & 1)
+        self._seq += 1
+        hb["control"][0], hb["control"][1] = drought, poison
+        ph = phases | (PH_REUSE_GRID if (self.exclusive and self._grid_valid and (phases & PH_THINK)) else 0)
+        self._grid_valid = bool(phases & PH_STEP) if n > 0 else self._grid_valid
+        with torch.cuda.device(self.world.device):
+            _lib.check(self.lib.sapio_tick_host_begin(
+                self._ref(), *self._ws, ph, n, ctypes.c_void_p(hb["control"].data_ptr()), ctypes.c_void_p(hb["header"].data_ptr()),
+                ctypes.c_void_p(hb["cells"].data_ptr()), hb["cells"].shape[0], ctypes.c_void_p(hb["dead"].data_ptr()), hb["dead"].shape[0],
+                self._stream_ptr()), "sapio_tick_host_begin")
+        self._inflight.append(hb)
+
+    def tick_host_end(self):
+        """The oldest frame in flight: (header dict, cells [n,4], dead [m,4], (h2d, d2h) bytes). Valid until two more begins."""
+        hb = self._inflight.pop(0)
+        with torch.cuda.device(self.world.device):
+            _lib.check(self.lib.sapio_tick_host_end(), "sapio_tick_host_end")
+        return self._parse_frame(hb)
 
     def tick_host(self, n: int = 1, phases: int = PH_ALL, drought: float = 0.0, poison: float = 0.0):
         """n ticks through sapio_tick_host: uploads the event block from pinned host memory, downloads the frame
@@ -190,13 +225,7 @@ class Engine:
                 self._ref(), *self._ws, ph, n, ctypes.c_void_p(hb["control"].data_ptr()), ctypes.c_void_p(hb["header"].data_ptr()),
                 ctypes.c_void_p(hb["cells"].data_ptr()), hb["cells"].shape[0], ctypes.c_void_p(hb["dead"].data_ptr()), hb["dead"].shape[0],
                 self._stream_ptr()), "sapio_tick_host")
-        raw = hb["header"].numpy()
-        hdr = dict(co2=float(raw[:1].view("float64")[0]), o2=float(raw[1:2].view("float64")[0]), tick=int(raw[2]),
-                   population=int(raw[3:4].view("int32")[0]), n_cells=int(raw[3:4].view("int32")[1]), n_dead=int(raw[4:5].view("int32")[0]),
-                   stats=[int(v) for v in raw[5:21]])
-        h2d = 16
-        d2h = 168 + 16 * (hdr["n_cells"] + hdr["n_dead"])
-        return hdr, hb["cells"][:hdr["n_cells"]], hb["dead"][:hdr["n_dead"]], (h2d, d2h)
+        return self._parse_frame(hb)
 
     # -- measurement hooks ---------------------------------------------------------------------------------------
     def profile(self, enable: bool):

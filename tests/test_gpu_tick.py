@@ -158,3 +158,26 @@ def test_crowded_world_of_300_matches_oracle_tick_by_tick(oracle):
     st = w.stats()
     print({k: st[k] - b0[k] for k in ("births", "deaths", "cell_deaths")}, "xcontacts", st["xcontacts"], "coupled", st["coupled"], "levels", st["levels"])
     assert st["births"] > b0["births"] + 50 and st["cell_deaths"] > b0["cell_deaths"] + 500 and st["xcontacts"] > 500
+
+
+def test_pipelined_host_frames_equal_the_synchronous_ones(oracle):
+    """sapio_tick_host_begin/_end with two frames in flight delivers, tick for tick, the frames sapio_tick_host delivers."""
+    w = fast_world(oracle, 20, 41, 0.5, 50)
+    assert oracle.tick(w, PH_ALL, 4) == 0
+    wa, ea = engine_for(w)
+    wb, eb = engine_for(w)
+    ref = []                                                                   # host buffers are reused: keep copies
+    for k in range(6):
+        h, c, d, _ = ea.tick_host(1, PH_ALL, poison=0.01 * k)
+        ref.append((h, c.clone(), d.clone()))
+    got = []
+    eb.tick_host_begin(1, PH_ALL, poison=0.0)
+    for k in range(1, 6):
+        eb.tick_host_begin(1, PH_ALL, poison=0.01 * k)
+        h, c, d, _ = eb.tick_host_end(); got.append((h, c.clone(), d.clone()))
+    h, c, d, _ = eb.tick_host_end(); got.append((h, c.clone(), d.clone()))
+    key = lambda a: a[np.lexsort(a.numpy().T[::-1])] if len(a) else a           # packed order is unspecified
+    for (hr, cr, dr), (hg, cg, dg) in zip(ref, got):
+        assert hr == hg
+        assert torch.equal(key(cr), key(cg)) and torch.equal(key(dr), key(dg))
+    assert ref[-1][0]["tick"] == w.tick + 6 and ref[-1][0]["n_cells"] > 0
