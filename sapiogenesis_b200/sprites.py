@@ -212,6 +212,34 @@ class Organism:
         cascade runs in the next update_organisms (kill_cell, sprites.py:1326-1354)."""
         self.environment.world.t["c_health"][self.slot * MAXC] = 0.0
 
+    # -- manual controls of the selected organism (Sapiogenesis.py:209-242, 534-557) -----------------------------------------
+    def heal(self):                                      # heal_btn_clicked: every living cell back to max_health
+        base, m = self._living()
+        t = self.environment.world.t
+        t["c_health"][base:base + MAXC][m] = t["c_maxhealth"][base:base + MAXC][m]
+
+    def feed(self):                                      # feed_btn_clicked: every living cell's energy to its storage
+        base, m = self._living()
+        t = self.environment.world.t
+        t["c_energy"][base:base + MAXC][m] = t["c_storage"][base:base + MAXC][m]
+
+    def hurt(self):                                      # hurt_btn_clicked: 10 % of max_health off every living cell, floor 0
+        base, m = self._living()
+        t = self.environment.world.t
+        h = t["c_health"][base:base + MAXC]
+        h[m] = torch.clamp(h[m] - 0.10 * t["c_maxhealth"][base:base + MAXC][m], min=0.0)
+
+    @property
+    def finite_memory(self) -> bool:
+        from .world import F_FINITE_MEMORY
+        return bool(int(self._t("org_flags")) & F_FINITE_MEMORY)
+
+    @finite_memory.setter
+    def finite_memory(self, v: bool):
+        from .world import F_FINITE_MEMORY
+        f = self.environment.world.t["org_flags"]
+        f[self.slot] = (int(f[self.slot]) | F_FINITE_MEMORY) if v else (int(f[self.slot]) & ~F_FINITE_MEMORY)
+
     def update(self):
         raise NotImplementedError("organisms are updated together by update_organisms(environment): the canonical tick "
                                   "(DESIGN.md section 2) has no per-organism order")
@@ -247,3 +275,27 @@ class OrganismList:
 def disperse_all_dead(environment) -> None:
     """sprites.py:1747-1750: remove every dead cell (disperse_cell returns no gas: sprites.py:1733-1745)."""
     environment.world.t["d_state"].zero_()
+
+
+# -- world-wide controls (Sapiogenesis.py:396-412) -----------------------------------------------------------------------
+def feed_all(environment) -> None:
+    """feed_all_clicked: every living cell of every organism gets its storage full."""
+    t = environment.world.t
+    live = (t["c_alive"] == 1) & (t["org_state"].repeat_interleave(MAXC) == 1)
+    t["c_energy"][live] = t["c_storage"][live]
+
+
+def kill_all(environment) -> None:
+    """kill_all_clicked: org.kill() for every organism (the cascades run in the next update_organisms)."""
+    t = environment.world.t
+    hearts = torch.nonzero(t["org_state"] == 1).view(-1) * MAXC
+    t["c_health"][hearts] = 0.0
+
+
+def reset(environment) -> None:
+    """reset_clicked: kill everything, clear the dead cells, gases back to 30000 / 0."""
+    kill_all(environment)
+    update_organisms(environment)                        # the cascades turn every organism into dead cells ...
+    disperse_all_dead(environment)                       # ... which are removed
+    environment.info["co2"] = 30000
+    environment.info["oxygen"] = 0

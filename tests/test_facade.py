@@ -114,3 +114,35 @@ def test_activate_and_train_network_on_demand(oracle):
     net = orgs[0].brain
     dims = net.structure
     assert [tuple(W.shape) for W, _ in net.layers()] == [(dims[i + 1], dims[i]) for i in range(len(dims) - 1)]
+
+
+@pytest.mark.gpu
+def test_manual_controls_and_headless_runner(oracle, tmp_path):
+    """heal / feed / hurt / kill / feed_all / kill_all / reset (Sapiogenesis.py:209-242, 396-412) and the headless runner."""
+    from sapiogenesis_b200 import sprites
+    w = make_world(oracle, n_org=8, seed=5, n_food=10, crowd=0.8, extra_slots=4, n_dead_cap=64 * 16)
+    assert oracle.tick(w, PH_ALL, 3) == 0
+    env = _env_from(w)
+    t = env.world.t
+    org = env.info["organism_list"][0]
+    rows = slice(org.slot * MAXC, org.slot * MAXC + int(t["org_ncells"][org.slot]))
+    org.hurt()
+    assert org.health_percent() < 95.0
+    org.heal(); org.feed()
+    assert abs(org.health_percent() - 100.0) < 1e-3 and abs(org.energy_percent() - 100.0) < 1e-3
+    org.immortal = True; org.maladaptive = True; org.finite_memory = False
+    assert org.immortal and org.maladaptive and not org.finite_memory
+    org.immortal = False
+    org.kill()
+    sprites.update_organisms(env)
+    assert not org.alive() and int((t["c_alive"][rows] == 1).sum()) == 0 and int((t["d_state"] > 0).sum()) > 10
+    sprites.feed_all(env)
+    live = t["c_alive"] == 1
+    assert torch.equal(t["c_energy"][live], t["c_storage"][live])
+    sprites.reset(env)
+    assert env.info["population"] == 0 and len(env.sprites) == 0 and env.info["co2"] == 30000 and env.info["oxygen"] == 0
+    from sapiogenesis_b200 import run
+    out = tmp_path / "frame.npz"
+    run.main(["--organisms", "6", "--ticks", "20", "--every", "10", "--dump", str(out)])
+    z = np.load(out)
+    assert z["cells"].shape[1] == 4 and len(z["cells"]) > 6
