@@ -107,7 +107,7 @@ def _cpu_island(args):
     from oracle import oracle as orc
     w = cpu_world(orc, n_org, seed)
     orc.tick(w, 127, max(warm, 3))                        # warm-up: contacts and adjacency exist
-    barrier.wait()
+    barrier.wait(600)
     out = []
     for _ in range(steps):
         before = w.stats()["org_ticks"]
@@ -128,18 +128,25 @@ def cpu_islands(n_org, warm, steps, ticks, cores=None):
     with ctx.Manager() as mgr:
         barrier = mgr.Barrier(cores)
         with ctx.Pool(cores) as pool:
-            res = pool.map(_cpu_island, [(n_org, seed, warm, steps, ticks, barrier) for seed in range(cores)])
+            res = pool.map_async(_cpu_island, [(n_org, seed, warm, steps, ticks, barrier) for seed in range(cores)]).get(timeout=1200)
     units = sum(u for r in res for u, _ in r)
     step_s = [max(r[k][1] for r in res) for k in range(steps)]
     return units / sum(step_s), step_s, cores
 
 
 def cpu_baseline(n_org=1000, ticks=24):
-    v, step_s, cores = cpu_islands(n_org, 3, 1, ticks)
-    return {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{cores} independent worlds (one per host core) x {n_org} organisms x {ticks} ticks of the same synthetic recipe, full tick, "
-                      f"oracle/ (C restatement of the reference; single-threaded like it), {step_s[0]:.1f} s",
-            "host_cores_available": os.cpu_count()}
+    """The CPU arm as a bounded sample, in a fresh interpreter (forking worker processes out of a process that holds a CUDA
+    context is not safe)."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "3",
+           "--ref-organisms", str(n_org), "--ref-ticks", str(ticks)]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env={**os.environ, "RANK": "0", "WORLD_SIZE": "1"})
+        line = json.loads(r.stdout.strip().splitlines()[-1])
+        out = line["cpu_baseline"]
+        out["host_cores_available"] = os.cpu_count()
+        return out
+    except Exception as e:                                   # the GPU numbers do not depend on it
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"CPU arm failed: {e!r}"[:300]}
 
 
 def run_reference(args):
