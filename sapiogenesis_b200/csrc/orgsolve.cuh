@@ -444,6 +444,7 @@ struct OrgCtx {
         if (sl == 0) { g->nic = nic; g->nsteps = s.nsteps; }
     }
     __device__ void restore_static(const S *g) {
+        if (!g) { if (sl == 0) { s.nic = 0; s.nsteps = 0; } __syncwarp(); return; }       // idle lane group of a packed warp
         const int NPn = n * (n - 1) / 2, nic = g->nic, ns = g->nsteps;
         for (int q = sl; q < NPn; q += G) s.pair[q] = g->pair[q];
         for (int c = sl; c < nic; c += G) {
@@ -521,26 +522,30 @@ __global__ void __launch_bounds__(OrgCfg<CM>::WARPS * 32) k_org_solve(WORLD_ARG,
     if (nic_sum) atomicAdd(&W.flags[FL_NIC], nic_sum);
 }
 
-// organisms -> coupled list, or a list sorted by cell rows (counting sort: histogram, scan, scatter)
+// organisms -> two lists sorted by cell rows (counting sort: histogram, scan, scatter): coupled organisms and the rest
 __global__ void k_classify_count(WORLD_ARG, Workspace W) {
     for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < w.p.n_org; o += gridDim.x * blockDim.x) {
         if (w.org_state[o] != 1) continue;
-        if (W.org_coupled[o]) { W.coupled_list[atomicAdd(&W.flags[FL_NCOUPLED], 1)] = o; continue; }
-        atomicAdd(&W.size_hist[min(max(w.org_ncells[o], 1), MAXC)], 1);
+        const int nc = min(max(w.org_ncells[o], 1), MAXC);
+        if (W.org_coupled[o]) { atomicAdd(&W.flags[FL_NCOUPLED], 1); atomicAdd(&W.flags[FL_CHIST + nc], 1); }
+        else atomicAdd(&W.size_hist[nc], 1);
     }
 }
 __global__ void k_classify_scan(Workspace W) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    int acc = 0;
+    int acc = 0, cacc = 0;
     for (int nc = 1; nc <= MAXC; nc++) {
-        if (nc == 1 || ((nc - 1) & 7) == 0) W.flags[FL_CLS0 + org_class_of(nc)] = acc;       // first size of a class
+        if (nc == 1 || ((nc - 1) & 7) == 0) { W.flags[FL_CLS0 + org_class_of(nc)] = acc; W.flags[FL_CCLS0 + org_class_of(nc)] = cacc; }   // first size of a class
         int c = W.size_hist[nc]; W.size_hist[nc] = acc; acc += c;
+        c = W.flags[FL_CHIST + nc]; W.flags[FL_CHIST + nc] = cacc; cacc += c;
     }
-    W.flags[FL_CLS0 + ORG_CLASSES] = acc;
+    W.flags[FL_CLS0 + ORG_CLASSES] = acc; W.flags[FL_CCLS0 + ORG_CLASSES] = cacc;
 }
 __global__ void k_classify_scatter(WORLD_ARG, Workspace W) {
     for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < w.p.n_org; o += gridDim.x * blockDim.x) {
-        if (w.org_state[o] != 1 || W.org_coupled[o]) continue;
-        W.sorted_orgs[atomicAdd(&W.size_hist[min(max(w.org_ncells[o], 1), MAXC)], 1)] = o;
+        if (w.org_state[o] != 1) continue;
+        const int nc = min(max(w.org_ncells[o], 1), MAXC);
+        if (W.org_coupled[o]) W.coupled_list[atomicAdd(&W.flags[FL_CHIST + nc], 1)] = o;
+        else W.sorted_orgs[atomicAdd(&W.size_hist[nc], 1)] = o;
     }
 }

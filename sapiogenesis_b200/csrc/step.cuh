@@ -52,7 +52,8 @@ struct Workspace {
     char *cp_state; int cp_cap;     // parked solver state of the first cp_cap coupled organisms (sizeof(OrgS<MAXC>) each)
 };
 enum { FL_NX = 0, FL_NADJ = 1, FL_OVERFLOW = 2, FL_MAXLEVEL = 3, FL_CHANGED = 4, FL_NCOUPLED = 5, FL_NIC = 6, FL_CLS0 = 8 /* ..16: class starts + end */,
-       FL_WORK0 = 20 /* ..27 */, FL_TMPTOP = 28, FL_NHIT = 29, FL_HIST = 32 /* ..96 */, FL_BYTES = 512 };
+       FL_WORK0 = 20 /* ..27 */, FL_TMPTOP = 28, FL_NHIT = 29, FL_HIST = 32 /* ..96 */, FL_CHIST = 100 /* ..164: coupled organisms by rows */,
+       FL_CCLS0 = 168 /* ..176: class starts + end in coupled_list */, FL_BYTES = 1024 };
 
 #define COUPLED_STATE_BYTES 49152      /* >= sizeof(OrgS<MAXC>), checked where the struct is known */
 static size_t carve_workspace(const SapioParams &p, char *base, Workspace *W) {
@@ -86,7 +87,7 @@ static size_t carve_workspace(const SapioParams &p, char *base, Workspace *W) {
     W->ic_bounce = (float *)take((size_t)p.n_org * SAPIO_ICAP * 4);
     W->ic_jbias = (float *)take((size_t)p.n_org * SAPIO_ICAP * 4);
     W->pair_cst = (float4 *)take((size_t)4 * (148 * 32) * SAPIO_NPAIR * sizeof(float4));
-    W->cp_cap = p.n_org < 8192 ? p.n_org : 8192;
+    W->cp_cap = p.n_org < 65536 ? p.n_org : 65536;
     W->cp_state = take((size_t)W->cp_cap * COUPLED_STATE_BYTES);
     return off;
 }
@@ -361,17 +362,62 @@ __device__ __forceinline__ void cross_level_pass(const SapioWorld &w, const Work
     }
 }
 
-#define COUPLED_WARPS 4
+// Coupled organisms go through the same lane-packed, size-classed solver as the others, one pass at a time between the grid
+// barriers. A warp owns a slab of shared memory that holds one warp-item of any class up to 48 rows (8/4/2/2/1/1 organisms);
+// the two largest classes take two adjacent slabs (even warps only, in their own sub-phase).
+#define COUPLED_WARPS 8
+template <int CM> struct CpBytes { static constexpr size_t v = OrgCfg<CM>::NG * sizeof(OrgS<CM>); };
+constexpr size_t cp_max(size_t a, size_t b) { return a > b ? a : b; }
+constexpr size_t CP_SLAB = (cp_max(cp_max(cp_max(CpBytes<8>::v, CpBytes<16>::v), cp_max(CpBytes<24>::v, CpBytes<32>::v)), cp_max(CpBytes<40>::v, CpBytes<48>::v)) + 15) & ~size_t(15);
+static_assert(2 * CP_SLAB >= sizeof(OrgS<64>) && 2 * CP_SLAB >= sizeof(OrgS<56>), "two slabs must hold the largest organism");
+static_assert(sizeof(OrgS<MAXC>) <= COUPLED_STATE_BYTES, "COUPLED_STATE_BYTES too small");
+enum { CP_STAGE_A = 0, CP_WARM = 1, CP_ITER = 2, CP_LAST = 3 };
+
+template <int CM>
+__device__ void coupled_item(const SapioWorld &w, const Workspace &W, const StepK &K, unsigned char *slab, int item, int kind, float dt_coef) {
+    constexpr int G = OrgCfg<CM>::G, NG = OrgCfg<CM>::NG, cls = (CM - 1) >> 3;
+    typedef OrgCtx<CM, G> Ctx;
+    const int lane = lane_id();
+    OrgS<CM> &s = reinterpret_cast<OrgS<CM> *>(slab)[lane / G];
+    const int start = W.flags[FL_CCLS0 + cls], end = W.flags[FL_CCLS0 + cls + 1];
+    const int idx = start + item * NG + lane / G;                                 // position in the class-sorted coupled list
+    const int o = idx < end ? W.coupled_list[idx] : -1;
+    Ctx c(s, w, K, o);
+    OrgS<CM> *g = (o >= 0 && idx < W.cp_cap) ? reinterpret_cast<OrgS<CM> *>(W.cp_state + (size_t)idx * COUPLED_STATE_BYTES) : nullptr;
+    if (kind == CP_STAGE_A) {   // detect the intra contacts and take their bounce before any velocity changes; park the pre-stepped state
+        c.load(); c.prestep_pairs(); c.match_prev(); c.schedule(); c.template prestep_contacts<true>();
+        if (o >= 0) {
+            c.store_contacts(W.ic_bounce, W.ic_jbias);
+            if (g) c.save_static(g);
+            if (c.sl == 0) atomicAdd(&W.flags[FL_NIC], s.nic);
+        }
+        __syncwarp();
+        return;
+    }
+    const bool use_park = __all_sync(FULL, o < 0 || g != nullptr);                // warp-uniform: the two paths are collective
+    c.load();
+    if (use_park) c.restore_static(g);
+    else { c.prestep_pairs(); c.schedule(); c.template prestep_contacts<false>(); }
+    c.load_contact_state(W.ic_bounce, W.ic_jbias);
+    const int nsteps_max = Ctx::wmax(s.nsteps), tmax = 2 * Ctx::wmax(c.n) - 3;
+    if (kind == CP_WARM) { c.template contacts_pass<true>(dt_coef, nsteps_max); c.template joints_pass<true>(dt_coef, tmax); }
+    else { c.template contacts_pass<false>(0.f, nsteps_max); c.template joints_pass<false>(0.f, tmax); }
+    if (o >= 0) {
+        c.store_vel(!use_park || kind == CP_LAST);
+        if (use_park) c.save_pairs(g);
+        if (kind != CP_WARM) c.store_contacts(W.ic_bounce, W.ic_jbias);
+    }
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(COUPLED_WARPS * 32) k_coupled(WORLD_ARG, Workspace W, StepK K) {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    OrgS<MAXC> &s = reinterpret_cast<OrgS<MAXC> *>(smem_raw)[threadIdx.x >> 5];
-    typedef OrgCtx<MAXC, 32> Ctx;
     const int nx = W.flags[FL_NX];
     if (nx == 0) return;                                       // uniform over the grid: no barrier has been entered
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
-    const int gwarp = gtid >> 5, gwarps = gthreads >> 5;
-    const int ncoupled = W.flags[FL_NCOUPLED];
+    const int gwarp = gtid >> 5, gwarps = gthreads >> 5, warp = threadIdx.x >> 5;
+    unsigned char *slab = smem_raw + (size_t)warp * CP_SLAB;
     const float dt_coef = w.g_stepped[0] ? 1.0f : 0.0f;
     // dependency levels: level[c] = 1 + max(level of the previous contact on either body); fixed point == longest chain
     for (;;) {
@@ -390,43 +436,45 @@ __global__ void __launch_bounds__(COUPLED_WARPS * 32) k_coupled(WORLD_ARG, Works
         if (!any) break;
     }
     const int maxL = max(W.flags[FL_MAXLEVEL], 1);
-    // stage A: coupled organisms detect their intra contacts and take their bounce before any velocity changes
-    static_assert(sizeof(OrgS<MAXC>) <= COUPLED_STATE_BYTES, "COUPLED_STATE_BYTES too small");
-    auto parked = [&](int q) { return q < W.cp_cap ? reinterpret_cast<OrgS<MAXC> *>(W.cp_state + (size_t)q * COUPLED_STATE_BYTES) : nullptr; };
-    for (int q = gwarp; q < ncoupled; q += gwarps) {
-        Ctx c(s, w, K, W.coupled_list[q]);
-        c.load(); c.prestep_pairs(); c.match_prev(); c.schedule(); c.template prestep_contacts<true>();
-        c.store_contacts(W.ic_bounce, W.ic_jbias);
-        if (OrgS<MAXC> *g = parked(q)) c.save_static(g);
-        if (lane_id() == 0) atomicAdd(&W.flags[FL_NIC], s.nic);
-        __syncwarp();
+    // warp-items per class (prefix): classes 0..5 by every warp, classes 6..7 by the even warps on a double slab
+    int ibase[ORG_CLASSES + 1];
+    ibase[0] = 0;
+#pragma unroll
+    for (int c = 0; c < ORG_CLASSES; c++) {
+        const int cnt = W.flags[FL_CCLS0 + c + 1] - W.flags[FL_CCLS0 + c], ng = c == 0 ? 8 : c == 1 ? 4 : c <= 3 ? 2 : 1;
+        ibase[c + 1] = ibase[c] + (cnt + ng - 1) / ng;
     }
-    grid.sync();
-    // one pass of a coupled organism's own arbiters and constraints between two rounds of cross contacts
-    auto org_pass = [&](int q, bool warm, bool last) {
-        Ctx c(s, w, K, W.coupled_list[q]);
-        c.load();
-        OrgS<MAXC> *g = parked(q);
-        if (g) c.restore_static(g);
-        else { c.prestep_pairs(); c.schedule(); c.template prestep_contacts<false>(); }
-        c.load_contact_state(W.ic_bounce, W.ic_jbias);
-        if (warm) { c.template contacts_pass<true>(dt_coef, s.nsteps); c.template joints_pass<true>(dt_coef, 2 * c.n - 3); }
-        else { c.template contacts_pass<false>(0.f, s.nsteps); c.template joints_pass<false>(0.f, 2 * c.n - 3); }
-        c.store_vel(!g || last);
-        if (g) c.save_pairs(g);
-        if (!warm) c.store_contacts(W.ic_bounce, W.ic_jbias);
-        __syncwarp();
+    auto org_phase = [&](int kind) {
+        for (int it = gwarp; it < ibase[6]; it += gwarps) {
+            if (it < ibase[1]) coupled_item<8>(w, W, K, slab, it - ibase[0], kind, dt_coef);
+            else if (it < ibase[2]) coupled_item<16>(w, W, K, slab, it - ibase[1], kind, dt_coef);
+            else if (it < ibase[3]) coupled_item<24>(w, W, K, slab, it - ibase[2], kind, dt_coef);
+            else if (it < ibase[4]) coupled_item<32>(w, W, K, slab, it - ibase[3], kind, dt_coef);
+            else if (it < ibase[5]) coupled_item<40>(w, W, K, slab, it - ibase[4], kind, dt_coef);
+            else coupled_item<48>(w, W, K, slab, it - ibase[5], kind, dt_coef);
+        }
+        if (ibase[8] > ibase[6]) {                             // uniform over the grid
+            __syncthreads();                                   // the odd warps' slabs are borrowed now
+            if (!(warp & 1))
+                for (int it = ibase[6] + (gwarp >> 1); it < ibase[8]; it += gwarps >> 1) {
+                    if (it < ibase[7]) coupled_item<56>(w, W, K, slab, it - ibase[6], kind, dt_coef);
+                    else coupled_item<64>(w, W, K, slab, it - ibase[7], kind, dt_coef);
+                }
+            __syncthreads();
+        }
     };
+    org_phase(CP_STAGE_A);
+    grid.sync();
     // cached impulses: cross contacts by level, then each coupled organism's own arbiters and constraints
     if (dt_coef != 0.f) {
         for (int L = 1; L <= maxL; L++) { cross_level_pass<true>(w, W, L, nx, dt_coef, gtid, gthreads); grid.sync(); }
-        for (int q = gwarp; q < ncoupled; q += gwarps) org_pass(q, true, false);
+        org_phase(CP_WARM);
         grid.sync();
     }
     const int iterations = w.p.iterations;
     for (int it = 0; it < iterations; it++) {
         for (int L = 1; L <= maxL; L++) { cross_level_pass<false>(w, W, L, nx, 0.f, gtid, gthreads); grid.sync(); }
-        for (int q = gwarp; q < ncoupled; q += gwarps) org_pass(q, false, it == iterations - 1);
+        org_phase(it == iterations - 1 ? CP_LAST : CP_ITER);
         grid.sync();
     }
 }
@@ -482,7 +530,7 @@ static int launch_space_step(const SapioWorld &w, const Workspace &W, cudaStream
             STEP_TRY(cudaStreamCreateWithFlags(&g_plan.side[c], cudaStreamNonBlocking));
             STEP_TRY(cudaEventCreateWithFlags(&g_plan.join[c], cudaEventDisableTiming));
         }
-        g_plan.coop_smem = sizeof(OrgS<MAXC>) * COUPLED_WARPS;
+        g_plan.coop_smem = CP_SLAB * COUPLED_WARPS;
         STEP_TRY(cudaFuncSetAttribute(k_coupled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_plan.coop_smem));
         int per_sm = 0;
         STEP_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_coupled, COUPLED_WARPS * 32, g_plan.coop_smem));

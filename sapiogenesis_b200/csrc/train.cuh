@@ -159,7 +159,8 @@ __global__ void __launch_bounds__(TRAIN_THREADS, 4) k_train(WORLD_ARG, RulesWs R
             for (int l = 0; l < nl - 1; l++) off_out += ldim[l + 1] * ldim[l] + ldim[l + 1];
             float *Win = brain, *bin = brain + h0 * I, *Wout = brain + off_out, *bout = Wout + 4 * hl;
             // ---- epoch, forward: X^T, then layer by layer; thread = (unit r, sample m), m fastest ----
-            for (int e = tid; e < M * I; e += TRAIN_THREADS) { int m = e / I, c = e - m * I; XT[c * TR_S + m] = min_[(size_t)m * IN + c]; }
+            const int M4 = (M + 3) >> 2;                          // sample groups of four (the padding samples are zeros and never read back)
+            for (int e = tid; e < 4 * M4 * I; e += TRAIN_THREADS) { int m = e / I, c = e - m * I; XT[c * TR_S + m] = m < M ? min_[(size_t)m * IN + c] : 0.f; }
             __syncthreads();
             const float *cur = XT, *hlastT = XT;
             int off = 0;
@@ -167,13 +168,20 @@ __global__ void __launch_bounds__(TRAIN_THREADS, 4) k_train(WORLD_ARG, RulesWs R
                 const int fin = ldim[l], fout = ldim[l + 1];
                 const float *Wm = brain + off, *b = Wm + fout * fin;
                 float *dst = (l == nl - 1) ? dOT : (l == 0) ? H0T : (cur == P ? Q : P);
-                for (int e = tid; e < fout * M; e += TRAIN_THREADS) {
-                    const int r = e / M, m = e - r * M;
-                    float s = 0.f;
-                    for (int c = 0; c < fin; c++) s += Wm[r * fin + c] * cur[c * TR_S + m];
-                    s += b[r];
-                    if (l == 0) s = 1.0f / (1.0f + expf(-s));
-                    dst[r * TR_S + m] = s;
+                // four samples per thread: one weight load feeds four independent FMA chains, activations move as float4
+                // (columns are padded to a multiple of 4 samples; per output the summation order over c is unchanged)
+                for (int e = tid; e < fout * M4; e += TRAIN_THREADS) {
+                    const int r = e / M4, m = 4 * (e - r * M4);
+                    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int c = 0; c < fin; c++) {
+                        const float wv = Wm[r * fin + c];
+                        const float4 a = *reinterpret_cast<const float4 *>(cur + c * TR_S + m);
+                        s.x += wv * a.x; s.y += wv * a.y; s.z += wv * a.z; s.w += wv * a.w;
+                    }
+                    const float bv = b[r];
+                    s.x += bv; s.y += bv; s.z += bv; s.w += bv;
+                    if (l == 0) { s.x = 1.0f / (1.0f + expf(-s.x)); s.y = 1.0f / (1.0f + expf(-s.y)); s.z = 1.0f / (1.0f + expf(-s.z)); s.w = 1.0f / (1.0f + expf(-s.w)); }
+                    *reinterpret_cast<float4 *>(dst + r * TR_S + m) = s;
                 }
                 __syncthreads();
                 if (l == nl - 2) hlastT = dst;
@@ -192,12 +200,16 @@ __global__ void __launch_bounds__(TRAIN_THREADS, 4) k_train(WORLD_ARG, RulesWs R
             if (tid == 0) w.org_loss[o] = red_f[0] / (float)(M * 4);
             // ---- backward down to the first layer's pre-activation (hidden layers have no activation) ----
             float *d = D, *d2 = (hlastT == P) ? Q : P;
-            for (int e = tid; e < hl * M; e += TRAIN_THREADS) {
-                const int c = e / M, m = e - c * M;
-                float s = 0.f;
+            for (int e = tid; e < hl * M4; e += TRAIN_THREADS) {
+                const int c = e / M4, m = 4 * (e - c * M4);
+                float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (int z = 0; z < 4; z++) s += dOT[z * TR_S + m] * Wout[z * hl + c];
-                d[c * TR_S + m] = s;
+                for (int z = 0; z < 4; z++) {
+                    const float wv = Wout[z * hl + c];
+                    const float4 a = *reinterpret_cast<const float4 *>(dOT + z * TR_S + m);
+                    s.x += a.x * wv; s.y += a.y * wv; s.z += a.z * wv; s.w += a.w * wv;
+                }
+                *reinterpret_cast<float4 *>(d + c * TR_S + m) = s;
             }
             __syncthreads();
             for (int l = nl - 2; l >= 1; l--) {
@@ -205,17 +217,21 @@ __global__ void __launch_bounds__(TRAIN_THREADS, 4) k_train(WORLD_ARG, RulesWs R
                 int offl = 0;
                 for (int t = 0; t < l; t++) offl += ldim[t + 1] * ldim[t] + ldim[t + 1];
                 const float *Wm = brain + offl;
-                for (int e = tid; e < fin * M; e += TRAIN_THREADS) {
-                    const int c = e / M, m = e - c * M;
-                    float s = 0.f;
-                    for (int r = 0; r < fout; r++) s += d[r * TR_S + m] * Wm[r * fin + c];
-                    d2[c * TR_S + m] = s;
+                for (int e = tid; e < fin * M4; e += TRAIN_THREADS) {
+                    const int c = e / M4, m = 4 * (e - c * M4);
+                    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int r = 0; r < fout; r++) {
+                        const float wv = Wm[r * fin + c];
+                        const float4 a = *reinterpret_cast<const float4 *>(d + r * TR_S + m);
+                        s.x += a.x * wv; s.y += a.y * wv; s.z += a.z * wv; s.w += a.w * wv;
+                    }
+                    *reinterpret_cast<float4 *>(d2 + c * TR_S + m) = s;
                 }
                 __syncthreads();
                 float *t2 = d; d = d2; d2 = t2;
             }
             float *dz0T = d2;
-            for (int e = tid; e < h0 * M; e += TRAIN_THREADS) { const int r = e / M, m = e - r * M; float hv = H0T[r * TR_S + m]; dz0T[r * TR_S + m] = d[r * TR_S + m] * hv * (1.0f - hv); }
+            for (int e = tid; e < h0 * 4 * M4; e += TRAIN_THREADS) { const int r = e / (4 * M4), m = e - r * 4 * M4; float hv = H0T[r * TR_S + m]; dz0T[r * TR_S + m] = d[r * TR_S + m] * hv * (1.0f - hv); }
             __syncthreads();
             // ---- one thread per optimizer parameter: gradient (samples in ascending order) and the Adam step ----
             const int t = w.org_adam_t[o] + 1;

@@ -78,6 +78,9 @@ def test_every_size_class_boundary(oracle):
     t["c_angvel"][live] = (torch.rand(int(live.sum()), generator=g) - 0.5) * 4.0
     for d in range(12):
         add_food(w, d, 260.0 + 330.0 * d, 330.0, vx=0.0, vy=25.0)
+    for k, slot in enumerate(range(len(SIZES) - 6, len(SIZES))):      # food lying on the largest organisms: every size class also takes the coupled path
+        hx, hy = w.np("c_pos")[slot * MAXC]
+        add_food(w, 12 + k, float(hx) + 40.0, float(hy) + 35.0, vx=-10.0, vy=5.0)
     assert oracle.post(w) == 0
     for step in range(4):
         wg, eng = engine_for(w)
@@ -86,7 +89,7 @@ def test_every_size_class_boundary(oracle):
         assert wg.stats()["overflow"] == 0
         compare_step(wg, w, f"size classes step {step}")
     st = w.stats()
-    assert st["xcontacts"] > 0 and st["icontacts"] > 300
+    assert st["xcontacts"] > 6 and st["icontacts"] > 300
     codes = w.np("ic_code").reshape(p.n_org, -1)[len(SIZES), : int(w.np("org_ic_n")[len(SIZES)])]
     assert ((codes & 127) >= MAXC).any(), "the organism at the left wall has wall contacts"
     for _ in range(3):                                       # and whole ticks (rules, think, train, settle, reproduce) on the same zoo
