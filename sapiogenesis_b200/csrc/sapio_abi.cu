@@ -119,7 +119,7 @@ static int launch_grid_only(const SapioWorld &w, const Workspace &W, cudaStream_
     const int NC = w.p.n_org * MAXC, NB = NC + w.p.n_dead, NG = w.p.grid_nx * w.p.grid_ny;
     k_integrate<false><<<stream_grid(NB), 256, 0, st>>>(w, W.gkey, W.gval);
     size_t tmp = W.cub_bytes;
-    CUDA_TRY(cub::DeviceRadixSort::SortPairs(W.cub_tmp, tmp, W.gkey, W.skey, W.gval, W.sval, NB, 0, 32, st));
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(W.cub_tmp, tmp, W.gkey, W.skey, W.gval, W.sval, NB, 0, grid_key_bits(NG), st));
     CUDA_TRY(cudaMemsetAsync(W.cell_start, 0, (size_t)NG * 4, st));
     CUDA_TRY(cudaMemsetAsync(W.cell_end, 0, (size_t)NG * 4, st));
     k_cell_bounds<<<stream_grid(NB), 256, 0, st>>>(W.skey, NB, NG, W.cell_start, W.cell_end);

@@ -56,6 +56,9 @@ enum { FL_NX = 0, FL_NADJ = 1, FL_OVERFLOW = 2, FL_MAXLEVEL = 3, FL_CHANGED = 4,
        FL_CCLS0 = 168 /* ..176: class starts + end in coupled_list */, FL_BYTES = 1024 };
 
 #define COUPLED_STATE_BYTES 49152      /* >= sizeof(OrgS<MAXC>), checked where the struct is known */
+// sort only the bits a grid key can have; the key of an empty slot (all ones) still sorts behind every cell: its low bits are all ones
+static inline int grid_key_bits(int ncell) { int b = 1; while (b < 32 && ((1ll << b) - 1) < (long long)ncell) b++; return b; }
+
 static size_t carve_workspace(const SapioParams &p, char *base, Workspace *W) {
     size_t off = 0;
     auto take = [&](size_t bytes) -> char * { char *r = base ? base + off : nullptr; off += (bytes + 255) & ~size_t(255); return r; };
@@ -551,7 +554,7 @@ static int launch_space_step(const SapioWorld &w, const Workspace &W, cudaStream
     STEP_TRY(cudaMemsetAsync(W.org_coupled, 0, (size_t)p.n_org, st));
     k_integrate<true><<<sgrid(NB, 256), 256, 0, st>>>(w, W.gkey, W.gval);
     size_t tmp = W.cub_bytes;
-    STEP_TRY(cub::DeviceRadixSort::SortPairs(W.cub_tmp, tmp, W.gkey, W.skey, W.gval, W.sval, NB, 0, 32, st));
+    STEP_TRY(cub::DeviceRadixSort::SortPairs(W.cub_tmp, tmp, W.gkey, W.skey, W.gval, W.sval, NB, 0, grid_key_bits(NG), st));
     STEP_TRY(cudaMemsetAsync(W.cell_start, 0, (size_t)NG * 4, st));
     STEP_TRY(cudaMemsetAsync(W.cell_end, 0, (size_t)NG * 4, st));
     k_cell_bounds<<<sgrid(NB, 256), 256, 0, st>>>(W.skey, NB, NG, W.cell_start, W.cell_end);
