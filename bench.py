@@ -194,6 +194,11 @@ def run_ours(args):
     w, eng = build_world(M, device=dev, seed=rank)
     # N > 1: population islands with ring migration of whole organisms (the only exchange step of the path; NCCL p2p)
     from sapiogenesis_b200.islands import Island
+    if args.forward_only:                                # the same as maladaptive=True for everybody and population_limit=0
+        from sapiogenesis_b200.world import PH_REPRODUCE, PH_TRAIN
+        w.t["org_flags"] |= 2
+        w.p.population_limit = 0
+        eng.refresh()
     isl = Island(w, eng, every=args.migrate_every if world_size > 1 else 0, count=args.migrate_count, seed=1234)
     isl.step(max(args.warmup, 3))
     if world_size > 1 and args.migrate_every:
@@ -277,8 +282,9 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"full world tick (rules + think + dopamine training + reproduction/mutation + Space.step + friction), "
-                                   f"{M} organisms per GPU island (BASELINE configs[2]); state {w.nbytes() / 2**30:.1f} GiB per GPU, far larger than L2",
+            "config": {"workload": ("forward-only tick (rules + think + Space.step + friction; no dopamine training, no reproduction: BASELINE configs[1]), " if args.forward_only
+                                    else "full world tick (rules + think + dopamine training + reproduction/mutation + Space.step + friction), ") +
+                                   f"{M} organisms per GPU island" + ("" if args.forward_only else " (BASELINE configs[2])") + f"; state {w.nbytes() / 2**30:.1f} GiB per GPU, far larger than L2",
                        "organisms_per_gpu": M, "living_after": s["organisms"], "cells": s["cells"], "pin_joints": s["pairs"],
                        "dead_cells": s["dead"], "cross_contacts": s["cross_contacts"], "intra_contacts": s["intra_contacts"],
                        "l2_policy": "inputs larger than L2",
@@ -310,6 +316,8 @@ def main():
     ap.add_argument("--ref-organisms", type=int, default=1000, help="organisms per host core of the CPU arm's bounded sample")
     ap.add_argument("--ref-ticks", type=int, default=0, help="ticks per CPU step (default: 40 for cpu_baseline, 2 per step for --impl reference)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--forward-only", action="store_true",
+                    help="BASELINE configs[1]: physics + sensors + brain forward only (no dopamine training, no reproduction); use with --organisms 10000")
     ap.add_argument("--migrate-every", type=int, default=50, help="N > 1: ticks between ring migrations (0 = never)")
     ap.add_argument("--migrate-count", type=int, default=64, help="organisms each island sends per migration")
     args = ap.parse_args()

@@ -369,6 +369,7 @@ __device__ __forceinline__ void cross_level_pass(const SapioWorld &w, const Work
 // barriers. A warp owns a slab of shared memory that holds one warp-item of any class up to 48 rows (8/4/2/2/1/1 organisms);
 // the two largest classes take two adjacent slabs (even warps only, in their own sub-phase).
 #define COUPLED_WARPS 8
+#define COUPLED_PACK_FROM 2400            /* coupled organisms (last tick) from which the packed form is launched: ~4 per warp of the simple one */
 template <int CM> struct CpBytes { static constexpr size_t v = OrgCfg<CM>::NG * sizeof(OrgS<CM>); };
 constexpr size_t cp_max(size_t a, size_t b) { return a > b ? a : b; }
 constexpr size_t CP_SLAB = (cp_max(cp_max(cp_max(CpBytes<8>::v, CpBytes<16>::v), cp_max(CpBytes<24>::v, CpBytes<32>::v)), cp_max(CpBytes<40>::v, CpBytes<48>::v)) + 15) & ~size_t(15);
@@ -482,8 +483,81 @@ __global__ void __launch_bounds__(COUPLED_WARPS * 32) k_coupled(WORLD_ARG, Works
     }
 }
 
+// The light-load form of the same pass (a few thousand coupled organisms at most): one warp per organism on a full-size tile, four
+// warps per SM, every phase on the whole grid. Its phases are short, which is what counts when the barriers outnumber the work;
+// k_coupled above wins once the coupled organisms queue up behind the warps (launch_space_step picks by last tick's count).
+#define SIMPLE_WARPS 4
+__global__ void __launch_bounds__(SIMPLE_WARPS * 32) k_coupled_simple(WORLD_ARG, Workspace W, StepK K) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    OrgS<MAXC> &s = reinterpret_cast<OrgS<MAXC> *>(smem_raw)[threadIdx.x >> 5];
+    typedef OrgCtx<MAXC, 32> Ctx;
+    const int nx = W.flags[FL_NX];
+    if (nx == 0) return;                                       // uniform over the grid: no barrier has been entered
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+    const int gwarp = gtid >> 5, gwarps = gthreads >> 5;
+    const int ncoupled = W.flags[FL_NCOUPLED];
+    const float dt_coef = w.g_stepped[0] ? 1.0f : 0.0f;
+    // dependency levels: level[c] = 1 + max(level of the previous contact on either body); fixed point == longest chain
+    for (;;) {
+        if (gtid == 0) W.flags[FL_CHANGED] = 0;
+        grid.sync();
+        bool ch = false;
+        for (int c = gtid; c < nx; c += gthreads) {
+            int pa = W.nx_prev_a[c], pb = W.nx_prev_b[c];
+            int L = 1 + max(pa >= 0 ? W.nx_level[pa] : 0, pb >= 0 ? W.nx_level[pb] : 0);
+            if (L > W.nx_level[c]) { W.nx_level[c] = L; ch = true; atomicMax(&W.flags[FL_MAXLEVEL], L); }
+        }
+        if (ch) W.flags[FL_CHANGED] = 1;
+        grid.sync();
+        int any = W.flags[FL_CHANGED];
+        grid.sync();
+        if (!any) break;
+    }
+    const int maxL = max(W.flags[FL_MAXLEVEL], 1);
+    // stage A: coupled organisms detect their intra contacts and take their bounce before any velocity changes
+    static_assert(sizeof(OrgS<MAXC>) <= COUPLED_STATE_BYTES, "COUPLED_STATE_BYTES too small");
+    auto parked = [&](int q) { return q < W.cp_cap ? reinterpret_cast<OrgS<MAXC> *>(W.cp_state + (size_t)q * COUPLED_STATE_BYTES) : nullptr; };
+    for (int q = gwarp; q < ncoupled; q += gwarps) {
+        Ctx c(s, w, K, W.coupled_list[q]);
+        c.load(); c.prestep_pairs(); c.match_prev(); c.schedule(); c.template prestep_contacts<true>();
+        c.store_contacts(W.ic_bounce, W.ic_jbias);
+        if (OrgS<MAXC> *g = parked(q)) c.save_static(g);
+        if (lane_id() == 0) atomicAdd(&W.flags[FL_NIC], s.nic);
+        __syncwarp();
+    }
+    grid.sync();
+    // one pass of a coupled organism's own arbiters and constraints between two rounds of cross contacts
+    auto org_pass = [&](int q, bool warm, bool last) {
+        Ctx c(s, w, K, W.coupled_list[q]);
+        c.load();
+        OrgS<MAXC> *g = parked(q);
+        if (g) c.restore_static(g);
+        else { c.prestep_pairs(); c.schedule(); c.template prestep_contacts<false>(); }
+        c.load_contact_state(W.ic_bounce, W.ic_jbias);
+        if (warm) { c.template contacts_pass<true>(dt_coef, s.nsteps); c.template joints_pass<true>(dt_coef, 2 * c.n - 3); }
+        else { c.template contacts_pass<false>(0.f, s.nsteps); c.template joints_pass<false>(0.f, 2 * c.n - 3); }
+        c.store_vel(!g || last);
+        if (g) c.save_pairs(g);
+        if (!warm) c.store_contacts(W.ic_bounce, W.ic_jbias);
+        __syncwarp();
+    };
+    // cached impulses: cross contacts by level, then each coupled organism's own arbiters and constraints
+    if (dt_coef != 0.f) {
+        for (int L = 1; L <= maxL; L++) { cross_level_pass<true>(w, W, L, nx, dt_coef, gtid, gthreads); grid.sync(); }
+        for (int q = gwarp; q < ncoupled; q += gwarps) org_pass(q, true, false);
+        grid.sync();
+    }
+    const int iterations = w.p.iterations;
+    for (int it = 0; it < iterations; it++) {
+        for (int L = 1; L <= maxL; L++) { cross_level_pass<false>(w, W, L, nx, 0.f, gtid, gthreads); grid.sync(); }
+        for (int q = gwarp; q < ncoupled; q += gwarps) org_pass(q, false, it == iterations - 1);
+        grid.sync();
+    }
+}
+
 // publish: the new arbiter list becomes w.x_*, the adjacency w.xa_*; created-this-tick marks are cleared
-__global__ void __launch_bounds__(256) k_step_finish(WORLD_ARG, Workspace W) {
+__global__ void __launch_bounds__(256) k_step_finish(WORLD_ARG, Workspace W, int *mail) {
     const int NC = w.p.n_org * MAXC, ND = w.p.n_dead, NB = NC + ND;
     const int nx = W.flags[FL_NX], na = W.flags[FL_NADJ];
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
@@ -493,6 +567,7 @@ __global__ void __launch_bounds__(256) k_step_finish(WORLD_ARG, Workspace W) {
     for (int d = gtid; d < ND; d += gthreads) if (w.d_state[d] == 2) w.d_state[d] = 1;
     if (gtid == 0) {
         w.g_x_n[0] = nx; w.g_stepped[0] = 1;
+        if (mail) mail[0] = W.flags[FL_NCOUPLED];
         w.g_stats[SAPIO_STAT_XCONTACTS] = nx; w.g_stats[SAPIO_STAT_ICONTACTS] = W.flags[FL_NIC];
         w.g_stats[SAPIO_STAT_LEVELS] = W.flags[FL_MAXLEVEL]; w.g_stats[SAPIO_STAT_COUPLED] = W.flags[FL_NCOUPLED];
         if (W.flags[FL_OVERFLOW]) w.g_stats[SAPIO_STAT_OVERFLOW] += 1;
@@ -502,7 +577,7 @@ __global__ void __launch_bounds__(256) k_step_finish(WORLD_ARG, Workspace W) {
 // ------------------------------------------------------------------------------------------------------------------
 // host-side launch sequence
 // ------------------------------------------------------------------------------------------------------------------
-struct StepPlan { bool ready; int sms; int coop_blocks; int org_blocks[ORG_CLASSES]; size_t org_smem[ORG_CLASSES]; size_t coop_smem; cudaStream_t side[ORG_CLASSES]; cudaEvent_t fork, join[ORG_CLASSES]; };
+struct StepPlan { bool ready; int sms; int coop_blocks, simple_blocks; size_t simple_smem; int *h_mail, *d_mail; int org_blocks[ORG_CLASSES]; size_t org_smem[ORG_CLASSES]; size_t coop_smem; cudaStream_t side[ORG_CLASSES]; cudaEvent_t fork, join[ORG_CLASSES]; };
 static StepPlan g_plan = {};
 
 template <int CM>
@@ -533,6 +608,15 @@ static int launch_space_step(const SapioWorld &w, const Workspace &W, cudaStream
             STEP_TRY(cudaStreamCreateWithFlags(&g_plan.side[c], cudaStreamNonBlocking));
             STEP_TRY(cudaEventCreateWithFlags(&g_plan.join[c], cudaEventDisableTiming));
         }
+        g_plan.simple_smem = sizeof(OrgS<MAXC>) * SIMPLE_WARPS;
+        STEP_TRY(cudaFuncSetAttribute(k_coupled_simple, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_plan.simple_smem));
+        { int ps = 0; STEP_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ps, k_coupled_simple, SIMPLE_WARPS * 32, g_plan.simple_smem)); g_plan.simple_blocks = ps * g_plan.sms; }
+        if (g_plan.simple_blocks < 1) { snprintf(err, errlen, "k_coupled_simple does not fit on an SM"); return SAPIO_E_CUDA; }
+        // mailbox: the device leaves the number of coupled organisms of the tick here (mapped host memory); the host reads it, one tick
+        // stale and without waiting, to pick the form of the coupled pass
+        STEP_TRY(cudaHostAlloc((void **)&g_plan.h_mail, 64, cudaHostAllocMapped));
+        STEP_TRY(cudaHostGetDevicePointer((void **)&g_plan.d_mail, g_plan.h_mail, 0));
+        g_plan.h_mail[0] = 0;
         g_plan.coop_smem = CP_SLAB * COUPLED_WARPS;
         STEP_TRY(cudaFuncSetAttribute(k_coupled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_plan.coop_smem));
         int per_sm = 0;
@@ -595,10 +679,12 @@ static int launch_space_step(const SapioWorld &w, const Workspace &W, cudaStream
     {
         SapioWorld wc = w; Workspace Wc = W; StepK Kc = K;
         void *args[] = { (void *)&wc, (void *)&Wc, (void *)&Kc };
-        STEP_TRY(cudaLaunchCooperativeKernel((void *)k_coupled, dim3(g_plan.coop_blocks), dim3(COUPLED_WARPS * 32), args, g_plan.coop_smem, st));
+        const int last = *(volatile int *)g_plan.h_mail;
+        if (last > COUPLED_PACK_FROM) STEP_TRY(cudaLaunchCooperativeKernel((void *)k_coupled, dim3(g_plan.coop_blocks), dim3(COUPLED_WARPS * 32), args, g_plan.coop_smem, st));
+        else STEP_TRY(cudaLaunchCooperativeKernel((void *)k_coupled_simple, dim3(g_plan.simple_blocks), dim3(SIMPLE_WARPS * 32), args, g_plan.simple_smem, st));
     }
     prof_mark(st, PT_STEP_FINISH);
-    k_step_finish<<<sgrid(NB + 1, 256), 256, 0, st>>>(w, W);
+    k_step_finish<<<sgrid(NB + 1, 256), 256, 0, st>>>(w, W, g_plan.d_mail);
     LAUNCHES(2);
     prof_mark(st, PT_END);
     STEP_TRY(cudaGetLastError());
