@@ -36,7 +36,14 @@ __device__ __forceinline__ double g_triangular(RngStream &u, double low, double 
     return low + (high - low) * sqrt(x * c);
 }
 __device__ __forceinline__ int g_index_of(const DGenome &g, int id) { for (int j = 0; j < g.n; j++) if (g.id[j] == id) return j; return -1; }
-__device__ __forceinline__ int g_new_cell_id(const DGenome &g) { int cid = 1; while (g_index_of(g, cid) >= 0) cid++; return cid; }   // sprites.py:528-532
+// DNA new cell id (sprites.py:528-532): the smallest positive id not in use. One pass over a bitmap instead of a search per candidate.
+__device__ __forceinline__ int g_new_cell_id(const DGenome &g) {
+    uint64_t used[4] = {0, 0, 0, 0};
+    for (int j = 0; j < g.n; j++) { const int id = g.id[j]; if (id >= 0 && id < 256) used[id >> 6] |= 1ull << (id & 63); }
+    used[0] |= 1ull;                                             // ids start at 1
+    for (int q = 0; q < 4; q++) if (~used[q]) return q * 64 + __ffsll((long long)~used[q]) - 1;
+    int cid = 256; while (g_index_of(g, cid) >= 0) cid++; return cid;
+}
 // finish_cell_info (sprites.py:238-253)
 __device__ __forceinline__ void g_finish_cell_info(DGenome &g, int j) {
     int t = g.type[j]; double s = g.size[j], m = g.mass[j];
@@ -47,7 +54,38 @@ __device__ __forceinline__ void g_finish_cell_info(DGenome &g, int j) {
     g.storage[j] = C_BASE_STORAGE[t] * s + C_BASE_STORAGE[t] * m;
 }
 // DNA._closest_cell_to_point (sprites.py:705-718)
-__device__ __forceinline__ double g_closest_dist(const DGenome &g, double x, double y) {
+// The genome logic is scalar (one lane walks the reference's dict code), but its one hot loop -- the distance of a candidate
+// position to every cell, in double, tried up to 31 times per added cell -- is served by the other lanes of the warp:
+// lane 0 posts (x, y) in shared memory, everybody takes the cells lane, lane + 32, the partial minima come back through shared
+// memory. min is exact in any order: the result is the serial loop's. Barriers are __syncwarp (legal from different code paths).
+struct GenomeSvc { int cmd; double x, y; double part[32]; };      // cmd: 1 = closest distance, 0 = done
+__device__ __forceinline__ double g_closest_part(const DGenome &g, double x, double y, int lane) {
+    double best = INFINITY;
+    for (int j = lane; j < g.n; j += 32) {
+        double dx = g.relx[j] - x, dy = g.rely[j] - y;
+        double d = sqrt(dx * dx + dy * dy) - g.size[j] / 2.0;
+        if (d < best) best = d;
+    }
+    return best;
+}
+__device__ __forceinline__ void g_svc_worker(const DGenome &g, GenomeSvc *svc, int lane) {       // lanes 1..31
+    for (;;) {
+        __syncwarp();                                             // a request is posted
+        if (svc->cmd == 0) break;
+        svc->part[lane] = g_closest_part(g, svc->x, svc->y, lane);
+        __syncwarp();                                             // partial minima are in
+    }
+}
+__device__ __forceinline__ void g_svc_done(GenomeSvc *svc) { if (svc) { svc->cmd = 0; __syncwarp(); } }
+__device__ __forceinline__ double g_closest_dist(const DGenome &g, double x, double y, GenomeSvc *svc = nullptr) {
+    if (svc) {
+        svc->cmd = 1; svc->x = x; svc->y = y;
+        __syncwarp();
+        double best = g_closest_part(g, x, y, 0);
+        __syncwarp();
+        for (int l = 1; l < 32; l++) { double d = svc->part[l]; if (d < best) best = d; }
+        return best;
+    }
     double best = INFINITY;
     for (int j = 0; j < g.n; j++) {
         double dx = g.relx[j] - x, dy = g.rely[j] - y;
@@ -57,19 +95,19 @@ __device__ __forceinline__ double g_closest_dist(const DGenome &g, double x, dou
     return best;
 }
 // DNA._viable_cell_position + _cell_mirrorable (sprites.py:732-764), distanceThreshold .8
-__device__ __forceinline__ bool g_viable_cell_position(const DGenome &g, double x, double y, double size) {
-    double dist = g_closest_dist(g, x, y), r = size / 2.0;
+__device__ __forceinline__ bool g_viable_cell_position(const DGenome &g, double x, double y, double size, GenomeSvc *svc = nullptr) {
+    double dist = g_closest_dist(g, x, y, svc), r = size / 2.0;
     if (g.mirror_x || g.mirror_y) {
         double nx = g.mirror_x ? -x : x, ny = g.mirror_y ? -y : y;
         double ddx = nx - x, ddy = ny - y;
         double distance = sqrt(ddx * ddx + ddy * ddy) - size / 2.0;
-        double distance2 = g_closest_dist(g, nx, ny);
+        double distance2 = g_closest_dist(g, nx, ny, svc);
         if (!(distance > r * 0.8 && distance2 > r * 0.8)) return false;
     }
     return dist > r * 0.8;
 }
 // DNA.add_randomized_cell + _make_random_cell (sprites.py:797-825, 551-582): new id, 0 = no room after 31 tries, -1 = tile full
-__device__ __forceinline__ int g_add_randomized_cell(DGenome &g, const SapioParams &p, RngStream &u, bool first_cell) {
+__device__ __forceinline__ int g_add_randomized_cell(DGenome &g, const SapioParams &p, RngStream &u, bool first_cell, GenomeSvc *svc = nullptr) {
     int cid = g_new_cell_id(g);
     double size = (double)g_randrange(u, p.size_lo, p.size_hi), mass = (double)g_randrange(u, p.mass_lo, p.mass_hi);
     double elast = (double)u.next(), fric = (double)u.next();
@@ -86,7 +124,7 @@ __device__ __forceinline__ int g_add_randomized_cell(DGenome &g, const SapioPara
             double reach = g.size[from] / 2.1 + size / 2.1;
             rx = g.relx[from] + gx * reach; ry = g.rely[from] + gy * reach;
             parent = g.id[from];
-            ok = g_viable_cell_position(g, rx, ry, size);
+            ok = g_viable_cell_position(g, rx, ry, size, svc);
         }
     }
     if (g.n >= MAXC) return -1;
@@ -157,7 +195,7 @@ __device__ __forceinline__ int g_randomize(DGenome &g, const SapioParams &p, Rng
     return 0;
 }
 // DNA.mutate_* (sprites.py:915-1060) except the weight carry-over, which needs the parent's tensors (repro.cuh)
-__device__ __forceinline__ int g_mutate_cells(DGenome &g, const SapioParams &p, double severity, RngStream &u) {
+__device__ __forceinline__ int g_mutate_cells(DGenome &g, const SapioParams &p, double severity, RngStream &u, GenomeSvc *svc = nullptr) {
     {   // mutate_cell_count: the removal branch drops remove_cell()'s returned copy (sprites.py:932) -> draws only
         int current = g.n, cr = (int)(severity * 18.0);
         if (cr) {
@@ -170,7 +208,7 @@ __device__ __forceinline__ int g_mutate_cells(DGenome &g, const SapioParams &p, 
             } else for (int i = 0; i < added; i++) {
                 if (g.n + ((g.mirror_x || g.mirror_y) ? 2 : 1) > MAXC) return -1;
                 int id = 0;
-                while (!id) { id = g_add_randomized_cell(g, p, u, false); if (id < 0) return -1; }
+                while (!id) { id = g_add_randomized_cell(g, p, u, false, svc); if (id < 0) return -1; }
                 if (g.mirror_x || g.mirror_y) if (g_apply_mirror(g, id) < 0) return -1;
             }
         }

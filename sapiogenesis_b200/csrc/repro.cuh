@@ -86,16 +86,20 @@ __global__ void __launch_bounds__(REPRO_WARPS * 32) k_repro_prepare(WORLD_ARG, R
     const int lane = lane_id(), n_req = Q.counters[0];
     const int32_t T = (int32_t)w.g_tick[0];
     __shared__ DGenome sg[REPRO_WARPS];
+    __shared__ GenomeSvc ssvc[REPRO_WARPS];
     for (int r = blockIdx.x * REPRO_WARPS + (threadIdx.x >> 5); r < n_req; r += gridDim.x * REPRO_WARPS) {
         Birth &B = Q.births[r];
         const int parent = Q.req_list[r];
         DGenome &g = sg[threadIdx.x >> 5];                    // the dict-walking logic runs on shared memory, not on global
-        if (lane == 0) {
+        GenomeSvc *svc = &ssvc[threadIdx.x >> 5];
+        if (lane != 0) g_svc_worker(g, svc, lane);            // serve lane 0's distance queries until it is done mutating
+        else {
             B.parent = parent; B.accepted = 0; B.slot = -1; B.ok = 0;
             g_from_world(w, parent, g);
             double prect[2]; g_get_size(g, prect);                                  // old_organism.dna.get_size()
             RngStream u(p.seed, w.org_uid[parent], T, RNG_GENOME, (uint32_t)sibling << 20);
-            int rc = g_mutate_cells(g, p, (double)p.mutation_severity, u);
+            int rc = g_mutate_cells(g, p, (double)p.mutation_severity, u, svc);
+            g_svc_done(svc);
             bool changed = false;
             if (rc == 0) {
                 g_mutate_brain_structure(g, (double)p.brain_mutation_severity, u, B.old_h, B.old_n, changed);
