@@ -273,6 +273,23 @@ class Environment:
         self.engine.spawn(np.array([slot], dtype=np.int32), np.array([[float(pos[0]), float(pos[1])]]))
         return Organism(self, slot)
 
+    def import_organism(self, path_or_dna, pos):
+        """import_organism_clicked + paste (Sapiogenesis.py:413-424, 325-335): a `sprites.DNA` pickle (or its attribute dict)
+        becomes a new organism at `pos`. Returns the Organism view."""
+        from .dna_io import import_dna, loads_reference_pickle
+        from .sprites import Organism
+        dna = path_or_dna
+        if not isinstance(dna, dict):
+            with open(path_or_dna, "rb") as f:
+                dna = loads_reference_pickle(f.read())
+        free = torch.nonzero(self.world.t["org_state"] == 0).view(-1)
+        if free.numel() == 0:
+            raise RuntimeError("organism capacity exhausted")
+        slot = int(free[0])
+        import_dna(self.world, slot, pos, dna)
+        self.engine._grid_valid = False
+        return Organism(self, slot)
+
     def removeSprite(self, sprite: Sprite):              # physics.py:444-451
         t = self.world.t
         if sprite._kind == "dead":

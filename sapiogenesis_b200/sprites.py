@@ -116,6 +116,17 @@ class DNA:
     def curiosity(self) -> float:
         return float(self._o.environment.world.t["org_curiosity"][self._o.slot])
 
+    def export(self) -> dict:
+        """The attribute dict of the reference's `sprites.DNA` for this organism (sapiogenesis_b200.dna_io)."""
+        from .dna_io import export_dna
+        return export_dna(self._o.environment.world, self._o.slot)
+
+    def save(self, path: str) -> None:
+        """save_organism_clicked (Sapiogenesis.py:243-254): a pickle the reference's "Import organism" opens."""
+        from .dna_io import dumps_reference_pickle
+        with open(path, "wb") as f:
+            f.write(dumps_reference_pickle(self.export()))
+
 
 class Organism:
     """View of one organism slot (sprites.py:1089-1125)."""
