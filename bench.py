@@ -277,6 +277,17 @@ def run_ours(args):
                     "share_of_step": stage_ms["org_solve"] / (ms / args.steps), "dominant_stage": dom,
                     "note": "not HBM-bound: each sweep is a dependent chain of 2n-3 pin wavefronts per organism; ncu shows issue-slot "
                             "utilisation 36-48 % at 8-12 resident warps per SM (shared-memory limited), DRAM at 1-2 % of peak"}
+        # the streaming stages against the same peak (algorithmic bytes: DESIGN.md section 4; slots = every body slot the kernel scans)
+        slots = w.p.n_org * 64 + w.p.n_dead
+        bodies = s["cells"] + s["dead"]
+        stream_bytes = {
+            "friction": 24 * bodies + slots,                                                   # vel2 + angvel r/w, liveness flag per slot
+            "broadphase": 36 * s["cells"] + 24 * s["sensors"] + 36 * s["dead"] + 8 * slots + 16 * slots,   # integrate + key/value write, sort r/w
+            "settle": 12 * bodies + slots,
+            "rules_main": 60 * s["cells"] + 128 * s["organisms"], "rules_begin": 60 * s["cells"] + 128 * s["organisms"],
+        }
+        stage_roof = {k: {"bytes": int(b), "ms": round(stage_ms[k], 4), "GB/s": round(b / (stage_ms[k] / 1e3) / 1e9, 1),
+                          "frac": round(b / (stage_ms[k] / 1e3) / 1e9 / peak, 4)} for k, b in stream_bytes.items() if stage_ms.get(k)}
         cpu = cpu_baseline(args.ref_organisms, args.ref_ticks or 40) if (not args.no_cpu and world_size == 1) else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -299,6 +310,7 @@ def run_ours(args):
         }
         if roof:
             line["roofline"] = roof
+            line["stage_roofline"] = stage_roof
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
