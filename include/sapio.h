@@ -171,7 +171,7 @@ int sapio_release_organisms(const SapioWorld *w, const int32_t *d_slots, int n, 
  * Uploads the per-tick event block updateUI applies (Sapiogenesis.py:37-47), runs n_ticks ticks, then downloads what the
  * reference pushes to Qt every frame: the UI counters (Sapiogenesis.py:62-69) and the pose of every solid sprite
  * (Sprite.setPos / setRotation, physics.py:253-272), packed. Host pointers should be page-locked. Synchronises `stream`. */
-typedef struct SapioControl { float drought, poison; int32_t pad[2]; } SapioControl;   /* amounts per tick = severity * uDiff */
+typedef struct SapioControl { float drought, poison, random_cells; int32_t pad; } SapioControl;   /* amounts / probability per tick = severity * uDiff */
 typedef struct SapioFrameHeader {
     double co2, o2; int64_t tick; int32_t population, n_cells, n_dead, pad; int64_t stats[16];
 } SapioFrameHeader;
@@ -189,8 +189,9 @@ int sapio_tick_host_begin(const SapioWorld *w, void *ws, size_t ws_bytes, uint32
                           SapioFrameHeader *h_header, float *h_cells, int cell_cap, float *h_dead, int dead_cap, void *stream);
 int sapio_tick_host_end(void);
 
-/* the same events as a stage (applied after the step, before sapio_post) */
-int sapio_events(const SapioWorld *w, void *ws, size_t ws_bytes, float drought, float poison, void *stream);
+/* the same events as a stage (applied after the step, before sapio_post): drought and poison amounts, and the probability that
+ * one piece of food (add_dead_clicked: size 30, mass 12) appears at a random place this tick   Sapiogenesis.py:37-53, 490-507 */
+int sapio_events(const SapioWorld *w, void *ws, size_t ws_bytes, float drought, float poison, float random_cells, void *stream);
 
 /* ---- measurement hooks ------------------------------------------------------------------------------------------- */
 /* per-stage device time (CUDA events on the launching stream); names: sapio_profile_name(i), i < sapio_profile_stages() */

@@ -54,7 +54,7 @@ def lib():
         L.oracle_forward.argtypes = [fp, ctypes.POINTER(ctypes.c_int32), i32, fp, fp, fp]; L.oracle_forward.restype = None
         L.oracle_train_one.argtypes = [vp, i32]; L.oracle_train_one.restype = i32
         L.oracle_think_now.argtypes = [vp, i32]; L.oracle_think_now.restype = i32
-        L.oracle_events.argtypes = [vp, dbl, dbl]; L.oracle_events.restype = i32
+        L.oracle_events.argtypes = [vp, dbl, dbl, dbl]; L.oracle_events.restype = i32
         L.oracle_set_think_uniforms.argtypes = [ctypes.c_void_p]; L.oracle_set_think_uniforms.restype = None
         L.oracle_rotation.argtypes = [vp, i32]; L.oracle_rotation.restype = dbl
         L.oracle_think.argtypes = [vp, i32, dp, dp, ctypes.POINTER(ctypes.c_uint8), dbl]; L.oracle_think.restype = i32
@@ -85,7 +85,7 @@ def train(world) -> int: return lib().oracle_train(_ref(world))
 def settle(world) -> int: return lib().oracle_settle(_ref(world))
 def reproduce(world) -> int: return lib().oracle_reproduce(_ref(world))
 def post(world) -> int: return lib().oracle_post(_ref(world))
-def events(world, drought=0.0, poison=0.0) -> int: return lib().oracle_events(_ref(world), float(drought), float(poison))
+def events(world, drought=0.0, poison=0.0, random_cells=0.0) -> int: return lib().oracle_events(_ref(world), float(drought), float(poison), float(random_cells))
 def spawn(world, slot: int, x: float, y: float) -> int: return lib().oracle_spawn(_ref(world), slot, x, y)
 
 

@@ -379,14 +379,30 @@ double oracle_rotation(const SapioWorld *w, int o) {
     return org_rotation(w, &g);
 }
 
-/* updateUI world events (Sapiogenesis.py:37-47): drought takes `drought` from both gases, poison takes 5 * `poison` health
- * from every cell of every organism; amounts are severity * uDiff, computed by the host */
-int oracle_events(SapioWorld *w, double drought, double poison) {
+/* updateUI world events (Sapiogenesis.py:37-53): drought takes `drought` from both gases, poison takes 5 * `poison` health
+ * from every cell of every organism, with probability `random_cells` a piece of food appears; all = severity * uDiff, computed by the host */
+int oracle_events(SapioWorld *w, double drought, double poison, double random_cells) {
     if (poison != 0)
         for (int o = 0; o < w->p.n_org; o++) {
             if (w->org_state[o] != 1) continue;
             for (int k = 0; k < w->org_ncells[o]; k++) w->c_health[o * MAXC + k] = (float)((double)w->c_health[o * MAXC + k] - poison * 5.0);
         }
     if (drought != 0) { w->g_o2[0] -= drought; w->g_co2[0] -= drought; }
+    if (random_cells > 0) {   /* Sapiogenesis.py:48-53: random.random() <= rVal -> add_dead_clicked at (randrange(10, int(W)), randrange(10, int(H))) */
+        uint32_t r[4];
+        sapio_rng4(w->p.seed, -1, (int32_t)w->g_tick[0], 11u, 0u, r);
+        if (sapio_u01(r[0]) <= (float)random_cells) {
+            int d = 0;
+            while (d < w->p.n_dead && w->d_state[d] != 0) d++;
+            if (d >= w->p.n_dead) { w->g_stats[SAPIO_STAT_OVERFLOW] += 1; return 0; }
+            const int wi = (int)w->p.width, hi = (int)w->p.height;
+            w->d_state[d] = 2;
+            w->d_pos[2 * d] = (float)(10 + (int)floor((double)sapio_u01(r[1]) * (double)(wi - 10)));
+            w->d_pos[2 * d + 1] = (float)(10 + (int)floor((double)sapio_u01(r[2]) * (double)(hi - 10)));
+            w->d_vel[2 * d] = w->d_vel[2 * d + 1] = 0.f; w->d_ang[d] = w->d_angvel[d] = 0.f;
+            w->d_vbias[2 * d] = w->d_vbias[2 * d + 1] = 0.f; w->d_wbias[d] = 0.f;
+            w->d_mass[d] = w->d_mass0[d] = 12.f; w->d_size[d] = 30.f; w->d_elast[d] = w->d_fric[d] = 0.5f; w->d_owner[d] = -1; w->d_eaten[d] = 0.f;
+        }
+    }
     return 0;
 }

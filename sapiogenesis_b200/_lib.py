@@ -51,7 +51,7 @@ def load() -> ctypes.CDLL:
     L.sapio_unpack_organisms.argtypes = [wp, vp, i32, vp, sz, vp]; L.sapio_unpack_organisms.restype = i32
     L.sapio_release_organisms.argtypes = [wp, vp, i32, vp]; L.sapio_release_organisms.restype = i32
     f32 = ctypes.c_float
-    L.sapio_events.argtypes = [wp, vp, sz, f32, f32, vp]; L.sapio_events.restype = i32
+    L.sapio_events.argtypes = [wp, vp, sz, f32, f32, f32, vp]; L.sapio_events.restype = i32
     L.sapio_tick_host.argtypes = [wp, vp, sz, u32, i32, vp, vp, vp, i32, vp, i32, vp]; L.sapio_tick_host.restype = i32
     L.sapio_tick_host_begin.argtypes = [wp, vp, sz, u32, i32, vp, vp, vp, i32, vp, i32, vp]; L.sapio_tick_host_begin.restype = i32
     L.sapio_tick_host_end.argtypes = []; L.sapio_tick_host_end.restype = i32

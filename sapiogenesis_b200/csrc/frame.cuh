@@ -4,6 +4,7 @@
 //        (Sprite.setPos / setRotation, physics.py:253-272)
 #pragma once
 #include "common.cuh"
+#include "rng.cuh"
 
 struct FrameWs { SapioControl *control; SapioFrameHeader *header; float4 *cells; float4 *dead; int *counts; };
 
@@ -19,6 +20,33 @@ __global__ void __launch_bounds__(256) k_events(WORLD_ARG, const SapioControl *_
         }
     }
     if (gtid == 0 && drought != 0.f) { w.g_o2[0] -= (double)drought; w.g_co2[0] -= (double)drought; }   // Sapiogenesis.py:38-41
+}
+
+// random dead cell event (Sapiogenesis.py:48-53): with probability `random_cells` one piece of food (add_dead_clicked,
+// Sapiogenesis.py:490-507) appears at (randrange(10, int(width)), randrange(10, int(height))), in the lowest free dead slot
+__global__ void __launch_bounds__(256) k_event_food(WORLD_ARG, const SapioControl *__restrict__ ctl) {
+    const float rate = ctl->random_cells;
+    if (!(rate > 0.f)) return;
+    uint32_t r[4];
+    rng4(w.p.seed, -1, (int32_t)w.g_tick[0], RNG_EVENTS, 0, r);
+    if (!(u01(r[0]) <= rate)) return;
+    __shared__ int s_free;
+    if (threadIdx.x == 0) s_free = 1 << 30;
+    __syncthreads();
+    for (int d = threadIdx.x; d < w.p.n_dead; d += blockDim.x) {
+        if (d >= s_free) break;
+        if (w.d_state[d] == 0) { atomicMin(&s_free, d); break; }
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    const int d = s_free;
+    if (d >= w.p.n_dead) { stat_add(w, SAPIO_STAT_OVERFLOW, 1); return; }
+    const int wi = (int)w.p.width, hi = (int)w.p.height;
+    const float x = (float)(10 + (int)floor((double)u01(r[1]) * (double)(wi - 10))), y = (float)(10 + (int)floor((double)u01(r[2]) * (double)(hi - 10)));
+    w.d_state[d] = 2;
+    w.d_pos[2 * d] = x; w.d_pos[2 * d + 1] = y; w.d_vel[2 * d] = 0.f; w.d_vel[2 * d + 1] = 0.f;
+    w.d_ang[d] = 0.f; w.d_angvel[d] = 0.f; w.d_vbias[2 * d] = 0.f; w.d_vbias[2 * d + 1] = 0.f; w.d_wbias[d] = 0.f;
+    w.d_mass[d] = 12.f; w.d_mass0[d] = 12.f; w.d_size[d] = 30.f; w.d_elast[d] = 0.5f; w.d_fric[d] = 0.5f; w.d_owner[d] = -1; w.d_eaten[d] = 0.f;
 }
 
 // packed poses: (x, y, angle, organism slot) per living cell, (x, y, angle, mass) per dead cell; order is unspecified

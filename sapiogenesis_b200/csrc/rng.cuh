@@ -15,7 +15,8 @@ enum {
     RNG_WEIGHT_FILL = 7,  // torch.rand rows of mutate_brain_layers    sprites.py:1041
     RNG_SYNTH = 8,        // synthetic world placement
     RNG_GENOME_INIT = 9,  // nn.Linear init of the tempNet in _setup_brain_structure  sprites.py:868
-    RNG_WEIGHT_GARBAGE = 10 // uninitialised tail of resize_()d rows   sprites.py:1039
+    RNG_WEIGHT_GARBAGE = 10, // uninitialised tail of resize_()d rows  sprites.py:1039
+    RNG_EVENTS = 11       // random dead cell event: gate, x, y (uid -1) Sapiogenesis.py:48-53
 };
 
 __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {

@@ -244,7 +244,7 @@ static int launch_tick(const SapioWorld &w, AllWs &A, uint32_t phases, const Sap
     }
     if (phases & SAPIO_PH_STEP) { rc = launch_space_step(w, A.step, st, g_err, sizeof(g_err)); if (rc) return rc; }
     if (phases & SAPIO_PH_FRICTION) { prof_mark(st, PT_FRICTION); k_friction<<<stream_grid(nb), 256, 0, st>>>(w); LAUNCHES(1); }
-    if (d_control) { k_events<<<stream_grid(nb), 256, 0, st>>>(w, d_control); LAUNCHES(1); }
+    if (d_control) { k_events<<<stream_grid(nb), 256, 0, st>>>(w, d_control); k_event_food<<<1, 256, 0, st>>>(w, d_control); LAUNCHES(2); }
     return launch_post(w, A, st, (phases & SAPIO_PH_POST) ? 1 : 0, 1);
 }
 
@@ -357,14 +357,15 @@ int sapio_tick(const SapioWorld *w, void *ws, size_t ws_bytes, uint32_t phases, 
     return 0;
 }
 
-int sapio_events(const SapioWorld *w, void *ws, size_t ws_bytes, float drought, float poison, void *stream) {
+int sapio_events(const SapioWorld *w, void *ws, size_t ws_bytes, float drought, float poison, float random_cells, void *stream) {
     AllWs A; int rc = check(w, ws, ws_bytes, &A); if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    SapioControl c = {drought, poison, {0, 0}};
+    SapioControl c = {drought, poison, random_cells, 0};
     CUDA_TRY(cudaMemcpyAsync(A.frame.control, &c, sizeof(c), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaStreamSynchronize(st));                       // `c` lives on this stack frame
     k_events<<<stream_grid((long)w->p.n_org * MAXC), 256, 0, st>>>(*w, A.frame.control);
-    LAUNCHES(1);
+    k_event_food<<<1, 256, 0, st>>>(*w, A.frame.control);
+    LAUNCHES(2);
     LAUNCH_CHECK();
     return 0;
 }
@@ -380,7 +381,7 @@ int sapio_tick_host(const SapioWorld *w, void *ws, size_t ws_bytes, uint32_t pha
     CUDA_TRY(cudaMemcpyAsync(A.frame.control, h_control, sizeof(SapioControl), cudaMemcpyHostToDevice, st));
     for (int t = 0; t < n_ticks; t++) {
         if ((rc = launch_tick(*w, A, phases, A.frame.control, st))) return rc;
-        if (phases & SAPIO_PH_STEP) phases |= SAPIO_PH_REUSE_GRID;
+        if ((phases & SAPIO_PH_STEP) && !(h_control->random_cells > 0.f)) phases |= SAPIO_PH_REUSE_GRID;      // event food is not in the step's grid
     }
     prof_mark(st, PT_FRAME);
     CUDA_TRY(cudaMemsetAsync(A.frame.counts, 0, 256, st));
@@ -476,7 +477,7 @@ int sapio_tick_host_begin(const SapioWorld *w, void *ws, size_t ws_bytes, uint32
     CUDA_TRY(cudaMemcpyAsync(A.frame.control, h_control, sizeof(SapioControl), cudaMemcpyHostToDevice, st));
     for (int t = 0; t < n_ticks; t++) {
         if ((rc = launch_tick(*w, A, phases, A.frame.control, st))) return rc;
-        if (phases & SAPIO_PH_STEP) phases |= SAPIO_PH_REUSE_GRID;
+        if ((phases & SAPIO_PH_STEP) && !(h_control->random_cells > 0.f)) phases |= SAPIO_PH_REUSE_GRID;      // event food is not in the step's grid
     }
     prof_mark(st, PT_FRAME);
     CUDA_TRY(cudaMemsetAsync(F.counts, 0, 256, st));

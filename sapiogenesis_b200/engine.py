@@ -161,10 +161,12 @@ class Engine:
         n = int(cnt.item())
         return out[:min(n, cap)].cpu().numpy().astype("uint32")
 
-    def events(self, drought: float = 0.0, poison: float = 0.0):
-        """updateUI's world events (Sapiogenesis.py:37-47), amounts = severity * uDiff."""
+    def events(self, drought: float = 0.0, poison: float = 0.0, random_cells: float = 0.0):
+        """updateUI's world events (Sapiogenesis.py:37-53): drought / poison amounts and the random-food probability, each = severity * uDiff."""
         with torch.cuda.device(self.world.device):
-            _lib.check(self.lib.sapio_events(self._ref(), *self._ws, drought, poison, self._stream_ptr()), "sapio_events")
+            _lib.check(self.lib.sapio_events(self._ref(), *self._ws, drought, poison, random_cells, self._stream_ptr()), "sapio_events")
+        if random_cells:
+            self._grid_valid = False
 
     # -- end-to-end path: host buffers in, host buffers out (what a GUI host does every frame) ------------------
     def _new_host_buffers(self):
@@ -191,14 +193,14 @@ class Engine:
         return hdr, hb["cells"][:hdr["n_cells"]], hb["dead"][:hdr["n_dead"]], (16, 168 + 16 * (hdr["n_cells"] + hdr["n_dead"]))
 
     # pipelined form: begin(k + 1) may be called before end(k); frames come back in order, each in its own pinned buffers
-    def tick_host_begin(self, n: int = 1, phases: int = PH_ALL, drought: float = 0.0, poison: float = 0.0):
+    def tick_host_begin(self, n: int = 1, phases: int = PH_ALL, drought: float = 0.0, poison: float = 0.0, random_cells: float = 0.0):
         self._seq = getattr(self, "_seq", 0)
         self._inflight = getattr(self, "_inflight", [])
         hb = self._host_buffers(self._seq & 1)
         self._seq += 1
-        hb["control"][0], hb["control"][1] = drought, poison
+        hb["control"][0], hb["control"][1], hb["control"][2] = drought, poison, random_cells
         ph = phases | (PH_REUSE_GRID if (self.exclusive and self._grid_valid and (phases & PH_THINK)) else 0)
-        self._grid_valid = bool(phases & PH_STEP) if n > 0 else self._grid_valid
+        self._grid_valid = (bool(phases & PH_STEP) and not random_cells) if n > 0 else self._grid_valid
         with torch.cuda.device(self.world.device):
             _lib.check(self.lib.sapio_tick_host_begin(
                 self._ref(), *self._ws, ph, n, ctypes.c_void_p(hb["control"].data_ptr()), ctypes.c_void_p(hb["header"].data_ptr()),
@@ -213,13 +215,13 @@ class Engine:
             _lib.check(self.lib.sapio_tick_host_end(), "sapio_tick_host_end")
         return self._parse_frame(hb)
 
-    def tick_host(self, n: int = 1, phases: int = PH_ALL, drought: float = 0.0, poison: float = 0.0):
+    def tick_host(self, n: int = 1, phases: int = PH_ALL, drought: float = 0.0, poison: float = 0.0, random_cells: float = 0.0):
         """n ticks through sapio_tick_host: uploads the event block from pinned host memory, downloads the frame
         (counters + packed sprite poses) into pinned host memory. Returns (header dict, cells [n,4], dead [m,4], bytes)."""
         hb = self._host_buffers()
-        hb["control"][0], hb["control"][1] = drought, poison
+        hb["control"][0], hb["control"][1], hb["control"][2] = drought, poison, random_cells
         ph = phases | (PH_REUSE_GRID if (self.exclusive and self._grid_valid and (phases & PH_THINK)) else 0)
-        self._grid_valid = bool(phases & PH_STEP) if n > 0 else self._grid_valid
+        self._grid_valid = (bool(phases & PH_STEP) and not random_cells) if n > 0 else self._grid_valid
         with torch.cuda.device(self.world.device):
             _lib.check(self.lib.sapio_tick_host(
                 self._ref(), *self._ws, ph, n, ctypes.c_void_p(hb["control"].data_ptr()), ctypes.c_void_p(hb["header"].data_ptr()),

@@ -26,6 +26,7 @@ def main(argv=None):
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--drought", type=float, default=0.0, help="severity of the drought event (Sapiogenesis.py:37-41)")
     ap.add_argument("--poison", type=float, default=0.0, help="severity of the poison event (Sapiogenesis.py:42-47)")
+    ap.add_argument("--random-cells", type=float, default=0.0, help="severity of the random dead cell event (Sapiogenesis.py:48-53)")
     ap.add_argument("--dump", default=None, help="write the last frame and the report series to this .npz")
     args = ap.parse_args(argv)
 
@@ -47,14 +48,15 @@ def main(argv=None):
     series, done, t0 = [], 0, time.perf_counter()
     while done < args.ticks:
         run = min(args.every, args.ticks - done)
-        if env is not None and not (args.drought or args.poison):
+        ev = dict(drought=args.drought * dt, poison=args.poison * dt, random_cells=args.random_cells * dt)
+        if env is not None and not any(ev.values()):
             for _ in range(run):
                 env.update(None)
             frame = None
         else:
             for _ in range(run - 1):
-                engine.tick_host(1, drought=args.drought * dt, poison=args.poison * dt) if (args.drought or args.poison) else engine.tick(1)
-            frame = engine.tick_host(1, drought=args.drought * dt, poison=args.poison * dt)
+                engine.tick_host(1, **ev) if any(ev.values()) else engine.tick(1)
+            frame = engine.tick_host(1, **ev)
         done += run
         engine.synchronize()
         st = world.stats()

@@ -181,3 +181,29 @@ def test_pipelined_host_frames_equal_the_synchronous_ones(oracle):
         assert hr == hg
         assert torch.equal(key(cr), key(cg)) and torch.equal(key(dr), key(dg))
     assert ref[-1][0]["tick"] == w.tick + 6 and ref[-1][0]["n_cells"] > 0
+
+
+def test_world_events_match_oracle(oracle):
+    """updateUI's events (Sapiogenesis.py:37-53): drought, poison and the random dead cell, as a stage and inside the host tick."""
+    w = fast_world(oracle, 12, 51, 0.6, 30)
+    assert oracle.tick(w, PH_ALL, 3) == 0
+    born = 0
+    for k in range(12):
+        wg, eng = engine_for(w)
+        d0 = int((w.np("d_state") > 0).sum())
+        eng.events(drought=0.4, poison=0.02, random_cells=0.6); eng.synchronize()
+        assert oracle.events(w, 0.4, 0.02, 0.6) == 0
+        compare_worlds(wg, w, f"events at tick {w.tick}", verbose=False)
+        born += int((w.np("d_state") > 0).sum()) - d0
+        assert oracle.tick(w, PH_ALL, 1) == 0
+    assert 3 <= born <= 11                                   # probability 0.6 per tick
+    fresh = np.nonzero(w.np("d_size") == 30.0)[0]
+    assert len(fresh) >= born and (w.np("d_pos")[fresh] >= 10).all()
+    # inside the tick with host buffers: same effect as tick + events
+    wg, eng = engine_for(w)
+    eng.tick_host(1, PH_ALL, drought=0.3, poison=0.01, random_cells=1.0)
+    for stage in (lambda: oracle.rules(w, PH_ALL), lambda: oracle.train(w), lambda: oracle.settle(w), lambda: oracle.reproduce(w),
+                  lambda: oracle.space_step(w), lambda: oracle.friction(w), lambda: oracle.events(w, 0.3, 0.01, 1.0), lambda: oracle.post(w)):
+        assert stage() == 0                                  # the events sit between friction and the end-of-tick bookkeeping
+    w.t["g_tick"] += 1
+    compare_worlds(wg, w, "tick_host with events", verbose=False)
