@@ -41,6 +41,9 @@ __device__ __forceinline__ int tri_f(int m) { return ((m + 1) >> 1) * ((m >> 1) 
 // first slot of wavefront t (pairs i + j == t) for n cells
 __device__ __forceinline__ int wf_off(int t, int n) { return t <= n ? tri_f(t - 1) : n * (n - 1) / 2 - tri_f(2 * n - 2 - t); }
 
+// the cross contacts of the step as seen from a body (its adjacency), for the warm start of coupled organisms
+struct CrossView { const int *off_all; const int *adj_c; const uint64_t *key; const float2 *n; const float *jn, *jt; int nx; };
+
 template <int CM, int G, bool GC = false>
 struct OrgCtx {
     typedef OrgS<CM, GC> S;
@@ -292,15 +295,22 @@ struct OrgCtx {
                         const float vbn = (bbv.x - ba.x) * nx + (bbv.y - ba.y) * ny;
                         const float vrn = dvx * nx + dvy * ny;
                         const float vrt = (dvy * nx - dvx * ny) - bbv.w * vb.z - ba.w * va.z;
+                        // accumulate and clamp in double, apply the difference: a resting contact squeezed between pinned cells carries
+                        // 1e5 of impulse, and ulp(1e5) = 0.008 in fp32 would quantise what a sweep can add to it
                         const float jbnOld = s.cjb[c], jBias = fmaxf(jbnOld + (s.cbias[c] - vbn) * nMass, 0.0f);
-                        const float jnOld = s.cjn[c], jnAcc = fmaxf(jnOld + -(s.cbo[c] + vrn) * nMass, 0.0f);
-                        const float jtMax = s.cmu[c] * jnAcc;
-                        const float jtOld = s.cjt[c], jtAcc = fminf(fmaxf(jtOld + -vrt * tMass, -jtMax), jtMax);
-                        s.cjb[c] = jBias; s.cjn[c] = jnAcc; s.cjt[c] = jtAcc;
+                        const float jnO = s.cjn[c], jtO = s.cjt[c], jnI = -(s.cbo[c] + vrn) * nMass, jtI = -vrt * tMass, mu = s.cmu[c];
+                        float dn, dtg;
+                        if (fabsf(jnO) < 256.f && fabsf(jtO) < 256.f) {           // ordinary contact: fp32 resolves its accumulators to 3e-5
+                            const float jnA = fmaxf(jnO + jnI, 0.0f), jtM = mu * jnA, jtA = fminf(fmaxf(jtO + jtI, -jtM), jtM);
+                            s.cjn[c] = jnA; s.cjt[c] = jtA; dn = jnA - jnO; dtg = jtA - jtO;
+                        } else {
+                            const double jnA = fmax((double)jnO + (double)jnI, 0.0), jtM = (double)mu * jnA, jtA = fmin(fmax((double)jtO + (double)jtI, -jtM), jtM);
+                            s.cjn[c] = (float)jnA; s.cjt[c] = (float)jtA; dn = (float)(jnA - (double)jnO); dtg = (float)(jtA - (double)jtO);
+                        }
+                        s.cjb[c] = jBias;
                         const float bj = jBias - jbnOld;
                         ba.x -= nx * bj * va.w; ba.y -= ny * bj * va.w;
                         bbv.x += nx * bj * vb.w; bbv.y += ny * bj * vb.w;
-                        const float dn = jnAcc - jnOld, dtg = jtAcc - jtOld;
                         const float jx = nx * dn - ny * dtg, jy = nx * dtg + ny * dn;
                         va.x -= jx * va.w; va.y -= jy * va.w; va.z -= ba.z * dtg;
                         vb.x += jx * vb.w; vb.y += jy * vb.w; vb.z -= bbv.z * dtg;
@@ -313,6 +323,97 @@ struct OrgCtx {
             }
             __syncwarp();
         }
+    }
+
+    // Warm start (cpArbiterApplyCachedImpulse, cached pin impulses), exact. Cached impulses do not depend on the velocities, so
+    // their order is immaterial -- and they must not be applied one by one in fp32: the n(n-1)/2 pins of an organism are redundant,
+    // their cached impulses drift in the null space (1e4..1e5 after a few hundred ticks) and cancel to a few px/s; a dead cell
+    // wedged between pinned cells carries contact impulses of 1e5. Every lane sums, in double, everything its cells receive
+    // (pins, intra contacts, the sensor pin, and for a coupled organism its cross contacts) and applies the sum once.
+    __device__ void warm_start(float dt_coef, const CrossView *X) {
+        const double dt = (double)dt_coef;
+        // pins of the lane's two cells in one loop: two independent chains of loads and double FMAs
+        double pax[2] = {0.0, 0.0}, pay[2] = {0.0, 0.0};
+        {
+            const int r0 = sl, r1 = sl + G;
+            const bool v1 = r1 < n;
+            if (r0 < n) {
+                int off0 = r0 >= 1 ? wf_off(r0, n) : 0, off1 = v1 ? wf_off(r1, n) : 0;     // first slot of wavefront t = r + j, kept incrementally
+#pragma unroll 4
+                for (int j = 0; j < n; j++) {
+                    {
+                        const int t = r0 + j, imin = max(0, t - (n - 1));
+                        if (j != r0) {
+                            const int q = off0 + min(r0, j) - imin;
+                            float nx, ny, jn;
+                            if (GC) { const float4 c4 = __ldcg(&cst[q]); nx = c4.x; ny = c4.y; jn = s.jn[q]; }
+                            else { const float4 pr = s.pair[q]; nx = pr.x; ny = pr.y; jn = pr.w; }
+                            const double imp = (r0 < j ? -dt : dt) * (double)jn;                 // body a of a pin gets -n j, body b +n j
+                            pax[0] = fma((double)nx, imp, pax[0]); pay[0] = fma((double)ny, imp, pay[0]);
+                        }
+                        off0 += max(((t - 1) >> 1) - imin + 1, 0);
+                    }
+                    if (v1) {
+                        const int t = r1 + j, imin = max(0, t - (n - 1));
+                        if (j != r1) {
+                            const int q = off1 + min(r1, j) - imin;
+                            float nx, ny, jn;
+                            if (GC) { const float4 c4 = __ldcg(&cst[q]); nx = c4.x; ny = c4.y; jn = s.jn[q]; }
+                            else { const float4 pr = s.pair[q]; nx = pr.x; ny = pr.y; jn = pr.w; }
+                            const double imp = (r1 < j ? -dt : dt) * (double)jn;
+                            pax[1] = fma((double)nx, imp, pax[1]); pay[1] = fma((double)ny, imp, pay[1]);
+                        }
+                        off1 += max(((t - 1) >> 1) - imin + 1, 0);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int r = sl + G * h;
+            if (r < n) {
+                double ax = pax[h], ay = pay[h], at = 0.0;         // linear impulse received; tangential impulses (both bodies: w -= r/I * jt)
+                const int nic = s.nic;
+                for (int c = 0; c < nic; c++) {
+                    const int a = s.ca[c], b = s.cbk[c];
+                    if (a != r && b != r) continue;
+                    const double jn = (double)s.cjn[c] * dt, jt = (double)s.cjt[c] * dt, nx = (double)s.cnx[c], ny = (double)s.cny[c];
+                    const double jx = nx * jn - ny * jt, jy = nx * jt + ny * jn;
+                    if (a == r) { ax -= jx; ay -= jy; } else { ax += jx; ay += jy; }
+                    at += jt;
+                }
+                if (X) {
+                    const uint32_t row = (uint32_t)(o * MAXC + s.row_of[r]);
+                    for (int q = X->off_all[row], e = X->off_all[row + 1]; q < e; q++) {
+                        const int c = X->adj_c[q];
+                        if (c < 0 || c >= X->nx) continue;
+                        const float2 nn = X->n[c];
+                        const double jn = (double)X->jn[c] * dt, jt = (double)X->jt[c] * dt, nx = (double)nn.x, ny = (double)nn.y;
+                        const double jx = nx * jn - ny * jt, jy = nx * jt + ny * jn;
+                        if ((uint32_t)(X->key[c] >> 32) == row) { ax -= jx; ay -= jy; } else { ax += jx; ay += jy; }
+                        at += jt;
+                    }
+                }
+                if ((sens >> r) & 1ull) {                            // sensor pin: the cell is its body b, the sensor body (mass 1) its body a
+                    const float4 sp = s.spin[r];
+                    const double jn = (double)sp.w * dt;
+                    ax = fma((double)sp.x, jn, ax); ay = fma((double)sp.y, jn, ay);
+                    const float2 vs = s.sv[r];
+                    s.sv[r] = make_float2((float)((double)vs.x - (double)sp.x * jn), (float)((double)vs.y - (double)sp.y * jn));
+                }
+                const float4 v = s.vm[r];
+                s.vm[r] = make_float4((float)fma(ax, (double)v.w, (double)v.x), (float)fma(ay, (double)v.w, (double)v.y),
+                                      (float)((double)v.z - (double)s.bb[r].z * at), v.w);
+            }
+        }
+        __syncwarp();
+        zero_pin_acc();
+    }
+    // from here on the pin accumulators hold what this step adds (store_vel adds it to the cached impulse in global memory)
+    __device__ void zero_pin_acc() {
+        const int NPn = n * (n - 1) / 2;
+        for (int q = sl; q < NPn; q += G) { if (GC) s.jn[q] = 0.f; else s.pair[q].w = 0.f; }
+        __syncwarp();
     }
 
     // cpPinJoint.c with anchors at the centres: sensor pins (sensor body -> cell, rest 0), then all pairs (i<j) in
@@ -418,9 +519,20 @@ struct OrgCtx {
         if (!pins) return;
         float *gj = w.j_jn + (size_t)max(o, 0) * SAPIO_NPAIR;
         const int NPn = n * (n - 1) / 2;
-        for (int pidx = sl; pidx < NPn; pidx += G) {
-            int i, j; pair_of(pidx, n, i, j);
-            gj[pair_index(s.row_of[i], s.row_of[j])] = GC ? s.jn[slot_of(i, j)] : s.pair[slot_of(i, j)].w;
+        for (int base = 0; base < NPn; base += 4 * G) {          // cached impulse + what this step added; four loads in flight per lane
+            float *dst[4]; float old[4], add[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int pidx = base + sl + G * u;
+                dst[u] = nullptr; old[u] = 0.f; add[u] = 0.f;
+                if (pidx < NPn) {
+                    int i, j; pair_of(pidx, n, i, j);
+                    dst[u] = &gj[pair_index(s.row_of[i], s.row_of[j])]; old[u] = *dst[u];
+                    add[u] = GC ? s.jn[slot_of(i, j)] : s.pair[slot_of(i, j)].w;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) if (dst[u]) *dst[u] = (float)((double)old[u] + (double)add[u]);
         }
     }
     __device__ void store_contacts(float *ws_bounce, float *ws_jbias) {
@@ -514,7 +626,8 @@ __global__ void __launch_bounds__(OrgCfg<CM>::WARPS * 32) k_org_solve(WORLD_ARG,
         c.schedule();
         c.template prestep_contacts<true>();
         const int nsteps_max = OrgCtx<CM, G, GC>::wmax(s.nsteps), tmax = 2 * OrgCtx<CM, G, GC>::wmax(c.n) - 3;
-        if (dt_coef != 0.f) { c.template contacts_pass<true>(dt_coef, nsteps_max); c.template joints_pass<true>(dt_coef, tmax); }
+        if (dt_coef != 0.f) c.warm_start(dt_coef, nullptr);
+        else c.zero_pin_acc();
         for (int it = 0; it < iterations; it++) { c.template contacts_pass<false>(0.f, nsteps_max); c.template joints_pass<false>(0.f, tmax); }
         if (c.o >= 0) { c.store_vel(); c.store_contacts(nullptr, nullptr); if (c.sl == 0) nic_sum += s.nic; }
         __syncwarp();

@@ -41,6 +41,7 @@ struct Workspace {
     float2 *nx_n;                   // contact normal (a -> b)
     int *nx_level, *nx_prev_a, *nx_prev_b;
     uint32_t *adj_other;            // adjacency: partner body id per entry [2*x_cap]
+    int *adj_c;                     // contact index of every adjacency entry [2*x_cap]
     uint32_t *adj_tmp;              // partner runs in discovery order [2*x_cap]
     int2 *hit_list;                 // (body, start of its run) [2*x_cap]
     uint8_t *org_coupled;           // [n_org]
@@ -82,6 +83,7 @@ static size_t carve_workspace(const SapioParams &p, char *base, Workspace *W) {
     W->nx_bias = (float *)take(XC * 4); W->nx_n = (float2 *)take(XC * 8);
     W->nx_level = (int *)take(XC * 4); W->nx_prev_a = (int *)take(XC * 4); W->nx_prev_b = (int *)take(XC * 4);
     W->adj_other = (uint32_t *)take(2 * XC * 4);
+    W->adj_c = (int *)take(2 * XC * 4);
     W->adj_tmp = (uint32_t *)take(2 * XC * 4);
     W->hit_list = (int2 *)take(2 * XC * 8);
     W->org_coupled = (uint8_t *)take((size_t)p.n_org);
@@ -226,15 +228,15 @@ __device__ __forceinline__ void contact_apply(CBody &A, CBody &B, float nx, floa
     float vrt = (dvy * nx - dvx * ny) - B.r * B.w - A.r * A.w;
     float jbn = (bias - vbn) * nMass, jbnOld = jBias;
     jBias = fmaxf(jbnOld + jbn, 0.0f);
-    float jn = -(bounce + vrn) * nMass, jnOld = jnAcc;
-    jnAcc = fmaxf(jnOld + jn, 0.0f);
-    float jtMax = mu * jnAcc;
-    float jt = -vrt * tMass, jtOld = jtAcc;
-    jtAcc = fminf(fmaxf(jtOld + jt, -jtMax), jtMax);
+    // accumulate and clamp in double, apply the difference (see OrgCtx::contacts_pass)
+    const double jnOld = (double)jnAcc, jnNew = fmax(jnOld + (double)(-(bounce + vrn) * nMass), 0.0);
+    const double jtMax = (double)mu * jnNew;
+    const double jtOld = (double)jtAcc, jtNew = fmin(fmax(jtOld + (double)(-vrt * tMass), -jtMax), jtMax);
+    jnAcc = (float)jnNew; jtAcc = (float)jtNew;
     float bj = jBias - jbnOld;
     A.vbx -= nx * bj * A.minv; A.vby -= ny * bj * A.minv;
     B.vbx += nx * bj * B.minv; B.vby += ny * bj * B.minv;
-    float dn = jnAcc - jnOld, dtg = jtAcc - jtOld;
+    float dn = (float)(jnNew - jnOld), dtg = (float)(jtNew - jtOld);
     float jx = nx * dn - ny * dtg, jy = nx * dtg + ny * dn;
     A.vx -= jx * A.minv; A.vy -= jy * A.minv; A.w -= A.iinv * A.r * dtg;
     B.vx += jx * B.minv; B.vy += jy * B.minv; B.w -= B.iinv * B.r * dtg;
@@ -299,6 +301,7 @@ __global__ void __launch_bounds__(128) k_cross_links(WORLD_ARG, Workspace W) {
                 while (lo < hi) { int mid = (lo + hi) >> 1; if (W.nx_key[mid] < key) lo = mid + 1; else hi = mid; }
                 c = lo;
             }
+            W.adj_c[q] = c < nx ? c : -1;
             if (c < nx) { if (y > (uint32_t)b) W.nx_prev_a[c] = prev; else W.nx_prev_b[c] = prev; }
             prev = c;
         }
@@ -365,6 +368,37 @@ __device__ __forceinline__ void cross_level_pass(const SapioWorld &w, const Work
     }
 }
 
+// Warm start of the cross contacts (cpArbiterApplyCachedImpulse), exact: cached impulses do not depend on the velocities, so every
+// body receives the sum of its contacts' impulses at once, summed in double (OrgCtx::warm_start has the reasons). Dead cells are
+// done here, one thread per dead body with partners; living cells get theirs inside their organism's warm start (CrossView).
+__device__ __forceinline__ CrossView cross_view(const Workspace &W) {
+    return CrossView{W.off_all, W.adj_c, W.nx_key, W.nx_n, W.nx_jn, W.nx_jt, W.flags[FL_NX]};
+}
+__device__ __forceinline__ void cross_warm_dead(const SapioWorld &w, const Workspace &W, float dt_coef, int tid, int nthreads) {
+    const int NC = w.p.n_org * MAXC, ND = w.p.n_dead, nx = W.flags[FL_NX];
+    const int nh = min(W.flags[FL_NHIT], 2 * w.p.x_cap);
+    const double dt = (double)dt_coef;
+    for (int h = tid; h < nh; h += nthreads) {
+        const uint32_t body = (uint32_t)W.hit_list[h].x;
+        if ((int)body < NC || (int)body >= NC + ND) continue;
+        const int d = (int)body - NC;
+        double ax = 0.0, ay = 0.0, at = 0.0;
+        for (int q = W.off_all[body], e = W.off_all[body + 1]; q < e; q++) {
+            const int c = W.adj_c[q];
+            if (c < 0 || c >= nx) continue;
+            const float2 nn = W.nx_n[c];
+            const double jn = (double)W.nx_jn[c] * dt, jt = (double)W.nx_jt[c] * dt, nxx = (double)nn.x, nyy = (double)nn.y;
+            const double jx = nxx * jn - nyy * jt, jy = nxx * jt + nyy * jn;
+            if ((uint32_t)(W.nx_key[c] >> 32) == body) { ax -= jx; ay -= jy; } else { ax += jx; ay += jy; }
+            at += jt;
+        }
+        const float r = w.d_size[d] * 0.5f, minv = 1.0f / w.d_mass[d], iinv = 1.0f / (0.5f * w.d_mass0[d] * r * r);
+        float2 v = reinterpret_cast<const float2 *>(w.d_vel)[d];
+        reinterpret_cast<float2 *>(w.d_vel)[d] = make_float2((float)fma(ax, (double)minv, (double)v.x), (float)fma(ay, (double)minv, (double)v.y));
+        w.d_angvel[d] = (float)((double)w.d_angvel[d] - (double)(iinv * r) * at);
+    }
+}
+
 // Coupled organisms go through the same lane-packed, size-classed solver as the others, one pass at a time between the grid
 // barriers. A warp owns a slab of shared memory that holds one warp-item of any class up to 48 rows (8/4/2/2/1/1 organisms);
 // the two largest classes take two adjacent slabs (even warps only, in their own sub-phase).
@@ -390,6 +424,7 @@ __device__ void coupled_item(const SapioWorld &w, const Workspace &W, const Step
     OrgS<CM> *g = (o >= 0 && idx < W.cp_cap) ? reinterpret_cast<OrgS<CM> *>(W.cp_state + (size_t)idx * COUPLED_STATE_BYTES) : nullptr;
     if (kind == CP_STAGE_A) {   // detect the intra contacts and take their bounce before any velocity changes; park the pre-stepped state
         c.load(); c.prestep_pairs(); c.match_prev(); c.schedule(); c.template prestep_contacts<true>();
+        if (dt_coef == 0.f) c.zero_pin_acc();                                     // no warm start will consume the cached pin impulses
         if (o >= 0) {
             c.store_contacts(W.ic_bounce, W.ic_jbias);
             if (g) c.save_static(g);
@@ -401,10 +436,10 @@ __device__ void coupled_item(const SapioWorld &w, const Workspace &W, const Step
     const bool use_park = __all_sync(FULL, o < 0 || g != nullptr);                // warp-uniform: the two paths are collective
     c.load();
     if (use_park) c.restore_static(g);
-    else { c.prestep_pairs(); c.schedule(); c.template prestep_contacts<false>(); }
+    else { c.prestep_pairs(); c.schedule(); c.template prestep_contacts<false>(); if (kind != CP_WARM) c.zero_pin_acc(); }   // the cached total stays in global memory
     c.load_contact_state(W.ic_bounce, W.ic_jbias);
     const int nsteps_max = Ctx::wmax(s.nsteps), tmax = 2 * Ctx::wmax(c.n) - 3;
-    if (kind == CP_WARM) { c.template contacts_pass<true>(dt_coef, nsteps_max); c.template joints_pass<true>(dt_coef, tmax); }
+    if (kind == CP_WARM) { const CrossView X = cross_view(W); c.warm_start(dt_coef, &X); }
     else { c.template contacts_pass<false>(0.f, nsteps_max); c.template joints_pass<false>(0.f, tmax); }
     if (o >= 0) {
         c.store_vel(!use_park || kind == CP_LAST);
@@ -471,7 +506,7 @@ __global__ void __launch_bounds__(COUPLED_WARPS * 32) k_coupled(WORLD_ARG, Works
     grid.sync();
     // cached impulses: cross contacts by level, then each coupled organism's own arbiters and constraints
     if (dt_coef != 0.f) {
-        for (int L = 1; L <= maxL; L++) { cross_level_pass<true>(w, W, L, nx, dt_coef, gtid, gthreads); grid.sync(); }
+        cross_warm_dead(w, W, dt_coef, gtid, gthreads);       // disjoint from what the organisms touch: no barrier in between
         org_phase(CP_WARM);
         grid.sync();
     }
@@ -521,6 +556,7 @@ __global__ void __launch_bounds__(SIMPLE_WARPS * 32) k_coupled_simple(WORLD_ARG,
     for (int q = gwarp; q < ncoupled; q += gwarps) {
         Ctx c(s, w, K, W.coupled_list[q]);
         c.load(); c.prestep_pairs(); c.match_prev(); c.schedule(); c.template prestep_contacts<true>();
+        if (dt_coef == 0.f) c.zero_pin_acc();                  // no warm start will consume the cached pin impulses
         c.store_contacts(W.ic_bounce, W.ic_jbias);
         if (OrgS<MAXC> *g = parked(q)) c.save_static(g);
         if (lane_id() == 0) atomicAdd(&W.flags[FL_NIC], s.nic);
@@ -533,9 +569,9 @@ __global__ void __launch_bounds__(SIMPLE_WARPS * 32) k_coupled_simple(WORLD_ARG,
         c.load();
         OrgS<MAXC> *g = parked(q);
         if (g) c.restore_static(g);
-        else { c.prestep_pairs(); c.schedule(); c.template prestep_contacts<false>(); }
+        else { c.prestep_pairs(); c.schedule(); c.template prestep_contacts<false>(); if (!warm) c.zero_pin_acc(); }
         c.load_contact_state(W.ic_bounce, W.ic_jbias);
-        if (warm) { c.template contacts_pass<true>(dt_coef, s.nsteps); c.template joints_pass<true>(dt_coef, 2 * c.n - 3); }
+        if (warm) { const CrossView X = cross_view(W); c.warm_start(dt_coef, &X); }
         else { c.template contacts_pass<false>(0.f, s.nsteps); c.template joints_pass<false>(0.f, 2 * c.n - 3); }
         c.store_vel(!g || last);
         if (g) c.save_pairs(g);
@@ -544,7 +580,7 @@ __global__ void __launch_bounds__(SIMPLE_WARPS * 32) k_coupled_simple(WORLD_ARG,
     };
     // cached impulses: cross contacts by level, then each coupled organism's own arbiters and constraints
     if (dt_coef != 0.f) {
-        for (int L = 1; L <= maxL; L++) { cross_level_pass<true>(w, W, L, nx, dt_coef, gtid, gthreads); grid.sync(); }
+        cross_warm_dead(w, W, dt_coef, gtid, gthreads);       // disjoint from what the organisms touch: no barrier in between
         for (int q = gwarp; q < ncoupled; q += gwarps) org_pass(q, true, false);
         grid.sync();
     }

@@ -127,7 +127,7 @@ def test_imported_organism_lives_on_the_gpu_like_in_the_oracle(oracle):
         wg2 = w.to("cuda"); e2 = Engine(wg2)
         e2.tick(1, PH_ALL); e2.synchronize()
         assert oracle.tick(w, PH_ALL, 1) == 0
-        # this world (seed 13) is one where the fp32 solver leaves up to 6e-5 of a slow field's own rms (dead-cell and sensor-body
-        # velocities next to cells moving at 60 px/s): the import is what is under test here, the solver gets 1e-4
-        compare_worlds(wg2, w, f"imported organism, tick {w.tick}", verbose=False, phys_tol=1e-4)
+        # seed 13 has a dead cell wedged between pinned cells (cached contact impulses of 1e5): the case the exact warm start and the
+        # double accumulators of large contact impulses exist for
+        compare_worlds(wg2, w, f"imported organism, tick {w.tick}", verbose=False)
     assert int(w.np("org_state")[free]) == 1 and int(w.np("org_hist_n")[free]) > int(dna_io.export_dna(w, donor)["generation"]) * 0
