@@ -104,14 +104,16 @@ struct OrgR {
             if (die) { alive[h] = SAPIO_CELL_DYING; health[h] = 0.f; }
             n += __popc(__ballot_sync(FULL, die));
         }
-        if (pk >= 0 && lane == (pk & 31)) { int h = pk >> 5; if (alive[h] == SAPIO_CELL_ALIVE) health[h] -= w.p.break_damage * sz; }
+        if (pk >= 0 && lane == (pk & 31)) {
+            if (pk >> 5) { if (alive[1] == SAPIO_CELL_ALIVE) health[1] -= w.p.break_damage * sz; }
+            else if (alive[0] == SAPIO_CELL_ALIVE) health[0] -= w.p.break_damage * sz;
+        }
         return n;
     }
     // Organism.add_energy (sprites.py:1380-1398): equal shares in row order, overflow carried to the next living cell.
     // The carry is a max-plus recurrence c' = max(0, c + e + share - cap): composed with a warp scan of (A, S) pairs,
     // f(c) = max(A, c + S). Returns the overflow of the last living cell.
-    __device__ float add_energy(float amount) {
-        int n = n_living();
+    __device__ float add_energy(float amount, int n) {
         if (!n) return 0.f;
         float per = amount / (float)n, carry = 0.f;
 #pragma unroll
@@ -133,8 +135,7 @@ struct OrgR {
         return carry;
     }
     // Organism.take_energy (sprites.py:1400-1407)
-    __device__ void take_energy(float amount) {
-        int n = n_living();
+    __device__ void take_energy(float amount, int n) {
         float per = amount / (float)n;
 #pragma unroll
         for (int h = 0; h < 2; h++) if (alive[h] == SAPIO_CELL_ALIVE) energy[h] = fmaxf(energy[h] - per, 0.f);
@@ -165,6 +166,10 @@ __global__ void __launch_bounds__(RULES_WARPS * 32) k_rules_begin(WORLD_ARG, Rul
     for (int o = blockIdx.x * RULES_WARPS + (threadIdx.x >> 5); o < p.n_org; o += warps) {
         if (w.org_state[o] != 1) { if (lane == 0) { R.gas_map[o] = Aff{1.0, 0.0}; w.org_req[o] = 0; } continue; }
         OrgR g; g.load(w, o, false);
+        // exchange rate of a cell (sprites.py:1413-1416), two double divisions: every lane computes its own cells' once, the loop broadcasts
+        double rho2[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) rho2[h] = (double)g.size[h] / ((double)p.width + (double)p.height) * 100.0 * (double)dt / 100.0;
         const bool immortal = w.org_flags[o] & SAPIO_F_IMMORTAL;
         int died = 0, req = 0;
         if (T - w.org_birth_tick[o] >= p.age_ticks && !immortal) died += g.kill(w, 0);          // sprites.py:1826-1827
@@ -176,7 +181,7 @@ __global__ void __launch_bounds__(RULES_WARPS * 32) k_rules_begin(WORLD_ARG, Rul
             if (consumed != 0.f) {
                 float dig = 95.0f / 100.0f * consumed * dt;
                 consumed -= dig;
-                consumed += g.add_energy(dig * 1.2f);
+                consumed += g.add_energy(dig * 1.2f, g.n_living());
             }
             if ((phases & SAPIO_PH_THINK) && w.org_nlayers[o] > 0 && T - w.org_think_tick[o] >= p.think_ticks) {
                 double ddt = (double)(T - w.org_dopa_tick[o]) * (double)dt;                       // _update_brain, sprites.py:1608-1625
@@ -204,7 +209,7 @@ __global__ void __launch_bounds__(RULES_WARPS * 32) k_rules_begin(WORLD_ARG, Rul
                 sim &= ~((((uint64_t)d1 << 32) | d0) | (1ull << k));
                 continue;
             }
-            double rho = (double)bcast2(g.size[0], g.size[1], k) / ((double)p.width + (double)p.height) * 100.0 * (double)dt / 100.0;
+            double rho = __shfl_sync(FULL, (k >> 5) ? rho2[1] : rho2[0], k & 31);
             int tk = bcast2i(g.type[0], g.type[1], k);
             if (tk == SAPIO_T_CO2C) { m.a = (1.0 - rho) * m.a; m.b = (1.0 - rho) * m.b; }         // co2 -> o2
             else { m.a = (1.0 - rho) * m.a; m.b = (1.0 - rho) * m.b + rho * Ttot; }             // o2 -> co2, o2 = Ttot - co2
@@ -214,7 +219,10 @@ __global__ void __launch_bounds__(RULES_WARPS * 32) k_rules_begin(WORLD_ARG, Rul
     }
 }
 
-__global__ void __launch_bounds__(RULES_WARPS * 32) k_rules_main(WORLD_ARG, RulesWs R, uint32_t phases) {
+#ifndef RULES_MAIN_MINB
+#define RULES_MAIN_MINB 4       // resident CTAs per SM the register allocation aims for: the per-cell loop is a dependent shuffle chain, warps in flight hide it
+#endif
+__global__ void __launch_bounds__(RULES_WARPS * 32, RULES_MAIN_MINB) k_rules_main(WORLD_ARG, RulesWs R, uint32_t phases) {
     const SapioParams &p = w.p;
     const int32_t T = (int32_t)w.g_tick[0];
     const float dt = p.dt_wall;
@@ -224,6 +232,9 @@ __global__ void __launch_bounds__(RULES_WARPS * 32) k_rules_main(WORLD_ARG, Rule
     for (int o = blockIdx.x * RULES_WARPS + (threadIdx.x >> 5); o < p.n_org; o += warps) {
         if (w.org_state[o] != 1) { if (lane == 0) w.org_gas_refund[o] = 0.0; continue; }
         OrgR g; g.load(w, o, true);
+        // exchange rate of a cell (sprites.py:1413-1416), two double divisions: every lane computes its own cells' once, the loop broadcasts
+        const double rho_0 = (double)g.size[0] / ((double)p.width + (double)p.height) * 100.0 * (double)dt / 100.0;
+        const double rho_1 = (double)g.size[1] / ((double)p.width + (double)p.height) * 100.0 * (double)dt / 100.0;
         const bool immortal = w.org_flags[o] & SAPIO_F_IMMORTAL;
         Aff pre = o > 0 ? R.gas_scan[o - 1] : Aff{1.0, 0.0};
         double x = pre.a * co2_0 + pre.b, refund = 0.0;                                          // co2 level met by this organism
@@ -249,11 +260,12 @@ __global__ void __launch_bounds__(RULES_WARPS * 32) k_rules_main(WORLD_ARG, Rule
                 lh = g.health_percent(); le = g.energy_percent();
             }
             if (lane == 0) { w.org_last_health[o] = lh; w.org_last_energy[o] = le; }
+            int nliv = g.n_living();                                                             // kept current across kills below
             // Organism.rotation (sprites.py:1179-1201) is only used as an angle: cur - old (the % 360 cancels in cos/sin)
             for (int k = 0; k < g.nc; k++) {                                                     // _update_cell, sprites.py:1470-1606
                 float hk = bcast2(g.health[0], g.health[1], k);
                 int ak = bcast2i(g.alive[0], g.alive[1], k);
-                if (hk <= 0.f && !immortal) { if (ak == SAPIO_CELL_ALIVE) died += g.kill(w, k); continue; }
+                if (hk <= 0.f && !immortal) { if (ak == SAPIO_CELL_ALIVE) { const int nd = g.kill(w, k); died += nd; nliv -= nd; } continue; }
                 if (ak != SAPIO_CELL_ALIVE) continue;
                 const int tk = bcast2i(g.type[0], g.type[1], k), hsel = k >> 5;
                 const bool mine = lane == (k & 31);
@@ -280,34 +292,35 @@ __global__ void __launch_bounds__(RULES_WARPS * 32) k_rules_main(WORLD_ARG, Rule
                             rot = atan2f(ry, rx) - atan2f(w.c_rel[2 * rrow + 1], w.c_rel[2 * rrow]);
                         }
                         float ang = atan2f(mv3, mv2) + rot, speed = mv1 * p.max_push * dt;
-                        if (mine) { g.vx[hsel] += cosf(ang) * speed; g.vy[hsel] += sinf(ang) * speed; }
+                        if (mine) { const float dvx = cosf(ang) * speed, dvy = sinf(ang) * speed; if (hsel) { g.vx[1] += dvx; g.vy[1] += dvy; } else { g.vx[0] += dvx; g.vy[0] += dvy; } }
                         inuse_k = 1;
                     } else inuse_k = 0;
                 }
                 if (tk == SAPIO_T_ROTATE) {                                                      // sprites.py:1546-1552: per tick, not per second
-                    if (mine) g.av[hsel] += mv0 * p.max_rot;
+                    if (mine) { if (hsel) g.av[1] += mv0 * p.max_rot; else g.av[0] += mv0 * p.max_rot; }
                     inuse_k = fabsf(mv0) >= 0.1f;
                 }
-                if (mine) g.inuse[hsel] = inuse_k;
+                if (mine) { if (hsel) g.inuse[1] = inuse_k; else g.inuse[0] = inuse_k; }
                 float idle = bcast2(g.use_idle[0], g.use_idle[1], k), act = bcast2(g.use_act[0], g.use_act[1], k), usage;   // sprites.py:1554-1574
                 if (inuse_k) {
                     if (tk == SAPIO_T_PUSH || tk == SAPIO_T_ROTATE) { float e = (act - idle) * (tk == SAPIO_T_PUSH ? mv1 : mv0); usage = e < 0.f ? fabsf(-idle + e) : idle + e; }
                     else usage = act;
                 } else usage = idle;
-                g.take_energy(usage * dt);
-                double rho = (double)bcast2(g.size[0], g.size[1], k) / ((double)p.width + (double)p.height) * 100.0 * (double)dt / 100.0;
+                g.take_energy(usage * dt, nliv);
+                const double rho = __shfl_sync(FULL, hsel ? rho_1 : rho_0, k & 31);
                 if (tk == SAPIO_T_CO2C) {                                                        // convert_co2, sprites.py:1409-1428 (C4)
                     double gq = rho * x;
                     x -= gq;
-                    float spare = g.add_energy((float)(gq * (double)p.co2_ratio));
+                    float spare = g.add_energy((float)(gq * (double)p.co2_ratio), nliv);
                     refund += (double)spare / (double)p.co2_ratio;
                 } else { double gq = rho * (Ttot - x); x += gq; }                               // convert_o2, sprites.py:1430-1439
                 if (mine) {
-                    float cap = g.storage[hsel], mh = g.maxhealth[hsel], e = g.energy[hsel], hh = g.health[hsel];
+                    // static indices only: a runtime index would move these per-lane arrays from registers to local memory
+                    float cap = hsel ? g.storage[1] : g.storage[0], mh = hsel ? g.maxhealth[1] : g.maxhealth[0], e = hsel ? g.energy[1] : g.energy[0], hh = hsel ? g.health[1] : g.health[0];
                     if (e > cap) e = cap;
                     if (e >= cap / 2 && hh < mh) { hh += p.heal_rate / 100.0f * mh * dt; if (hh > mh) hh = mh; }        // sprites.py:1589-1594
                     if (e <= 2.0f / 100.0f * cap) hh -= p.starvation_rate / 100.0f * mh * dt;                           // sprites.py:1603-1606
-                    g.energy[hsel] = e; g.health[hsel] = hh;
+                    if (hsel) { g.energy[1] = e; g.health[1] = hh; } else { g.energy[0] = e; g.health[0] = hh; }
                 }
             }
             if ((phases & SAPIO_PH_TRAIN) && !(w.org_flags[o] & SAPIO_F_MALADAPTIVE) && w.org_nlayers[o] > 0 && T - w.org_train_tick[o] >= p.train_ticks) req |= SAPIO_REQ_TRAIN;
