@@ -201,6 +201,10 @@ const char *sapio_profile_name(int i);
 int sapio_profile_read(double *ms_out, int64_t *count_out, int reset);
 /* number of kernels of this library launched so far in this process */
 uint64_t sapio_launch_count(void);
+/* Organisms in contact with other bodies ("coupled") are solved by one of two cooperative kernels with identical results: one
+ * warp per organism, or lane-packed size classes. The packed one is launched when the previous tick counted more than `n`
+ * coupled organisms (default 2400; -1 = always, INT_MAX = never). Returns the previous threshold. Tuning / test knob. */
+int sapio_set_coupled_pack_from(int n);
 
 #ifdef __cplusplus
 }

@@ -524,5 +524,6 @@ int sapio_profile_read(double *ms_out, int64_t *count_out, int reset) {
     return 0;
 }
 uint64_t sapio_launch_count(void) { return g_prof.launches; }
+int sapio_set_coupled_pack_from(int n) { const int old = g_coupled_pack_from; g_coupled_pack_from = n; return old; }
 
 }  // extern "C"

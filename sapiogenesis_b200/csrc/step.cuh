@@ -404,6 +404,7 @@ __device__ __forceinline__ void cross_warm_dead(const SapioWorld &w, const Works
 // the two largest classes take two adjacent slabs (even warps only, in their own sub-phase).
 #define COUPLED_WARPS 8
 #define COUPLED_PACK_FROM 2400            /* coupled organisms (last tick) from which the packed form is launched: ~4 per warp of the simple one */
+static int g_coupled_pack_from = COUPLED_PACK_FROM;       // sapio_set_coupled_pack_from
 template <int CM> struct CpBytes { static constexpr size_t v = OrgCfg<CM>::NG * sizeof(OrgS<CM>); };
 constexpr size_t cp_max(size_t a, size_t b) { return a > b ? a : b; }
 constexpr size_t CP_SLAB = (cp_max(cp_max(cp_max(CpBytes<8>::v, CpBytes<16>::v), cp_max(CpBytes<24>::v, CpBytes<32>::v)), cp_max(CpBytes<40>::v, CpBytes<48>::v)) + 15) & ~size_t(15);
@@ -716,7 +717,7 @@ static int launch_space_step(const SapioWorld &w, const Workspace &W, cudaStream
         SapioWorld wc = w; Workspace Wc = W; StepK Kc = K;
         void *args[] = { (void *)&wc, (void *)&Wc, (void *)&Kc };
         const int last = *(volatile int *)g_plan.h_mail;
-        if (last > COUPLED_PACK_FROM) STEP_TRY(cudaLaunchCooperativeKernel((void *)k_coupled, dim3(g_plan.coop_blocks), dim3(COUPLED_WARPS * 32), args, g_plan.coop_smem, st));
+        if (last > g_coupled_pack_from) STEP_TRY(cudaLaunchCooperativeKernel((void *)k_coupled, dim3(g_plan.coop_blocks), dim3(COUPLED_WARPS * 32), args, g_plan.coop_smem, st));
         else STEP_TRY(cudaLaunchCooperativeKernel((void *)k_coupled_simple, dim3(g_plan.simple_blocks), dim3(SIMPLE_WARPS * 32), args, g_plan.simple_smem, st));
     }
     prof_mark(st, PT_STEP_FINISH);

@@ -242,5 +242,9 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.sapio_launch_count())
 
+    def set_coupled_pack_from(self, n: int) -> int:
+        """Threshold (coupled organisms of the previous tick) above which the lane-packed coupled kernel runs; returns the old one."""
+        return int(self.lib.sapio_set_coupled_pack_from(int(n)))
+
     def synchronize(self):
         torch.cuda.synchronize(self.world.device)

@@ -18,3 +18,14 @@ def oracle():
     from oracle import oracle as orc
     orc.build()
     return orc
+
+
+@pytest.fixture(params=["simple", "packed"])
+def coupled_kernel(request):
+    """Runs a GPU test once with each of the two coupled-organism kernels (sapio_set_coupled_pack_from): the library
+    picks by load, and small test worlds would otherwise only ever see the one-warp-per-organism form."""
+    from sapiogenesis_b200._lib import load
+    lib = load()
+    old = lib.sapio_set_coupled_pack_from(-1 if request.param == "packed" else 2 ** 31 - 1)
+    yield request.param
+    lib.sapio_set_coupled_pack_from(old)

@@ -54,7 +54,7 @@ def test_food_only_world(oracle):
 SIZES = [1, 2, 8, 9, 16, 17, 24, 25, 32, 33, 40, 41, 48, 49, 56, 57, 64]
 
 
-def test_every_size_class_boundary(oracle):
+def test_every_size_class_boundary(oracle, coupled_kernel):
     p = default_params(n_org=len(SIZES) + 2, n_dead=32, width=6000.0, height=2500.0, seed=7)
     w = World(p)
     x = 200.0

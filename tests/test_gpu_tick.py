@@ -131,7 +131,7 @@ def test_reusing_the_step_grid_for_the_next_think_changes_nothing(oracle):
         assert torch.equal(a, b) or torch.equal(torch.nan_to_num(a.double()), torch.nan_to_num(b.double())), name
 
 
-def test_crowded_world_of_300_matches_oracle_tick_by_tick(oracle):
+def test_crowded_world_of_300_matches_oracle_tick_by_tick(oracle, coupled_kernel):
     """A denser, larger world than the stage-by-stage trajectories: hundreds of organisms and food pieces in contact (2500
     cross contacts, chains of coupled organisms), every solver class populated, a hundred births at once, 1800 cell deaths.
     Whole ticks (the fused call), re-synchronised every tick. Decisions and contact sets exact, fp32 fields at 1e-5 as everywhere.
