@@ -159,6 +159,32 @@ def test_crowded_world_of_300_matches_oracle_tick_by_tick(oracle, coupled_kernel
     assert st["births"] > b0["births"] + 50 and st["cell_deaths"] > b0["cell_deaths"] + 500 and st["xcontacts"] > 500
 
 
+def test_training_memories_at_their_limit_match_oracle(oracle):
+    """train_network with the long-term memory at memory_limit (neural.py:399-404: lowest reward leaves first) -- the state every
+    brain is in after a few thousand ticks, reached here in a few dozen by a limit of 5 rows. Every other organism has
+    finite_memory switched off (Sapiogenesis.py:548-557) and keeps growing up to the capacity of the table. Curation decisions exact, weights at 1e-5."""
+    from sapiogenesis_b200.world import F_FINITE_MEMORY
+    w = fast_world(oracle, 24, 19, 0.45, 60)
+    w.p.think_ticks, w.p.train_ticks, w.p.memory_limit = 1, 2, 5
+    w.p.repro_ticks = 10 ** 6
+    w.t["org_flags"][1::2] &= ~F_FINITE_MEMORY
+    trimmed = grown = 0
+    for t in range(48):
+        if t % 6 == 0:                                     # swings of the energy level: dopamine / pain above 0.1, memories get written
+            w.t["c_energy"][:] = w.t["c_storage"] * (0.9 if (t // 6) % 2 == 0 else 0.3)
+        wg, eng = engine_for(w)
+        eng.tick(1, PH_ALL); eng.synchronize()
+        assert oracle.tick(w, PH_ALL, 1) == 0
+        compare_worlds(wg, w, f"memory limit tick {w.tick}", verbose=False)
+        live = w.np("org_state") == 1
+        m, stm = w.np("org_mem_n")[live], w.np("org_stm_n")[live]
+        fin = (w.np("org_flags")[live] & F_FINITE_MEMORY) != 0
+        assert (m[fin] <= 5).all()
+        trimmed += int((m[fin] == 5).sum()); grown = max(grown, int(m[~fin].max(initial=0)))
+    print("rows at the limit", trimmed, "largest unbounded memory", grown, "trains", w.stats()["trains"])
+    assert trimmed > 20 and grown == 232                   # SAPIO_MEMROWS: the unbounded memories reach the table's capacity
+
+
 def test_pipelined_host_frames_equal_the_synchronous_ones(oracle):
     """sapio_tick_host_begin/_end with two frames in flight delivers, tick for tick, the frames sapio_tick_host delivers."""
     w = fast_world(oracle, 20, 41, 0.5, 50)
