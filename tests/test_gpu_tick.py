@@ -162,20 +162,24 @@ def test_crowded_world_of_300_matches_oracle_tick_by_tick(oracle, coupled_kernel
 def test_training_memories_at_their_limit_match_oracle(oracle):
     """train_network with the long-term memory at memory_limit (neural.py:399-404: lowest reward leaves first) -- the state every
     brain is in after a few thousand ticks, reached here in a few dozen by a limit of 5 rows. Every other organism has
-    finite_memory switched off (Sapiogenesis.py:548-557) and keeps growing up to the capacity of the table. Curation decisions exact, weights at 1e-5."""
+    finite_memory switched off (Sapiogenesis.py:548-557) and keeps growing up to the capacity of the table. Compared after the rules
+    (think) and train stages of every tick: curation decisions exact, weights at 1e-5."""
     from sapiogenesis_b200.world import F_FINITE_MEMORY
     w = fast_world(oracle, 24, 19, 0.45, 60)
     w.p.think_ticks, w.p.train_ticks, w.p.memory_limit = 1, 2, 5
     w.p.repro_ticks = 10 ** 6
     w.t["org_flags"][1::2] &= ~F_FINITE_MEMORY
+    assert oracle.tick(w, PH_ALL, 6) == 0                 # warm up: the initial overlaps of the crowded start are resolved
     trimmed = grown = 0
-    for t in range(48):
+    for t in range(54):
         if t % 6 == 0:                                     # swings of the energy level: dopamine / pain above 0.1, memories get written
-            w.t["c_energy"][:] = w.t["c_storage"] * (0.9 if (t // 6) % 2 == 0 else 0.3)
-        wg, eng = engine_for(w)
-        eng.tick(1, PH_ALL); eng.synchronize()
-        assert oracle.tick(w, PH_ALL, 1) == 0
+            w.t["c_energy"][:] = w.t["c_storage"] * (0.7 if (t // 6) % 2 == 0 else 0.3)
+        wg, eng = engine_for(w)                            # the brain stages of the tick on the GPU; the oracle carries the world on
+        eng.rules(PH_ALL); eng.train(); eng.synchronize()
+        assert oracle.rules(w, PH_ALL) == 0 and oracle.train(w) == 0
         compare_worlds(wg, w, f"memory limit tick {w.tick}", verbose=False)
+        assert oracle.settle(w) == 0 and oracle.reproduce(w) == 0 and oracle.space_step(w) == 0
+        oracle.friction(w); oracle.post(w); w.t["g_tick"] += 1
         live = w.np("org_state") == 1
         m, stm = w.np("org_mem_n")[live], w.np("org_stm_n")[live]
         fin = (w.np("org_flags")[live] & F_FINITE_MEMORY) != 0
