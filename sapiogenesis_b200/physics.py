@@ -176,6 +176,10 @@ class _Info(dict):
             p.population_limit = int(v); self._env.engine.refresh(); super().__setitem__(k, v)
         elif k == "reproduction_limit":
             p.offspring_amount = int(v); self._env.engine.refresh(); super().__setitem__(k, v)
+        elif k == "use_rnn":
+            if v:
+                raise NotImplementedError("use_rnn=True: recurrent brains (networks.py:111-175) are not part of this world step yet (DESIGN.md 6b)")
+            super().__setitem__(k, v)
         elif k == "weight_persistence":
             if not v:
                 raise NotImplementedError("weight_persistence=False crashes the reference (SURVEY C-12); not reproduced")
