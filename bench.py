@@ -8,7 +8,7 @@ post) over one synthetic world of M organisms per GPU (population islands: weak 
 `value` is device-timed with CUDA events, state resident in HBM; `e2e` goes through sapio_tick_host with pinned HOST buffers
 (event block up, counters + packed sprite poses down, copies inside the timed region).
 `--impl reference` times the CPU restatement of the reference (oracle/, kind "port": pymunk is not installable here, see
-DESIGN.md) on a bounded sample of the same workload, single-threaded like the reference.
+DESIGN.md) on a bounded sample of the same workload: the reference is single-threaded, so every host core runs its own world.
 """
 from __future__ import annotations
 
@@ -119,7 +119,7 @@ def _cpu_island(args):
 
 def cpu_islands(n_org, warm, steps, ticks, cores=None):
     """The restated reference on every host core: one independent world per core, started together.
-    Returns (organism-ticks/s over all cores, per-step wall seconds (max over cores), cores)."""
+    Returns (organism-ticks/s over all cores, per-step wall seconds (region time of the slowest core / steps), cores)."""
     import multiprocessing as mp
     from oracle import oracle as orc
     orc.build()
@@ -130,8 +130,9 @@ def cpu_islands(n_org, warm, steps, ticks, cores=None):
         with ctx.Pool(cores) as pool:
             res = pool.map_async(_cpu_island, [(n_org, seed, warm, steps, ticks, barrier) for seed in range(cores)]).get(timeout=1200)
     units = sum(u for r in res for u, _ in r)
-    step_s = [max(r[k][1] for r in res) for k in range(steps)]
-    return units / sum(step_s), step_s, cores
+    total = max(sum(t for _, t in r) for r in res)         # the timed region of K steps, max over cores (as for the GPU ranks)
+    step_s = [total / steps] * steps
+    return units / total, step_s, cores
 
 
 def cpu_baseline(n_org=1000, ticks=24):
