@@ -78,7 +78,7 @@ def cpu_world(orc, n_org, seed):
     from sapiogenesis_b200.world import World, default_params
     side = math.sqrt(n_org * REF_AREA)
     n_slots = int(math.ceil(n_org * 1.25 / 64.0) * 64)
-    p = default_params(n_org=n_slots, n_dead=max(1024, 8 * n_org), width=side, height=side, seed=seed, population_limit=n_slots,
+    p = default_params(n_org=n_slots, n_dead=max(1024, 8 * n_org), width=side, height=side, seed=seed, population_limit=n_slots - max(64, n_slots // 100),
                        x_cap=max(4096, 4 * n_org))
     w = World(p)
     rng = np.random.default_rng(seed)

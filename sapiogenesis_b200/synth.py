@@ -32,7 +32,7 @@ def build_world(n_organisms: int, device="cuda", seed: int = 0, area_per_org: fl
     n_dead = max(1024, int(n_organisms * 24))          # a starvation wave leaves ~20 dead cells per organism lying around for ~1400 ticks
     side = math.sqrt(n_organisms * area_per_org)
     p = default_params(n_org=n_slots, n_dead=n_dead, width=side, height=side, in_cap=in_cap, brain_cap=brain_cap, seed=seed,
-                       population_limit=population_limit if population_limit is not None else n_slots,
+                       population_limit=population_limit if population_limit is not None else n_slots - max(64, n_slots // 100),
                        x_cap=max(4096, 4 * n_organisms))
     w = World(p, device=device)
     eng = Engine(w)
