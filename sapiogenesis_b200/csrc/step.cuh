@@ -52,9 +52,9 @@ struct Workspace {
     float4 *pair_cst;               // [4 classes][ORG_GC_WARPS][NPAIR] pin constants of the organism a warp is solving (GC classes)
     char *cp_state; int cp_cap;     // parked solver state of the first cp_cap coupled organisms (sizeof(OrgS<MAXC>) each)
 };
-enum { FL_NX = 0, FL_NADJ = 1, FL_OVERFLOW = 2, FL_MAXLEVEL = 3, FL_CHANGED = 4, FL_NCOUPLED = 5, FL_NIC = 6, FL_CLS0 = 8 /* ..16: class starts + end */,
+enum { FL_NX = 0, FL_NADJ = 1, FL_OVERFLOW = 2, FL_MAXLEVEL = 3, FL_NCOUPLED = 5, FL_NIC = 6, FL_CLS0 = 8 /* ..16: class starts + end */,
        FL_WORK0 = 20 /* ..27 */, FL_TMPTOP = 28, FL_NHIT = 29, FL_HIST = 32 /* ..96 */, FL_CHIST = 100 /* ..164: coupled organisms by rows */,
-       FL_CCLS0 = 168 /* ..176: class starts + end in coupled_list */, FL_BYTES = 1024 };
+       FL_CCLS0 = 168 /* ..176: class starts + end in coupled_list */, FL_CHG0 = 180 /* ..182 */, FL_BYTES = 1024 };
 
 #define COUPLED_STATE_BYTES 49152      /* >= sizeof(OrgS<MAXC>), checked where the struct is known */
 // sort only the bits a grid key can have; the key of an empty slot (all ones) still sorts behind every cell: its low bits are all ones
@@ -349,6 +349,46 @@ __global__ void __launch_bounds__(128) k_cross_prestep(WORLD_ARG, Workspace W, S
 // ------------------------------------------------------------------------------------------------------------------
 // coupled path: cooperative kernel
 // ------------------------------------------------------------------------------------------------------------------
+// dependency levels of the cross contacts: level[c] = 1 + max(level of the previous contact on either body), relaxed upwards
+// from all ones to the fixed point (== longest chain ending in c; the relaxation is monotone, so any sweep order ends there).
+// A short list is done by one CTA between block barriers while the rest of the grid waits once; a long one by the whole grid
+// with one grid barrier per sweep (three rotating "changed" flags: sweep r clears the flag of sweep r + 1 and sets its own).
+#define LEVELS_ONE_CTA 4096
+__device__ __forceinline__ bool cross_levels_relax(const Workspace &W, int c) {
+    const int pa = W.nx_prev_a[c], pb = W.nx_prev_b[c];
+    const int L = 1 + max(pa >= 0 ? W.nx_level[pa] : 0, pb >= 0 ? W.nx_level[pb] : 0);
+    if (L <= W.nx_level[c]) return false;
+    W.nx_level[c] = L; atomicMax(&W.flags[FL_MAXLEVEL], L);
+    return true;
+}
+__device__ __forceinline__ void cross_levels(cg::grid_group &grid, const Workspace &W, int nx, int gtid, int gthreads) {
+    if (nx <= LEVELS_ONE_CTA) {
+        if (blockIdx.x == 0) {
+            __shared__ int s_changed;
+            for (;;) {
+                __syncthreads();
+                if (threadIdx.x == 0) s_changed = 0;
+                __syncthreads();
+                bool ch = false;
+                for (int c = threadIdx.x; c < nx; c += blockDim.x) ch |= cross_levels_relax(W, c);
+                if (ch) s_changed = 1;
+                __syncthreads();
+                if (!s_changed) break;
+            }
+        }
+        grid.sync();
+        return;
+    }
+    for (int r = 0;; r++) {
+        if (gtid == 0) W.flags[FL_CHG0 + (r + 1) % 3] = 0;
+        bool ch = false;
+        for (int c = gtid; c < nx; c += gthreads) ch |= cross_levels_relax(W, c);
+        if (ch) W.flags[FL_CHG0 + r % 3] = 1;
+        grid.sync();
+        if (!W.flags[FL_CHG0 + r % 3]) break;
+    }
+}
+
 template <bool WARM>
 __device__ __forceinline__ void cross_level_pass(const SapioWorld &w, const Workspace &W, int L, int nx, float dt_coef, int gtid, int gthreads) {
     const int NC = w.p.n_org * MAXC, ND = w.p.n_dead;
@@ -459,22 +499,7 @@ __global__ void __launch_bounds__(COUPLED_WARPS * 32) k_coupled(WORLD_ARG, Works
     const int gwarp = gtid >> 5, gwarps = gthreads >> 5, warp = threadIdx.x >> 5;
     unsigned char *slab = smem_raw + (size_t)warp * CP_SLAB;
     const float dt_coef = w.g_stepped[0] ? 1.0f : 0.0f;
-    // dependency levels: level[c] = 1 + max(level of the previous contact on either body); fixed point == longest chain
-    for (;;) {
-        if (gtid == 0) W.flags[FL_CHANGED] = 0;
-        grid.sync();
-        bool ch = false;
-        for (int c = gtid; c < nx; c += gthreads) {
-            int pa = W.nx_prev_a[c], pb = W.nx_prev_b[c];
-            int L = 1 + max(pa >= 0 ? W.nx_level[pa] : 0, pb >= 0 ? W.nx_level[pb] : 0);
-            if (L > W.nx_level[c]) { W.nx_level[c] = L; ch = true; atomicMax(&W.flags[FL_MAXLEVEL], L); }
-        }
-        if (ch) W.flags[FL_CHANGED] = 1;
-        grid.sync();
-        int any = W.flags[FL_CHANGED];
-        grid.sync();
-        if (!any) break;
-    }
+    cross_levels(grid, W, nx, gtid, gthreads);
     const int maxL = max(W.flags[FL_MAXLEVEL], 1);
     // warp-items per class (prefix): classes 0..5 by every warp, classes 6..7 by the even warps on a double slab
     int ibase[ORG_CLASSES + 1];
@@ -534,22 +559,7 @@ __global__ void __launch_bounds__(SIMPLE_WARPS * 32) k_coupled_simple(WORLD_ARG,
     const int gwarp = gtid >> 5, gwarps = gthreads >> 5;
     const int ncoupled = W.flags[FL_NCOUPLED];
     const float dt_coef = w.g_stepped[0] ? 1.0f : 0.0f;
-    // dependency levels: level[c] = 1 + max(level of the previous contact on either body); fixed point == longest chain
-    for (;;) {
-        if (gtid == 0) W.flags[FL_CHANGED] = 0;
-        grid.sync();
-        bool ch = false;
-        for (int c = gtid; c < nx; c += gthreads) {
-            int pa = W.nx_prev_a[c], pb = W.nx_prev_b[c];
-            int L = 1 + max(pa >= 0 ? W.nx_level[pa] : 0, pb >= 0 ? W.nx_level[pb] : 0);
-            if (L > W.nx_level[c]) { W.nx_level[c] = L; ch = true; atomicMax(&W.flags[FL_MAXLEVEL], L); }
-        }
-        if (ch) W.flags[FL_CHANGED] = 1;
-        grid.sync();
-        int any = W.flags[FL_CHANGED];
-        grid.sync();
-        if (!any) break;
-    }
+    cross_levels(grid, W, nx, gtid, gthreads);
     const int maxL = max(W.flags[FL_MAXLEVEL], 1);
     // stage A: coupled organisms detect their intra contacts and take their bounce before any velocity changes
     static_assert(sizeof(OrgS<MAXC>) <= COUPLED_STATE_BYTES, "COUPLED_STATE_BYTES too small");
