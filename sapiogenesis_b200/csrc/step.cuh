@@ -54,7 +54,7 @@ struct Workspace {
 };
 enum { FL_NX = 0, FL_NADJ = 1, FL_OVERFLOW = 2, FL_MAXLEVEL = 3, FL_NCOUPLED = 5, FL_NIC = 6, FL_CLS0 = 8 /* ..16: class starts + end */,
        FL_WORK0 = 20 /* ..27 */, FL_TMPTOP = 28, FL_NHIT = 29, FL_HIST = 32 /* ..96 */, FL_CHIST = 100 /* ..164: coupled organisms by rows */,
-       FL_CCLS0 = 168 /* ..176: class starts + end in coupled_list */, FL_CHG0 = 180 /* ..182 */, FL_BYTES = 1024 };
+       FL_CCLS0 = 168 /* ..176: class starts + end in coupled_list */, FL_CHG0 = 180 /* ..182 */, FL_CWORK0 = 200 /* ..203: two alternating pairs of work counters of k_coupled */, FL_BYTES = 1024 };
 
 #define COUPLED_STATE_BYTES 49152      /* >= sizeof(OrgS<MAXC>), checked where the struct is known */
 // sort only the bits a grid key can have; the key of an empty slot (all ones) still sorts behind every cell: its low bits are all ones
@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(COUPLED_WARPS * 32) k_coupled(WORLD_ARG, Works
     const int nx = W.flags[FL_NX];
     if (nx == 0) return;                                       // uniform over the grid: no barrier has been entered
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
-    const int gwarp = gtid >> 5, gwarps = gthreads >> 5, warp = threadIdx.x >> 5;
+    const int warp = threadIdx.x >> 5;
     unsigned char *slab = smem_raw + (size_t)warp * CP_SLAB;
     const float dt_coef = w.g_stepped[0] ? 1.0f : 0.0f;
     cross_levels(grid, W, nx, gtid, gthreads);
@@ -509,8 +509,18 @@ __global__ void __launch_bounds__(COUPLED_WARPS * 32) k_coupled(WORLD_ARG, Works
         const int cnt = W.flags[FL_CCLS0 + c + 1] - W.flags[FL_CCLS0 + c], ng = c == 0 ? 8 : c == 1 ? 4 : c <= 3 ? 2 : 1;
         ibase[c + 1] = ibase[c] + (cnt + ng - 1) / ng;
     }
+    // Work is pulled, heaviest class first, from a pair of counters: a phase ends at a grid barrier, so what counts is when its last
+    // warp finishes. Two pairs alternate; a phase zeroes the pair of the next one (idle since the barrier before this phase; the
+    // first pair starts at zero with the flags block).
+    int phase_no = 0;
+    auto pull = [&](int counter) { int t = 0; if (lane_id() == 0) t = atomicAdd(&W.flags[counter], 1); return __shfl_sync(FULL, t, 0); };
     auto org_phase = [&](int kind) {
-        for (int it = gwarp; it < ibase[6]; it += gwarps) {
+        const int ca = FL_CWORK0 + 2 * (phase_no & 1), cb = ca + 1;
+        if (gtid == 0) { W.flags[FL_CWORK0 + 2 * ((phase_no + 1) & 1)] = 0; W.flags[FL_CWORK0 + 2 * ((phase_no + 1) & 1) + 1] = 0; }
+        phase_no++;
+        for (;;) {
+            const int it = ibase[6] - 1 - pull(ca);
+            if (it < 0) break;
             if (it < ibase[1]) coupled_item<8>(w, W, K, slab, it - ibase[0], kind, dt_coef);
             else if (it < ibase[2]) coupled_item<16>(w, W, K, slab, it - ibase[1], kind, dt_coef);
             else if (it < ibase[3]) coupled_item<24>(w, W, K, slab, it - ibase[2], kind, dt_coef);
@@ -521,7 +531,9 @@ __global__ void __launch_bounds__(COUPLED_WARPS * 32) k_coupled(WORLD_ARG, Works
         if (ibase[8] > ibase[6]) {                             // uniform over the grid
             __syncthreads();                                   // the odd warps' slabs are borrowed now
             if (!(warp & 1))
-                for (int it = ibase[6] + (gwarp >> 1); it < ibase[8]; it += gwarps >> 1) {
+                for (;;) {
+                    const int it = ibase[8] - 1 - pull(cb);
+                    if (it < ibase[6]) break;
                     if (it < ibase[7]) coupled_item<56>(w, W, K, slab, it - ibase[6], kind, dt_coef);
                     else coupled_item<64>(w, W, K, slab, it - ibase[7], kind, dt_coef);
                 }

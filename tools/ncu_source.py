@@ -23,7 +23,7 @@ def main():
     rep, want = sys.argv[1], sys.argv[2]
     which = int(sys.argv[3]) if len(sys.argv) > 3 else 0
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 30
-    maps = line_map('sapiogenesis_b200/libsapio_b200.so', want)
+    maps = line_map(os.environ.get('SAPIO_SO', 'sapiogenesis_b200/libsapio_b200.so'), want)
     assert len(maps) == 1, list(maps)
     mp = next(iter(maps.values()))
     out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
