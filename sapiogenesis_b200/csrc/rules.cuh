@@ -32,7 +32,7 @@ struct RulesWs {
     double *disp_prod;              // [1]
     int *train_list, *repro_list;   // [n_org]
 };
-enum { RC_NTHINK = 0, RC_NTRAIN = 1, RC_NREPRO = 2, RC_NDYING = 3, RC_NFREE = 4 };
+enum { RC_NTHINK = 0, RC_NTRAIN = 1, RC_NREPRO = 2, RC_NDYING = 3, RC_NFREE = 4, RC_TRAIN_TICKET = 8 /* work counter of k_train */ };
 
 __device__ __forceinline__ float warp_sum(float v) { for (int s = 16; s; s >>= 1) v += __shfl_xor_sync(FULL, v, s); return v; }
 __device__ __forceinline__ float bcast2(float v0, float v1, int k) { return __shfl_sync(FULL, (k >> 5) ? v1 : v0, k & 31); }

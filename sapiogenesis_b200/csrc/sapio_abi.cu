@@ -161,6 +161,7 @@ static int launch_train(const SapioWorld &w, AllWs &A, cudaStream_t st) {
     const SapioParams &p = w.p;
     int ctas = p.n_org < A.train_ctas ? p.n_org : A.train_ctas;
     prof_mark(st, PT_TRAIN);
+    CUDA_TRY(cudaMemsetAsync(A.rules.counters + RC_TRAIN_TICKET, 0, sizeof(int), st));
     k_train<<<ctas, TRAIN_THREADS, 0, st>>>(w, A.rules, A.train);
     LAUNCHES(1);
     prof_mark(st, PT_END);

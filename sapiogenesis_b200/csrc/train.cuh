@@ -65,7 +65,13 @@ __global__ void __launch_bounds__(TRAIN_THREADS, 4) k_train(WORLD_ARG, RulesWs R
     float *XT = TW.buf + (size_t)blockIdx.x * TW.per_cta, *H0T = XT + (size_t)IN * TR_S, *P = H0T + TRAIN_MAXW * TR_S, *Q = P + TRAIN_MAXW * TR_S,
           *D = Q + TRAIN_MAXW * TR_S, *dOT = D + TRAIN_MAXW * TR_S;
     const int n_train = R.counters[RC_NTRAIN];
-    for (int q = blockIdx.x; q < n_train; q += gridDim.x) {
+    __shared__ int sh_q;
+    for (;;) {                                             // organisms differ by the size of their memory and of their brain: pulled, not dealt
+        __syncthreads();
+        if (tid == 0) sh_q = atomicAdd(&R.counters[RC_TRAIN_TICKET], 1);
+        __syncthreads();
+        const int q = sh_q;
+        if (q >= n_train) break;
         const int o = R.train_list[q];
         const int32_t *ldim = w.org_ldim + o * 16;
         const int nl = w.org_nlayers[o], I = ldim[0];
