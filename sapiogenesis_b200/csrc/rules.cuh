@@ -156,6 +156,38 @@ struct OrgR {
 
 __device__ __forceinline__ void stat_add(const SapioWorld &w, int which, int n) { if (n) atomicAdd(reinterpret_cast<unsigned long long *>(w.g_stats + which), (unsigned long long)n); }
 
+// Ordered composition of the organisms' gas maps (contract C4) as a scan with a FIXED association: chunk-local scans
+// (cub::BlockScan, one CTA per GAS_CHUNK maps), the chunk aggregates composed in order by one thread, the prefix applied.
+// cub::DeviceScan's decoupled look-back groups the partial products by arrival time, and the composition of doubles is only
+// approximately associative: its results differ in the last bit from run to run, which a world that promises to be
+// reproducible from its seed cannot have.
+#define GAS_THREADS 256
+#define GAS_ITEMS 4
+#define GAS_CHUNK (GAS_THREADS * GAS_ITEMS)
+__global__ void __launch_bounds__(GAS_THREADS) k_gas_local(const Aff *in, Aff *out, Aff *agg, int n) {
+    typedef cub::BlockScan<Aff, GAS_THREADS> Scan;
+    __shared__ typename Scan::TempStorage tmp;
+    const int base = blockIdx.x * GAS_CHUNK + threadIdx.x * GAS_ITEMS;
+    Aff v[GAS_ITEMS];
+#pragma unroll
+    for (int i = 0; i < GAS_ITEMS; i++) v[i] = base + i < n ? in[base + i] : Aff{1.0, 0.0};
+    Aff total;
+    Scan(tmp).InclusiveScan(v, v, AffCompose(), total);
+#pragma unroll
+    for (int i = 0; i < GAS_ITEMS; i++) if (base + i < n) out[base + i] = v[i];
+    if (threadIdx.x == 0) agg[blockIdx.x] = total;
+}
+__global__ void k_gas_chunks(Aff *agg, int nchunks) {          // agg[c] becomes the composition of the chunks before c
+    if (blockIdx.x || threadIdx.x) return;
+    Aff run{1.0, 0.0};
+    for (int c = 0; c < nchunks; c++) { const Aff a = agg[c]; agg[c] = run; run = AffCompose()(run, a); }
+}
+__global__ void __launch_bounds__(GAS_THREADS) k_gas_apply(Aff *out, const Aff *agg, int n) {
+    const int c = blockIdx.x + 1;                               // chunk 0 has nothing before it
+    const Aff pre = agg[c];
+    for (int i = threadIdx.x; i < GAS_CHUNK; i += GAS_THREADS) { const int k = c * GAS_CHUNK + i; if (k < n) out[k] = AffCompose()(pre, out[k]); }
+}
+
 #define RULES_WARPS 8
 __global__ void __launch_bounds__(RULES_WARPS * 32) k_rules_begin(WORLD_ARG, RulesWs R, uint32_t phases) {
     const SapioParams &p = w.p;

@@ -134,8 +134,15 @@ static int launch_rules(const SapioWorld &w, AllWs &A, uint32_t phases, cudaStre
     const int org_grid = stream_grid((long)p.n_org * 32, RULES_WARPS * 32);
     k_rules_begin<<<org_grid, RULES_WARPS * 32, 0, st>>>(w, R, phases);
     prof_mark(st, PT_GAS_SCAN);
-    size_t tmp = A.step.cub_bytes;
-    CUDA_TRY(cub::DeviceScan::InclusiveScan(A.step.cub_tmp, tmp, R.gas_map, R.gas_scan, AffCompose(), p.n_org, st));
+    {
+        const int nchunks = (p.n_org + GAS_CHUNK - 1) / GAS_CHUNK;
+        if ((size_t)nchunks * sizeof(Aff) > A.step.cub_bytes) return fail(SAPIO_E_ARG, "workspace too small for the gas scan%s");
+        Aff *agg = (Aff *)A.step.cub_tmp;
+        k_gas_local<<<nchunks, GAS_THREADS, 0, st>>>(R.gas_map, R.gas_scan, agg, p.n_org);
+        k_gas_chunks<<<1, 32, 0, st>>>(agg, nchunks);
+        if (nchunks > 1) k_gas_apply<<<nchunks - 1, GAS_THREADS, 0, st>>>(R.gas_scan, agg, p.n_org);
+        LAUNCHES(nchunks > 1 ? 3 : 2);
+    }
     if (phases & SAPIO_PH_THINK) {
         prof_mark(st, PT_GRID);
         if (!(phases & SAPIO_PH_REUSE_GRID)) { int rc = launch_grid_only(w, A.step, st); if (rc) return rc; }
@@ -148,7 +155,7 @@ static int launch_rules(const SapioWorld &w, AllWs &A, uint32_t phases, cudaStre
     }
     prof_mark(st, PT_RULES_MAIN);
     k_rules_main<<<org_grid, RULES_WARPS * 32, 0, st>>>(w, R, phases);
-    tmp = A.step.cub_bytes;
+    size_t tmp = A.step.cub_bytes;
     CUDA_TRY(cub::DeviceReduce::Sum(A.step.cub_tmp, tmp, w.org_gas_refund, R.refund_sum, p.n_org, st));
     k_rules_finish<<<1, 1, 0, st>>>(w, R);
     LAUNCHES(3);
