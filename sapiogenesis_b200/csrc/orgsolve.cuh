@@ -13,6 +13,7 @@
 //   * eight size classes (8..64 rows) so that the shared-memory footprint, which sets the occupancy, follows the size
 #pragma once
 #include "common.cuh"
+#include "solver_api.h"
 
 // GC ("global constants"): the read-only part of a pin joint (nx, ny, bias) lives in a per-warp scratch in global memory (L2
 // resident: it is rewritten for every organism the warp takes) and is fetched three wavefronts ahead; shared memory keeps only
@@ -585,7 +586,7 @@ struct OrgCtx {
 // ------------------------------------------------------------------------------------------------------------------
 // organisms with no cross contact: the whole solve in one launch, everything on chip
 // ------------------------------------------------------------------------------------------------------------------
-#define ORG_CLASSES 8
+
 #ifndef ORG_GC
 #define ORG_GC 0          /* measured (profiles/r1c_org_solve.md): 15 instead of 8 warps per SM, same time -- kept as a switch */
 #endif
@@ -598,7 +599,7 @@ template <int CM> struct OrgCfg {
     static constexpr int FIT = (227 * 1024 - 2048) / WARP_BYTES;                          // warps an SM can hold
     static constexpr int WARPS = FIT <= 8 ? (FIT < 1 ? 1 : FIT) : (FIT <= 16 ? FIT / 2 : 8);
 };
-__host__ __device__ inline int org_class_of(int nc) { return nc <= 8 ? 0 : (nc - 1) >> 3; }      // rows 1..8 -> 0, 9..16 -> 1, ...
+
 
 template <int CM>
 __global__ void __launch_bounds__(OrgCfg<CM>::WARPS * 32) k_org_solve(WORLD_ARG, Workspace W, StepK K, int cls) {
@@ -635,30 +636,3 @@ __global__ void __launch_bounds__(OrgCfg<CM>::WARPS * 32) k_org_solve(WORLD_ARG,
     if (nic_sum) atomicAdd(&W.flags[FL_NIC], nic_sum);
 }
 
-// organisms -> two lists sorted by cell rows (counting sort: histogram, scan, scatter): coupled organisms and the rest
-__global__ void k_classify_count(WORLD_ARG, Workspace W) {
-    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < w.p.n_org; o += gridDim.x * blockDim.x) {
-        if (w.org_state[o] != 1) continue;
-        const int nc = min(max(w.org_ncells[o], 1), MAXC);
-        if (W.org_coupled[o]) { atomicAdd(&W.flags[FL_NCOUPLED], 1); atomicAdd(&W.flags[FL_CHIST + nc], 1); }
-        else atomicAdd(&W.size_hist[nc], 1);
-    }
-}
-__global__ void k_classify_scan(Workspace W) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    int acc = 0, cacc = 0;
-    for (int nc = 1; nc <= MAXC; nc++) {
-        if (nc == 1 || ((nc - 1) & 7) == 0) { W.flags[FL_CLS0 + org_class_of(nc)] = acc; W.flags[FL_CCLS0 + org_class_of(nc)] = cacc; }   // first size of a class
-        int c = W.size_hist[nc]; W.size_hist[nc] = acc; acc += c;
-        c = W.flags[FL_CHIST + nc]; W.flags[FL_CHIST + nc] = cacc; cacc += c;
-    }
-    W.flags[FL_CLS0 + ORG_CLASSES] = acc; W.flags[FL_CCLS0 + ORG_CLASSES] = cacc;
-}
-__global__ void k_classify_scatter(WORLD_ARG, Workspace W) {
-    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < w.p.n_org; o += gridDim.x * blockDim.x) {
-        if (w.org_state[o] != 1) continue;
-        const int nc = min(max(w.org_ncells[o], 1), MAXC);
-        if (W.org_coupled[o]) W.coupled_list[atomicAdd(&W.flags[FL_CHIST + nc], 1)] = o;
-        else W.sorted_orgs[atomicAdd(&W.size_hist[nc], 1)] = o;
-    }
-}

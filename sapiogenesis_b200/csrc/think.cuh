@@ -17,9 +17,11 @@ __device__ __forceinline__ double warp_sum_d(double v) { for (int s = 16; s; s >
 
 struct SenseOut { double eye[8]; double smell; int hits; };
 
-// Enumerates the view of the sensor at (sx, sy) radius R of organism o; encodes relative to the cell at (px, py).
-template <bool EYE>
-__device__ __forceinline__ void sense(const SapioWorld &w, const Workspace &W, int o, int64_t uid, float sx, float sy, float R, float px, float py, double rot, SenseOut &out) {
+// The view of the sensor disc at (sx, sy) radius R of organism o: lanes stride over the grid cells the disc can reach and call
+// on_hit(body id, x, y, r, dead) for every member (exact double predicate, contract C3). The one enumeration of the library:
+// k_think encodes from it, the parity probe k_sensor_view lists its hits.
+template <class F>
+__device__ __forceinline__ void sense_enumerate(const SapioWorld &w, const Workspace &W, int o, int64_t uid, float sx, float sy, float R, F &&on_hit) {
     const SapioParams &p = w.p;
     const int NC = p.n_org * MAXC, lane = lane_id();
     const float gc = p.grid_cell, reach = R + 0.5f * gc;            // grid_cell >= 2 * largest solid radius
@@ -27,42 +29,49 @@ __device__ __forceinline__ void sense(const SapioWorld &w, const Workspace &W, i
     int cy0 = (int)floorf((sy - reach) / gc) + 1, cy1 = (int)floorf((sy + reach) / gc) + 1;
     cx0 = max(cx0, 0); cy0 = max(cy0, 0); cx1 = min(cx1, p.grid_nx - 1); cy1 = min(cy1, p.grid_ny - 1);
     const int nbx = cx1 - cx0 + 1, nby = cy1 - cy0 + 1;
-    double eye[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
-    double smell = 0.; int hits = 0;
-    if (nbx > 0 && nby > 0) {
-        for (int idx = lane; idx < nbx * nby; idx += 32) {
-            int c = (cy0 + idx / nbx) * p.grid_nx + cx0 + idx % nbx;
-            for (int i = W.cell_start[c], e = W.cell_end[c]; i < e; i++) {
-                int j = (int)W.sval[i];
-                float x, y, r; bool dead;
-                if (j < NC) {
-                    if ((j >> 6) == o || w.c_alive[j] == 0) continue;
-                    float2 q = reinterpret_cast<const float2 *>(w.c_pos)[j]; x = q.x; y = q.y; r = w.c_size[j] * 0.5f; dead = false;
-                } else {
-                    int d = j - NC;
-                    if (!w.d_state[d] || w.d_owner[d] == uid) continue;            // own dead cells are invisible (sprites.py:233)
-                    float2 q = reinterpret_cast<const float2 *>(w.d_pos)[d]; x = q.x; y = q.y; r = w.d_size[d] * 0.5f; dead = true;
-                }
-                double d2;
-                if (!circles_overlap(sx, sy, R, x, y, r, &d2)) continue;
-                hits++;
-                // encoding in double like the reference's Python floats: the values are rounded to 3 decimals next, and a
-                // 1e-7 fp32 error would flip a digit at every tie; this path runs once per think, not per tick
-                double ddx = (double)x - (double)px, ddy = (double)y - (double)py;
-                double dist = sqrt(ddx * ddx + ddy * ddy);
-                double val = fabs(((double)R - (dist + (double)r)) / (double)R);
-                if (EYE) {
-                    double ang = atan2(ddy, ddx) - rot;
-                    double dx = cos(ang), dy = sin(ang);
-                    int s;
-                    if (dx >= 0.0) { if (dy < 0.0) s = dx < .707 ? 0 : 1; else s = dx >= .707 ? 2 : 3; }
-                    else { if (dy >= 0.0) s = dy >= .707 ? 4 : 5; else s = dx < -.707 ? 6 : 7; }
-#pragma unroll
-                    for (int q = 0; q < 8; q++) if (q == s) eye[q] = fmax(eye[q], val);
-                } else if (dead) smell = fmax(smell, val);
+    if (nbx <= 0 || nby <= 0) return;
+    for (int idx = lane; idx < nbx * nby; idx += 32) {
+        int c = (cy0 + idx / nbx) * p.grid_nx + cx0 + idx % nbx;
+        for (int i = W.cell_start[c], e = W.cell_end[c]; i < e; i++) {
+            int j = (int)W.sval[i];
+            float x, y, r; bool dead;
+            if (j < NC) {
+                if ((j >> 6) == o || w.c_alive[j] == 0) continue;
+                float2 q = reinterpret_cast<const float2 *>(w.c_pos)[j]; x = q.x; y = q.y; r = w.c_size[j] * 0.5f; dead = false;
+            } else {
+                int d = j - NC;
+                if (!w.d_state[d] || w.d_owner[d] == uid) continue;            // own dead cells are invisible (sprites.py:233)
+                float2 q = reinterpret_cast<const float2 *>(w.d_pos)[d]; x = q.x; y = q.y; r = w.d_size[d] * 0.5f; dead = true;
             }
+            double d2;
+            if (!circles_overlap(sx, sy, R, x, y, r, &d2)) continue;
+            on_hit(j, x, y, r, dead);
         }
     }
+}
+
+// Encodes the view relative to the cell at (px, py) (neural.py:123-218).
+template <bool EYE>
+__device__ __forceinline__ void sense(const SapioWorld &w, const Workspace &W, int o, int64_t uid, float sx, float sy, float R, float px, float py, double rot, SenseOut &out) {
+    double eye[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
+    double smell = 0.; int hits = 0;
+    sense_enumerate(w, W, o, uid, sx, sy, R, [&](int, float x, float y, float r, bool dead) {
+        hits++;
+        // encoding in double like the reference's Python floats: the values are rounded to 3 decimals next, and a
+        // 1e-7 fp32 error would flip a digit at every tie; this path runs once per think, not per tick
+        double ddx = (double)x - (double)px, ddy = (double)y - (double)py;
+        double dist = sqrt(ddx * ddx + ddy * ddy);
+        double val = fabs(((double)R - (dist + (double)r)) / (double)R);
+        if (EYE) {
+            double ang = atan2(ddy, ddx) - rot;
+            double dx = cos(ang), dy = sin(ang);
+            int s;
+            if (dx >= 0.0) { if (dy < 0.0) s = dx < .707 ? 0 : 1; else s = dx >= .707 ? 2 : 3; }
+            else { if (dy >= 0.0) s = dy >= .707 ? 4 : 5; else s = dx < -.707 ? 6 : 7; }
+#pragma unroll
+            for (int q = 0; q < 8; q++) if (q == s) eye[q] = fmax(eye[q], val);
+        } else if (dead) smell = fmax(smell, val);
+    });
     if (EYE) {
 #pragma unroll
         for (int q = 0; q < 8; q++) out.eye[q] = warp_max(eye[q]);
@@ -249,23 +258,23 @@ __global__ void __launch_bounds__(THINK_WARPS * 32) k_think(WORLD_ARG, Workspace
     }
 }
 
-// parity probe: the view of one sensor cell as a sorted id list (tests only: "sensor hit indices bit-exact")
+// parity probe: the view of one sensor cell as a sorted id list ("sensor hit indices bit-exact"), listed by the production
+// enumeration above (one warp, like k_think)
 __global__ void k_sensor_view(WORLD_ARG, Workspace W, int o, int k, uint32_t *out, int cap, int *out_n) {
     const SapioParams &p = w.p;
-    const int NC = p.n_org * MAXC, row = o * MAXC + k;
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int row = o * MAXC + k;
+    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
     float sx = w.c_spos[2 * row], sy = w.c_spos[2 * row + 1];
     float R = w.c_size[row] * (w.c_type[row] == SAPIO_T_EYE ? p.eyesight_mult : p.olfactory_mult);
-    int n = 0;
-    for (int c = 0; c < p.grid_nx * p.grid_ny; c++)
-        for (int i = W.cell_start[c]; i < W.cell_end[c]; i++) {
-            int j = (int)W.sval[i];
-            float x, y, r;
-            if (j < NC) { if ((j >> 6) == o || w.c_alive[j] == 0) continue; x = w.c_pos[2 * j]; y = w.c_pos[2 * j + 1]; r = w.c_size[j] * 0.5f; }
-            else { int d = j - NC; if (!w.d_state[d] || w.d_owner[d] == w.org_uid[o]) continue; x = w.d_pos[2 * d]; y = w.d_pos[2 * d + 1]; r = w.d_size[d] * 0.5f; }
-            double d2;
-            if (circles_overlap(sx, sy, R, x, y, r, &d2)) { if (n < cap) out[n] = (uint32_t)j; n++; }
-        }
-    for (int i = 1; i < min(n, cap); i++) { uint32_t v = out[i]; int j = i - 1; while (j >= 0 && out[j] > v) { out[j + 1] = out[j]; j--; } out[j + 1] = v; }
-    *out_n = n;
+    if (threadIdx.x == 0) *out_n = 0;
+    __syncwarp();
+    sense_enumerate(w, W, o, w.org_uid[o], sx, sy, R, [&](int j, float, float, float, bool) {
+        int n = atomicAdd(out_n, 1);
+        if (n < cap) out[n] = (uint32_t)j;
+    });
+    __syncwarp();
+    if (threadIdx.x == 0) {
+        const int n = min(*out_n, cap);
+        for (int i = 1; i < n; i++) { uint32_t v = out[i]; int j = i - 1; while (j >= 0 && out[j] > v) { out[j + 1] = out[j]; j--; } out[j + 1] = v; }
+    }
 }

@@ -42,6 +42,16 @@ def field_err(got, ref, floor=1e-3, elementwise=False):
     return float(np.max(np.abs(got - ref)) / scale)
 
 
+def elem_rel_err(got, ref):
+    """max over entries of |got - ref| / |ref|, entries with |ref| <= 1e-3 * rms(ref) left out (their relative error is noise)."""
+    got = np.asarray(got, dtype=np.float64).reshape(-1); ref = np.asarray(ref, dtype=np.float64).reshape(-1)
+    if ref.size == 0:
+        return 0.0
+    rms = float(np.sqrt(np.mean(ref * ref)))
+    m = np.abs(ref) > 1e-3 * rms
+    return float(np.max(np.abs(got[m] - ref[m]) / np.abs(ref[m]))) if m.any() else 0.0
+
+
 # cached impulses span orders of magnitude inside one list (a settled pile: one resting contact carries the weight, the rest
 # are ~0): each entry is held to 1e-5 of its own size, with an absolute floor of 1e-5 of max(the list's rms, the momentum
 # scale). The momentum scale m/2 * rms(v) is the size of the ten increments -(bounce + v_rel.n) * nMass an accumulated
@@ -71,6 +81,7 @@ SOLVER_FIELDS = {"c_vel", "c_angvel", "c_vbias", "c_svel", "c_spin_jn", "c_wbias
 class Report:
     def __init__(self, tag, phys_tol=None):
         self.tag, self.errs, self.bad, self.phys_tol = tag, {}, [], phys_tol
+        self.rel = {}          # per-element relative error max |got - ref| / |ref| over entries with |ref| > 1e-3 * rms: reported, not asserted
 
     def exact(self, name, got, ref):
         got, ref = np.asarray(got), np.asarray(ref)
@@ -81,7 +92,8 @@ class Report:
 
     def close(self, name, got, ref, tol=None, floor=None):
         e = field_err(got, ref, FLOORS.get(name, 1e-3) if floor is None else floor, elementwise=name in ELEMENTWISE)
-        self.errs[name] = e
+        self.errs[name] = max(e, self.errs.get(name, 0.0))
+        self.rel[name] = max(elem_rel_err(got, ref), self.rel.get(name, 0.0))
         lim = TOLS.get(name, TOL) if tol is None else tol
         if self.phys_tol is not None and name in SOLVER_FIELDS:
             lim = max(lim, self.phys_tol)
@@ -92,20 +104,41 @@ class Report:
         if verbose:
             worst = sorted(self.errs.items(), key=lambda kv: -kv[1])[:8]
             print(f"{self.tag}: worst " + " ".join(f"{k}={v:.1e}" for k, v in worst))
+            wr = sorted(self.rel.items(), key=lambda kv: -kv[1])[:8]
+            print(f"{self.tag}: per-element relative (reported) " + " ".join(f"{k}={v:.1e}" for k, v in wr))
         assert not self.bad, f"{self.tag}: " + "; ".join(self.bad[:12])
 
 
-def compare_worlds(wg, w, tag, brain_tol=TOL, check_brain=True, skip=(), verbose=True, phys_tol=None):
-    """wg: GPU world after the stage(s); w: oracle world after the same stage(s)."""
+class _Lazy(dict):
+    """Field name -> host array, fetched from the world on first use (a 100k-organism world is tens of GB: one field at a time)."""
+    def __init__(self, world):
+        super().__init__(); self.world = world
+
+    def __missing__(self, k):
+        v = self.world.np(k); self[k] = v
+        return v
+
+    def drop(self, *names):
+        for n in names:
+            self.pop(n, None)
+
+
+_PAIR_I, _PAIR_J = np.triu_indices(MAXC, 1)            # lexicographic (i, j), i < j == pair_index order
+
+
+def compare_worlds(wg, w, tag, brain_tol=TOL, check_brain=True, skip=(), verbose=True, phys_tol=None, detail_orgs=None, before=None):
+    """wg: GPU world after the stage(s); w: oracle world after the same stage(s).
+    detail_orgs: organism slots whose brains / rings / memories are compared entry by entry (default: all). With `before` (the common
+    start state) every OTHER living organism's brain, optimiser state and memories must be bit-identical on both sides to what they
+    were before -- nothing may touch an organism that neither thought nor trained nor was born."""
     rep = Report(tag, phys_tol)
     p = w.p
-    G = {f.name: wg.np(f.name) for f in FIELDS}
-    O = {f.name: w.np(f.name) for f in FIELDS}
+    G = _Lazy(wg)
+    O = _Lazy(w)
     rep.exact("org_state", G["org_state"], O["org_state"])
     orgs = np.nonzero(O["org_state"] == 1)[0]
-    org_rows = np.zeros(p.n_org * MAXC, dtype=bool)
-    for o in orgs:
-        org_rows[o * MAXC: o * MAXC + int(O["org_ncells"][o])] = True
+    alive_org = O["org_state"] == 1
+    org_rows = ((np.arange(MAXC)[None, :] < O["org_ncells"].astype(np.int64)[:, None]) & alive_org[:, None]).reshape(-1)
     rep.exact("c_alive", G["c_alive"][org_rows], O["c_alive"][org_rows])
     live = org_rows & (O["c_alive"] == 1)
     rep.exact("d_state", G["d_state"] > 0, O["d_state"] > 0)
@@ -138,6 +171,8 @@ def compare_worlds(wg, w, tag, brain_tol=TOL, check_brain=True, skip=(), verbose
                 rep.close(name, g, o)
         else:
             rep.exact(name, g, o)
+        if G[name].nbytes > (1 << 26) and name not in ("c_vel", "d_vel", "c_type", "c_mass", "d_mass"):
+            G.drop(name); O.drop(name)
     # sensors
     for name in ("c_spos",):
         rep.exact(name, G[name][sens], O[name][sens])
@@ -154,20 +189,29 @@ def compare_worlds(wg, w, tag, brain_tol=TOL, check_brain=True, skip=(), verbose
     rep.exact("xa_off", G["xa_off"], O["xa_off"])
     na = int(O["xa_off"][-1])
     rep.exact("xa_other", G["xa_other"].reshape(-1)[:na], O["xa_other"].reshape(-1)[:na])
-    icm = np.zeros(p.n_org * ICAP, dtype=bool)
-    jm = np.zeros(p.n_org * NPAIR, dtype=bool)
-    for o in orgs:
-        icm[o * ICAP: o * ICAP + int(O["org_ic_n"][o])] = True
-        nc = int(O["org_ncells"][o]); al = O["c_alive"][o * MAXC: o * MAXC + nc] == 1
-        for i in np.nonzero(al)[0]:
-            js = np.nonzero(al[i + 1:])[0] + i + 1
-            jm[o * NPAIR + i * (2 * MAXC - i - 1) // 2 + (js - i - 1)] = True
+    icm = ((np.arange(ICAP)[None, :] < O["org_ic_n"].astype(np.int64)[:, None]) & alive_org[:, None]).reshape(-1)
+    al2 = live.reshape(p.n_org, MAXC)
+    jm = np.empty((p.n_org, NPAIR), dtype=bool)
+    for s0 in range(0, p.n_org, 8192):                   # pin (i, j) exists iff both cells live
+        jm[s0:s0 + 8192] = al2[s0:s0 + 8192][:, _PAIR_I] & al2[s0:s0 + 8192][:, _PAIR_J]
+    jm = jm.reshape(-1)
     rep.exact("ic_code", G["ic_code"][icm], O["ic_code"][icm])
     rep.close("ic_jn", G["ic_jn"][icm], O["ic_jn"][icm], floor=pf); rep.close("ic_jt", G["ic_jt"][icm], O["ic_jt"][icm], floor=max(pf, rms(O["ic_jn"][icm])))
     rep.close("j_jn", G["j_jn"][jm], O["j_jn"][jm], floor=pf)
+    G.drop("j_jn", "ic_jn", "ic_jt", "ic_code"); O.drop("j_jn", "ic_jn", "ic_jt", "ic_code")
+    del jm, icm
     # brains and memories
     IN = p.in_cap
-    for o in orgs:
+    detail = orgs if detail_orgs is None else np.intersect1d(orgs, np.asarray(detail_orgs, dtype=np.int64))
+    if detail_orgs is not None and before is not None:
+        rest = np.setdiff1d(np.intersect1d(orgs, np.nonzero(before.np("org_state") == 1)[0]), detail)
+        for name in ("org_brain", "org_adam_m", "org_adam_v", "org_mem_in", "org_mem_out", "org_mem_rew", "org_stm_in", "org_stm_out",
+                     "org_stm_rew", "org_hist_in", "org_hist_out", "org_hist_dopa", "org_ldim", "org_incell"):
+            b = before.np(name)[rest]
+            rep.exact(name + "[untouched, gpu]", G[name][rest].view(np.uint8), b.view(np.uint8))
+            rep.exact(name + "[untouched, oracle]", O[name][rest].view(np.uint8), b.view(np.uint8))
+            del b
+    for o in detail:
         nl = int(O["org_nlayers"][o]); ld = O["org_ldim"][o]
         rep.exact(f"org_ldim[{o}]", G["org_ldim"][o][: nl + 1], ld[: nl + 1])
         nin = int(O["org_nincell"][o])
