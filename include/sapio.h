@@ -56,8 +56,12 @@ enum {
     SAPIO_STAT_BIRTHS = 0, SAPIO_STAT_DEATHS = 1, SAPIO_STAT_CELL_DEATHS = 2, SAPIO_STAT_DEAD_REMOVED = 3,
     SAPIO_STAT_THINKS = 4, SAPIO_STAT_TRAINS = 5, SAPIO_STAT_XCONTACTS = 6, SAPIO_STAT_ICONTACTS = 7,
     SAPIO_STAT_BIRTH_FAIL_PLACE = 8, SAPIO_STAT_BIRTH_FAIL_CAPS = 9, SAPIO_STAT_OVERFLOW = 10,
-    SAPIO_STAT_ORG_TICKS = 11, SAPIO_STAT_LEVELS = 12, SAPIO_STAT_COUPLED = 13
+    SAPIO_STAT_ORG_TICKS = 11, SAPIO_STAT_LEVELS = 12, SAPIO_STAT_COUPLED = 13,
+    SAPIO_STAT_RARE_PATHS = 14,    /* bits: SAPIO_RARE_* -- branches only large or aged worlds reach (set, never cleared: test evidence) */
+    SAPIO_STAT_FULL_SCANS = 15     /* birth placements that scanned every organism (more than REPRO_NEAR_CAP neighbours within reach) */
 };
+
+enum { SAPIO_RARE_GRID_LEVELS = 1, SAPIO_RARE_PACKED_COUPLED = 2, SAPIO_RARE_FULL_SCAN = 4, SAPIO_RARE_TRAIN_QUEUE = 8, SAPIO_RARE_BIRTH_CAP = 16 };
 
 /* phase mask for sapio_tick */
 enum {

@@ -36,6 +36,7 @@ __device__ __forceinline__ void cross_levels(cg::grid_group &grid, const Workspa
         grid.sync();
         return;
     }
+    if (gtid == 0) W.flags[FL_RARE] |= SAPIO_RARE_GRID_LEVELS;
     for (int r = 0;; r++) {
         if (gtid == 0) W.flags[FL_CHG0 + (r + 1) % 3] = 0;
         bool ch = false;
@@ -156,6 +157,7 @@ __global__ void __launch_bounds__(COUPLED_WARPS * 32) k_coupled(WORLD_ARG, Works
     const int warp = threadIdx.x >> 5;
     unsigned char *slab = smem_raw + (size_t)warp * CP_SLAB;
     const float dt_coef = w.g_stepped[0] ? 1.0f : 0.0f;
+    if (gtid == 0) W.flags[FL_RARE] |= SAPIO_RARE_PACKED_COUPLED;
     cross_levels(grid, W, nx, gtid, gthreads);
     const int maxL = max(W.flags[FL_MAXLEVEL], 1);
     // warp-items per class (prefix): classes 0..5 by every warp, classes 6..7 by the even warps on a double slab

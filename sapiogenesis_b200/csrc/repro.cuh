@@ -76,7 +76,8 @@ __global__ void __launch_bounds__(256) k_repro_lists(WORLD_ARG, ReproWs Q) {
         if (Q.req_flag[o]) Q.req_list[Q.req_off[o]] = o;
         if (Q.free_flag[o]) Q.free_list[Q.free_off[o]] = o;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) { Q.counters[0] = min(Q.req_off[n], Q.birth_cap); Q.counters[1] = Q.free_off[n]; Q.counters[2] = 0; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { Q.counters[0] = min(Q.req_off[n], Q.birth_cap); Q.counters[1] = Q.free_off[n]; Q.counters[2] = 0;
+        if (Q.req_off[n] > Q.birth_cap) { w.g_stats[SAPIO_STAT_OVERFLOW] += 1; w.g_stats[SAPIO_STAT_RARE_PATHS] |= SAPIO_RARE_BIRTH_CAP; } }   // more requests than the tick can serve: counted, never silent
 }
 
 #define REPRO_WARPS 2
@@ -190,6 +191,7 @@ __global__ void __launch_bounds__(REPRO_WARPS * 32) k_repro_place(WORLD_ARG, Rep
             const int nn = B.near_n;
             const bool listed = nn <= REPRO_NEAR_CAP;
             const int total = listed ? nn : p.n_org;
+            if (!listed && lane == 0) { atomicAdd((unsigned long long *)&w.g_stats[SAPIO_STAT_FULL_SCANS], 1ull); atomicOr((unsigned long long *)&w.g_stats[SAPIO_STAT_RARE_PATHS], (unsigned long long)SAPIO_RARE_FULL_SCAN); }
             for (int base = 0; base < total; base += 32) {
                 const int e = base + lane;
                 int o = -1;

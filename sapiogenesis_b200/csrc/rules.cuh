@@ -41,7 +41,9 @@ __device__ __forceinline__ int bcast2i(int v0, int v1, int k) { return __shfl_sy
 // per-lane view of one organism: cell rows lane and lane + 32
 struct OrgR {
     int o, nc, lane;
-    float health[2], energy[2], storage[2], maxhealth[2], size[2], use_idle[2], use_act[2], damage[2];
+    float health[2], storage[2], maxhealth[2], size[2], use_idle[2], use_act[2], damage[2];
+    double energy[2];                // Python floats in the reference: an organism's energies pass through ~2n dependent updates per tick and the co2
+                                     // refund is what is left of them; held in double here, rounded once when stored
     float vx[2], vy[2], av[2], px[2], py[2];
     int alive[2], type[2], inuse[2], parent[2];
     uint64_t anc[2];                 // ancestors in the growth tree (dna.grows_from chain)
@@ -55,7 +57,7 @@ struct OrgR {
             alive[h] = in ? w.c_alive[row] : 0;
             type[h] = in ? w.c_type[row] : 0;
             parent[h] = in ? (int)w.c_parent[row] : -1;
-            health[h] = in ? w.c_health[row] : 0.f; energy[h] = in ? w.c_energy[row] : 0.f;
+            health[h] = in ? w.c_health[row] : 0.f; energy[h] = in ? (double)w.c_energy[row] : 0.0;
             storage[h] = in ? w.c_storage[row] : 0.f; maxhealth[h] = in ? w.c_maxhealth[row] : 0.f;
             size[h] = in ? w.c_size[row] : 0.f;
             inuse[h] = in ? w.c_inuse[row] : 0;
@@ -74,20 +76,22 @@ struct OrgR {
         return ((uint64_t)a1 << 32) | a0;
     }
     __device__ int n_living() const { return __popcll(alive_mask()); }
+    __device__ static double dsum(double v) { for (int s = 16; s; s >>= 1) v += __shfl_xor_sync(FULL, v, s); return v; }
     __device__ float sum_living(const float v[2]) const { return warp_sum((alive[0] == 1 ? v[0] : 0.f) + (alive[1] == 1 ? v[1] : 0.f)); }
     __device__ float sum_all(const float v[2]) const { return warp_sum(v[0] + v[1]); }
     // Organism.health_percent / energy_percent (sprites.py:1306-1324)
     __device__ float health_percent() const { float cur = sum_living(health), mx = sum_all(maxhealth); return (cur == 0.f || mx == 0.f) ? 0.f : cur / mx * 100.0f; }
-    __device__ float energy_percent() const { float t = sum_living(energy), m = sum_living(storage); return (t == 0.f || m == 0.f) ? 0.f : t / m * 100.0f; }
+    __device__ float energy_percent() const { return (float)energy_percent_d(); }
+    __device__ double max_energy_d() const { return dsum((alive[0] == 1 ? (double)storage[0] : 0.0) + (alive[1] == 1 ? (double)storage[1] : 0.0)); }
+    __device__ double total_energy_d() const { return dsum((alive[0] == 1 ? energy[0] : 0.0) + (alive[1] == 1 ? energy[1] : 0.0)); }
     // double versions for the dopamine / pain signal: it is a difference of two nearly equal percentages (sprites.py:1610-1611)
-    __device__ static double dsum(double v) { for (int s = 16; s; s >>= 1) v += __shfl_xor_sync(FULL, v, s); return v; }
     __device__ double health_percent_d() const {
         double cur = dsum((alive[0] == 1 ? (double)health[0] : 0.0) + (alive[1] == 1 ? (double)health[1] : 0.0)), mx = dsum((double)maxhealth[0] + (double)maxhealth[1]);
         return (cur == 0.0 || mx == 0.0) ? 0.0 : cur / mx * 100.0;
     }
     __device__ double energy_percent_d() const {
-        double t = dsum((alive[0] == 1 ? (double)energy[0] : 0.0) + (alive[1] == 1 ? (double)energy[1] : 0.0));
-        double m = dsum((alive[0] == 1 ? (double)storage[0] : 0.0) + (alive[1] == 1 ? (double)storage[1] : 0.0));
+        double t = total_energy_d();
+        double m = max_energy_d();
         return (t == 0.0 || m == 0.0) ? 0.0 : t / m * 100.0;
     }
 
@@ -113,39 +117,50 @@ struct OrgR {
     // Organism.add_energy (sprites.py:1380-1398): equal shares in row order, overflow carried to the next living cell.
     // The carry is a max-plus recurrence c' = max(0, c + e + share - cap): composed with a warp scan of (A, S) pairs,
     // f(c) = max(A, c + S). Returns the overflow of the last living cell.
-    __device__ float add_energy(float amount, int n) {
-        if (!n) return 0.f;
-        float per = amount / (float)n, carry = 0.f;
+    // The scan is carried in double: its partial sums of (energy + share - cap) reach 1e4 over 64 cells while the carry they
+    // cancel to is O(1) -- in fp32 the refund and the energies behind it were off by 1e-3 (absolute) in well-fed organisms.
+    __device__ double add_energy(double amount, int n) {
+        if (!n) return 0.0;
+        const double per = amount / (double)n;
+        double carry = 0.0;
+        {   // nobody overflows (the usual case: only a well-fed organism is full): the carry stays zero, no scan
+            const bool over = (alive[0] == SAPIO_CELL_ALIVE && energy[0] + per > (double)storage[0]) || (alive[1] == SAPIO_CELL_ALIVE && energy[1] + per > (double)storage[1]);
+            if (!__any_sync(FULL, over)) {
+#pragma unroll
+                for (int h = 0; h < 2; h++) if (alive[h] == SAPIO_CELL_ALIVE) energy[h] += per;
+                return 0.0;
+            }
+        }
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             bool a = alive[h] == SAPIO_CELL_ALIVE;
-            float A = a ? 0.f : -INFINITY, S = a ? (energy[h] + per - storage[h]) : 0.f;
-            float iA = A, iS = S;                       // inclusive scan over lanes
+            double A = a ? 0.0 : -INFINITY, S = a ? (energy[h] + per - (double)storage[h]) : 0.0;
+            double iA = A, iS = S;                      // inclusive scan over lanes
             for (int d = 1; d < 32; d <<= 1) {
-                float pA = __shfl_up_sync(FULL, iA, d), pS = __shfl_up_sync(FULL, iS, d);
-                if (lane >= d) { iA = fmaxf(iA, pA + iS); iS = pS + iS; }
+                double pA = __shfl_up_sync(FULL, iA, d), pS = __shfl_up_sync(FULL, iS, d);
+                if (lane >= d) { iA = fmax(iA, pA + iS); iS = pS + iS; }
             }
-            float eA = __shfl_up_sync(FULL, iA, 1), eS = __shfl_up_sync(FULL, iS, 1);   // exclusive
-            if (lane == 0) { eA = -INFINITY; eS = 0.f; }
-            float cin = fmaxf(eA, carry + eS);
-            if (a) { float e = energy[h] + per + cin; energy[h] = e > storage[h] ? storage[h] : e; }
-            float lA = __shfl_sync(FULL, iA, 31), lS = __shfl_sync(FULL, iS, 31);
-            carry = fmaxf(lA, carry + lS);
+            double eA = __shfl_up_sync(FULL, iA, 1), eS = __shfl_up_sync(FULL, iS, 1);   // exclusive
+            if (lane == 0) { eA = -INFINITY; eS = 0.0; }
+            double cin = fmax(eA, carry + eS);
+            if (a) { double e = energy[h] + per + cin; energy[h] = e > (double)storage[h] ? (double)storage[h] : e; }
+            double lA = __shfl_sync(FULL, iA, 31), lS = __shfl_sync(FULL, iS, 31);
+            carry = fmax(lA, carry + lS);
         }
         return carry;
     }
     // Organism.take_energy (sprites.py:1400-1407)
-    __device__ void take_energy(float amount, int n) {
-        float per = amount / (float)n;
+    __device__ void take_energy_sum(double per) {
+        if (per == 0.0) return;
 #pragma unroll
-        for (int h = 0; h < 2; h++) if (alive[h] == SAPIO_CELL_ALIVE) energy[h] = fmaxf(energy[h] - per, 0.f);
+        for (int h = 0; h < 2; h++) if (alive[h] == SAPIO_CELL_ALIVE) energy[h] = fmax(energy[h] - per, 0.0);
     }
     __device__ void store(const SapioWorld &w, bool with_body) const {
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             int k = lane + 32 * h, row = o * MAXC + k;
             if (k >= nc) continue;
-            w.c_health[row] = health[h]; w.c_energy[row] = energy[h]; w.c_alive[row] = (uint8_t)alive[h];
+            w.c_health[row] = health[h]; w.c_energy[row] = (float)energy[h]; w.c_alive[row] = (uint8_t)alive[h];
             if (with_body) {
                 w.c_inuse[row] = (uint8_t)inuse[h];
                 reinterpret_cast<float2 *>(w.c_vel)[row] = make_float2(vx[h], vy[h]); w.c_angvel[row] = av[h];
@@ -213,7 +228,7 @@ __global__ void __launch_bounds__(RULES_WARPS * 32) k_rules_begin(WORLD_ARG, Rul
             if (consumed != 0.f) {
                 float dig = 95.0f / 100.0f * consumed * dt;
                 consumed -= dig;
-                consumed += g.add_energy(dig * 1.2f, g.n_living());
+                consumed += (float)g.add_energy((double)dig * 1.2, g.n_living());
             }
             if ((phases & SAPIO_PH_THINK) && w.org_nlayers[o] > 0 && T - w.org_think_tick[o] >= p.think_ticks) {
                 double ddt = (double)(T - w.org_dopa_tick[o]) * (double)dt;                       // _update_brain, sprites.py:1608-1625
@@ -252,7 +267,7 @@ __global__ void __launch_bounds__(RULES_WARPS * 32) k_rules_begin(WORLD_ARG, Rul
 }
 
 #ifndef RULES_MAIN_MINB
-#define RULES_MAIN_MINB 4       // resident CTAs per SM the register allocation aims for: the per-cell loop is a dependent shuffle chain, warps in flight hide it
+#define RULES_MAIN_MINB 3       // resident CTAs per SM the register allocation aims for: the per-cell loop is a dependent shuffle chain, warps in flight hide it
 #endif
 __global__ void __launch_bounds__(RULES_WARPS * 32, RULES_MAIN_MINB) k_rules_main(WORLD_ARG, RulesWs R, uint32_t phases) {
     const SapioParams &p = w.p;
@@ -278,12 +293,12 @@ __global__ void __launch_bounds__(RULES_WARPS * 32, RULES_MAIN_MINB) k_rules_mai
             float lh = g.health_percent(), le = g.energy_percent();                              // sprites.py:1653-1654
             if (g.n_living() == 1) died += g.kill(w, 0);                                         // sprites.py:1656-1657
             if (lane == 0 && g.alive[0] == SAPIO_CELL_ALIVE) { w.org_pos[2 * o] = g.px[0]; w.org_pos[2 * o + 1] = g.py[0]; }
-            float emax = g.sum_living(g.storage);
-            if (g.n_living() > 0 && g.sum_living(g.energy) >= emax / 1.01f && T - w.org_lastbirth_tick[o] >= p.repro_ticks) {
+            const double emax = g.max_energy_d();
+            if (g.n_living() > 0 && g.total_energy_d() >= emax / 1.01 && T - w.org_lastbirth_tick[o] >= p.repro_ticks) {
                 uint32_t r[4];
                 rng4(p.seed, w.org_uid[o], T, RNG_REPRO_GATE, 0, r);
                 float u = u01(r[0]);
-                if (u * 100.0f <= g.health_percent() && !(w.g_population[0] >= p.population_limit)) {
+                if ((double)u * 100.0 <= g.health_percent_d() && !(w.g_population[0] >= p.population_limit)) {
                     if (phases & SAPIO_PH_REPRODUCE) req |= SAPIO_REQ_REPRODUCE;
                     if (lane == 0) w.org_lastbirth_tick[o] = T;                                  // sprites.py:1442
                 }
@@ -293,6 +308,10 @@ __global__ void __launch_bounds__(RULES_WARPS * 32, RULES_MAIN_MINB) k_rules_mai
             }
             if (lane == 0) { w.org_last_health[o] = lh; w.org_last_energy[o] = le; }
             int nliv = g.n_living();                                                             // kept current across kills below
+            // take_energy of every cell's usage from every living cell (sprites.py:1400-1407, O(C^2) in the reference): the shares are
+            // uniform, and max(max(e - a, 0) - b, 0) == max(e - a - b, 0), so they are summed and taken when somebody looks
+            double pending = 0.0;
+            uint64_t rot_am = 0; double rot = 0.0;                                               // Organism.rotation, cached per set of living cells
             // Organism.rotation (sprites.py:1179-1201) is only used as an angle: cur - old (the % 360 cancels in cos/sin)
             for (int k = 0; k < g.nc; k++) {                                                     // _update_cell, sprites.py:1470-1606
                 float hk = bcast2(g.health[0], g.health[1], k);
@@ -316,45 +335,57 @@ __global__ void __launch_bounds__(RULES_WARPS * 32, RULES_MAIN_MINB) k_rules_mai
                 }
                 if (tk == SAPIO_T_PUSH) {                                                        // sprites.py:1519-1544
                     if (fabsf(mv1) >= 0.1f) {
-                        uint64_t am = g.alive_mask() & ~1ull;
-                        float rot = 0.f;
-                        if (am) {
+                        // In double like the reference's Python floats, rounded once into the fp32 velocity: a push that is one ulp off
+                        // flips the rounding of the integrated position (ulp 0.002 px at x = 2e4, 0.016 px at 2e5), and the pin joints turn
+                        // that into 0.01 .. 0.08 px/s of bias velocity -- single-tick parity at 10k organisms and more hangs on this.
+                        const uint64_t am = g.alive_mask() & ~1ull;
+                        if (am != rot_am) {                                                      // Organism.rotation (sprites.py:1179-1201)
+                            rot_am = am;
                             int rel = __ffsll((long long)am) - 1, rrow = o * MAXC + rel;
-                            float rx = bcast2(g.px[0], g.px[1], rel) - bcast2(g.px[0], g.px[1], 0), ry = bcast2(g.py[0], g.py[1], rel) - bcast2(g.py[0], g.py[1], 0);
-                            rot = atan2f(ry, rx) - atan2f(w.c_rel[2 * rrow + 1], w.c_rel[2 * rrow]);
+                            double rx = (double)bcast2(g.px[0], g.px[1], rel) - (double)bcast2(g.px[0], g.px[1], 0), ry = (double)bcast2(g.py[0], g.py[1], rel) - (double)bcast2(g.py[0], g.py[1], 0);
+                            double deg = (atan2(ry, rx) - atan2((double)w.c_rel[2 * rrow + 1], (double)w.c_rel[2 * rrow])) * (180.0 / 3.14159265358979323846);
+                            deg = fmod(deg, 360.0); if (deg < 0.0) deg += 360.0;
+                            rot = deg * (3.14159265358979323846 / 180.0);
                         }
-                        float ang = atan2f(mv3, mv2) + rot, speed = mv1 * p.max_push * dt;
-                        if (mine) { const float dvx = cosf(ang) * speed, dvy = sinf(ang) * speed; if (hsel) { g.vx[1] += dvx; g.vy[1] += dvy; } else { g.vx[0] += dvx; g.vy[0] += dvy; } }
+                        if (mine) {
+                            const double ang = atan2((double)mv3, (double)mv2) + rot, speed = (double)mv1 * (double)p.max_push * (double)dt;
+                            const double dvx = cos(ang) * speed, dvy = sin(ang) * speed;
+                            if (hsel) { g.vx[1] = (float)((double)g.vx[1] + dvx); g.vy[1] = (float)((double)g.vy[1] + dvy); }
+                            else { g.vx[0] = (float)((double)g.vx[0] + dvx); g.vy[0] = (float)((double)g.vy[0] + dvy); }
+                        }
                         inuse_k = 1;
                     } else inuse_k = 0;
                 }
                 if (tk == SAPIO_T_ROTATE) {                                                      // sprites.py:1546-1552: per tick, not per second
-                    if (mine) { if (hsel) g.av[1] += mv0 * p.max_rot; else g.av[0] += mv0 * p.max_rot; }
+                    if (mine) { if (hsel) g.av[1] = (float)((double)g.av[1] + (double)mv0 * (double)p.max_rot); else g.av[0] = (float)((double)g.av[0] + (double)mv0 * (double)p.max_rot); }
                     inuse_k = fabsf(mv0) >= 0.1f;
                 }
                 if (mine) { if (hsel) g.inuse[1] = inuse_k; else g.inuse[0] = inuse_k; }
-                float idle = bcast2(g.use_idle[0], g.use_idle[1], k), act = bcast2(g.use_act[0], g.use_act[1], k), usage;   // sprites.py:1554-1574
+                float idle = bcast2(g.use_idle[0], g.use_idle[1], k), act = bcast2(g.use_act[0], g.use_act[1], k); double usage;   // sprites.py:1554-1574
                 if (inuse_k) {
-                    if (tk == SAPIO_T_PUSH || tk == SAPIO_T_ROTATE) { float e = (act - idle) * (tk == SAPIO_T_PUSH ? mv1 : mv0); usage = e < 0.f ? fabsf(-idle + e) : idle + e; }
-                    else usage = act;
-                } else usage = idle;
-                g.take_energy(usage * dt, nliv);
+                    if (tk == SAPIO_T_PUSH || tk == SAPIO_T_ROTATE) { double e = ((double)act - (double)idle) * (double)(tk == SAPIO_T_PUSH ? mv1 : mv0); usage = e < 0.0 ? fabs(-(double)idle + e) : (double)idle + e; }
+                    else usage = (double)act;
+                } else usage = (double)idle;
+                pending += usage * (double)dt / (double)nliv;
                 const double rho = __shfl_sync(FULL, hsel ? rho_1 : rho_0, k & 31);
                 if (tk == SAPIO_T_CO2C) {                                                        // convert_co2, sprites.py:1409-1428 (C4)
                     double gq = rho * x;
                     x -= gq;
-                    float spare = g.add_energy((float)(gq * (double)p.co2_ratio), nliv);
-                    refund += (double)spare / (double)p.co2_ratio;
+                    g.take_energy_sum(pending); pending = 0.0;
+                    const double spare = g.add_energy(gq * (double)p.co2_ratio, nliv);
+                    refund += spare / (double)p.co2_ratio;
                 } else { double gq = rho * (Ttot - x); x += gq; }                               // convert_o2, sprites.py:1430-1439
                 if (mine) {
                     // static indices only: a runtime index would move these per-lane arrays from registers to local memory
-                    float cap = hsel ? g.storage[1] : g.storage[0], mh = hsel ? g.maxhealth[1] : g.maxhealth[0], e = hsel ? g.energy[1] : g.energy[0], hh = hsel ? g.health[1] : g.health[0];
-                    if (e > cap) e = cap;
-                    if (e >= cap / 2 && hh < mh) { hh += p.heal_rate / 100.0f * mh * dt; if (hh > mh) hh = mh; }        // sprites.py:1589-1594
-                    if (e <= 2.0f / 100.0f * cap) hh -= p.starvation_rate / 100.0f * mh * dt;                           // sprites.py:1603-1606
-                    if (hsel) { g.energy[1] = e; g.health[1] = hh; } else { g.energy[0] = e; g.health[0] = hh; }
+                    float cap = hsel ? g.storage[1] : g.storage[0], mh = hsel ? g.maxhealth[1] : g.maxhealth[0], hh = hsel ? g.health[1] : g.health[0];
+                    double e = fmax((hsel ? g.energy[1] : g.energy[0]) - pending, 0.0);
+                    if (e > (double)cap) { e = (double)cap; if (hsel) g.energy[1] = e + pending; else g.energy[0] = e + pending; }
+                    if (e >= (double)cap / 2 && hh < mh) { hh += p.heal_rate / 100.0f * mh * dt; if (hh > mh) hh = mh; }        // sprites.py:1589-1594
+                    if (e <= 2.0 / 100.0 * (double)cap) hh -= p.starvation_rate / 100.0f * mh * dt;                           // sprites.py:1603-1606
+                    if (hsel) g.health[1] = hh; else g.health[0] = hh;
                 }
             }
+            g.take_energy_sum(pending);
             if ((phases & SAPIO_PH_TRAIN) && !(w.org_flags[o] & SAPIO_F_MALADAPTIVE) && w.org_nlayers[o] > 0 && T - w.org_train_tick[o] >= p.train_ticks) req |= SAPIO_REQ_TRAIN;
             if (lane == 0) stat_add(w, SAPIO_STAT_ORG_TICKS, 1);
         }

@@ -227,6 +227,7 @@ __global__ void __launch_bounds__(256) k_step_finish(WORLD_ARG, Workspace W, int
         w.g_stats[SAPIO_STAT_XCONTACTS] = nx; w.g_stats[SAPIO_STAT_ICONTACTS] = W.flags[FL_NIC];
         w.g_stats[SAPIO_STAT_LEVELS] = W.flags[FL_MAXLEVEL]; w.g_stats[SAPIO_STAT_COUPLED] = W.flags[FL_NCOUPLED];
         if (W.flags[FL_OVERFLOW]) w.g_stats[SAPIO_STAT_OVERFLOW] += 1;
+        w.g_stats[SAPIO_STAT_RARE_PATHS] |= W.flags[FL_RARE];
     }
 }
 

@@ -31,7 +31,7 @@ struct Workspace {
     char *cp_state; int cp_cap;     // parked solver state of the first cp_cap coupled organisms (sizeof(OrgS<MAXC>) each)
 };
 enum { FL_NX = 0, FL_NADJ = 1, FL_OVERFLOW = 2, FL_MAXLEVEL = 3, FL_NCOUPLED = 5, FL_NIC = 6, FL_CLS0 = 8 /* ..16: class starts + end */,
-       FL_WORK0 = 20 /* ..27 */, FL_TMPTOP = 28, FL_NHIT = 29, FL_HIST = 32 /* ..96 */, FL_CHIST = 100 /* ..164: coupled organisms by rows */,
+       FL_WORK0 = 20 /* ..27 */, FL_TMPTOP = 28, FL_NHIT = 29, FL_RARE = 30, FL_HIST = 32 /* ..96 */, FL_CHIST = 100 /* ..164: coupled organisms by rows */,
        FL_CCLS0 = 168 /* ..176: class starts + end in coupled_list */, FL_CHG0 = 180 /* ..182 */, FL_CWORK0 = 200 /* ..203: two alternating pairs of work counters of k_coupled */, FL_BYTES = 1024 };
 
 #define COUPLED_STATE_BYTES 49152      /* >= sizeof(OrgS<MAXC>), checked where the struct is known */

@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(TRAIN_THREADS, 4) k_train(WORLD_ARG, RulesWs R
         __syncthreads();
         const int q = sh_q;
         if (q >= n_train) break;
+        if (tid == 0 && q >= (int)gridDim.x) atomicOr((unsigned long long *)&w.g_stats[SAPIO_STAT_RARE_PATHS], (unsigned long long)SAPIO_RARE_TRAIN_QUEUE);   // a CTA came back for more
         const int o = R.train_list[q];
         const int32_t *ldim = w.org_ldim + o * 16;
         const int nl = w.org_nlayers[o], I = ldim[0];

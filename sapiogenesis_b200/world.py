@@ -44,7 +44,7 @@ PH_REUSE_GRID = 128
 
 STAT_NAMES = ["births", "deaths", "cell_deaths", "dead_removed", "thinks", "trains", "xcontacts",
               "icontacts", "birth_fail_place", "birth_fail_caps", "overflow", "org_ticks", "levels",
-              "coupled", "r14", "r15"]
+              "coupled", "rare_paths", "full_scans"]
 
 # per-type tables: sprites.base_cell_info (sprites.py:67-121); index = T_*
 BASE_HEALTH = [30, 30, 8, 24, 15, 24, 24, 24, 15]
@@ -214,7 +214,7 @@ class World:
         w = World.__new__(World)
         w.p = SapioParams.from_buffer_copy(bytes(self.p))
         w.device = torch.device(device)
-        w.t = {k: v.to(w.device).clone() for k, v in self.t.items()}
+        w.t = {k: v.to(w.device, copy=True) for k, v in self.t.items()}
         w._struct = None
         return w
 

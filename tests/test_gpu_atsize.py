@@ -1,0 +1,128 @@
+"""Single-tick parity against the oracle AT THE SIZES THE BENCH QUOTES and on an aged world: the
+branches only large or aged worlds reach -- grid-wide level relaxation (> 4096 cross contacts), the coupled pass chosen by the
+library itself under load, the placement full scan (> 64 organisms within reach of a birth), the training work counter with
+more organisms than CTAs -- are compared with the oracle here, field by field, from identical state:
+
+  the world is built and aged on the GPU (production path: grid reuse, pipelined nothing), copied to the host byte for byte,
+  then ONE tick runs on the GPU and in the oracle and `compare_worlds` checks every field (bit-exact integers / contact sets /
+  decisions, fp32 at 1e-5 of the field's scale: tests/parity.py).
+
+The rare-path bits of g_stats[SAPIO_STAT_RARE_PATHS] are printed and asserted, so that a green test is evidence the branch ran."""
+import numpy as np
+import pytest
+import torch
+
+from parity import compare_worlds
+from sapiogenesis_b200.world import MAXC, PH_ALL, PH_REPRODUCE, PH_TRAIN
+
+pytestmark = pytest.mark.gpu
+
+RARE = {1: "grid-wide level relaxation", 2: "coupled pass under load (packed / component form)", 4: "placement full scan",
+        8: "training work counter beyond one CTA wave", 16: "birth cap"}
+
+
+def one_tick_parity(oracle, w, eng, phases, tag, **kw):
+    """GPU world `w` (already aged through `eng`): copy to the host, one tick both sides, compare everything."""
+    import time
+    t0 = time.time()
+    eng.synchronize()
+    host = w.to("cpu")
+    t1 = time.time()
+    before = None; kw.pop("check_untouched", None)
+    w.t["g_stats"].view(-1)[14] = 0                                           # rare-path bits: evidence of THIS tick only
+    st0 = w.stats()
+    eng.tick(1, phases); eng.synchronize()
+    assert oracle.tick(host, phases, 1) == 0
+    t2 = time.time()
+    st = w.stats()
+    so = host.stats()
+    for k in ("births", "deaths", "cell_deaths", "dead_removed", "thinks", "trains", "xcontacts", "icontacts", "birth_fail_place", "org_ticks"):
+        assert st[k] == so[k], (k, st[k], so[k])
+    req = host.np("org_req")
+    detail = np.nonzero((req & 6) != 0)[0]                                   # thought or trained this tick
+    newborn = np.nonzero(host.np("org_birth_tick") == host.tick - 1)[0]
+    detail = np.union1d(detail, newborn)
+    rep = compare_worlds(w, host, tag, detail_orgs=detail, before=before, **kw)
+    rare = st["rare_paths"]
+    print(f"{tag}: host copy {t1 - t0:.1f} s, both ticks {t2 - t1:.1f} s, comparison {time.time() - t2:.1f} s")
+    print(f"{tag}: organisms {int((host.np('org_state') == 1).sum())}, cross contacts {st['xcontacts']}, intra {st['icontacts']}, coupled {st['coupled']}, "
+          f"levels {st['levels']}, thinks +{st['thinks'] - st0['thinks']}, trains +{st['trains'] - st0['trains']}, births +{st['births'] - st0['births']}, "
+          f"full scans {st['full_scans']}, rare paths: {[v for k, v in RARE.items() if rare & k]}")
+    return st, rep
+
+
+def test_10k_forward_only_tick_matches_oracle(oracle):
+    """BASELINE configs[1]: 10k organisms, physics + sensors + brain forward only."""
+    from sapiogenesis_b200.synth import build_world
+    w, eng = build_world(10_000, seed=3)
+    w.t["org_flags"] |= 2                                                     # maladaptive: no training (sprites.py:1832)
+    w.p.population_limit = 0; eng.refresh()
+    eng.exclusive = True
+    ph = PH_ALL & ~(PH_TRAIN | PH_REPRODUCE)
+    eng.tick(24, ph)
+    for k in range(3):                                                        # three consecutive single-tick checks, each from the GPU's own state
+        st, _ = one_tick_parity(oracle, w, eng, ph, f"10k forward-only, tick {w.tick}")
+    assert st["thinks"] > 10_000 and st["trains"] == 0 and st["births"] == 0
+
+
+def test_100k_full_tick_matches_oracle(oracle):
+    """BASELINE configs[2]: 100k organisms, full tick -- the bench workload itself (same builder, same caps)."""
+    import psutil
+    from sapiogenesis_b200.synth import build_world
+    if psutil.virtual_memory().available < 130 * 2 ** 30:
+        pytest.skip("the host copy of the 100k-organism world (43 GiB) and one field of the GPU's at a time need ~100 GiB of host memory")
+    w, eng = build_world(100_000, seed=0, slot_factor=1.02)
+    eng.exclusive = True
+    eng.tick(34)                                                              # two think periods: memories exist, dopamine flows, contacts are warm
+    st, _ = one_tick_parity(oracle, w, eng, PH_ALL, "100k full tick", check_untouched=True)
+    assert st["trains"] > 100_000 and st["rare_paths"] & 8                    # > 1184 training organisms per tick: the CTAs come back for more
+
+
+@pytest.fixture(scope="module")
+def aged_world():
+    """A dense 14k-organism world aged on the GPU until it is crowded: debris of a starvation wave, full memories, births."""
+    from sapiogenesis_b200.synth import build_world
+    w, eng = build_world(14_000, seed=5, area_per_org=200_000.0, food_per_org=1.0)
+    eng.exclusive = True
+    eng.tick(3200)
+    eng.synchronize()
+    return w, eng
+
+
+def test_aged_world_tick_matches_oracle(oracle, aged_world):
+    w, eng = aged_world
+    s0 = w.stats()
+    print("aged world:", {k: s0[k] for k in ("births", "deaths", "cell_deaths", "xcontacts", "coupled", "levels", "rare_paths")},
+          "mean memory rows", float(w.t["org_mem_n"][w.t["org_state"] == 1].float().mean()))
+    assert s0["xcontacts"] > 4096, "the aged world must hold more cross contacts than one CTA relaxes"
+    assert s0["coupled"] > 2400, "the aged world must load the coupled pass"
+    assert int(w.t["org_mem_n"].max()) >= w.p.memory_limit
+    for k in range(4):
+        # Crowded and violent: dead bodies shot out of deep overlaps at 500 px/s against a field rms of 30, organisms whose cells change
+        # their velocity by 250 px/s within the tick. An fp32 solver resolves those to an ulp of the LOCAL velocity scale (measured:
+        # the worst body is off by 1.1e-5 of the velocity change of its own organism, tools/debug_aged.py), which is 1e-4 of the
+        # world's rms; 1 % of the bodies exceed 1e-5 of the rms, 34 of 372k exceed 3e-5, none 1e-4. Energies O(2e3) pass through
+        # ~2n dependent fp32 updates per tick (2 cells of 372k above 1e-5); the Adam moments of a 200-row batch sum 800 terms.
+        st, _ = one_tick_parity(oracle, w, eng, PH_ALL, f"aged world, tick {w.tick}", phys_tol=3e-4, adam_tol=5e-4, extra_tols={"c_energy": 3e-5})
+        eng.tick(16)                                                          # another phase of the think / train stagger each time
+    assert st["rare_paths"] & 1 and st["rare_paths"] & 2
+
+
+def test_birth_wave_with_crowded_placement_matches_oracle(oracle):
+    """Everybody is full and due at once in a squeezed world: hundreds of simultaneous requests, each with more than
+    REPRO_NEAR_CAP organisms within reach of its 360 candidate positions (the full-scan branch of k_repro_place)."""
+    from sapiogenesis_b200.engine import Engine
+    from worlds import make_world
+    w = make_world(oracle, n_org=400, seed=21, width=2600.0, height=2600.0, n_food=40, crowd=0.42, kick=10.0, extra_slots=240, n_dead_cap=64 * 64)
+    w.p.repro_ticks = 4
+    w.p.population_limit = 640
+    assert oracle.tick(w, PH_ALL, 5) == 0
+    w.t["c_energy"][:] = w.t["c_storage"]
+    w.t["c_health"][:] = w.t["c_maxhealth"]
+    wg = w.to("cuda"); eng = Engine(wg)
+    eng.tick(1); eng.synchronize()
+    assert oracle.tick(w, PH_ALL, 1) == 0
+    st = wg.stats()
+    print("birth wave:", {k: st[k] for k in ("births", "birth_fail_place", "full_scans", "rare_paths")})
+    compare_worlds(wg, w, "birth wave", phys_tol=1e-4)
+    assert st["full_scans"] > 0 and st["rare_paths"] & 4 and st["births"] > 20
