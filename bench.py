@@ -163,18 +163,113 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total_t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"full world tick, {cores} x {n_org} organisms x {ticks} ticks per step (bounded sample of the 100k-organism workload)",
-                   "organisms": cores * n_org},
+        "config": {"workload": workload_name(args, args.organisms), "organisms_per_gpu": args.organisms,
+                   "sample": f"bounded sample of that workload: {cores} x {n_org} organisms x {ticks} ticks per step, young worlds (the port's cost per organism-tick "
+                             f"does not depend on the world size: broadphase grid and per-organism loops are linear)", "organisms": cores * n_org},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
+def world_shape(w, eng):
+    """Realised sizes of the world, the inputs of the algorithmic-byte formulas, split into organisms without
+    and with cross contacts (the organism solver and the coupled pass share the formula, on their own organisms)."""
+    import torch
+    from sapiogenesis_b200.world import MAXC
+    t = w.t
+    org = t["org_state"] == 1
+    alive = (t["c_alive"] == 1).view(-1, MAXC) & org[:, None]
+    cells_per = alive.sum(1).to(torch.int64)
+    types = t["c_type"].view(-1, MAXC)
+    sens_per = (alive & ((types == 2) | (types == 3))).sum(1).to(torch.int64)
+    off = t["xa_off"].to(torch.int64)
+    deg = (off[1:] - off[:-1])
+    NC = w.p.n_org * MAXC
+    org_deg = deg[:NC].view(-1, MAXC).sum(1)
+    coupled = org & (org_deg > 0)
+    free = org & ~coupled
+    icn = t["org_ic_n"].to(torch.int64)
+    dead_live = t["d_state"] > 0
+    dead_coupled = int((dead_live & (deg[NC:NC + w.p.n_dead] > 0)).sum())
+    def part(m):
+        c = cells_per[m]
+        return dict(organisms=int(m.sum()), cells=int(c.sum()), sensors=int(sens_per[m].sum()), pairs=int((c * (c - 1) // 2).sum()), intra_contacts=int(icn[m].sum()))
+    return dict(free=part(free), coupled=part(coupled), all=part(org), dead=int(dead_live.sum()), dead_coupled=dead_coupled,
+                cross_contacts=int(t["g_x_n"].item()), cells_hist=torch.bincount(cells_per[free], minlength=MAXC + 1).cpu().tolist(),
+                icn_by_cells=(torch.zeros(MAXC + 1, dtype=torch.float64, device=cells_per.device).index_add_(0, cells_per[free], icn[free].double())).cpu().tolist(),
+                mean_memory_rows=float(t["org_mem_n"][org].float().mean()) if int(org.sum()) else 0.0)
+
+
+def solver_bytes(part):
+    return 74 * part["cells"] + 32 * part["sensors"] + 8 * part["pairs"] + 20 * part["intra_contacts"]
+
+
+def chain_bound(shape, info, ms, mhz, iterations=10, ideal_cycles=70.0):
+    """The yardstick that applies to the organism solver (it is not memory-bound): a sweep over an organism of n living cells is a
+    dependent chain of 2n-3 pin wavefronts + the sensor-pin step + its contact level steps; organisms in flight per SM are what the
+    shared-memory footprint of a size class admits. ideal = steps / (SMs x lane groups in flight) x 70 cycles (one shared-memory load,
+    seven dependent fp32 operations, the store and the warp barrier) at the clock of the run; achieved cycles per step next to it."""
+    hist, icn = shape["cells_hist"], shape["icn_by_cells"]
+    ideal_ms = 0.0; steps_total = 0.0; slots = 0.0
+    for n in range(1, len(hist)):
+        if not hist[n]:
+            continue
+        cls = 0 if n <= 8 else (n - 1) >> 3
+        i = info[cls]
+        groups = max(1, i["resident_ctas"] // max(i["sms"], 1)) * i["warps_per_cta"] * i["orgs_per_warp"]
+        k = icn[n] / hist[n]
+        contact_steps = max(1.0, 2.0 * k / n) if k > 0 else 0.0          # levels of a tree-like contact set, lanes >= the widest level
+        steps = hist[n] * iterations * (max(2 * n - 3, 0) + 1 + contact_steps)
+        steps_total += steps; slots += steps / (i["sms"] * groups)
+    ideal_ms = slots * ideal_cycles / (mhz * 1e3)
+    return {"model": "sum over size classes of wavefront steps / (SMs x organisms in flight per SM) x cycles per step; classes run back to back",
+            "wavefront_steps_per_tick": steps_total, "serial_steps_per_lane_group": slots, "ideal_cycles_per_step": ideal_cycles,
+            "ideal_ms": ideal_ms, "achieved_ms": ms, "frac": ideal_ms / ms if ms else None,
+            "achieved_cycles_per_step": ms * mhz * 1e3 / slots if slots else None, "sm_mhz": mhz}
+
+
+def ncu_traffic():
+    """DRAM bytes per tick of the solver kernels from the committed ncu capture (tools/ncu_capture.sh -> profiles/ncu_traffic.json),
+    only if it was taken on exactly these kernel sources."""
+    try:
+        from sapiogenesis_b200.build import source_hash
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            d = json.load(f)
+        return d if d.get("source_sha") == source_hash() else None
+    except Exception:
+        return None
+
+
+def timed_ticks(isl, eng, w, n, barrier, dist, world_size, dev, profile=False):
+    """n ticks, device-timed (CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks)."""
+    import torch
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ticks0 = w.stats()["org_ticks"]; launches0 = eng.launch_count()
+    if profile:
+        eng.profile(True)
+    barrier()
+    ev0.record()
+    isl.step(n)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    prof = None
+    if profile:
+        prof = eng.profile_read(reset=True); eng.profile(False)
+    units = w.stats()["org_ticks"] - ticks0
+    t = torch.tensor([ms, float(units)], dtype=torch.float64, device=dev)
+    if world_size > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, units = float(tmax[0]), float(tsum[1])
+    return ms, units, prof, eng.launch_count() - launches0
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from sapiogenesis_b200.synth import build_world, world_stats
-    from sapiogenesis_b200.world import PH_ALL
+    from sapiogenesis_b200.synth import build_world
+    from sapiogenesis_b200.world import PH_ALL, PH_REPRODUCE, PH_TRAIN
 
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -191,44 +286,51 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    clk = ClockSampler(local_rank)
+    clk.__enter__()                                        # sampled over the whole run (ageing included): the timed region is a fraction of a second
     M = args.organisms
     w, eng = build_world(M, device=dev, seed=rank)
-    # N > 1: population islands with ring migration of whole organisms (the only exchange step of the path; NCCL p2p)
     from sapiogenesis_b200.islands import Island
     if args.forward_only:                                # the same as maladaptive=True for everybody and population_limit=0
-        from sapiogenesis_b200.world import PH_REPRODUCE, PH_TRAIN
         w.t["org_flags"] |= 2
         w.p.population_limit = 0
         eng.refresh()
-    isl = Island(w, eng, every=args.migrate_every if world_size > 1 else 0, count=args.migrate_count, seed=1234)
-    isl.step(max(args.warmup, 3))
-    if world_size > 1 and args.migrate_every:
+    # N > 1: population islands with ring migration of whole organisms (the only exchange step of the path; NCCL p2p). The period is
+    # chosen so that the exchange fires INSIDE the timed region whatever --steps is.
+    every = min(args.migrate_every, max(args.steps // 2, 1)) if (world_size > 1 and args.migrate_every) else 0
+    isl = Island(w, eng, every=every, count=args.migrate_count, seed=1234)
+    warm = max(args.warmup, 3)
+    isl.step(warm)
+    if every:
         isl.migrate()                                   # warm-up of the exchange step too (NCCL p2p channels are set up lazily)
     eng.synchronize()
-    stats0 = world_stats(w)
+
+    # ---- the young world (round-1 headline, kept as a secondary figure): ticks warm .. warm + 20 -----------------------------------
+    y_ms, y_units, _, _ = timed_ticks(isl, eng, w, 20, barrier, dist, world_size, dev)
+    young = {"value": y_units / (y_ms / 1e3), "ms_per_step": y_ms / 20, "world_age_ticks": warm + 20,
+             "note": "the same world before ageing: memories empty, nobody reproduces, hardly any contact between organisms"}
+
+    # ---- ageing prelude, untimed: the measured world is a mature one ---------------------------------------------------------------
+    age = 0 if args.forward_only else max(args.age - (warm + 20), 0)
+    t_age = time.perf_counter()
+    done = 0
+    while done < age:                                   # in chunks: the launch queue stays short and a hung tick shows up
+        run = min(500, age - done)
+        isl.step(run); eng.synchronize(); done += run
+    t_age = time.perf_counter() - t_age
+    migr0 = (isl.migrated_out, getattr(isl, "migration_ms", 0.0), getattr(isl, "migrations", 0))
 
     # ---- device-resident throughput -------------------------------------------------------------------------------------
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = eng.launch_count()
-    ticks0 = w.stats()["org_ticks"]
-    eng.profile(True)
-    barrier()
-    with ClockSampler(local_rank) as clk:
-        ev0.record()
-        isl.step(args.steps)
-        ev1.record()
-        barrier()
-    ms = ev0.elapsed_time(ev1)
-    prof = eng.profile_read(reset=True)
-    eng.profile(False)
-    units = w.stats()["org_ticks"] - ticks0
-    launches = eng.launch_count() - launches0
-    t = torch.tensor([ms, float(units)], dtype=torch.float64, device=dev)
-    if world_size > 1:
-        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms, units = float(tmax[0]), float(tsum[1])
+    w.t["g_stats"].view(-1)[14] = 0                      # rare-path bits: evidence of the timed region only
+    st0 = w.stats()
+    region0 = len(clk.samples)
+    ms, units, prof, launches = timed_ticks(isl, eng, w, args.steps, barrier, dist, world_size, dev, profile=True)
+    region_samples = len(clk.samples) - region0
+    st1 = w.stats()
     value = units / (ms / 1e3)
+    migr = {"migrations_in_region": getattr(isl, "migrations", 0) - migr0[2], "organisms_sent_by_rank0": isl.migrated_out - migr0[0],
+            "migration_ms_total": round(isl.collect_migration_ms() - migr0[1], 3) if hasattr(isl, "collect_migration_ms") else None,
+            "bytes_per_migration": getattr(isl, "last_bytes", None)} if every else None
 
     # ---- end to end through the C-ABI with host buffers ---------------------------------------------------------------------
     e2e_steps = max(3, min(args.steps, 20))
@@ -255,60 +357,90 @@ def run_ours(args):
         tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         e2e_s, e2e_units = float(tmax[0]), float(tsum[1])
     e2e_value = e2e_units / e2e_s
+    clk.__exit__()
 
     if rank == 0:
+        shape = world_shape(w, eng)
+        s = shape["all"]
+        info = eng.solver_info()
+        state_gib = w.nbytes() / 2 ** 30
+        # ---- BASELINE configs[1] as a sub-record: 10k organisms, physics + sensors + brain forward only --------------------------
+        fwd = None
+        if world_size == 1 and not args.forward_only and not args.no_forward_record:
+            del isl
+            w2, eng2 = build_world(10_000, device=dev, seed=rank)
+            w2.t["org_flags"] |= 2; w2.p.population_limit = 0; eng2.refresh(); eng2.exclusive = True
+            ph = PH_ALL & ~(PH_TRAIN | PH_REPRODUCE)
+            eng2.tick(200, ph); eng2.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            u0 = w2.stats()["org_ticks"]
+            e0.record(); eng2.tick(200, ph); e1.record(); eng2.synchronize()
+            fms = e0.elapsed_time(e1)
+            fwd = {"workload": "BASELINE configs[1]: 10k organisms, one world, physics + sensors + brain forward only (no dopamine training, no reproduction)",
+                   "value": (w2.stats()["org_ticks"] - u0) / (fms / 1e3), "unit": UNIT, "ms_per_step": fms / 200, "steps": 200, "world_age_ticks": 400}
+            del w2, eng2
         # ---- roofline of the dominant kernel (algorithmic bytes: DESIGN.md "Kernels") -----------------------------------
-        s = world_stats(w)
         peak, peak_src = peaks()
         stage_ms = {k: v[0] / max(v[1], 1) for k, v in prof.items() if v[1] > 0}
         dom = max(stage_ms, key=stage_ms.get) if stage_ms else "org_solve"
-        alg = {  # bytes per launch group, every array touched once
-            "org_solve": 74 * s["cells"] + 32 * s["sensors"] + 8 * s["pairs"] + 20 * s["intra_contacts"],
+        traffic = ncu_traffic()
+        clocks = clk.summary()
+        mhz = clocks["sm_mhz"] or 1965.0
+        kernels = {
+            "org_solve": ("k_org_solve<8|16|24|32|40|48|56|64> (organisms without cross contacts: intra contacts + sensor pins + all-pairs pin joints, warm start + 10 "
+                          "Gauss-Seidel sweeps in shared memory; one launch per size class, concurrent streams)", solver_bytes(shape["free"])),
+            "coupled": ("coupled pass (organisms and dead bodies that share a cross contact: the same per-organism solve interleaved with the cross contacts)",
+                        solver_bytes(shape["coupled"]) + 64 * shape["cross_contacts"] + 36 * shape["dead_coupled"]),
         }
         roof = None
-        if "org_solve" in stage_ms:
-            ach = alg["org_solve"] / (stage_ms["org_solve"] / 1e3) / 1e9
-            # DRAM traffic of the same launch group from the committed ncu capture (profiles/r1c_org_solve.md): sum over the class
-            # kernels of dram__bytes_read + dram__bytes_write per tick at this workload
-            roof = {"bound": "hbm", "kernel": "k_org_solve<8|16|24|32|40|48|56|64> (organism solver: intra contacts + sensor pins + all-pairs pin joints, "
-                                               "warm start + 10 Gauss-Seidel sweeps in shared memory; one launch per size class, concurrent streams)",
-                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": 771.0e6 if abs(M - 100000) < 1000 else None, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": alg["org_solve"], "avg_ms": stage_ms["org_solve"],
-                    "share_of_step": stage_ms["org_solve"] / (ms / args.steps), "dominant_stage": dom,
-                    "note": "not HBM-bound: each sweep is a dependent chain of 2n-3 pin wavefronts per organism; ncu shows issue-slot "
-                            "utilisation 36-48 % at 8-12 resident warps per SM (shared-memory limited), DRAM at 1-2 % of peak"}
-        # the streaming stages against the same peak (algorithmic bytes: DESIGN.md section 4; slots = every body slot the kernel scans)
-        slots = w.p.n_org * 64 + w.p.n_dead
-        bodies = s["cells"] + s["dead"]
+        rk = dom if dom in kernels else "org_solve"
+        if rk in stage_ms:
+            name, alg = kernels[rk]
+            ach = alg / (stage_ms[rk] / 1e3) / 1e9
+            tr = traffic["kernels"].get(rk) if (traffic and traffic.get("organisms") == M and traffic.get("world_age_ticks") == args.age) else None
+            roof = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": tr, "traffic_source": (f"profiles/ncu_traffic.json (ncu --set full, kernel sources {traffic['source_sha']})" if tr else
+                                                      "null: no ncu capture of exactly these kernel sources and this workload is committed"),
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "avg_ms": stage_ms[rk], "share_of_step": stage_ms[rk] / (ms / args.steps),
+                    "dominant_stage": dom,
+                    "note": "not HBM-bound: each sweep is a dependent chain of 2n-3 pin wavefronts per organism; the yardstick that applies is chain_bound below"}
+            if "org_solve" in stage_ms:
+                roof["chain_bound"] = chain_bound(shape, info, stage_ms["org_solve"], mhz)
+        # the streaming stages against the same peak (algorithmic bytes: DESIGN.md section 4)
+        bodies = s["cells"] + shape["dead"]
         stream_bytes = {
-            "friction": 24 * bodies + slots,                                                   # vel2 + angvel r/w, liveness flag per slot
-            "broadphase": 36 * s["cells"] + 24 * s["sensors"] + 36 * s["dead"] + 8 * slots + 16 * slots,   # integrate + key/value write, sort r/w
-            "settle": 12 * bodies + slots,
-            "rules_main": 60 * s["cells"] + 128 * s["organisms"], "rules_begin": 60 * s["cells"] + 128 * s["organisms"],
+            "friction": 24 * bodies, "broadphase": 36 * s["cells"] + 24 * s["sensors"] + 36 * shape["dead"] + 16 * bodies,
+            "settle": 12 * bodies, "rules_main": 60 * s["cells"] + 128 * s["organisms"], "rules_begin": 60 * s["cells"] + 128 * s["organisms"],
         }
         stage_roof = {k: {"bytes": int(b), "ms": round(stage_ms[k], 4), "GB/s": round(b / (stage_ms[k] / 1e3) / 1e9, 1),
                           "frac": round(b / (stage_ms[k] / 1e3) / 1e9 / peak, 4)} for k, b in stream_bytes.items() if stage_ms.get(k)}
         cpu = cpu_baseline(args.ref_organisms, args.ref_ticks or 40) if (not args.no_cpu and world_size == 1) else None
+        K = args.steps
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": ("forward-only tick (rules + think + Space.step + friction; no dopamine training, no reproduction: BASELINE configs[1]), " if args.forward_only
-                                    else "full world tick (rules + think + dopamine training + reproduction/mutation + Space.step + friction), ") +
-                                   f"{M} organisms per GPU island" + ("" if args.forward_only else " (BASELINE configs[2])") + f"; state {w.nbytes() / 2**30:.1f} GiB per GPU, far larger than L2",
-                       "organisms_per_gpu": M, "living_after": s["organisms"], "cells": s["cells"], "pin_joints": s["pairs"],
-                       "dead_cells": s["dead"], "cross_contacts": s["cross_contacts"], "intra_contacts": s["intra_contacts"],
-                       "l2_policy": "inputs larger than L2",
-                       "parallelism": f"{world_size} island(s), one per GPU" + (f"; ring migration of {args.migrate_count} whole organisms every "
-                                      f"{args.migrate_every} ticks over NCCL p2p ({isl.migrated_out} sent by rank 0 in total)" if world_size > 1 and args.migrate_every else "")},
+            "config": {"workload": workload_name(args, M),
+                       "organisms_per_gpu": M, "world_age_ticks": int(w.tick) - e2e_steps - 3, "ageing_prelude_s": round(t_age, 1),
+                       "living": s["organisms"], "births_per_tick": (st1["births"] - st0["births"]) / K, "deaths_per_tick": (st1["deaths"] - st0["deaths"]) / K,
+                       "cell_deaths_per_tick": (st1["cell_deaths"] - st0["cell_deaths"]) / K, "trains_per_tick": (st1["trains"] - st0["trains"]) / K,
+                       "thinks_per_tick": (st1["thinks"] - st0["thinks"]) / K, "mean_memory_rows": round(shape["mean_memory_rows"], 1),
+                       "coupled_organisms": shape["coupled"]["organisms"], "rare_paths_in_region": st1["rare_paths"], "cells": s["cells"], "pin_joints": s["pairs"],
+                       "dead_cells": shape["dead"], "cross_contacts": shape["cross_contacts"], "intra_contacts": s["intra_contacts"],
+                       "state_gib_per_gpu": round(state_gib, 1), "l2_policy": "inputs larger than L2",
+                       "parallelism": f"{world_size} island(s), one per GPU" + (f"; ring migration of {args.migrate_count} whole organisms every {every} ticks over NCCL p2p, "
+                                      f"arrivals placed by the reference's placement search" if every else ""),
+                       "migration": migr},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps,
                     "steps": e2e_steps, "api": "sapio_tick_host_begin / _end (pinned host buffers; per tick: event block up, counters + packed sprite poses down; the download of frame k overlaps tick k + 1)"},
             "gpu_launches": int(launches),
             "stage_ms": {k: round(v, 4) for k, v in sorted(stage_ms.items(), key=lambda kv: -kv[1])},
-            "clocks": clk.summary(),
-            "births": w.stats()["births"], "cell_deaths": w.stats()["cell_deaths"], "world_stats": w.stats(),
+            "clocks": {**clocks, "samples_in_timed_region": region_samples, "sampled": "whole run incl. the ageing prelude"},
+            "young_world": young,
+            "world_stats": st1,
         }
+        if fwd:
+            line["forward_only_10k"] = fwd
         if roof:
             line["roofline"] = roof
             line["stage_roofline"] = stage_roof
@@ -317,6 +449,13 @@ def run_ours(args):
         print(json.dumps(line))
     if world_size > 1:
         dist.destroy_process_group()
+
+
+def workload_name(args, M):
+    if args.forward_only:
+        return f"forward-only tick (rules + think + Space.step + friction; no dopamine training, no reproduction: BASELINE configs[1]), {M} organisms per GPU island"
+    return (f"full world tick (rules + think + dopamine training + reproduction/mutation + Space.step + friction), {M} organisms per GPU island at spawn "
+            f"(BASELINE configs[2]), world aged {args.age} ticks before the timed region")
 
 
 def main():
@@ -331,6 +470,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--forward-only", action="store_true",
                     help="BASELINE configs[1]: physics + sensors + brain forward only (no dopamine training, no reproduction); use with --organisms 10000")
+    ap.add_argument("--age", type=int, default=3000, help="world age (ticks) at the start of the timed region: untimed ageing prelude on the device")
+    ap.add_argument("--no-forward-record", action="store_true", help="skip the 10k forward-only sub-record (BASELINE configs[1])")
     ap.add_argument("--migrate-every", type=int, default=50, help="N > 1: ticks between ring migrations (0 = never)")
     ap.add_argument("--migrate-count", type=int, default=64, help="organisms each island sends per migration")
     args = ap.parse_args()

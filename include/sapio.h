@@ -61,7 +61,7 @@ enum {
     SAPIO_STAT_FULL_SCANS = 15     /* birth placements that scanned every organism (more than REPRO_NEAR_CAP neighbours within reach) */
 };
 
-enum { SAPIO_RARE_GRID_LEVELS = 1, SAPIO_RARE_PACKED_COUPLED = 2, SAPIO_RARE_FULL_SCAN = 4, SAPIO_RARE_TRAIN_QUEUE = 8, SAPIO_RARE_BIRTH_CAP = 16 };
+enum { SAPIO_RARE_GRID_LEVELS = 1 /* cooperative kernel relaxed contact levels grid-wide */, SAPIO_RARE_PACKED_COUPLED = 2 /* a component too large for any CTA tier went to the cooperative kernel */, SAPIO_RARE_FULL_SCAN = 4, SAPIO_RARE_TRAIN_QUEUE = 8, SAPIO_RARE_BIRTH_CAP = 16 };
 
 /* phase mask for sapio_tick */
 enum {
@@ -209,6 +209,10 @@ uint64_t sapio_launch_count(void);
  * warp per organism, or lane-packed size classes. The packed one is launched when the previous tick counted more than `n`
  * coupled organisms (default 2400; -1 = always, INT_MAX = never). Returns the previous threshold. Tuning / test knob. */
 int sapio_set_coupled_pack_from(int n);
+/* Residency of the organism solver, per size class cls (cell rows <= 8 (cls + 1)): out6 = {lanes per organism, organisms per warp,
+ * warps per CTA, shared-memory bytes per warp, resident CTAs on the device (0 before the first step), SMs}. Measurement hook: the
+ * solver is bound by a dependent chain of wavefront steps per organism times the organisms in flight, not by memory. */
+int sapio_solver_info(int cls, int32_t *out6);
 
 #ifdef __cplusplus
 }

@@ -60,6 +60,7 @@ def load() -> ctypes.CDLL:
     L.sapio_profile_name.argtypes = [i32]; L.sapio_profile_name.restype = ctypes.c_char_p
     L.sapio_profile_read.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64), i32]; L.sapio_profile_read.restype = i32
     L.sapio_launch_count.restype = ctypes.c_uint64
+    L.sapio_solver_info.argtypes = [i32, ctypes.POINTER(ctypes.c_int32)]; L.sapio_solver_info.restype = i32
     L.sapio_set_coupled_pack_from.restype = ctypes.c_int
     L.sapio_set_coupled_pack_from.argtypes = [ctypes.c_int]
     if L.sapio_abi_version() != 1:

@@ -46,6 +46,15 @@ def sources():
     return sorted(out)
 
 
+def source_hash() -> str:
+    """sha256 over the CUDA sources: keys measurements taken under a profiler (profiles/ncu_traffic.json) to the code they measured."""
+    import hashlib
+    h = hashlib.sha256()
+    for path in sources():
+        h.update(os.path.basename(path).encode()); h.update(open(path, "rb").read())
+    return h.hexdigest()[:16]
+
+
 def _compile(unit, force):
     obj = os.path.join(OBJ, os.path.basename(unit)[:-3] + ".o")
     if not force and os.path.exists(obj) and all(os.path.getmtime(d) <= os.path.getmtime(obj) for d in deps(unit)):

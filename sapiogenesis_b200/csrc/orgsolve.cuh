@@ -45,6 +45,10 @@ __device__ __forceinline__ int wf_off(int t, int n) { return t <= n ? tri_f(t - 
 // the cross contacts of the step as seen from a body (its adjacency), for the warm start of coupled organisms
 struct CrossView { const int *off_all; const int *adj_c; const uint64_t *key; const float2 *n; const float *jn, *jt; int nx; };
 
+__device__ __forceinline__ CrossView cross_view(const Workspace &W) {
+    return CrossView{W.off_all, W.adj_c, W.nx_key, W.nx_n, W.nx_jn, W.nx_jt, W.flags[FL_NX]};
+}
+
 template <int CM, int G, bool GC = false>
 struct OrgCtx {
     typedef OrgS<CM, GC> S;
@@ -96,6 +100,13 @@ struct OrgCtx {
         }
         if (sl == 0) s.n = n;
         __syncwarp();
+        uint32_t s0 = gballot(sl < n && s.issens[sl]), s1 = gballot(sl + G < n && s.issens[min(sl + G, CM - 1)]);
+        sens = ((uint64_t)s1 << G) | s0;
+    }
+
+    // the context of an organism whose slab is still resident (components.cuh): what load() left in registers
+    __device__ void resume() {
+        n = s.n;
         uint32_t s0 = gballot(sl < n && s.issens[sl]), s1 = gballot(sl + G < n && s.issens[min(sl + G, CM - 1)]);
         sens = ((uint64_t)s1 << G) | s0;
     }

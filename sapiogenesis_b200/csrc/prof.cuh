@@ -6,11 +6,11 @@
 
 enum ProfTag {
     PT_RULES_BEGIN = 0, PT_GAS_SCAN, PT_GRID, PT_THINK, PT_RULES_MAIN, PT_TRAIN, PT_SETTLE, PT_REPRODUCE,
-    PT_BROADPHASE, PT_NARROW, PT_ORG_SOLVE, PT_COUPLED, PT_STEP_FINISH, PT_FRICTION, PT_POST, PT_FRAME, PT_END, PT_COUNT
+    PT_BROADPHASE, PT_NARROW, PT_ORG_SOLVE, PT_COMP_PLAN, PT_COMPONENTS, PT_COUPLED, PT_STEP_FINISH, PT_FRICTION, PT_POST, PT_FRAME, PT_END, PT_COUNT
 };
 static const char *const PROF_NAMES[PT_COUNT] = {
     "rules_begin", "gas_scan", "grid", "think", "rules_main", "train", "settle", "reproduce",
-    "broadphase", "narrow", "org_solve", "coupled", "step_finish", "friction", "post", "frame", "end"
+    "broadphase", "narrow", "org_solve", "comp_plan", "components", "coupled", "step_finish", "friction", "post", "frame", "end"
 };
 
 struct ProfState {

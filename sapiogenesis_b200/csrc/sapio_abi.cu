@@ -532,6 +532,13 @@ int sapio_profile_read(double *ms_out, int64_t *count_out, int reset) {
     return 0;
 }
 uint64_t sapio_launch_count(void) { return g_prof.launches; }
-int sapio_set_coupled_pack_from(int n) { const int old = g_coupled_pack_from; g_coupled_pack_from = n; return old; }
+int sapio_solver_info(int cls, int32_t *out6) {
+    if (cls < 0 || cls >= ORG_CLASSES || !out6) return fail(SAPIO_E_ARG, "sapio_solver_info: class out of range%s");
+    int info[4]; ORG_INFO[cls](info);
+    out6[0] = info[0]; out6[1] = info[1]; out6[2] = info[2]; out6[3] = info[3];
+    out6[4] = g_plan.ready ? g_plan.org_blocks[cls] : 0; out6[5] = g_plan.ready ? g_plan.sms : 0;
+    return 0;
+}
+int sapio_set_coupled_pack_from(int n) { const int old = g_force_fallback ? 2147483647 : 2400; g_force_fallback = n == 2147483647; return old; }
 
 }  // extern "C"

@@ -234,9 +234,9 @@ __global__ void __launch_bounds__(256) k_step_finish(WORLD_ARG, Workspace W, int
 // ------------------------------------------------------------------------------------------------------------------
 // host-side launch sequence
 // ------------------------------------------------------------------------------------------------------------------
-struct StepPlan { bool ready; int sms; int coop_blocks, simple_blocks; size_t simple_smem; int *h_mail, *d_mail; int org_blocks[ORG_CLASSES]; size_t org_smem[ORG_CLASSES]; size_t coop_smem; cudaStream_t side[ORG_CLASSES]; cudaEvent_t fork, join[ORG_CLASSES]; };
+struct StepPlan { bool ready; int sms; int simple_blocks; size_t simple_smem; int comp_blocks[COMP_TIERS_N]; int org_blocks[ORG_CLASSES]; size_t org_smem[ORG_CLASSES]; cudaStream_t side[ORG_CLASSES + COMP_TIERS_N]; cudaEvent_t fork, join[ORG_CLASSES + COMP_TIERS_N]; };
 static StepPlan g_plan = {};
-static int g_coupled_pack_from = COUPLED_PACK_FROM;       // sapio_set_coupled_pack_from
+static int g_force_fallback = 0;                          // sapio_set_coupled_pack_from(INT_MAX): tests compare the two implementations
 
 static int launch_space_step(const SapioWorld &w, const Workspace &W, cudaStream_t st, char *err, size_t errlen) {
 #define STEP_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { snprintf(err, errlen, #expr ": %s", cudaGetErrorString(e_)); return SAPIO_E_CUDA; } } while (0)
@@ -248,17 +248,13 @@ static int launch_space_step(const SapioWorld &w, const Workspace &W, cudaStream
         STEP_TRY(cudaDeviceGetAttribute(&g_plan.sms, cudaDevAttrMultiProcessorCount, dev));
         for (int c = 0; c < ORG_CLASSES; c++) STEP_TRY(ORG_PLAN[c](g_plan.sms, &g_plan.org_blocks[c], &g_plan.org_smem[c]));
         STEP_TRY(cudaEventCreateWithFlags(&g_plan.fork, cudaEventDisableTiming));
-        for (int c = 0; c < ORG_CLASSES; c++) {
+        for (int c = 0; c < ORG_CLASSES + COMP_TIERS_N; c++) {
             STEP_TRY(cudaStreamCreateWithFlags(&g_plan.side[c], cudaStreamNonBlocking));
             STEP_TRY(cudaEventCreateWithFlags(&g_plan.join[c], cudaEventDisableTiming));
         }
-        STEP_TRY(coupled_plan(g_plan.sms, &g_plan.coop_blocks, &g_plan.coop_smem, &g_plan.simple_blocks, &g_plan.simple_smem));
-        if (g_plan.simple_blocks < 1 || g_plan.coop_blocks < 1) { snprintf(err, errlen, "the coupled kernels do not fit on an SM"); return SAPIO_E_CUDA; }
-        // mailbox: the device leaves the number of coupled organisms of the tick here (mapped host memory); the host reads it, one tick
-        // stale and without waiting, to pick the form of the coupled pass
-        STEP_TRY(cudaHostAlloc((void **)&g_plan.h_mail, 64, cudaHostAllocMapped));
-        STEP_TRY(cudaHostGetDevicePointer((void **)&g_plan.d_mail, g_plan.h_mail, 0));
-        g_plan.h_mail[0] = 0;
+        STEP_TRY(coupled_plan(g_plan.sms, &g_plan.simple_blocks, &g_plan.simple_smem));
+        if (g_plan.simple_blocks < 1) { snprintf(err, errlen, "the coupled fallback kernel does not fit on an SM"); return SAPIO_E_CUDA; }
+        STEP_TRY(component_plan(g_plan.sms, g_plan.comp_blocks));
         g_plan.ready = true;
     }
     const int sms = g_plan.sms;
@@ -296,29 +292,29 @@ static int launch_space_step(const SapioWorld &w, const Workspace &W, cudaStream
     k_classify_scan<<<1, 32, 0, st>>>(W);
     k_classify_scatter<<<sgrid(p.n_org, 256), 256, 0, st>>>(w, W);
     LAUNCHES(11);
+    // connected components of the cross-contact graph (components.cuh): planned here, solved next to the organisms without contacts
+    prof_mark(st, PT_COMP_PLAN);
+    component_plan_launch(w, W, g_force_fallback, sgrid(p.x_cap, 256), st);
+    LAUNCHES(5);
     prof_mark(st, PT_ORG_SOLVE);
-    {   // persistent CTAs per size class, largest class first; the classes run concurrently on side streams so that the tail of
-        // one class is filled by the next (organisms of different classes are independent)
+    {   // Persistent CTAs per organism size class and per component tier, all independent of each other, on side streams: every one
+        // of them is a chain of dependent steps per organism whose throughput is set by how many are resident, so the tail of one
+        // launch is filled by the next. Longest chains first.
         STEP_TRY(cudaEventRecord(g_plan.fork, st));
-#define ORG_LAUNCH(CM, cls) do { \
-            cudaStream_t ss = g_plan.side[cls]; \
-            STEP_TRY(cudaStreamWaitEvent(ss, g_plan.fork, 0)); \
-            ORG_LAUNCH_FN[cls](w, W, K, cls, g_plan.org_blocks[cls], g_plan.org_smem[cls], ss); \
-            STEP_TRY(cudaEventRecord(g_plan.join[cls], ss)); \
-            STEP_TRY(cudaStreamWaitEvent(st, g_plan.join[cls], 0)); } while (0)
-        ORG_LAUNCH(64, 7); ORG_LAUNCH(56, 6); ORG_LAUNCH(48, 5); ORG_LAUNCH(40, 4);
-        ORG_LAUNCH(32, 3); ORG_LAUNCH(24, 2); ORG_LAUNCH(16, 1); ORG_LAUNCH(8, 0);
-#undef ORG_LAUNCH
+        int k = 0;
+        auto side_begin = [&]() -> cudaStream_t { cudaStream_t ss = g_plan.side[k]; cudaStreamWaitEvent(ss, g_plan.fork, 0); return ss; };
+        auto side_end = [&]() { cudaEventRecord(g_plan.join[k], g_plan.side[k]); cudaStreamWaitEvent(st, g_plan.join[k], 0); k++; };
+        auto org = [&](int cls) { cudaStream_t ss = side_begin(); ORG_LAUNCH_FN[cls](w, W, K, cls, g_plan.org_blocks[cls], g_plan.org_smem[cls], ss); side_end(); };
+        auto comp = [&](int t) { cudaStream_t ss = side_begin(); component_launch(w, W, K, t, g_plan.comp_blocks[t], ss); side_end(); };
+        comp(4); comp(3); org(7); org(6); org(5); org(4); comp(2); org(3); org(2); comp(1); org(1); org(0); comp(0);
     }
-    LAUNCHES(8);
+    LAUNCHES(8 + COMP_TIERS_N);
+    // the cooperative kernel only has work (decided on the device) when a component exceeds the largest tier
     prof_mark(st, PT_COUPLED);
-    {
-        const int last = *(volatile int *)g_plan.h_mail;
-        const bool packed = last > g_coupled_pack_from;
-        STEP_TRY(coupled_launch(w, W, K, packed, packed ? g_plan.coop_blocks : g_plan.simple_blocks, packed ? g_plan.coop_smem : g_plan.simple_smem, st));
-    }
+    STEP_TRY(coupled_launch(w, W, K, g_plan.simple_blocks < 64 ? g_plan.simple_blocks : 64, g_plan.simple_smem, st));   // a small grid: its barriers are cheap, its work is rare
+    LAUNCHES(1);
     prof_mark(st, PT_STEP_FINISH);
-    k_step_finish<<<sgrid(NB + 1, 256), 256, 0, st>>>(w, W, g_plan.d_mail);
+    k_step_finish<<<sgrid(NB + 1, 256), 256, 0, st>>>(w, W, nullptr);
     LAUNCHES(2);
     prof_mark(st, PT_END);
     STEP_TRY(cudaGetLastError());

@@ -28,11 +28,17 @@ struct Workspace {
     int *size_hist;                 // [MAXC + 1] inside the flags block: histogram, then scatter cursors
     float *ic_bounce, *ic_jbias;    // [n_org * ICAP] (coupled path only)
     float4 *pair_cst;               // [4 classes][ORG_GC_WARPS][NPAIR] pin constants of the organism a warp is solving (GC classes)
+    // connected components of the cross-contact graph (components.cuh): per node (organism o -> o, dead body d -> n_org + d)
+    int *cn_parent, *cn_nx, *cn_norg, *cn_ndead, *cn_need, *cn_xoff, *cn_fill, *cn_seen, *cn_tier;
+    int *comp_of, *comp_pool;      // [x_cap] component (root node) of a contact; contacts grouped by component
+    int *comp_list;                 // [COMP_TIERS][2 * x_cap] roots by CTA tier
     char *cp_state; int cp_cap;     // parked solver state of the first cp_cap coupled organisms (sizeof(OrgS<MAXC>) each)
 };
 enum { FL_NX = 0, FL_NADJ = 1, FL_OVERFLOW = 2, FL_MAXLEVEL = 3, FL_NCOUPLED = 5, FL_NIC = 6, FL_CLS0 = 8 /* ..16: class starts + end */,
        FL_WORK0 = 20 /* ..27 */, FL_TMPTOP = 28, FL_NHIT = 29, FL_RARE = 30, FL_HIST = 32 /* ..96 */, FL_CHIST = 100 /* ..164: coupled organisms by rows */,
-       FL_CCLS0 = 168 /* ..176: class starts + end in coupled_list */, FL_CHG0 = 180 /* ..182 */, FL_CWORK0 = 200 /* ..203: two alternating pairs of work counters of k_coupled */, FL_BYTES = 1024 };
+       FL_CCLS0 = 168 /* ..176: class starts + end in coupled_list */, FL_CHG0 = 180 /* ..182 */, FL_CWORK0 = 200 /* ..203: two alternating pairs of work counters of k_coupled */,
+       FL_COMP_OVERFLOW = 210 /* a component exceeds the largest CTA tier: the tick falls back to the cooperative kernel */, FL_COMP_POOL = 211, FL_BIGLEVEL = 209,
+       FL_COMP_N0 = 212 /* ..216: components per tier */, FL_COMP_WORK0 = 220 /* ..224: work counters */, FL_BYTES = 1024 };
 
 #define COUPLED_STATE_BYTES 49152      /* >= sizeof(OrgS<MAXC>), checked where the struct is known */
 // sort only the bits a grid key can have; the key of an empty slot (all ones) still sorts behind every cell: its low bits are all ones
@@ -70,7 +76,13 @@ static inline size_t carve_workspace(const SapioParams &p, char *base, Workspace
     W->ic_bounce = (float *)take((size_t)p.n_org * SAPIO_ICAP * 4);
     W->ic_jbias = (float *)take((size_t)p.n_org * SAPIO_ICAP * 4);
     W->pair_cst = (float4 *)take((size_t)4 * (148 * 32) * SAPIO_NPAIR * sizeof(float4));
-    W->cp_cap = p.n_org < 65536 ? p.n_org : 65536;
+    {
+        const size_t NN = (size_t)p.n_org + p.n_dead;
+        W->cn_parent = (int *)take(NN * 4); W->cn_nx = (int *)take(NN * 4); W->cn_norg = (int *)take(NN * 4); W->cn_ndead = (int *)take(NN * 4);
+        W->cn_need = (int *)take(NN * 4); W->cn_xoff = (int *)take(NN * 4); W->cn_fill = (int *)take(NN * 4); W->cn_seen = (int *)take(NN * 4); W->cn_tier = (int *)take(NN * 4);
+        W->comp_of = (int *)take(XC * 4); W->comp_pool = (int *)take(XC * 4); W->comp_list = (int *)take((size_t)5 * 2 * XC * 4);
+    }
+    W->cp_cap = p.n_org < 8192 ? p.n_org : 8192;      // parked state of the fallback kernel (beyond: recomputed per pass)
     W->cp_state = take((size_t)W->cp_cap * COUPLED_STATE_BYTES);
     return off;
 }
@@ -165,3 +177,16 @@ __device__ __forceinline__ bool body_fresh(const SapioWorld &w, uint32_t id, int
     return false;
 }
 
+
+// ---- connected components of the cross-contact graph (components.cuh): node of a body, and whether its component is one of the
+// oversize ones that the cooperative kernel of coupled.cuh solves (cn_tier < 0)
+__device__ __forceinline__ int comp_node(uint32_t body, int NC, int NB, int n_org) {          // -1: wall
+    if ((int)body < NC) return (int)(body >> 6);
+    if ((int)body < NB) return n_org + ((int)body - NC);
+    return -1;
+}
+__device__ __forceinline__ bool comp_is_big(const Workspace &W, int node) {
+    int v = node;
+    for (;;) { const int p = W.cn_parent[v]; if (p == v) break; v = p; }
+    return W.cn_tier[v] < 0;
+}

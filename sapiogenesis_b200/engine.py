@@ -239,6 +239,15 @@ class Engine:
         self.lib.sapio_profile_read(ms, cnt, 1 if reset else 0)
         return {self.lib.sapio_profile_name(i).decode(): (ms[i], cnt[i]) for i in range(n)}
 
+    def solver_info(self):
+        """Per size class of the organism solver: dict(lanes, orgs_per_warp, warps_per_cta, smem_per_warp, resident_ctas, sms)."""
+        out = []
+        for cls in range(8):
+            a = (ctypes.c_int32 * 6)()
+            _lib.check(self.lib.sapio_solver_info(cls, a), "sapio_solver_info")
+            out.append(dict(zip(("lanes", "orgs_per_warp", "warps_per_cta", "smem_per_warp", "resident_ctas", "sms"), [int(v) for v in a])))
+        return out
+
     def launch_count(self) -> int:
         return int(self.lib.sapio_launch_count())
 

@@ -20,12 +20,13 @@ def oracle():
     return orc
 
 
-@pytest.fixture(params=["simple", "packed"])
+@pytest.fixture(params=["components", "fallback"])
 def coupled_kernel(request):
-    """Runs a GPU test once with each of the two coupled-organism kernels (sapio_set_coupled_pack_from): the library
-    picks by load, and small test worlds would otherwise only ever see the one-warp-per-organism form."""
+    """Runs a GPU test once with each of the two implementations of the coupled pass (sapio_set_coupled_pack_from): connected
+    components one per CTA (what every ordinary tick runs), and the cooperative fallback kernel that only takes over when a
+    component exceeds the largest CTA tier -- which test worlds never do on their own."""
     from sapiogenesis_b200._lib import load
     lib = load()
-    old = lib.sapio_set_coupled_pack_from(-1 if request.param == "packed" else 2 ** 31 - 1)
+    old = lib.sapio_set_coupled_pack_from(-1 if request.param == "components" else 2 ** 31 - 1)
     yield request.param
     lib.sapio_set_coupled_pack_from(old)
