@@ -171,6 +171,19 @@ int sapio_unpack_organisms(const SapioWorld *w, const int32_t *d_slots, int n, c
 /* frees the slots of organisms that left (no dead cells remain: they live on in another world) */
 int sapio_release_organisms(const SapioWorld *w, const int32_t *d_slots, int n, void *stream);
 
+/* Island migration without a host round trip (wire format: include/sapio_migrate.h; order of every choice: csrc/migrate2.cuh).
+ * _out: picks up to `count` living organisms (seeded walk), packs their ragged records into d_buf until it is full, frees their
+ *       slots and scrubs what pointed at them. _in: places every record of d_buf by the reference's rule for a new organism
+ *       (box inside the world, blocks no living organism's box: viable_organism_position, sprites.py:156-192; first viable of 360
+ *       seeded candidates), scatters it into a free slot with a fresh uid, removes dead cells inside its box (sprites.py:184-190).
+ * Arrivals that find no place or no free slot are dropped and counted. The buffer has a fixed size (_buffer_bytes), so the
+ * transport (NCCL send/recv) needs no size exchange.
+ * _counts (synchronises the stream): {chosen, packed, accepted, dropped} of the last calls, then totals {out, in, dropped, stayed}. */
+size_t sapio_migrate_buffer_bytes(const SapioParams *p, int count, int bytes_per_organism);
+int sapio_migrate_out(const SapioWorld *w, void *ws, size_t ws_bytes, int count, int rank, void *d_buf, size_t buf_bytes, void *stream);
+int sapio_migrate_in(const SapioWorld *w, void *ws, size_t ws_bytes, void *d_buf, size_t buf_bytes, void *stream);
+int sapio_migrate_counts(const SapioWorld *w, void *ws, size_t ws_bytes, int32_t *h_out8, void *stream);
+
 /* ---- end-to-end path for a GUI host (host buffers; the copies are inside the call) --------------------------------
  * Uploads the per-tick event block updateUI applies (Sapiogenesis.py:37-47), runs n_ticks ticks, then downloads what the
  * reference pushes to Qt every frame: the UI counters (Sapiogenesis.py:62-69) and the pose of every solid sprite

@@ -18,7 +18,7 @@ _lib = None
 
 def build(force: bool = False) -> str:
     srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
-    srcs += [os.path.join(_HERE, "..", "include", f) for f in ("sapio.h", "sapio_fields.def")]
+    srcs += [os.path.join(_HERE, "..", "include", f) for f in ("sapio.h", "sapio_fields.def", "sapio_migrate.h")]
     stale = force or not os.path.exists(_SO) or any(
         os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
     if stale:
@@ -59,6 +59,8 @@ def lib():
         L.oracle_rotation.argtypes = [vp, i32]; L.oracle_rotation.restype = dbl
         L.oracle_think.argtypes = [vp, i32, dp, dp, ctypes.POINTER(ctypes.c_uint8), dbl]; L.oracle_think.restype = i32
         L.oracle_inputs.argtypes = [vp, i32, dp, ctypes.POINTER(ctypes.c_uint8), dbl, dp]; L.oracle_inputs.restype = i32
+        L.oracle_migrate_out.argtypes = [vp, i32, i32, ctypes.c_void_p, ctypes.c_size_t]; L.oracle_migrate_out.restype = i32
+        L.oracle_migrate_in.argtypes = [vp, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int32)]; L.oracle_migrate_in.restype = i32
         L.oracle_sensor_view.argtypes = [vp, i32, i32, ctypes.POINTER(ctypes.c_uint32), i32]; L.oracle_sensor_view.restype = i32
         _lib = L
     return _lib
@@ -170,3 +172,20 @@ def sensor_view(world, org, k, cap=4096):
     hits = np.zeros(cap, dtype=np.uint32)
     n = lib().oracle_sensor_view(_ref(world), org, k, hits.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), cap)
     return hits[:min(n, cap)]
+
+
+def migrate_out(world, count: int, rank: int, buf) -> int:
+    """buf: contiguous uint8 CPU tensor / numpy array (include/sapio_migrate.h). Returns the number of records written."""
+    import numpy as _np
+    a = buf.numpy() if hasattr(buf, "numpy") else _np.asarray(buf)
+    return lib().oracle_migrate_out(_ref(world), int(count), int(rank), a.ctypes.data_as(ctypes.c_void_p), a.nbytes)
+
+
+def migrate_in(world, buf):
+    """Returns (accepted, dropped)."""
+    import numpy as _np
+    a = buf.numpy() if hasattr(buf, "numpy") else _np.asarray(buf)
+    out = (ctypes.c_int32 * 2)()
+    rc = lib().oracle_migrate_in(_ref(world), a.ctypes.data_as(ctypes.c_void_p), a.nbytes, out)
+    assert rc == 0, rc
+    return int(out[0]), int(out[1])

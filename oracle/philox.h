@@ -24,7 +24,9 @@ enum {
     SAPIO_RNG_WEIGHT_FILL = 7,  /* torch.rand rows of mutate_brain_layers    sprites.py:1041 */
     SAPIO_RNG_SYNTH = 8,        /* synthetic world placement (ours) */
     SAPIO_RNG_GENOME_INIT = 9,  /* nn.Linear init of the tempNet in DNA._setup_brain_structure  sprites.py:868 */
-    SAPIO_RNG_WEIGHT_GARBAGE = 10 /* uninitialised tail of resize_()d rows in mutate_brain_layers sprites.py:1039 */
+    SAPIO_RNG_WEIGHT_GARBAGE = 10, /* uninitialised tail of resize_()d rows in mutate_brain_layers sprites.py:1039 */
+    SAPIO_RNG_EVENTS = 11,
+    SAPIO_RNG_MIGRATE = 12  /* island migration: start of the emigrant walk (uid -2 - rank), placement candidates of an arrival */
 };
 
 static inline void sapio_philox4x32_10(uint32_t ctr[4], const uint32_t key_in[2]) {

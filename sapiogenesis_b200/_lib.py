@@ -50,6 +50,10 @@ def load() -> ctypes.CDLL:
     L.sapio_pack_organisms.argtypes = [wp, vp, i32, vp, sz, vp]; L.sapio_pack_organisms.restype = i32
     L.sapio_unpack_organisms.argtypes = [wp, vp, i32, vp, sz, vp]; L.sapio_unpack_organisms.restype = i32
     L.sapio_release_organisms.argtypes = [wp, vp, i32, vp]; L.sapio_release_organisms.restype = i32
+    L.sapio_migrate_buffer_bytes.argtypes = [vp, i32, i32]; L.sapio_migrate_buffer_bytes.restype = sz
+    L.sapio_migrate_out.argtypes = [wp, vp, sz, i32, i32, vp, sz, vp]; L.sapio_migrate_out.restype = i32
+    L.sapio_migrate_in.argtypes = [wp, vp, sz, vp, sz, vp]; L.sapio_migrate_in.restype = i32
+    L.sapio_migrate_counts.argtypes = [wp, vp, sz, ctypes.POINTER(ctypes.c_int32), vp]; L.sapio_migrate_counts.restype = i32
     f32 = ctypes.c_float
     L.sapio_events.argtypes = [wp, vp, sz, f32, f32, f32, vp]; L.sapio_events.restype = i32
     L.sapio_tick_host.argtypes = [wp, vp, sz, u32, i32, vp, vp, vp, i32, vp, i32, vp]; L.sapio_tick_host.restype = i32

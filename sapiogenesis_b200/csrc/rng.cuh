@@ -16,7 +16,8 @@ enum {
     RNG_SYNTH = 8,        // synthetic world placement
     RNG_GENOME_INIT = 9,  // nn.Linear init of the tempNet in _setup_brain_structure  sprites.py:868
     RNG_WEIGHT_GARBAGE = 10, // uninitialised tail of resize_()d rows  sprites.py:1039
-    RNG_EVENTS = 11       // random dead cell event: gate, x, y (uid -1) Sapiogenesis.py:48-53
+    RNG_EVENTS = 11,      // random dead cell event: gate, x, y (uid -1) Sapiogenesis.py:48-53
+    RNG_MIGRATE = 12      // island migration: start of the emigrant walk (uid -2 - rank), placement candidates of an arrival (ours)
 };
 
 __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {

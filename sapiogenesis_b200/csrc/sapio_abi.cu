@@ -15,6 +15,7 @@
 #include "repro.cuh"
 #include "frame.cuh"
 #include "migrate.cuh"
+#include "migrate2.cuh"
 
 static thread_local char g_err[512] = "";
 static int fail(int code, const char *fmt, const char *a = "") {
@@ -52,7 +53,7 @@ static size_t cub_need(const SapioParams &p) {
     return m;
 }
 
-struct AllWs { Workspace step; RulesWs rules; TrainWs train; ReproWs repro; FrameWs frame, frame2; int train_ctas; int *probe; };
+struct AllWs { Workspace step; RulesWs rules; TrainWs train; ReproWs repro; FrameWs frame, frame2; MigWs mig; int train_ctas; int *probe; };
 
 static size_t carve_all(const SapioParams &p, char *base, AllWs *A) {
     size_t off = carve_workspace(p, base, &A->step);
@@ -79,6 +80,11 @@ static size_t carve_all(const SapioParams &p, char *base, AllWs *A) {
     Q.accepted = (int *)take((size_t)Q.birth_cap * 4);
     Q.counters = (int *)take(256);
     A->probe = (int *)take(256);
+    {
+        MigWs &M = A->mig; const size_t R = SAPIO_MIG_MAX_RECORDS;
+        M.emig = (int *)take(R * 4); M.counters = (int *)take(256); M.rect = (double *)take(R * 6 * 8); M.mask = (uint32_t *)take(R * 12 * 4);
+        M.slot = (int *)take(R * 4); M.delta = (double *)take(R * 2 * 8); M.acc_rect = (double *)take(R * 4 * 8);
+    }
     FrameWs &F = A->frame;
     F.control = (SapioControl *)take(256); F.header = (SapioFrameHeader *)take(512); F.counts = (int *)take(256);
     F.cells = (float4 *)take(NO * MAXC * sizeof(float4)); F.dead = (float4 *)take(ND * sizeof(float4));
@@ -438,9 +444,52 @@ int sapio_release_organisms(const SapioWorld *w, const int32_t *d_slots, int n, 
     int rc = check(w, nullptr, 0, nullptr); if (rc) return rc;
     if ((rc = check_list(w, d_slots, n))) return rc;
     if (n == 0) return 0;
-    k_release_slots<<<n < 4096 ? n : 4096, MAXC, 0, (cudaStream_t)stream>>>(*w, d_slots, n);
-    k_release_contacts<<<stream_grid(w->p.x_cap), 256, 0, (cudaStream_t)stream>>>(*w);
+    k_mig_release<<<n < 4096 ? n : 4096, MAXC, 0, (cudaStream_t)stream>>>(*w, d_slots, nullptr, n);
+    k_mig_scrub<<<stream_grid(2 * (long)w->p.x_cap), 256, 0, (cudaStream_t)stream>>>(*w);
     LAUNCHES(2); LAUNCH_CHECK();
+    return 0;
+}
+
+// ---- island migration on the device (csrc/migrate2.cuh, include/sapio_migrate.h) ---------------------------------------------
+size_t sapio_migrate_buffer_bytes(const SapioParams *p, int count, int bytes_per_organism) {
+    if (!p || count < 0) return 0;
+    if (count > SAPIO_MIG_MAX_RECORDS) count = SAPIO_MIG_MAX_RECORDS;
+    return ((sizeof(SapioMigBufHeader) + 15) & ~size_t(15)) + (size_t)count * (size_t)(bytes_per_organism > 0 ? bytes_per_organism : 65536);
+}
+int sapio_migrate_out(const SapioWorld *w, void *ws, size_t ws_bytes, int count, int rank, void *d_buf, size_t buf_bytes, void *stream) {
+    AllWs A; int rc = check(w, ws, ws_bytes, &A); if (rc) return rc;
+    if (!d_buf || buf_bytes < sizeof(SapioMigBufHeader) + 64) return fail(SAPIO_E_ARG, "sapio_migrate_out: buffer too small%s");
+    if (count < 0 || count > SAPIO_MIG_MAX_RECORDS) return fail(SAPIO_E_ARG, "sapio_migrate_out: count out of range%s");
+    cudaStream_t st = (cudaStream_t)stream;
+    SapioMigTable T; sapio_mig_table(&w->p, w, &T);
+    k_mig_choose<<<1, 256, 0, st>>>(*w, A.mig, count, rank);
+    k_mig_sizes<<<1, 256, 0, st>>>(*w, T, A.mig, (char *)d_buf, buf_bytes);
+    k_mig_pack<<<count > 0 ? count : 1, 256, 0, st>>>(*w, T, A.mig, (char *)d_buf);
+    k_mig_release<<<count > 0 ? count : 1, MAXC, 0, st>>>(*w, A.mig.emig, A.mig.counters + MC_PACKED, 0);
+    k_mig_scrub<<<stream_grid(2 * (long)w->p.x_cap), 256, 0, st>>>(*w);
+    LAUNCHES(5); LAUNCH_CHECK();
+    return 0;
+}
+int sapio_migrate_in(const SapioWorld *w, void *ws, size_t ws_bytes, void *d_buf, size_t buf_bytes, void *stream) {
+    AllWs A; int rc = check(w, ws, ws_bytes, &A); if (rc) return rc;
+    if (!d_buf || buf_bytes < sizeof(SapioMigBufHeader)) return fail(SAPIO_E_ARG, "sapio_migrate_in: buffer too small%s");
+    cudaStream_t st = (cudaStream_t)stream;
+    SapioMigTable T; sapio_mig_table(&w->p, w, &T);
+    const int cap = SAPIO_MIG_MAX_RECORDS;                              // the count lives in the buffer, on the device
+    k_org_rects<<<stream_grid(w->p.n_org), 256, 0, st>>>(*w, nullptr);
+    k_mig_prepare<<<(cap + 127) / 128, 128, 0, st>>>(*w, T, A.mig, (const char *)d_buf);
+    k_mig_viable<<<148, 384, 0, st>>>(*w, A.mig, (const char *)d_buf);
+    k_mig_resolve<<<1, 32, 0, st>>>(*w, A.mig, (const char *)d_buf);
+    k_mig_unpack<<<148, 256, 0, st>>>(*w, T, A.mig, (char *)d_buf);
+    k_mig_clear_dead<<<stream_grid(w->p.n_dead), 256, 0, st>>>(*w, A.mig);
+    k_mig_finish<<<1, 1, 0, st>>>(*w, A.mig);
+    LAUNCHES(7); LAUNCH_CHECK();
+    return 0;
+}
+int sapio_migrate_counts(const SapioWorld *w, void *ws, size_t ws_bytes, int32_t *h_out8, void *stream) {
+    AllWs A; int rc = check(w, ws, ws_bytes, &A); if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(h_out8, A.mig.counters, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     return 0;
 }
 

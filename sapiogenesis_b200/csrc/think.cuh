@@ -204,9 +204,10 @@ __global__ void __launch_bounds__(THINK_WARPS * 32) k_think(WORLD_ARG, Workspace
             rng4(p.seed, uid, T, RNG_RANDN, 0, rr4);
 #pragma unroll
             for (int h = 0; h < 2; h++) {                                                          // Box-Muller on (0,1] x [0,1)
-                float u1 = ((float)(rr4[2 * h] >> 8) + 1.0f) * (1.0f / 16777216.0f), u2 = u01(rr4[2 * h + 1]);
-                float rad = sqrtf(-2.0f * logf(u1)), th = 6.283185307179586f * u2;
-                outv[2 * h] = rad * cosf(th); outv[2 * h + 1] = rad * sinf(th);
+                // in double, rounded once: the action drives the push actuator, and a push one ulp off flips position roundings (rules.cuh)
+                const double u1 = ((double)(rr4[2 * h] >> 8) + 1.0) / 16777216.0, u2 = (double)u01(rr4[2 * h + 1]);
+                const double rad = sqrt(-2.0 * log(u1)), th = 2.0 * 3.14159265358979323846 * u2;
+                outv[2 * h] = (float)(rad * cos(th)); outv[2 * h + 1] = (float)(rad * sin(th));
             }
         }
         // history rings (slot = running count % capacity), short-term memory (neural.py:301-318)

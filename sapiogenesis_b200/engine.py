@@ -150,6 +150,34 @@ class Engine:
                        "sapio_release_organisms")
         self._keep = (lst,)
 
+    # -- island migration on the device: ragged records, placement of the arrivals, no host round trip (csrc/migrate2.cuh) -----------
+    def migrate_buffer(self, count: int, bytes_per_organism: int = 65536) -> torch.Tensor:
+        n = int(self.lib.sapio_migrate_buffer_bytes(ctypes.byref(self.world.p), int(count), int(bytes_per_organism)))
+        return torch.zeros(n, dtype=torch.uint8, device=self.world.device)
+
+    def migrate_out(self, count: int, rank: int, buf: torch.Tensor):
+        """Picks up to `count` living organisms, packs them into `buf` (as many as fit) and frees their slots."""
+        assert buf.is_cuda and buf.is_contiguous() and buf.dtype == torch.uint8
+        with torch.cuda.device(self.world.device):
+            _lib.check(self.lib.sapio_migrate_out(self._ref(), *self._ws, int(count), int(rank), ctypes.c_void_p(buf.data_ptr()), buf.numel(),
+                                                  self._stream_ptr()), "sapio_migrate_out")
+        self._grid_valid = False
+
+    def migrate_in(self, buf: torch.Tensor):
+        """Places every organism of `buf` by the reference's rule for a new organism and scatters it into a free slot."""
+        assert buf.is_cuda and buf.is_contiguous() and buf.dtype == torch.uint8
+        with torch.cuda.device(self.world.device):
+            _lib.check(self.lib.sapio_migrate_in(self._ref(), *self._ws, ctypes.c_void_p(buf.data_ptr()), buf.numel(), self._stream_ptr()),
+                       "sapio_migrate_in")
+        self._grid_valid = False
+
+    def migrate_counts(self) -> dict:
+        """(synchronises) last calls: chosen / packed / accepted / dropped; totals: out / in / dropped / stayed."""
+        a = (ctypes.c_int32 * 8)()
+        with torch.cuda.device(self.world.device):
+            _lib.check(self.lib.sapio_migrate_counts(self._ref(), *self._ws, a, self._stream_ptr()), "sapio_migrate_counts")
+        return dict(zip(("chosen", "packed", "accepted", "dropped", "total_out", "total_in", "total_dropped", "total_stayed"), [int(v) for v in a]))
+
     def sensor_view(self, org: int, cell: int, cap: int = 4096):
         """sprite.info["view"] of one eye / olfactory cell as ascending body ids (parity probe)."""
         dev = self.world.device

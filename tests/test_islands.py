@@ -104,6 +104,97 @@ def test_records_move_whole_organisms_between_worlds(oracle):
     assert int((gb.t["org_state"] == 1).sum()) >= 5 and np.isfinite(gb.np("c_pos")).all() and np.isfinite(ga.np("c_vel")).all()
 
 
+def _busy_world(oracle, n_org, seed, crowd, extra, food=30, ticks=30):
+    from worlds import make_world
+    w = make_world(oracle, n_org=n_org, seed=seed, n_food=food, crowd=crowd, kick=20.0, extra_slots=extra, n_dead_cap=64 * 16)
+    w.p.think_ticks = w.p.train_ticks = 3
+    assert oracle.tick(w, PH_ALL, ticks) == 0                    # brains, memories, contact caches, adjacency are populated
+    return w
+
+
+@pytest.mark.gpu
+def test_device_migration_matches_oracle_and_places_arrivals(oracle):
+    """sapio_migrate_out / _in against oracle/migrate.c: the same emigrants, byte-identical ragged records, the same places, slots and
+    uids; arrivals overlap nobody; nothing points at a slot whose occupant changed (no phantom bites on the next tick)."""
+    from parity import compare_worlds
+    from sapiogenesis_b200.engine import Engine
+    src = _busy_world(oracle, 14, 4, 0.4, 6)
+    dst = _busy_world(oracle, 30, 9, 0.55, 12, food=60)
+    assert src.p.n_org != dst.p.n_org                             # records do not depend on the slot count of either world
+    gs, gd = src.to("cuda"), dst.to("cuda")
+    es, ed = Engine(gs), Engine(gd)
+    buf = es.migrate_buffer(5)
+    es.migrate_out(5, 3, buf); es.synchronize()
+    hbuf = torch.zeros_like(buf, device="cpu")
+    assert oracle.migrate_out(src, 5, 3, hbuf) == 5
+    c = es.migrate_counts()
+    assert c["chosen"] == 5 and c["packed"] == 5
+    used = int(hbuf[8:12].view(torch.int32)[0])
+    assert 5 * 4000 < used < 5 * 120_000, used                    # ragged: a few dozen kB per organism, not the 431 kB of a slot
+    assert torch.equal(buf.cpu()[:used], hbuf[:used])
+    compare_worlds(gs, src, "source after migrate_out")
+    np.testing.assert_array_equal(gs.np("xa_other"), src.np("xa_other"))
+    # arrival
+    ed.migrate_in(buf); ed.synchronize()
+    acc, drop = oracle.migrate_in(dst, hbuf)
+    c = ed.migrate_counts()
+    assert (c["accepted"], c["dropped"]) == (acc, drop) and acc == 5
+    compare_worlds(gd, dst, "destination after migrate_in")
+    np.testing.assert_array_equal(gd.np("org_uid"), dst.np("org_uid"))
+    np.testing.assert_array_equal(gd.np("c_pos"), dst.np("c_pos"))
+    # nobody overlaps anybody: boxes of the living organisms, pairwise, by the reference's own predicate
+    live = np.nonzero(gd.np("org_state") == 1)[0]
+    rects = np.array([oracle.org_rect(dst, int(o)) for o in live])
+    arrivals = live[np.isin(gd.np("org_uid")[live], np.arange(int(dst.np("g_next_uid")[0]) - acc, int(dst.np("g_next_uid")[0])))]
+    assert len(arrivals) == acc
+    for a in arrivals:
+        ra = rects[list(live).index(a)]
+        for o, r in zip(live, rects):
+            if o == a: continue
+            inx = (ra[0] > r[0] and ra[0] < r[2]) or (ra[2] > r[0] and ra[2] < r[2]) or (r[0] > ra[0] and r[2] < ra[2])
+            iny = (ra[1] > r[1] and ra[1] < r[3]) or (ra[3] > r[1] and ra[3] < r[3]) or (r[1] > ra[1] and r[3] < ra[3])
+            assert not (inx and iny), (a, o)
+        assert ra[0] >= 0 and ra[1] >= 0 and ra[2] <= dst.p.width and ra[3] <= dst.p.height
+    # the next ticks agree too (adjacency scrubbed on both sides, arrivals think and train with their memories)
+    for t in range(3):
+        ed.tick(1); ed.synchronize(); es.tick(1); es.synchronize()
+        assert oracle.tick(dst, PH_ALL, 1) == 0 and oracle.tick(src, PH_ALL, 1) == 0
+        gd2 = dst.to("cuda"); compare_worlds(gd, dst, f"destination tick +{t + 1}", phys_tol=1e-4); gd = gd2; ed = Engine(gd)
+        gs2 = src.to("cuda"); compare_worlds(gs, src, f"source tick +{t + 1}", phys_tol=1e-4); gs = gs2; es = Engine(gs)
+
+
+@pytest.mark.gpu
+def test_migration_leaves_no_stale_adjacency(oracle):
+    """an arrival must not inherit the contact partners of the slot's previous occupant. Every organism leaves a
+    crowded world (whose carnivores are in contact with their neighbours) and comes back into the freed slots."""
+    from sapiogenesis_b200.engine import Engine
+    w = _busy_world(oracle, 24, 6, 0.35, 8, food=40)
+    g = w.to("cuda"); e = Engine(g)
+    nx = int(g.np("g_x_n")[0])
+    assert nx > 20
+    buf = e.migrate_buffer(10)
+    e.migrate_out(10, 0, buf); e.migrate_in(buf); e.synchronize()
+    c = e.migrate_counts()
+    assert c["packed"] == 10 and c["accepted"] + c["dropped"] == 10
+    NC = g.p.n_org * MAXC
+    off, other = g.np("xa_off"), g.np("xa_other").reshape(-1)
+    na = int(off[NC + g.p.n_dead])
+    uid = g.np("org_uid"); fresh = np.nonzero((g.np("org_state") == 1) & (uid >= int(g.np("g_next_uid")[0]) - c["accepted"]))[0]
+    assert len(fresh) == c["accepted"]
+    ent = other[:na]
+    cells = ent[ent < NC]
+    assert not np.isin(cells // MAXC, fresh).any(), "an adjacency entry points at an arrival"
+    for o in fresh:
+        rng = other[off[o * MAXC]: off[(o + 1) * MAXC]]
+        assert (rng == 0x7FFFFFFF).all(), "an arrival owns adjacency entries of the previous occupant"
+    hp0 = g.np("c_health").copy()
+    e.tick(1, 1); e.synchronize()                                 # rules only: carnivores bite what their adjacency lists
+    e.settle(); e.synchronize()
+    rows = (fresh[:, None] * MAXC + np.arange(MAXC)[None, :]).reshape(-1)
+    live = g.np("c_alive")[rows] == 1
+    assert (g.np("c_health")[rows][live] >= hp0[rows][live] - 1e-3).all(), "an arrival was bitten through a stale contact"
+
+
 @pytest.mark.gpu
 def test_island_self_ring_conserves_population():
     from sapiogenesis_b200.synth import build_world
@@ -111,9 +202,15 @@ def test_island_self_ring_conserves_population():
     isl = islands.Island(w, eng, every=5, count=16, seed=3)
     pop0 = int((w.t["org_state"] == 1).sum())
     births0, deaths0 = w.stats()["births"], w.stats()["deaths"]
+    xc0 = None
     isl.step(12)
     eng.synchronize()
     st = w.stats()
-    assert isl.migrated_out == 32 and isl.migrated_in == 32 and isl.dropped == 0
+    c = isl.counts()
+    assert isl.device_side and isl.migrations == 2
+    assert c["total_out"] == 32 and c["total_in"] + c["total_dropped"] == 32 and c["total_dropped"] == 0 and c["total_stayed"] == 0
     assert int((w.t["org_state"] == 1).sum()) == pop0 + (st["births"] - births0) - (st["deaths"] - deaths0)
     assert st["overflow"] == 0 and w.tick == 12
+    assert isl.collect_migration_ms() > 0 and isl.last_bytes < 16 * 70_000
+    uid = w.t["org_uid"][w.t["org_state"] == 1]
+    assert int(torch.unique(uid).numel()) == int(uid.numel())
