@@ -318,7 +318,8 @@ def run_ours(args):
         run = min(500, age - done)
         isl.step(run); eng.synchronize(); done += run
     t_age = time.perf_counter() - t_age
-    migr0 = (isl.migrated_out, getattr(isl, "migration_ms", 0.0), getattr(isl, "migrations", 0))
+    c0 = isl.counts() if every else {}
+    migr0 = (c0.get("total_out", 0), isl.collect_migration_ms() if every else 0.0, isl.migrations, c0.get("total_in", 0), c0.get("total_dropped", 0))
 
     # ---- device-resident throughput -------------------------------------------------------------------------------------
     w.t["g_stats"].view(-1)[14] = 0                      # rare-path bits: evidence of the timed region only
@@ -328,9 +329,13 @@ def run_ours(args):
     region_samples = len(clk.samples) - region0
     st1 = w.stats()
     value = units / (ms / 1e3)
-    migr = {"migrations_in_region": getattr(isl, "migrations", 0) - migr0[2], "organisms_sent_by_rank0": isl.migrated_out - migr0[0],
-            "migration_ms_total": round(isl.collect_migration_ms() - migr0[1], 3) if hasattr(isl, "collect_migration_ms") else None,
-            "bytes_per_migration": getattr(isl, "last_bytes", None)} if every else None
+    migr = None
+    if every:
+        c1 = isl.counts()
+        migr = {"migrations_in_region": isl.migrations - migr0[2], "organisms_sent_by_rank0": c1["total_out"] - migr0[0],
+                "organisms_placed_on_rank0": c1["total_in"] - migr0[3], "arrivals_dropped_on_rank0": c1["total_dropped"] - migr0[4],
+                "migration_ms_in_region": round(isl.collect_migration_ms() - migr0[1], 3), "buffer_bytes_per_migration": isl.last_bytes,
+                "record_format": "ragged (include/sapio_migrate.h): extents in use only, ~40 kB per organism"}
 
     # ---- end to end through the C-ABI with host buffers ---------------------------------------------------------------------
     e2e_steps = max(3, min(args.steps, 20))

@@ -48,6 +48,9 @@ enum { SAPIO_CELL_ABSENT = 0, SAPIO_CELL_ALIVE = 1, SAPIO_CELL_DYING = 2 /* died
 /* org_flags bits */
 enum { SAPIO_F_IMMORTAL = 1, SAPIO_F_MALADAPTIVE = 2, SAPIO_F_FINITE_MEMORY = 4, SAPIO_F_MIRROR_X = 8, SAPIO_F_MIRROR_Y = 16 };
 
+/* org_flags bits (bit0 immortal, bit1 maladaptive, bit2 finite_memory, bit3 mirror_x, bit4 mirror_y: sapio_fields.def) */
+#define SAPIO_F_GHOST 32          /* slab mode: a copy of an organism another slab owns */
+
 /* org_req bits */
 enum { SAPIO_REQ_REPRODUCE = 1, SAPIO_REQ_THOUGHT = 2, SAPIO_REQ_TRAIN = 4 };
 
@@ -102,7 +105,15 @@ typedef struct SapioParams {
     uint64_t seed;
     /* grid */
     float grid_cell;          /* broadphase cell edge (>= 2 * max solid radius) */
-    int32_t grid_nx, grid_ny, pad1;
+    int32_t grid_nx, grid_ny;
+    /* spatial slabs (second mode): this world is the slab [slab_x0, slab_x1) of a larger one, in the larger
+     * world's coordinates. slab_mode = 0: an ordinary whole world. In slab mode organisms flagged SAPIO_F_GHOST (copies of the
+     * neighbours' boundary organisms) take no part in the gas exchange, do not reproduce and are not counted; the global gas
+     * scalars and the population are composed across the slabs by the host (sapiogenesis_b200/slabs.py). */
+    int32_t slab_mode;
+    float grid_x0;            /* x of the first grid column (0 for a whole world) */
+    float slab_x0, slab_x1;
+    int32_t pad1;
 } SapioParams;
 
 /* The world: one raw pointer per SoA array of include/sapio_fields.def. */
@@ -179,6 +190,22 @@ int sapio_release_organisms(const SapioWorld *w, const int32_t *d_slots, int n, 
  * Arrivals that find no place or no free slot are dropped and counted. The buffer has a fixed size (_buffer_bytes), so the
  * transport (NCCL send/recv) needs no size exchange.
  * _counts (synchronises the stream): {chosen, packed, accepted, dropped} of the last calls, then totals {out, in, dropped, stayed}. */
+/* Spatial slabs of one large world (csrc/halo.cuh; driver: sapiogenesis_b200/slabs.py). The world step of a slab is the ordinary
+ * one; what the slabs exchange is (a) every tick, the organisms (ragged records) and dead cells next to a boundary -- _halo_pack /
+ * _halo_unpack / _halo_sweep, transport by the host (NCCL) -- and (b) three scalars composed in rank order: the slabs' gas maps
+ * (the reference updates co2 / oxygen cell by cell, sprites.py:1409-1439: the maps do not commute), refunds, dispersion products.
+ * sapio_rules_part: part 1 = begin + gas scan + think, 2 = main (+ finish outside slab mode), 3 = both (== sapio_rules). */
+int sapio_rules_part(const SapioWorld *w, void *ws, size_t ws_bytes, uint32_t phases, int part, void *stream);
+int sapio_post_advance(const SapioWorld *w, void *ws, size_t ws_bytes, void *stream);
+int sapio_slab_offsets(const SapioWorld *w, void *ws, size_t ws_bytes, int64_t *out4);   /* byte offsets in ws: gas map (2 doubles), refund sum, dispersion product, owned population (int) */
+int sapio_halo_pack(const SapioWorld *w, void *ws, size_t ws_bytes, float x_lo, float x_hi, void *d_buf, size_t buf_bytes, void *d_dead, size_t dead_bytes, void *stream);
+int sapio_halo_unpack(const SapioWorld *w, void *ws, size_t ws_bytes, int side, void *d_buf, size_t buf_bytes, void *d_dead, size_t dead_bytes, void *stream);
+int sapio_halo_sweep(const SapioWorld *w, void *ws, size_t ws_bytes, void *stream);
+int sapio_slab_gas_begin(const SapioWorld *w, void *ws, size_t ws_bytes, const double *d_maps, int n, int rank, void *stream);
+int sapio_slab_gas_finish(const SapioWorld *w, const double *d_maps, int n, const double *d_refunds, void *stream);
+int sapio_slab_disperse_finish(const SapioWorld *w, const double *d_prods, int n, void *stream);
+int sapio_slab_population(const SapioWorld *w, const int32_t *d_counts, int n, void *stream);
+
 size_t sapio_migrate_buffer_bytes(const SapioParams *p, int count, int bytes_per_organism);
 int sapio_migrate_out(const SapioWorld *w, void *ws, size_t ws_bytes, int count, int rank, void *d_buf, size_t buf_bytes, void *stream);
 int sapio_migrate_in(const SapioWorld *w, void *ws, size_t ws_bytes, void *d_buf, size_t buf_bytes, void *stream);

@@ -20,7 +20,7 @@
 #endif
 
 #define SAPIO_MIG_MAX_FIELDS 96
-#define SAPIO_MIG_MAX_RECORDS 1024
+#define SAPIO_MIG_MAX_RECORDS 4096
 #define SAPIO_MIG_MAGIC 0x53415031           /* "SAP1" */
 #define SAPIO_MIG_CANDIDATES 360             /* placement candidates per arrival, like the 360 bearings of get_new_organism_position */
 

@@ -54,6 +54,17 @@ def load() -> ctypes.CDLL:
     L.sapio_migrate_out.argtypes = [wp, vp, sz, i32, i32, vp, sz, vp]; L.sapio_migrate_out.restype = i32
     L.sapio_migrate_in.argtypes = [wp, vp, sz, vp, sz, vp]; L.sapio_migrate_in.restype = i32
     L.sapio_migrate_counts.argtypes = [wp, vp, sz, ctypes.POINTER(ctypes.c_int32), vp]; L.sapio_migrate_counts.restype = i32
+    f32_ = ctypes.c_float
+    L.sapio_rules_part.argtypes = [wp, vp, sz, u32, i32, vp]; L.sapio_rules_part.restype = i32
+    L.sapio_post_advance.argtypes = [wp, vp, sz, vp]; L.sapio_post_advance.restype = i32
+    L.sapio_slab_offsets.argtypes = [wp, vp, sz, ctypes.POINTER(ctypes.c_int64)]; L.sapio_slab_offsets.restype = i32
+    L.sapio_halo_pack.argtypes = [wp, vp, sz, f32_, f32_, vp, sz, vp, sz, vp]; L.sapio_halo_pack.restype = i32
+    L.sapio_halo_unpack.argtypes = [wp, vp, sz, i32, vp, sz, vp, sz, vp]; L.sapio_halo_unpack.restype = i32
+    L.sapio_halo_sweep.argtypes = [wp, vp, sz, vp]; L.sapio_halo_sweep.restype = i32
+    L.sapio_slab_gas_begin.argtypes = [wp, vp, sz, vp, i32, i32, vp]; L.sapio_slab_gas_begin.restype = i32
+    L.sapio_slab_gas_finish.argtypes = [wp, vp, i32, vp, vp]; L.sapio_slab_gas_finish.restype = i32
+    L.sapio_slab_disperse_finish.argtypes = [wp, vp, i32, vp]; L.sapio_slab_disperse_finish.restype = i32
+    L.sapio_slab_population.argtypes = [wp, vp, i32, vp]; L.sapio_slab_population.restype = i32
     f32 = ctypes.c_float
     L.sapio_events.argtypes = [wp, vp, sz, f32, f32, f32, vp]; L.sapio_events.restype = i32
     L.sapio_tick_host.argtypes = [wp, vp, sz, u32, i32, vp, vp, vp, i32, vp, i32, vp]; L.sapio_tick_host.restype = i32

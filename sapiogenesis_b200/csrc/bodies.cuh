@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) k_integrate(WORLD_ARG, uint32_t *__restri
         if (grid_key) {
             if (solid) {
                 // same cell function as the oracle's candidate grid; any superset generator is exact
-                int cx = (int)floorf(pos.x / p.grid_cell) + 1, cy = (int)floorf(pos.y / p.grid_cell) + 1;
+                int cx = (int)floorf((pos.x - p.grid_x0) / p.grid_cell) + 1, cy = (int)floorf(pos.y / p.grid_cell) + 1;
                 cx = min(max(cx, 0), p.grid_nx - 1); cy = min(max(cy, 0), p.grid_ny - 1);
                 key = (uint32_t)(cy * p.grid_nx + cx);
             }
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(256) k_friction(WORLD_ARG) {
 // updateUI (Sapiogenesis.py:57-65): clamp gases at zero, recount the population; plus the tick counter.
 __global__ void k_post_count(WORLD_ARG, int *__restrict__ scratch_pop) {
     int n = 0;
-    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < w.p.n_org; o += gridDim.x * blockDim.x) n += (w.org_state[o] == 1);
+    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < w.p.n_org; o += gridDim.x * blockDim.x) n += (w.org_state[o] == 1 && !(w.org_flags[o] & SAPIO_F_GHOST));
     for (int s = 16; s; s >>= 1) n += __shfl_xor_sync(FULL, n, s);
     if (lane_id() == 0 && n) atomicAdd(scratch_pop, n);
 }

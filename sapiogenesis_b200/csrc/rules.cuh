@@ -31,6 +31,10 @@ struct RulesWs {
     double *disp_factor;            // [n_dead] (1 - r) of each dispersing dead cell
     double *disp_prod;              // [1]
     int *train_list, *repro_list;   // [n_org]
+    // slab mode (p.slab_mode, sapiogenesis_b200/slabs.py): the co2 level the first organism of this slab meets (the slabs before it composed by
+    // the host), and which dead slots hold copies of a neighbour's dead cells (no part in the dispersion's gas exchange)
+    double *slab_co2_in;            // [1]
+    uint8_t *dead_ghost;            // [n_dead]
 };
 enum { RC_NTHINK = 0, RC_NTRAIN = 1, RC_NREPRO = 2, RC_NDYING = 3, RC_NFREE = 4, RC_TRAIN_TICKET = 8 /* work counter of k_train */ };
 
@@ -216,7 +220,7 @@ __global__ void __launch_bounds__(RULES_WARPS * 32) k_rules_begin(WORLD_ARG, Rul
         // exchange rate of a cell (sprites.py:1413-1416), two double divisions: every lane computes its own cells' once, the loop broadcasts
         double rho2[2];
 #pragma unroll
-        for (int h = 0; h < 2; h++) rho2[h] = (double)g.size[h] / ((double)p.width + (double)p.height) * 100.0 * (double)dt / 100.0;
+        for (int h = 0; h < 2; h++) rho2[h] = (w.org_flags[o] & SAPIO_F_GHOST) ? 0.0 : (double)g.size[h] / ((double)p.width + (double)p.height) * 100.0 * (double)dt / 100.0;   // a ghost's gas exchange belongs to its owner's slab
         const bool immortal = w.org_flags[o] & SAPIO_F_IMMORTAL;
         int died = 0, req = 0;
         if (T - w.org_birth_tick[o] >= p.age_ticks && !immortal) died += g.kill(w, 0);          // sprites.py:1826-1827
@@ -280,11 +284,13 @@ __global__ void __launch_bounds__(RULES_WARPS * 32, RULES_MAIN_MINB) k_rules_mai
         if (w.org_state[o] != 1) { if (lane == 0) w.org_gas_refund[o] = 0.0; continue; }
         OrgR g; g.load(w, o, true);
         // exchange rate of a cell (sprites.py:1413-1416), two double divisions: every lane computes its own cells' once, the loop broadcasts
-        const double rho_0 = (double)g.size[0] / ((double)p.width + (double)p.height) * 100.0 * (double)dt / 100.0;
-        const double rho_1 = (double)g.size[1] / ((double)p.width + (double)p.height) * 100.0 * (double)dt / 100.0;
+        const bool ghost = w.org_flags[o] & SAPIO_F_GHOST;
+        const double rho_0 = ghost ? 0.0 : (double)g.size[0] / ((double)p.width + (double)p.height) * 100.0 * (double)dt / 100.0;
+        const double rho_1 = ghost ? 0.0 : (double)g.size[1] / ((double)p.width + (double)p.height) * 100.0 * (double)dt / 100.0;
         const bool immortal = w.org_flags[o] & SAPIO_F_IMMORTAL;
         Aff pre = o > 0 ? R.gas_scan[o - 1] : Aff{1.0, 0.0};
-        double x = pre.a * co2_0 + pre.b, refund = 0.0;                                          // co2 level met by this organism
+        const double co2_in = p.slab_mode ? R.slab_co2_in[0] : co2_0;                            // slab mode: the slabs before this one have had their turn
+        double x = pre.a * co2_in + pre.b, refund = 0.0;                                          // co2 level met by this organism
         const double x_in = x;
         int died = 0, req = w.org_req[o];
         float consumed = w.org_consumed[o];
@@ -299,7 +305,7 @@ __global__ void __launch_bounds__(RULES_WARPS * 32, RULES_MAIN_MINB) k_rules_mai
                 rng4(p.seed, w.org_uid[o], T, RNG_REPRO_GATE, 0, r);
                 float u = u01(r[0]);
                 if ((double)u * 100.0 <= g.health_percent_d() && !(w.g_population[0] >= p.population_limit)) {
-                    if (phases & SAPIO_PH_REPRODUCE) req |= SAPIO_REQ_REPRODUCE;
+                    if ((phases & SAPIO_PH_REPRODUCE) && !ghost) req |= SAPIO_REQ_REPRODUCE;
                     if (lane == 0) w.org_lastbirth_tick[o] = T;                                  // sprites.py:1442
                 }
 #pragma unroll
@@ -387,7 +393,7 @@ __global__ void __launch_bounds__(RULES_WARPS * 32, RULES_MAIN_MINB) k_rules_mai
             }
             g.take_energy_sum(pending);
             if ((phases & SAPIO_PH_TRAIN) && !(w.org_flags[o] & SAPIO_F_MALADAPTIVE) && w.org_nlayers[o] > 0 && T - w.org_train_tick[o] >= p.train_ticks) req |= SAPIO_REQ_TRAIN;
-            if (lane == 0) stat_add(w, SAPIO_STAT_ORG_TICKS, 1);
+            if (lane == 0 && !ghost) stat_add(w, SAPIO_STAT_ORG_TICKS, 1);
         }
         g.store(w, true);
         if (lane == 0) {
@@ -400,6 +406,7 @@ __global__ void __launch_bounds__(RULES_WARPS * 32, RULES_MAIN_MINB) k_rules_mai
 
 // gases after the rules phase: the composed map of every organism, plus the refunds handed back at the end (C4)
 __global__ void k_rules_finish(WORLD_ARG, RulesWs R) {
+    if (w.p.slab_mode) return;                               // the host composes the slabs' maps and refunds (slabs.py)
     const double co2_0 = w.g_co2[0], Ttot = co2_0 + w.g_o2[0];
     Aff tot = R.gas_scan[w.p.n_org - 1];
     double co2 = tot.a * co2_0 + tot.b + R.refund_sum[0];
@@ -489,7 +496,7 @@ __global__ void __launch_bounds__(256) k_settle_disperse(WORLD_ARG, RulesWs R) {
             if (mass < p.mass_cutoff) remove = true;
             else {
                 float rate = p.dispersion_rate / 100.0f * mass * dt, nm = mass - rate;
-                if (nm > 0.f) { w.d_mass[d] = nm; factor = 1.0 - (double)rate / 100.0; } else remove = true;
+                if (nm > 0.f) { w.d_mass[d] = nm; factor = (w.p.slab_mode && R.dead_ghost[d]) ? 1.0 : 1.0 - (double)rate / 100.0; } else remove = true;
             }
             float2 q = reinterpret_cast<const float2 *>(w.d_pos)[d];
             if (q.x < 0.f || q.x > p.width || q.y < 0.f || q.y > p.height) remove = true;
@@ -505,6 +512,7 @@ __global__ void __launch_bounds__(256) k_settle_disperse(WORLD_ARG, RulesWs R) {
 }
 struct MulD { __host__ __device__ double operator()(double a, double b) const { return a * b; } };
 __global__ void k_settle_gas(WORLD_ARG, RulesWs R) {
+    if (w.p.slab_mode) return;
     const double co2 = w.g_co2[0], Ttot = co2 + w.g_o2[0];
     double c2 = Ttot + (co2 - Ttot) * R.disp_prod[0];
     w.g_co2[0] = c2; w.g_o2[0] = Ttot - c2;

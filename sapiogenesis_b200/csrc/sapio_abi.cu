@@ -16,6 +16,7 @@
 #include "frame.cuh"
 #include "migrate.cuh"
 #include "migrate2.cuh"
+#include "halo.cuh"
 
 static thread_local char g_err[512] = "";
 static int fail(int code, const char *fmt, const char *a = "") {
@@ -53,7 +54,7 @@ static size_t cub_need(const SapioParams &p) {
     return m;
 }
 
-struct AllWs { Workspace step; RulesWs rules; TrainWs train; ReproWs repro; FrameWs frame, frame2; MigWs mig; int train_ctas; int *probe; };
+struct AllWs { Workspace step; RulesWs rules; TrainWs train; ReproWs repro; FrameWs frame, frame2; MigWs mig; HaloWs halo; int train_ctas; int *probe; };
 
 static size_t carve_all(const SapioParams &p, char *base, AllWs *A) {
     size_t off = carve_workspace(p, base, &A->step);
@@ -67,6 +68,7 @@ static size_t carve_all(const SapioParams &p, char *base, AllWs *A) {
     R.dying_cnt = (int *)take((NO + 1) * 4); R.dying_off = (int *)take((NO + 1) * 4);
     R.free_flag = (int *)take((ND + 1) * 4); R.free_off = (int *)take((ND + 1) * 4); R.free_list = (int *)take(ND * 4);
     R.disp_factor = (double *)take(ND * 8); R.disp_prod = (double *)take(256);
+    R.slab_co2_in = (double *)take(256); R.dead_ghost = (uint8_t *)take(ND);
     A->train_ctas = (int)std::min<long>(8 * 148, std::max<long>(8, NO / 8));      // 8 CTAs of 256 threads per SM; ~1/17 of the organisms train per tick
     TrainWs &T = A->train;
     T.per_cta = (size_t)(p.in_cap + 4 * TRAIN_MAXW + 4) * SAPIO_MEMROWS;
@@ -84,6 +86,11 @@ static size_t carve_all(const SapioParams &p, char *base, AllWs *A) {
         MigWs &M = A->mig; const size_t R = SAPIO_MIG_MAX_RECORDS;
         M.emig = (int *)take(R * 4); M.counters = (int *)take(256); M.rect = (double *)take(R * 6 * 8); M.mask = (uint32_t *)take(R * 12 * 4);
         M.slot = (int *)take(R * 4); M.delta = (double *)take(R * 2 * 8); M.acc_rect = (double *)take(R * 4 * 8);
+    }
+    if (p.slab_mode) {
+        HaloWs &H = A->halo;
+        for (int sd = 0; sd < 2; sd++) { H.ghost_slot[sd] = (int *)take(NO * 4); H.ghost_dslot[sd] = (int *)take(ND * 4); }
+        H.refreshed = (int *)take(NO * 4); H.drefreshed = (int *)take(ND * 4); H.dcount = (int *)take(256); H.dlist = (int *)take(ND * 4);
     }
     FrameWs &F = A->frame;
     F.control = (SapioControl *)take(256); F.header = (SapioFrameHeader *)take(512); F.counts = (int *)take(256);
@@ -132,12 +139,13 @@ static int launch_grid_only(const SapioWorld &w, const Workspace &W, cudaStream_
     return 0;
 }
 
-static int launch_rules(const SapioWorld &w, AllWs &A, uint32_t phases, cudaStream_t st) {
+static int launch_rules(const SapioWorld &w, AllWs &A, uint32_t phases, cudaStream_t st, int part = 3) {   // part: 1 begin + gas scan + think, 2 main + finish
     const SapioParams &p = w.p;
     RulesWs &R = A.rules;
+    const int org_grid = stream_grid((long)p.n_org * 32, RULES_WARPS * 32);
+    if (part & 1) {
     prof_mark(st, PT_RULES_BEGIN);
     CUDA_TRY(cudaMemsetAsync(R.counters, 0, 256, st));
-    const int org_grid = stream_grid((long)p.n_org * 32, RULES_WARPS * 32);
     k_rules_begin<<<org_grid, RULES_WARPS * 32, 0, st>>>(w, R, phases);
     prof_mark(st, PT_GAS_SCAN);
     {
@@ -159,6 +167,8 @@ static int launch_rules(const SapioWorld &w, AllWs &A, uint32_t phases, cudaStre
         k_think<<<stream_grid((long)p.n_org * 32 / 4 + 1, THINK_WARPS * 32), THINK_WARPS * 32, smem, st>>>(w, A.step, R);
         LAUNCHES(3);
     }
+    }
+    if (!(part & 2)) { prof_mark(st, PT_END); LAUNCH_CHECK(); return 0; }
     prof_mark(st, PT_RULES_MAIN);
     k_rules_main<<<org_grid, RULES_WARPS * 32, 0, st>>>(w, R, phases);
     size_t tmp = A.step.cub_bytes;
@@ -447,6 +457,82 @@ int sapio_release_organisms(const SapioWorld *w, const int32_t *d_slots, int n, 
     k_mig_release<<<n < 4096 ? n : 4096, MAXC, 0, (cudaStream_t)stream>>>(*w, d_slots, nullptr, n);
     k_mig_scrub<<<stream_grid(2 * (long)w->p.x_cap), 256, 0, (cudaStream_t)stream>>>(*w);
     LAUNCHES(2); LAUNCH_CHECK();
+    return 0;
+}
+
+// ---- spatial slabs (csrc/halo.cuh, sapiogenesis_b200/slabs.py) ----------------------------------------------------------------------
+int sapio_rules_part(const SapioWorld *w, void *ws, size_t ws_bytes, uint32_t phases, int part, void *stream) {
+    AllWs A; int rc = check(w, ws, ws_bytes, &A); if (rc) return rc;
+    return launch_rules(*w, A, phases, (cudaStream_t)stream, part);
+}
+int sapio_post_advance(const SapioWorld *w, void *ws, size_t ws_bytes, void *stream) {
+    AllWs A; int rc = check(w, ws, ws_bytes, &A); if (rc) return rc;
+    return launch_post(*w, A, (cudaStream_t)stream, 1, 1);
+}
+int sapio_slab_offsets(const SapioWorld *w, void *ws, size_t ws_bytes, int64_t *out4) {
+    AllWs A; int rc = check(w, ws, ws_bytes, &A); if (rc) return rc;
+    out4[0] = (char *)(A.rules.gas_scan + (w->p.n_org - 1)) - (char *)ws;      /* this slab's composed gas map (a, b) */
+    out4[1] = (char *)A.rules.refund_sum - (char *)ws; out4[2] = (char *)A.rules.disp_prod - (char *)ws; out4[3] = (char *)A.step.pop - (char *)ws;
+    return 0;
+}
+int sapio_halo_pack(const SapioWorld *w, void *ws, size_t ws_bytes, float x_lo, float x_hi, void *d_buf, size_t buf_bytes, void *d_dead, size_t dead_bytes, void *stream) {
+    AllWs A; int rc = check(w, ws, ws_bytes, &A); if (rc) return rc;
+    if (!w->p.slab_mode) return fail(SAPIO_E_ARG, "sapio_halo_pack: not a slab world%s");
+    cudaStream_t st = (cudaStream_t)stream;
+    SapioMigTable T; sapio_mig_table(&w->p, w, &T);
+    k_halo_choose<<<1, 256, 0, st>>>(*w, A.mig, x_lo, x_hi, SAPIO_MIG_MAX_RECORDS);
+    k_mig_sizes<<<1, 256, 0, st>>>(*w, T, A.mig, (char *)d_buf, buf_bytes);
+    k_mig_pack<<<148 * 4, 256, 0, st>>>(*w, T, A.mig, (char *)d_buf);
+    k_halo_dead_header<<<1, 1, 0, st>>>((char *)d_dead);
+    k_halo_pack_dead<<<stream_grid(w->p.n_dead), 256, 0, st>>>(*w, A.rules, x_lo, x_hi, (char *)d_dead, dead_bytes);
+    LAUNCHES(5); LAUNCH_CHECK();
+    return 0;
+}
+int sapio_halo_unpack(const SapioWorld *w, void *ws, size_t ws_bytes, int side, void *d_buf, size_t buf_bytes, void *d_dead, size_t dead_bytes, void *stream) {
+    AllWs A; int rc = check(w, ws, ws_bytes, &A); if (rc) return rc;
+    if (!w->p.slab_mode || side < 0 || side > 1) return fail(SAPIO_E_ARG, "sapio_halo_unpack: not a slab world, or side not 0 / 1%s");
+    cudaStream_t st = (cudaStream_t)stream;
+    SapioMigTable T; sapio_mig_table(&w->p, w, &T);
+    k_halo_assign<<<1, 32, 0, st>>>(*w, T, A.mig, A.halo, side, (const char *)d_buf);
+    k_halo_unpack<<<148 * 4, 256, 0, st>>>(*w, T, A.mig, (char *)d_buf);
+    k_halo_assign_dead<<<1, 32, 0, st>>>(*w, A.rules, A.halo, side, (const char *)d_dead);
+    k_halo_unpack_dead<<<stream_grid(w->p.n_dead), 256, 0, st>>>(*w, A.rules, A.halo, (const char *)d_dead);
+    LAUNCHES(4); LAUNCH_CHECK();
+    (void)buf_bytes; (void)dead_bytes;
+    return 0;
+}
+int sapio_halo_sweep(const SapioWorld *w, void *ws, size_t ws_bytes, void *stream) {
+    AllWs A; int rc = check(w, ws, ws_bytes, &A); if (rc) return rc;
+    if (!w->p.slab_mode) return fail(SAPIO_E_ARG, "sapio_halo_sweep: not a slab world%s");
+    cudaStream_t st = (cudaStream_t)stream;
+    k_halo_sweep<<<stream_grid(w->p.n_org > w->p.n_dead ? w->p.n_org : w->p.n_dead), 256, 0, st>>>(*w, A.rules, A.halo);
+    k_mig_scrub<<<stream_grid(2 * (long)w->p.x_cap), 256, 0, st>>>(*w);
+    LAUNCHES(2); LAUNCH_CHECK();
+    return 0;
+}
+int sapio_slab_gas_begin(const SapioWorld *w, void *ws, size_t ws_bytes, const double *d_maps, int n, int rank, void *stream) {
+    AllWs A; int rc = check(w, ws, ws_bytes, &A); if (rc) return rc;
+    if (rank < 0 || rank >= n) return fail(SAPIO_E_ARG, "sapio_slab_gas_begin: rank out of range%s");
+    k_slab_gas_begin<<<1, 1, 0, (cudaStream_t)stream>>>(*w, A.rules, d_maps, rank);
+    LAUNCHES(1); LAUNCH_CHECK();
+    return 0;
+}
+int sapio_slab_gas_finish(const SapioWorld *w, const double *d_maps, int n, const double *d_refunds, void *stream) {
+    int rc = check(w, nullptr, 0, nullptr); if (rc) return rc;
+    k_slab_gas_finish<<<1, 1, 0, (cudaStream_t)stream>>>(*w, d_maps, n, d_refunds);
+    LAUNCHES(1); LAUNCH_CHECK();
+    return 0;
+}
+int sapio_slab_disperse_finish(const SapioWorld *w, const double *d_prods, int n, void *stream) {
+    int rc = check(w, nullptr, 0, nullptr); if (rc) return rc;
+    k_slab_disperse_finish<<<1, 1, 0, (cudaStream_t)stream>>>(*w, d_prods, n);
+    LAUNCHES(1); LAUNCH_CHECK();
+    return 0;
+}
+int sapio_slab_population(const SapioWorld *w, const int32_t *d_counts, int n, void *stream) {
+    int rc = check(w, nullptr, 0, nullptr); if (rc) return rc;
+    k_slab_population<<<1, 1, 0, (cudaStream_t)stream>>>(*w, d_counts, n);
+    LAUNCHES(1); LAUNCH_CHECK();
     return 0;
 }
 

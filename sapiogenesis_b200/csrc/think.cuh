@@ -25,7 +25,7 @@ __device__ __forceinline__ void sense_enumerate(const SapioWorld &w, const Works
     const SapioParams &p = w.p;
     const int NC = p.n_org * MAXC, lane = lane_id();
     const float gc = p.grid_cell, reach = R + 0.5f * gc;            // grid_cell >= 2 * largest solid radius
-    int cx0 = (int)floorf((sx - reach) / gc) + 1, cx1 = (int)floorf((sx + reach) / gc) + 1;
+    int cx0 = (int)floorf((sx - reach - p.grid_x0) / gc) + 1, cx1 = (int)floorf((sx + reach - p.grid_x0) / gc) + 1;
     int cy0 = (int)floorf((sy - reach) / gc) + 1, cy1 = (int)floorf((sy + reach) / gc) + 1;
     cx0 = max(cx0, 0); cy0 = max(cy0, 0); cx1 = min(cx1, p.grid_nx - 1); cy1 = min(cy1, p.grid_ny - 1);
     const int nbx = cx1 - cx0 + 1, nby = cy1 - cy0 + 1;

@@ -36,7 +36,7 @@ MEMROWS = 232
 CELL_TYPES = ["barrier", "carniv", "eye", "olfactory", "co2C", "push", "body", "rotate", "heart"]
 T_BARRIER, T_CARNIV, T_EYE, T_OLFACTORY, T_CO2C, T_PUSH, T_BODY, T_ROTATE, T_HEART = range(9)
 
-F_IMMORTAL, F_MALADAPTIVE, F_FINITE_MEMORY, F_MIRROR_X, F_MIRROR_Y = 1, 2, 4, 8, 16
+F_IMMORTAL, F_MALADAPTIVE, F_FINITE_MEMORY, F_MIRROR_X, F_MIRROR_Y, F_GHOST = 1, 2, 4, 8, 16, 32
 
 PH_RULES, PH_THINK, PH_TRAIN, PH_REPRODUCE, PH_STEP, PH_FRICTION, PH_POST = 1, 2, 4, 8, 16, 32, 64
 PH_ALL = 127
@@ -82,6 +82,7 @@ class SapioParams(ctypes.Structure):
         ("mirror_px", ctypes.c_float), ("mirror_py", ctypes.c_float),
         ("seed", ctypes.c_uint64),
         ("grid_cell", ctypes.c_float), ("grid_nx", ctypes.c_int32), ("grid_ny", ctypes.c_int32),
+        ("slab_mode", ctypes.c_int32), ("grid_x0", ctypes.c_float), ("slab_x0", ctypes.c_float), ("slab_x1", ctypes.c_float),
         ("pad1", ctypes.c_int32),
     ]
 
