@@ -116,9 +116,9 @@ class DistComm:
 
     def allgather(self, parts: List[torch.Tensor]) -> List[torch.Tensor]:
         p = parts[0].reshape(-1).contiguous()
-        out = torch.empty((self.n, p.numel()), dtype=p.dtype, device=p.device)
+        out = torch.empty(self.n * p.numel(), dtype=p.dtype, device=p.device)          # flat: gloo wants chunks of the input's shape
         dist.all_gather_into_tensor(out, p, group=self.group)
-        return [out]
+        return [out.view(self.n, p.numel())]
 
     def exchange(self, slabs: List[Slab]):
         s = slabs[0]

@@ -93,3 +93,92 @@ def test_split_world_lives_the_life_of_the_whole_world(n_slabs):
     st = [s.world.stats() for s in slabs]
     assert all(x["overflow"] == 0 for x in st) and pw.stats()["overflow"] == 0
     assert sum(x["org_ticks"] for x in st) == pw.stats()["org_ticks"] - whole.stats()["org_ticks"] + sum(0 for _ in st) or True
+
+
+@pytest.mark.gpu
+def test_ownership_moves_with_the_heart_and_births_cross_the_cut():
+    """Uniform cuts through a crowded, reproducing world: organisms drift across the cuts (hand-over), children are born next to them.
+    Every living organism is owned by exactly one slab -- the one its heart lies in --, uids are unique, nothing overflows, the gas
+    scalars stay the same number on every slab, and the population follows the whole world's within a few per cent (the order in which
+    the gas maps compose changes with every hand-over, so the two runs are no longer identical: SURVEY C-6)."""
+    from sapiogenesis_b200.engine import Engine
+    from sapiogenesis_b200.slabs import LocalComm, SlabDriver, split_world
+    from sapiogenesis_b200.synth import build_world
+    w, eng = build_world(1500, seed=5, area_per_org=120_000.0, food_per_org=1.0)
+    w.p.repro_ticks = 40; w.p.population_limit = 4000; eng.refresh()
+    w.t["c_vel"][:, 0] += 200.0 * torch.sign(torch.randn(w.t["c_vel"].shape[0], device="cuda"))      # everybody on the move, left or right
+    eng.tick(30); eng.synchronize()
+    whole = w.to("cpu")
+    slabs, perm = split_world(whole, 3, "cuda", slot_factor=3.0)
+    pw = perm.to("cuda"); pe = Engine(pw)
+    drv = SlabDriver(slabs, LocalComm(3))
+    owner0 = {}
+    for s in slabs:
+        for u in s.world.t["org_uid"][s.owned()].tolist(): owner0[u] = s.rank
+    for t in range(60):
+        if t % 20 == 0:
+            for s in slabs: s.world.t["c_energy"][:] = s.world.t["c_storage"]
+            pw.t["c_energy"][:] = pw.t["c_storage"]
+        drv.tick(1); pe.tick(1)
+    drv.synchronize(); pe.synchronize()
+    seen, moved = {}, 0
+    for s in slabs:
+        sw = s.world
+        own = s.owned()
+        hx = sw.t["c_pos"].view(-1, MAXC, 2)[own][:, 0, 0]
+        assert bool(((hx >= sw.p.slab_x0) & (hx < sw.p.slab_x1)).all()), "an organism is owned by a slab its heart is not in"
+        for u in sw.t["org_uid"][own].tolist():
+            assert u not in seen, "an organism is owned twice"
+            seen[u] = s.rank
+            moved += (u in owner0 and owner0[u] != s.rank)
+        assert sw.stats()["overflow"] == 0
+        assert float(sw.t["g_co2"][0]) == float(slabs[0].world.t["g_co2"][0]) and int(sw.t["g_population"][0]) == len(seen) or s.rank < 2
+    births = sum(s.world.stats()["births"] for s in slabs) - 3 * whole.stats()["births"]
+    pop_w = int((pw.t["org_state"] == 1).sum())
+    print(f"hand-over: {moved} organisms changed owner, {births} births in the slabs, population {len(seen)} vs {pop_w} in the whole world")
+    assert moved >= 3 and births >= 20
+    assert int(slabs[0].world.t["g_population"][0]) == len(seen)
+    assert abs(len(seen) - pop_w) <= 0.05 * pop_w
+    assert float(slabs[0].world.t["g_co2"][0]) == pytest.approx(float(pw.t["g_co2"][0]), rel=2e-2)
+
+
+def _dist_worker(rank, world, port, out):
+    import os
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from sapiogenesis_b200.slabs import DistComm
+        comm = DistComm()
+        g = comm.allgather([torch.tensor([float(rank), 10.0 + rank], dtype=torch.float64)])[0]
+        ok = g.shape == (world, 2) and g[:, 0].tolist() == [float(r) for r in range(world)]
+
+        class S:                                                   # a slab as far as the exchange is concerned
+            def __init__(s):
+                s.rank, s.n = rank, world
+                s.send = [(torch.full((8,), 10 * rank + side, dtype=torch.uint8), torch.full((4,), 100 + 10 * rank + side, dtype=torch.uint8)) for side in (0, 1)]
+                s.recv = [(torch.zeros(8, dtype=torch.uint8), torch.zeros(4, dtype=torch.uint8)) for _ in (0, 1)]
+            def has_neighbour(s, side): return s.rank > 0 if side == 0 else s.rank < s.n - 1
+        s = S()
+        comm.exchange([s])
+        if rank > 0: ok = ok and s.recv[0][0].tolist() == [10 * (rank - 1) + 1] * 8 and s.recv[0][1].tolist() == [100 + 10 * (rank - 1) + 1] * 4
+        if rank < world - 1: ok = ok and s.recv[1][0].tolist() == [10 * (rank + 1)] * 8
+        out.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_distributed_comm_gloo_world3():
+    """DistComm (what bench.py --mode slabs runs over NCCL): rank-ordered allgather, and what a slab sends to its right neighbour is
+    what that neighbour receives from its left."""
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as so:
+        so.bind(("127.0.0.1", 0)); port = so.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_dist_worker, args=(r, 3, port, q)) for r in range(3)]
+    for p in procs: p.start()
+    res = dict(q.get(timeout=120) for _ in procs)
+    for p in procs: p.join(timeout=60)
+    assert res == {0: True, 1: True, 2: True}
