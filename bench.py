@@ -456,6 +456,89 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_slabs(args):
+    """BASELINE configs[4]: ONE world of N x M organisms cut along x into N slabs, one per GPU; every tick the slabs exchange the organisms
+    and dead cells within the halo of their common boundaries (NCCL p2p) and compose the gas maps / refunds / dispersion / population in
+    rank order (small allgathers). M organisms per GPU: weak scaling in the driver's sense (1M organisms at N = 8 with --organisms 125000)."""
+    import torch
+    import torch.distributed as dist
+    from sapiogenesis_b200.slabs import DistComm, LocalComm, SlabDriver, build_slab
+
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the world step has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    clk = ClockSampler(local_rank); clk.__enter__()
+    M = args.organisms
+    slab = build_slab(M * world_size, rank, world_size, dev, seed=7)
+    drv = SlabDriver([slab], DistComm() if world_size > 1 else LocalComm(1))
+    warm = max(args.warmup, 3)
+    drv.tick(warm); drv.synchronize()
+    age = max(args.age - warm, 0)
+    t_age = time.perf_counter()
+    done = 0
+    while done < age:
+        run = min(250, age - done)
+        drv.tick(run); drv.synchronize(); done += run
+    t_age = time.perf_counter() - t_age
+    w, eng = slab.world, slab.engine
+    st0 = w.stats(); halo0 = slab.halo_bytes; launches0 = eng.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    eng.profile(True)
+    barrier()
+    ev0.record()
+    drv.tick(args.steps)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    prof = eng.profile_read(reset=True); eng.profile(False)
+    st1 = w.stats()
+    units = st1["org_ticks"] - st0["org_ticks"]                     # owned organisms only: a ghost is its owner's organism
+    owned = int(slab.owned().sum()); ghosts = int((w.t["org_state"] == 1).sum()) - owned
+    t = torch.tensor([ms, float(units), float(owned), float(ghosts), float(slab.halo_bytes - halo0)], dtype=torch.float64, device=dev)
+    if world_size > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, units, owned_all, ghosts_all, halo_all = float(tmax[0]), float(tsum[1]), float(tsum[2]), float(tsum[3]), float(tsum[4])
+    else:
+        owned_all, ghosts_all, halo_all = float(owned), float(ghosts), float(t[4])
+    clk.__exit__()
+    if rank == 0:
+        stage_ms = {k: v[0] / max(v[1], 1) for k, v in prof.items() if v[1] > 0}
+        line = {
+            "metric": METRIC, "value": units / (ms / 1e3), "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": warm,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"full world tick of ONE world of {M * world_size} organisms at spawn cut into {world_size} spatial slab(s) along x "
+                                   f"(BASELINE configs[4]), aged {args.age} ticks before the timed region",
+                       "mode": "slabs", "organisms_per_gpu": M, "world_age_ticks": int(w.tick), "ageing_prelude_s": round(t_age, 1),
+                       "living_owned": int(owned_all), "ghost_copies": int(ghosts_all), "halo_px": slab.halo,
+                       "halo_bytes_per_tick_all_ranks": int(halo_all / args.steps),
+                       "halo_buffer_bytes_per_side": int(slab.send[0][0].numel() + slab.send[0][1].numel()),
+                       "exchange": "per tick: ragged organism records + dead cells within the halo to each neighbour (NCCL send/recv), allgathers of the "
+                                   "gas map (16 B), refund (8 B), dispersion (8 B) and owned population (4 B) composed in rank order",
+                       "l2_policy": "inputs larger than L2",
+                       "parallelism": f"{world_size} slab(s) of one world, one per GPU"},
+            "e2e": None, "e2e_note": "the slab mode has no host-buffer entry point: frames are downloaded per slab with the island API (sapio_tick_host)",
+            "gpu_launches": int(eng.launch_count() - launches0),
+            "stage_ms": {k: round(v, 4) for k, v in sorted(stage_ms.items(), key=lambda kv: -kv[1])},
+            "clocks": clk.summary(), "world_stats_rank0": st1,
+        }
+        print(json.dumps(line))
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
 def workload_name(args, M):
     if args.forward_only:
         return f"forward-only tick (rules + think + Space.step + friction; no dopamine training, no reproduction: BASELINE configs[1]), {M} organisms per GPU island"
@@ -479,9 +562,14 @@ def main():
     ap.add_argument("--no-forward-record", action="store_true", help="skip the 10k forward-only sub-record (BASELINE configs[1])")
     ap.add_argument("--migrate-every", type=int, default=50, help="N > 1: ticks between ring migrations (0 = never)")
     ap.add_argument("--migrate-count", type=int, default=64, help="organisms each island sends per migration")
+    ap.add_argument("--mode", default="islands", choices=["islands", "slabs"],
+                    help="multi-GPU form: independent population islands with ring migration (BASELINE configs[3], default) or spatial slabs of "
+                         "one world of gpus x organisms with halo exchange (configs[4])")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "slabs":
+        run_slabs(args)
     else:
         run_ours(args)
 

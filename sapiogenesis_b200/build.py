@@ -18,7 +18,7 @@ OBJ = os.path.join(CSRC, "_obj")
 SO = os.path.join(HERE, "libsapio_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
-         "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+         "--expt-relaxed-constexpr", "-Xptxas", "-v"] + os.environ.get("SAPIO_NVCC_DEFS", "").split()      # e.g. -DORG_PHASE_PROF (diagnostic builds)
 _INC = re.compile(r'^\s*#\s*include\s+"([^"]+)"', re.M)
 
 

@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256) k_comp_count(WORLD_ARG, Workspace W) {
         for (int e = 0; e < 2; e++) {
             const int v = comp_node(e ? (uint32_t)key : (uint32_t)(key >> 32), NC, NB, n_org);
             if (v < 0 || atomicExch(&W.cn_seen[v], 1)) continue;
-            if (v < n_org) { atomicAdd(&W.cn_norg[root], 1); atomicAdd(&W.cn_need[root], comp_slab_bytes(comp_slab_class(w.org_ncells[v]))); }
+            if (v < n_org) { atomicAdd(&W.cn_norg[root], 1); atomicAdd(&W.cn_need[root], comp_slab_bytes(comp_slab_class(W.org_nlive[v]))); }
             else atomicAdd(&W.cn_ndead[root], 1);
         }
     }
@@ -210,7 +210,7 @@ template <int CM>
 __device__ void comp_org_load(const SapioWorld &w, const Workspace &W, const StepK &K, const CompView &V, int o, int wslot) {
     OrgS<CM> &s = comp_slab<CM>(V, wslot);
     OrgCtx<CM, 32> c(s, w, K, o);
-    c.load(); c.prestep_pairs(); c.match_prev(); c.schedule(); c.template prestep_contacts<true>();
+    c.load(); c.prestep_pairs(); c.schedule(); c.template prestep_contacts<true>();
     uint8_t *ro = V.rank_of + wslot * 64;                              // row -> rank of the living cells, for the contacts' body references
     const int lane = lane_id();
     ro[lane] = 255; ro[lane + 32] = 255;
@@ -242,7 +242,9 @@ __device__ void comp_org_store(const SapioWorld &w, const StepK &K, const CompVi
 }
 #define COMP_DISPATCH(cls, fn, ...) do { if ((cls) == 0) fn<24>(__VA_ARGS__); else if ((cls) == 1) fn<40>(__VA_ARGS__); else if ((cls) == 2) fn<48>(__VA_ARGS__); else fn<64>(__VA_ARGS__); } while (0)
 
-__global__ void __launch_bounds__(512, 1) k_component(WORLD_ARG, Workspace W, StepK K, int tier) {
+// TW: warps of the tier's CTA (one instantiation per CTA size, so that the small tiers are not compiled under the 16-warp register cap)
+template <int TW>
+__global__ void __launch_bounds__(TW * 32, TW == 1 ? 16 : (TW == 2 ? 5 : (TW == 4 ? 2 : 1))) k_component(WORLD_ARG, Workspace W, StepK K, int tier) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const CompTier T = comp_tier(tier);
     const int NC = w.p.n_org * MAXC, NB = NC + w.p.n_dead;
@@ -299,7 +301,7 @@ __global__ void __launch_bounds__(512, 1) k_component(WORLD_ARG, Workspace W, St
                 for (int i = 1; i < no; i++) { int v = V.hd->org[i], j = i - 1; while (j >= 0 && V.hd->org[j] > v) { V.hd->org[j + 1] = V.hd->org[j]; j--; } V.hd->org[j + 1] = v; }
                 int off = 0;
                 for (int i = 0; i < no; i++) {
-                    const int cls = comp_slab_class(w.org_ncells[V.hd->org[i]]);
+                    const int cls = comp_slab_class(W.org_nlive[V.hd->org[i]]);
                     V.hd->slab_cls[i] = cls; V.hd->slab_off[i] = off; off += comp_slab_bytes(cls);
                 }
                 if (off > slab_total) over = true;

@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(SIMPLE_WARPS * 32) k_coupled_simple(WORLD_ARG,
     for (int q = gwarp; q < ncoupled; q += gwarps) {
         if (!comp_is_big(W, W.coupled_list[q])) continue;                        // warp-uniform
         Ctx c(s, w, K, W.coupled_list[q]);
-        c.load(); c.prestep_pairs(); c.match_prev(); c.schedule(); c.template prestep_contacts<true>();
+        c.load(); c.prestep_pairs(); c.schedule(); c.template prestep_contacts<true>();
         if (dt_coef == 0.f) c.zero_pin_acc();                  // no warm start will consume the cached pin impulses
         c.store_contacts(W.ic_bounce, W.ic_jbias);
         if (OrgS<MAXC> *g = parked(q)) c.save_static(g);

@@ -6,6 +6,8 @@ cudaError_t org_plan_##CM(int sms, int *blocks, size_t *smem_out) { \
     size_t smem = (size_t)OrgCfg<CM>::WARP_BYTES * OrgCfg<CM>::WARPS; \
     cudaError_t e = cudaFuncSetAttribute(k_org_solve<CM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e != cudaSuccess) return e; \
+    e = cudaFuncSetAttribute(k_org_solve<CM>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);   /* two CTAs of 111 KB need the whole 228 KB */ \
+    if (e != cudaSuccess) return e; \
     int per_sm = 0; \
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_org_solve<CM>, OrgCfg<CM>::WARPS * 32, smem); \
     if (e != cudaSuccess) return e; \

@@ -24,15 +24,19 @@ struct alignas(16) OrgS {
     static constexpr int IC = 2 * CM < 16 ? 16 : 2 * CM;          // intra contacts kept on chip (global cap SAPIO_ICAP = 192)
     float4 pair[GC ? 1 : NP];        // wavefront-major: nx, ny, bias, jnAcc of a pin joint
     float jn[GC ? NP : 1];           // GC: jnAcc alone
-    float4 vm[CM];                   // vx, vy, w, 1/m                       (index = rank among the living cells)
-    float4 bb[CM];                   // bias velocity x, y, r/I, r
+    float4 vm[CM + 1];               // vx, vy, w, 1/m                       (index = rank among the living cells; [CM]: the walls' static body)
+    float4 bb[CM + 1];               // bias velocity x, y, r/I, r
     float4 spin[CM];                 // sensor pin: nx, ny, bias, jnAcc
+    // intra contacts: detected in canonical order (sorted code), then laid out in EXECUTION order (by dependency level, canonical
+    // within a level) so that a level step reads three consecutive runs of float4
+    float4 ce0[IC];                  // nx, ny, bias, bounce          (canonical order between detection and prestep_contacts)
+    float4 ce1[IC];                  // 1 / k_n, 1 / k_t, mu, bits: canonical index | rank a << 8 | rank b << 16 (255: wall)
+    float4 cacc[IC];                 // jnAcc, jtAcc, jBias, -
     float2 sv[CM];                   // sensor body velocity
     float2 p[CM], rel[CM];
-    float cnx[IC], cny[IC], cbias[IC], cbo[IC], cjn[IC], cjt[IC], cjb[IC], cnm[IC], ctm[IC], cmu[IC];
     uint16_t ccode[IC];              // canonical key: row_i * 128 + row_j (walls: 64 + wall)
-    uint8_t ca[IC], cbk[IC];         // ranks of the two cells (255: wall)
-    uint8_t corder[IC], clev[IC], sstart[IC + 2], lcnt[IC + 2];
+    uint8_t ca[IC], cbk[IC];         // ranks of the two cells (255: wall), canonical order
+    uint8_t corder[IC], cpos[IC], clev[IC], sstart[IC + 2], lcnt[IC + 2];      // execution position -> canonical index and back; level steps
     uint8_t row_of[CM], last[CM], issens[CM];
     int n, nic, nsteps;
 };
@@ -60,27 +64,24 @@ struct OrgCtx {
     float4 *cst;                                                    // GC: this warp's constants scratch
     __device__ OrgCtx(S &s_, const SapioWorld &w_, const StepK &K_, int o_, float4 *cst_ = nullptr) : s(s_), w(w_), K(K_), o(o_), cst(cst_) {
         lane = lane_id(); sl = lane % G; gshift = lane - sl;
-        nc = o >= 0 ? min(w.org_ncells[o], CM) : 0; n = 0; sens = 0;
+        nc = o >= 0 ? min(w.org_ncells[o], MAXC) : 0; n = 0; sens = 0;
     }
     __device__ uint32_t gballot(bool pred) const { return (__ballot_sync(FULL, pred) >> gshift) & GM; }
     __device__ static int wmax(int v) { for (int s_ = 16; s_; s_ >>= 1) v = max(v, __shfl_xor_sync(FULL, v, s_)); return v; }
 
     __device__ void load() {
-        uint32_t am[2];
-        bool a[2], sn[2];
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            int k = sl + G * h, row = o * MAXC + k;
-            a[h] = k < nc && w.c_alive[row] == SAPIO_CELL_ALIVE;
-            sn[h] = a[h] && is_sensor_type(w.c_type[row]);
-            am[h] = gballot(a[h]);
-        }
-        n = __popc(am[0]) + __popc(am[1]);
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            if (!a[h]) continue;
-            const int k = sl + G * h, row = o * MAXC + k;
-            const int r = (h ? __popc(am[0]) : 0) + __popc(am[h] & ((1u << sl) - 1u));
+        // rows in chunks of G: the living cells are compacted (rank = number of living cells in front), an organism of a class holds at
+        // most CM of them whatever the rows it occupies (step.cuh: k_classify_count)
+        int cnt = 0;
+        const int ncw = wmax(nc);
+        for (int h0 = 0; h0 < ncw; h0 += G) {
+            const int k = h0 + sl, row = o * MAXC + k;
+            const bool a = k < nc && w.c_alive[row] == SAPIO_CELL_ALIVE;
+            const uint32_t am = gballot(a);
+            const int r = cnt + __popc(am & ((1u << sl) - 1u));
+            cnt += __popc(am);
+            if (!a || r >= CM) continue;
+            const bool sn = is_sensor_type(w.c_type[row]);
             const float m = w.c_mass[row], rad = w.c_size[row] * 0.5f;
             const float2 pc = reinterpret_cast<const float2 *>(w.c_pos)[row], v = reinterpret_cast<const float2 *>(w.c_vel)[row];
             const float2 vb = reinterpret_cast<const float2 *>(w.c_vbias)[row];
@@ -88,8 +89,8 @@ struct OrgCtx {
             s.p[r] = pc; s.rel[r] = reinterpret_cast<const float2 *>(w.c_rel)[row];
             s.vm[r] = make_float4(v.x, v.y, w.c_angvel[row], minv);
             s.bb[r] = make_float4(vb.x, vb.y, iinv * rad, rad);
-            s.row_of[r] = (uint8_t)k; s.issens[r] = sn[h];
-            if (sn[h]) {   // cpPinJoint preStep of the sensor pin (sensor body -> cell, anchors at the centres, rest length 0)
+            s.row_of[r] = (uint8_t)k; s.issens[r] = sn;
+            if (sn) {   // cpPinJoint preStep of the sensor pin (sensor body -> cell, anchors at the centres, rest length 0)
                 const float2 ps = reinterpret_cast<const float2 *>(w.c_spos)[row];
                 float dx = pc.x - ps.x, dy = pc.y - ps.y;
                 float d = sqrtf(dx * dx + dy * dy);
@@ -98,7 +99,9 @@ struct OrgCtx {
                 s.sv[r] = reinterpret_cast<const float2 *>(w.c_svel)[row];
             }
         }
-        if (sl == 0) s.n = n;
+        n = min(cnt, CM);
+        if (cnt > CM && sl == 0) w.g_stats[SAPIO_STAT_OVERFLOW] = 1;                 // the classifier sized this organism wrongly: never silent
+        if (sl == 0) { s.n = n; s.vm[CM] = make_float4(0.f, 0.f, 0.f, 0.f); s.bb[CM] = make_float4(0.f, 0.f, 0.f, w.p.frame_width); }   // a wall: infinite mass, radius = frame
         __syncwarp();
         uint32_t s0 = gballot(sl < n && s.issens[sl]), s1 = gballot(sl + G < n && s.issens[min(sl + G, CM - 1)]);
         sens = ((uint64_t)s1 << G) | s0;
@@ -123,27 +126,22 @@ struct OrgCtx {
         j = pidx - i * (tn - i) / 2 + i + 1;
     }
     __device__ int slot_of(int i, int j) const { const int t = i + j; return wf_off(t, n) + i - max(0, t - (n - 1)); }
+    // the lexicographic pairs a lane visits (sl, sl + G, sl + 2G, ...) as (i, j) kept incrementally: row i holds j = i + 1 .. n - 1
+    __device__ static void pair_norm(int n, int &i, int &j) { while (j >= n && i < n - 1) { j += i + 2 - n; i++; } }
+    __device__ void pair_first(int &i, int &j) const { i = 0; j = 1 + sl; pair_norm(n, i, j); }
+    __device__ void pair_next(int &i, int &j) const { j += G; pair_norm(n, i, j); }       // valid while i < n - 1
 
     __device__ void prestep_pairs() {
         const int NPn = n * (n - 1) / 2, NPmax = wmax(NPn);
         int nic = 0; bool over = false;
         const float *gj = w.j_jn + (size_t)max(o, 0) * SAPIO_NPAIR;
-        // cached impulses first: a pure gather with several loads in flight per lane
-        for (int base = 0; base < NPn; base += 4 * G) {
-            float v[4]; int q[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int pidx = base + sl + G * u; q[u] = -1; v[u] = 0.f;
-                if (pidx < NPn) { int i, j; pair_of(pidx, n, i, j); q[u] = slot_of(i, j); v[u] = gj[pair_index(s.row_of[i], s.row_of[j])]; }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++) if (q[u] >= 0) { if (GC) s.jn[q[u]] = v[u]; else s.pair[q[u]].w = v[u]; }
-        }
-        for (int base = 0; base < NPmax; base += G) {
-            const int pidx = base + sl;
-            bool hit = false; float nxf = 0.f, nyf = 0.f, bias_c = 0.f; int i = 0, j = 0;
-            if (pidx < NPn) {
-                pair_of(pidx, n, i, j);
+        // one pass: the cached impulse of a pair is requested first (a gather from global memory) and arrives under the double-precision
+        // geometry of the same pair; constants and impulse go to the pair's wavefront slot as one float4
+        int i, j; pair_first(i, j);
+        for (int base = 0; base < NPmax; base += G, pair_next(i, j)) {
+            bool hit = false; float nxf = 0.f, nyf = 0.f, bias_c = 0.f;
+            if (i < n - 1) {
+                const float jn_cached = gj[pair_index(s.row_of[i], s.row_of[j])];
                 const float2 pi = s.p[i], pj = s.p[j], ri = s.rel[i], rj = s.rel[j];
                 const float radi = s.bb[i].w, radj = s.bb[j].w;
                 double dx = __dsub_rn((double)pj.x, (double)pi.x), dy = __dsub_rn((double)pj.y, (double)pi.y);
@@ -153,8 +151,9 @@ struct OrgCtx {
                 double lx = (double)rj.x - (double)ri.x, ly = (double)rj.y - (double)ri.y;
                 double rest = sqrt(lx * lx + ly * ly);                 // |relative_pos_i - relative_pos_j| (connectTo at spawn)
                 float bias = (float)(-K.bc_joint * (d - rest) / K.dt);
-                if (GC) cst[slot_of(i, j)] = make_float4(nxf, nyf, bias, 0.f);
-                else { float *pq = reinterpret_cast<float *>(&s.pair[slot_of(i, j)]); pq[0] = nxf; pq[1] = nyf; pq[2] = bias; }
+                const int q = slot_of(i, j);
+                if (GC) { cst[q] = make_float4(nxf, nyf, bias, 0.f); s.jn[q] = jn_cached; }
+                else s.pair[q] = make_float4(nxf, nyf, bias, jn_cached);
                 double md = __dadd_rn((double)radi, (double)radj);
                 hit = d2 < __dmul_rn(md, md);
                 if (hit) { if (d == 0.0) { nxf = 1.f; nyf = 0.f; } bias_c = contact_bias(d, radi, radj, w.p, K); }   // coincident centres: cpv(1, 0)
@@ -164,7 +163,7 @@ struct OrgCtx {
                 int slot = nic + __popc(m & ((1u << sl) - 1u));
                 if (slot < S::IC) {
                     s.ccode[slot] = (uint16_t)(s.row_of[i] * 128 + s.row_of[j]); s.ca[slot] = (uint8_t)i; s.cbk[slot] = (uint8_t)j;
-                    s.cnx[slot] = nxf; s.cny[slot] = nyf; s.cbias[slot] = bias_c;
+                    s.ce0[slot] = make_float4(nxf, nyf, bias_c, 0.f);
                 } else over = true;
             }
             nic += __popc(m);
@@ -188,7 +187,7 @@ struct OrgCtx {
                     int slot = nic + __popc(m & ((1u << sl) - 1u));
                     if (slot < S::IC) {
                         s.ccode[slot] = (uint16_t)(s.row_of[r] * 128 + MAXC + wl); s.ca[slot] = (uint8_t)r; s.cbk[slot] = 255;
-                        s.cnx[slot] = hw.nx; s.cny[slot] = hw.ny; s.cbias[slot] = contact_bias(hw.d, radi, w.p.frame_width, w.p, K);
+                        s.ce0[slot] = make_float4(hw.nx, hw.ny, contact_bias(hw.d, radi, w.p.frame_width, w.p, K), 0.f);
                     } else over = true;
                     anywall = true;
                 }
@@ -199,13 +198,13 @@ struct OrgCtx {
         if (sl == 0) s.nic = nic;
         __syncwarp();
         if (__any_sync(FULL, anywall)) {       // merge the wall contacts into canonical order: rank = number of smaller codes
-            uint16_t code[KC]; uint8_t a_[KC], b_[KC]; float x_[KC], y_[KC], bi_[KC]; int rk[KC];
+            uint16_t code[KC]; uint8_t a_[KC], b_[KC]; float4 g_[KC]; int rk[KC];
 #pragma unroll
             for (int q = 0; q < KC; q++) {
                 const int c = sl + G * q;
                 rk[q] = -1;
                 if (c < nic) {
-                    code[q] = s.ccode[c]; a_[q] = s.ca[c]; b_[q] = s.cbk[c]; x_[q] = s.cnx[c]; y_[q] = s.cny[c]; bi_[q] = s.cbias[c];
+                    code[q] = s.ccode[c]; a_[q] = s.ca[c]; b_[q] = s.cbk[c]; g_[q] = s.ce0[c];
                     int r = 0;
                     for (int e = 0; e < nic; e++) r += s.ccode[e] < code[q];
                     rk[q] = r;
@@ -214,25 +213,9 @@ struct OrgCtx {
             __syncwarp();
 #pragma unroll
             for (int q = 0; q < KC; q++)
-                if (rk[q] >= 0) { const int r = rk[q]; s.ccode[r] = code[q]; s.ca[r] = a_[q]; s.cbk[r] = b_[q]; s.cnx[r] = x_[q]; s.cny[r] = y_[q]; s.cbias[r] = bi_[q]; }
+                if (rk[q] >= 0) { const int r = rk[q]; s.ccode[r] = code[q]; s.ca[r] = a_[q]; s.cbk[r] = b_[q]; s.ce0[r] = g_[q]; }
             __syncwarp();
         }
-    }
-
-    // persistent arbiters: jnAcc/jtAcc of the previous step's intra list (sorted by code)
-    __device__ void match_prev() {
-        const int pn = o >= 0 ? w.org_ic_n[o] : 0;
-        const uint16_t *pc = w.ic_code + (size_t)max(o, 0) * SAPIO_ICAP;
-        for (int c = sl; c < s.nic; c += G) {
-            uint16_t code = s.ccode[c];
-            int lo = 0, hi = pn;
-            while (lo < hi) { int mid = (lo + hi) >> 1; if (pc[mid] < code) lo = mid + 1; else hi = mid; }
-            bool f = lo < pn && pc[lo] == code;
-            s.cjn[c] = f ? w.ic_jn[(size_t)o * SAPIO_ICAP + lo] : 0.f;
-            s.cjt[c] = f ? w.ic_jt[(size_t)o * SAPIO_ICAP + lo] : 0.f;
-            s.cjb[c] = 0.f;
-        }
-        __syncwarp();
     }
 
     // dependency levels: contact c runs after every earlier contact (list order) that shares a cell with it. The contacts are
@@ -260,81 +243,108 @@ struct OrgCtx {
                 s.lcnt[L] = (uint8_t)pos; pos += cnt;
             }
             s.sstart[ns] = (uint8_t)nic;
-            for (int c = 0; c < nic; c++) s.corder[s.lcnt[s.clev[c]]++] = (uint8_t)c;
+            for (int c = 0; c < nic; c++) { const int ps = s.lcnt[s.clev[c]]++; s.corder[ps] = (uint8_t)c; s.cpos[c] = (uint8_t)ps; }
             s.nsteps = ns;
         }
         __syncwarp();
     }
 
-    // cpArbiterPreStep: effective masses, friction, and (BOUNCE) the bounce from the velocities before any cached impulse
-    template <bool BOUNCE>
+    // cpArbiterPreStep, and the move from canonical to execution order: effective masses, friction, and (FRESH) the persistent
+    // arbiter's jnAcc / jtAcc of the previous step's intra list (sorted by code: binary search) and the bounce from the velocities
+    // before any cached impulse. !FRESH (a later pass of the cooperative kernel): impulses and bounce come from load_contact_state.
+    template <bool FRESH>
     __device__ void prestep_contacts() {
-        for (int c = sl; c < s.nic; c += G) {
-            const int a = s.ca[c], b = s.cbk[c];
-            const int rowa = o * MAXC + s.row_of[a];
-            const float4 va = s.vm[a], ba = s.bb[a];
-            float4 vb = make_float4(0.f, 0.f, 0.f, 0.f), bbv = make_float4(0.f, 0.f, 0.f, w.p.frame_width);
-            float e = w.c_elast[rowa] * w.p.wall_elast, mu = w.c_fric[rowa] * w.p.wall_fric;
-            if (b != 255) { const int rowb = o * MAXC + s.row_of[b]; vb = s.vm[b]; bbv = s.bb[b]; e = w.c_elast[rowa] * w.c_elast[rowb]; mu = w.c_fric[rowa] * w.c_fric[rowb]; }
-            s.cnm[c] = 1.0f / (va.w + vb.w);
-            s.ctm[c] = 1.0f / (va.w + vb.w + ba.z * ba.w + bbv.z * bbv.w);
-            s.cmu[c] = mu;
-            if (BOUNCE) s.cbo[c] = ((vb.x - va.x) * s.cnx[c] + (vb.y - va.y) * s.cny[c]) * e;
+        const int nic = s.nic;
+        const int pn = (FRESH && o >= 0) ? w.org_ic_n[o] : 0;
+        const uint16_t *pc = w.ic_code + (size_t)max(o, 0) * SAPIO_ICAP;
+        float4 gq[KC];                                               // the canonical geometry leaves ce0 before the execution-ordered records arrive
+#pragma unroll
+        for (int q = 0; q < KC; q++) { const int c = sl + G * q; if (c < nic) gq[q] = s.ce0[c]; }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < KC; q++) {
+            const int c = sl + G * q;
+            if (c < nic) {
+                const int a = s.ca[c], b = s.cbk[c];
+                const float4 g = gq[q];
+                const int rowa = o * MAXC + s.row_of[a];
+                const float4 va = s.vm[a], ba = s.bb[a];
+                float4 vb = make_float4(0.f, 0.f, 0.f, 0.f), bbv = make_float4(0.f, 0.f, 0.f, w.p.frame_width);
+                float e = w.c_elast[rowa] * w.p.wall_elast, mu = w.c_fric[rowa] * w.p.wall_fric;
+                if (b != 255) { const int rowb = o * MAXC + s.row_of[b]; vb = s.vm[b]; bbv = s.bb[b]; e = w.c_elast[rowa] * w.c_elast[rowb]; mu = w.c_fric[rowa] * w.c_fric[rowb]; }
+                float jn = 0.f, jt = 0.f, bo = 0.f;
+                if (FRESH) {
+                    const uint16_t code = s.ccode[c];
+                    int lo = 0, hi = pn;
+                    while (lo < hi) { int mid = (lo + hi) >> 1; if (pc[mid] < code) lo = mid + 1; else hi = mid; }
+                    if (lo < pn && pc[lo] == code) { jn = w.ic_jn[(size_t)o * SAPIO_ICAP + lo]; jt = w.ic_jt[(size_t)o * SAPIO_ICAP + lo]; }
+                    bo = ((vb.x - va.x) * g.x + (vb.y - va.y) * g.y) * e;
+                }
+                const int ps = s.cpos[c];
+                s.ce0[ps] = make_float4(g.x, g.y, g.z, bo);
+                s.ce1[ps] = make_float4(1.0f / (va.w + vb.w), 1.0f / (va.w + vb.w + ba.z * ba.w + bbv.z * bbv.w), mu, __int_as_float(c | (a << 8) | ((b == 255 ? CM : b) << 16)));
+                s.cacc[ps] = make_float4(jn, jt, 0.f, 0.f);
+            }
         }
         __syncwarp();
     }
 
-    // one sweep over the intra contacts in canonical order (level steps); WARM: cached impulses instead of the solver step
+    // one sweep over the intra contacts in canonical order (level steps): cpArbiterApplyImpulse (SURVEY A-5), circles: r x n = 0.
+    // The records of step st + 1 are fetched while step st computes (nobody else writes them); a wall is the static body in slot CM,
+    // whose state the arithmetic leaves unchanged (1/m = r/I = 0), so the step has no branch on the kind of contact.
     template <bool WARM>
     __device__ void contacts_pass(float dt_coef, int nsteps_max) {
+        static_assert(!WARM, "cached contact impulses are applied by warm_start");
+        const int ns = s.nsteps;
+        int s1 = s.sstart[1], s2 = s.sstart[2];
+        int pos = s.sstart[0] + sl;
+        bool act = 0 < ns && pos < s1;
+        float4 e0 = make_float4(0.f, 0.f, 0.f, 0.f), e1 = e0, ac = e0;
+        if (act) { e0 = s.ce0[pos]; e1 = s.ce1[pos]; ac = s.cacc[pos]; }
         for (int st = 0; st < nsteps_max; st++) {
-            if (st < s.nsteps) {
-                const int pos = s.sstart[st] + sl;
-                if (pos < s.sstart[st + 1]) {
-                    const int c = s.corder[pos], a = s.ca[c], b = s.cbk[c];
-                    float4 va = s.vm[a], ba = s.bb[a];
-                    float4 vb = make_float4(0.f, 0.f, 0.f, 0.f), bbv = make_float4(0.f, 0.f, 0.f, w.p.frame_width);
-                    if (b != 255) { vb = s.vm[b]; bbv = s.bb[b]; }
-                    const float nx = s.cnx[c], ny = s.cny[c];
-                    if (WARM) {   // cpArbiterApplyCachedImpulse
-                        const float jn = s.cjn[c] * dt_coef, jt = s.cjt[c] * dt_coef;
-                        const float jx = nx * jn - ny * jt, jy = nx * jt + ny * jn;
-                        va.x -= jx * va.w; va.y -= jy * va.w; va.z -= ba.z * jt;
-                        vb.x += jx * vb.w; vb.y += jy * vb.w; vb.z -= bbv.z * jt;
-                    } else {      // cpArbiterApplyImpulse (SURVEY A-5), circles: r x n = 0
-                        const float nMass = s.cnm[c], tMass = s.ctm[c];
-                        const float dvx = vb.x - va.x, dvy = vb.y - va.y;
-                        const float vbn = (bbv.x - ba.x) * nx + (bbv.y - ba.y) * ny;
-                        const float vrn = dvx * nx + dvy * ny;
-                        const float vrt = (dvy * nx - dvx * ny) - bbv.w * vb.z - ba.w * va.z;
-                        // accumulate and clamp in double, apply the difference: a resting contact squeezed between pinned cells carries
-                        // 1e5 of impulse, and ulp(1e5) = 0.008 in fp32 would quantise what a sweep can add to it
-                        const float jbnOld = s.cjb[c], jBias = fmaxf(jbnOld + (s.cbias[c] - vbn) * nMass, 0.0f);
-                        const float jnO = s.cjn[c], jtO = s.cjt[c], jnI = -(s.cbo[c] + vrn) * nMass, jtI = -vrt * tMass, mu = s.cmu[c];
-                        float dn, dtg;
-                        if (fabsf(jnO) < 256.f && fabsf(jtO) < 256.f) {           // ordinary contact: fp32 resolves its accumulators to 3e-5
-                            const float jnA = fmaxf(jnO + jnI, 0.0f), jtM = mu * jnA, jtA = fminf(fmaxf(jtO + jtI, -jtM), jtM);
-                            s.cjn[c] = jnA; s.cjt[c] = jtA; dn = jnA - jnO; dtg = jtA - jtO;
-                        } else {
-                            const double jnA = fmax((double)jnO + (double)jnI, 0.0), jtM = (double)mu * jnA, jtA = fmin(fmax((double)jtO + (double)jtI, -jtM), jtM);
-                            s.cjn[c] = (float)jnA; s.cjt[c] = (float)jtA; dn = (float)(jnA - (double)jnO); dtg = (float)(jtA - (double)jtO);
-                        }
-                        s.cjb[c] = jBias;
-                        const float bj = jBias - jbnOld;
-                        ba.x -= nx * bj * va.w; ba.y -= ny * bj * va.w;
-                        bbv.x += nx * bj * vb.w; bbv.y += ny * bj * vb.w;
-                        const float jx = nx * dn - ny * dtg, jy = nx * dtg + ny * dn;
-                        va.x -= jx * va.w; va.y -= jy * va.w; va.z -= ba.z * dtg;
-                        vb.x += jx * vb.w; vb.y += jy * vb.w; vb.z -= bbv.z * dtg;
-                        reinterpret_cast<float2 *>(&s.bb[a])[0] = make_float2(ba.x, ba.y);
-                        if (b != 255) reinterpret_cast<float2 *>(&s.bb[b])[0] = make_float2(bbv.x, bbv.y);
-                    }
-                    s.vm[a] = va;
-                    if (b != 255) s.vm[b] = vb;
+            const int s3 = s.sstart[min(st + 3, S::IC + 1)];
+            const int posn = s1 + sl;
+            const bool actn = st + 1 < ns && posn < s2;
+            float4 e0n = make_float4(0.f, 0.f, 0.f, 0.f), e1n = e0n, acn = e0n;
+            if (actn) { e0n = s.ce0[posn]; e1n = s.ce1[posn]; acn = s.cacc[posn]; }
+            if (act) {
+                const int desc = __float_as_int(e1.w), a = (desc >> 8) & 255, b = desc >> 16;
+                float4 va = s.vm[a], ba = s.bb[a], vb = s.vm[b], bbv = s.bb[b];
+                const float nx = e0.x, ny = e0.y;
+                const float nMass = e1.x, tMass = e1.y;
+                const float dvx = vb.x - va.x, dvy = vb.y - va.y;
+                const float vbn = (bbv.x - ba.x) * nx + (bbv.y - ba.y) * ny;
+                const float vrn = dvx * nx + dvy * ny;
+                const float vrt = (dvy * nx - dvx * ny) - bbv.w * vb.z - ba.w * va.z;
+                // accumulate and clamp in double, apply the difference: a resting contact squeezed between pinned cells carries
+                // 1e5 of impulse, and ulp(1e5) = 0.008 in fp32 would quantise what a sweep can add to it
+                const float jbnOld = ac.z, jBias = fmaxf(jbnOld + (e0.z - vbn) * nMass, 0.0f);
+                const float jnO = ac.x, jtO = ac.y, jnI = -(e0.w + vrn) * nMass, jtI = -vrt * tMass, mu = e1.z;
+                float dn, dtg, jnS, jtS;
+                if (fabsf(jnO) < 256.f && fabsf(jtO) < 256.f) {           // ordinary contact: fp32 resolves its accumulators to 3e-5
+                    const float jnA = fmaxf(jnO + jnI, 0.0f), jtM = mu * jnA, jtA = fminf(fmaxf(jtO + jtI, -jtM), jtM);
+                    jnS = jnA; jtS = jtA; dn = jnA - jnO; dtg = jtA - jtO;
+                } else {
+                    const double jnA = fmax((double)jnO + (double)jnI, 0.0), jtM = (double)mu * jnA, jtA = fmin(fmax((double)jtO + (double)jtI, -jtM), jtM);
+                    jnS = (float)jnA; jtS = (float)jtA; dn = (float)(jnA - (double)jnO); dtg = (float)(jtA - (double)jtO);
                 }
+                s.cacc[pos] = make_float4(jnS, jtS, jBias, 0.f);
+                const float bj = jBias - jbnOld;
+                ba.x -= nx * bj * va.w; ba.y -= ny * bj * va.w;
+                bbv.x += nx * bj * vb.w; bbv.y += ny * bj * vb.w;
+                const float jx = nx * dn - ny * dtg, jy = nx * dtg + ny * dn;
+                va.x -= jx * va.w; va.y -= jy * va.w; va.z -= ba.z * dtg;
+                vb.x += jx * vb.w; vb.y += jy * vb.w; vb.z -= bbv.z * dtg;
+                reinterpret_cast<float2 *>(&s.bb[a])[0] = make_float2(ba.x, ba.y);
+                s.vm[a] = va;
+                reinterpret_cast<float2 *>(&s.bb[b])[0] = make_float2(bbv.x, bbv.y);
+                s.vm[b] = vb;
             }
+            pos = posn; act = actn; e0 = e0n; e1 = e1n; ac = acn;
+            s1 = s2; s2 = s3;
             __syncwarp();
         }
+        (void)dt_coef;
     }
 
     // Warm start (cpArbiterApplyCachedImpulse, cached pin impulses), exact. Cached impulses do not depend on the velocities, so
@@ -386,10 +396,11 @@ struct OrgCtx {
             if (r < n) {
                 double ax = pax[h], ay = pay[h], at = 0.0;         // linear impulse received; tangential impulses (both bodies: w -= r/I * jt)
                 const int nic = s.nic;
-                for (int c = 0; c < nic; c++) {
-                    const int a = s.ca[c], b = s.cbk[c];
+                for (int c = 0; c < nic; c++) {                    // execution order (any order does: the sums are exact to 1e-16)
+                    const int desc = __float_as_int(s.ce1[c].w), a = (desc >> 8) & 255, b = desc >> 16;
                     if (a != r && b != r) continue;
-                    const double jn = (double)s.cjn[c] * dt, jt = (double)s.cjt[c] * dt, nx = (double)s.cnx[c], ny = (double)s.cny[c];
+                    const float4 e0 = s.ce0[c], ac = s.cacc[c];
+                    const double jn = (double)ac.x * dt, jt = (double)ac.y * dt, nx = (double)e0.x, ny = (double)e0.y;
                     const double jx = nx * jn - ny * jt, jy = nx * jt + ny * jn;
                     if (a == r) { ax -= jx; ay -= jy; } else { ax += jx; ay += jy; }
                     at += jt;
@@ -453,24 +464,42 @@ struct OrgCtx {
         // FMAs -> times the effective mass (hardware reciprocal: 1 ulp, multiplicative, so the error vanishes with the impulse) ->
         // two stores -> barrier.
         if (GC) { joints_wavefronts_gc<WARM>(dt_coef, tmax); return; }
-        int off = 0;
-        for (int t = 1; t <= tmax; t++) {
-            const int imin = max(0, t - (n - 1)), imax = (t - 1) >> 1, i = imin + sl;
-            if (i <= imax) {
-                const int j = t - i, q = off + sl;
-                const float4 pr = s.pair[q], vi = s.vm[i], vj = s.vm[j];
+        // Cursors instead of indices (everything in bytes, 16 per float4): in the first half of a sweep (t <= n - 1) a lane keeps its row
+        // i = sl and walks j = t - sl, in the second half it keeps its column and walks the rows; imin = max(t - (n - 1), 0) covers both,
+        // "this lane has a pair" is i < j, and the wavefront-major pair cursor advances by the width h + 1 - imin with h = (t - 1) / 2,
+        // which is the same number for the odd and the even step of a double step. ~10 integer instructions per step, none of them on
+        // the chain load -> impulse -> store -> barrier -> load.
+        // The body is branch-free (a lane without a pair computes on garbage and stores nothing): a predicate-dependent branch
+        // costs 12-25 cycles of a ~100-cycle step, and a straight-line body lets the next step's cursors be computed under the loads.
+        char *const vmb = reinterpret_cast<char *>(s.vm), *const pqb = reinterpret_cast<char *>(s.pair);
+        const int S16 = sl * 16, N16 = (n - 1) * 16;
+        int T16 = 16, Q16 = S16, H16 = 16;                      // 16 t; 16 (off(t) + sl); 16 (h + 1)
+        int M = max(T16 - N16, 0), I = S16 + M, J = T16 - I;
+        bool act = I < J;
+        for (int t = 1; t <= tmax; t += 2, H16 += 16) {
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                // an idle lane reads whatever lies at its cursors (always inside the CTA's shared memory: |J| < 16 G < the size of the pair
+                // table in front of vm, I and Q run at most 32 entries past their arrays) and stores nothing
+                float4 *const pp = reinterpret_cast<float4 *>(pqb + Q16);
+                float2 *const pi = reinterpret_cast<float2 *>(vmb + I), *const pj = reinterpret_cast<float2 *>(vmb + J);
+                const float4 pr = *pp, vi = *reinterpret_cast<const float4 *>(pi), vj = *reinterpret_cast<const float4 *>(pj);
+                const bool act_now = act;
+                Q16 += max(H16 - M, 0);                          // the next step's cursors and addresses, under the latency of the loads
+                T16 += 16;
+                M = max(T16 - N16, 0); I = S16 + M; J = T16 - I; act = I < J;
                 float jnv;
                 if (WARM) jnv = pr.w * dt_coef;
-                else {
-                    jnv = fmaf(-(vj.x - vi.x), pr.x, fmaf(-(vj.y - vi.y), pr.y, pr.z)) * rcp_approx(vi.w + vj.w);
-                    s.pair[q].w = pr.w + jnv;
-                }
+                else jnv = fmaf(-(vj.x - vi.x), pr.x, fmaf(-(vj.y - vi.y), pr.y, pr.z)) * rcp_approx(vi.w + vj.w);
                 const float jx = pr.x * jnv, jy = pr.y * jnv;
-                reinterpret_cast<float2 *>(&s.vm[i])[0] = make_float2(fmaf(-jx, vi.w, vi.x), fmaf(-jy, vi.w, vi.y));
-                reinterpret_cast<float2 *>(&s.vm[j])[0] = make_float2(fmaf(jx, vj.w, vj.x), fmaf(jy, vj.w, vj.y));
+                const float2 ni = make_float2(fmaf(-jx, vi.w, vi.x), fmaf(-jy, vi.w, vi.y)), nj = make_float2(fmaf(jx, vj.w, vj.x), fmaf(jy, vj.w, vj.y));
+                if (act_now) {
+                    if (!WARM) reinterpret_cast<float *>(pp)[3] = pr.w + jnv;
+                    *pi = ni;
+                    *pj = nj;
+                }
+                __syncwarp();
             }
-            off += max(imax - imin + 1, 0);
-            __syncwarp();
         }
     }
 
@@ -531,17 +560,17 @@ struct OrgCtx {
         if (!pins) return;
         float *gj = w.j_jn + (size_t)max(o, 0) * SAPIO_NPAIR;
         const int NPn = n * (n - 1) / 2;
+        int i, j; pair_first(i, j);
         for (int base = 0; base < NPn; base += 4 * G) {          // cached impulse + what this step added; four loads in flight per lane
             float *dst[4]; float old[4], add[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const int pidx = base + sl + G * u;
                 dst[u] = nullptr; old[u] = 0.f; add[u] = 0.f;
-                if (pidx < NPn) {
-                    int i, j; pair_of(pidx, n, i, j);
+                if (i < n - 1) {
                     dst[u] = &gj[pair_index(s.row_of[i], s.row_of[j])]; old[u] = *dst[u];
                     add[u] = GC ? s.jn[slot_of(i, j)] : s.pair[slot_of(i, j)].w;
                 }
+                pair_next(i, j);
             }
 #pragma unroll
             for (int u = 0; u < 4; u++) if (dst[u]) *dst[u] = (float)((double)old[u] + (double)add[u]);
@@ -550,8 +579,10 @@ struct OrgCtx {
     __device__ void store_contacts(float *ws_bounce, float *ws_jbias) {
         for (int c = sl; c < s.nic; c += G) {
             size_t g = (size_t)o * SAPIO_ICAP + c;
-            w.ic_code[g] = s.ccode[c]; w.ic_jn[g] = s.cjn[c]; w.ic_jt[g] = s.cjt[c];
-            if (ws_bounce) { ws_bounce[g] = s.cbo[c]; ws_jbias[g] = s.cjb[c]; }
+            const int pos = s.cpos[c];
+            const float4 ac = s.cacc[pos];
+            w.ic_code[g] = s.ccode[c]; w.ic_jn[g] = ac.x; w.ic_jt[g] = ac.y;
+            if (ws_bounce) { ws_bounce[g] = s.ce0[pos].w; ws_jbias[g] = ac.z; }
         }
         if (sl == 0 && o >= 0) w.org_ic_n[o] = s.nic;
     }
@@ -560,10 +591,7 @@ struct OrgCtx {
     __device__ void save_static(S *g) const {
         const int NPn = n * (n - 1) / 2, nic = s.nic;
         for (int q = sl; q < NPn; q += G) g->pair[q] = s.pair[q];
-        for (int c = sl; c < nic; c += G) {
-            g->cnx[c] = s.cnx[c]; g->cny[c] = s.cny[c]; g->cbias[c] = s.cbias[c]; g->cnm[c] = s.cnm[c]; g->ctm[c] = s.ctm[c]; g->cmu[c] = s.cmu[c];
-            g->ccode[c] = s.ccode[c]; g->ca[c] = s.ca[c]; g->cbk[c] = s.cbk[c]; g->corder[c] = s.corder[c];
-        }
+        for (int c = sl; c < nic; c += G) { g->ce0[c] = s.ce0[c]; g->ce1[c] = s.ce1[c]; g->ccode[c] = s.ccode[c]; g->cpos[c] = s.cpos[c]; }
         for (int q = sl; q <= s.nsteps; q += G) g->sstart[q] = s.sstart[q];
         if (sl == 0) { g->nic = nic; g->nsteps = s.nsteps; }
     }
@@ -571,10 +599,7 @@ struct OrgCtx {
         if (!g) { if (sl == 0) { s.nic = 0; s.nsteps = 0; } __syncwarp(); return; }       // idle lane group of a packed warp
         const int NPn = n * (n - 1) / 2, nic = g->nic, ns = g->nsteps;
         for (int q = sl; q < NPn; q += G) s.pair[q] = g->pair[q];
-        for (int c = sl; c < nic; c += G) {
-            s.cnx[c] = g->cnx[c]; s.cny[c] = g->cny[c]; s.cbias[c] = g->cbias[c]; s.cnm[c] = g->cnm[c]; s.ctm[c] = g->ctm[c]; s.cmu[c] = g->cmu[c];
-            s.ccode[c] = g->ccode[c]; s.ca[c] = g->ca[c]; s.cbk[c] = g->cbk[c]; s.corder[c] = g->corder[c];
-        }
+        for (int c = sl; c < nic; c += G) { s.ce0[c] = g->ce0[c]; s.ce1[c] = g->ce1[c]; s.ccode[c] = g->ccode[c]; s.cpos[c] = g->cpos[c]; }
         for (int q = sl; q <= ns; q += G) s.sstart[q] = g->sstart[q];
         if (sl == 0) { s.nic = nic; s.nsteps = ns; }
         __syncwarp();
@@ -588,7 +613,8 @@ struct OrgCtx {
     __device__ void load_contact_state(const float *ws_bounce, const float *ws_jbias) {
         for (int c = sl; c < s.nic; c += G) {
             size_t g = (size_t)o * SAPIO_ICAP + c;
-            s.cjn[c] = w.ic_jn[g]; s.cjt[c] = w.ic_jt[g]; s.cbo[c] = ws_bounce[g]; s.cjb[c] = ws_jbias[g];
+            const int pos = s.cpos[c];
+            s.cacc[pos] = make_float4(w.ic_jn[g], w.ic_jt[g], ws_jbias[g], 0.f); s.ce0[pos].w = ws_bounce[g];
         }
         __syncwarp();
     }
@@ -607,13 +633,17 @@ template <int CM> struct OrgCfg {
     static constexpr int NG = 32 / G;                                                     // organisms per warp
     static constexpr bool GC = ORG_GC && CM > 32;                                         // pin constants in global scratch
     static constexpr int WARP_BYTES = (int)sizeof(OrgS<CM, GC>) * NG;
-    static constexpr int FIT = (227 * 1024 - 2048) / WARP_BYTES;                          // warps an SM can hold
-    static constexpr int WARPS = FIT <= 8 ? (FIT < 1 ? 1 : FIT) : (FIT <= 16 ? FIT / 2 : 8);
+    // an SM has 228 KB of shared memory, a CTA at most 227 KB, and every resident CTA reserves 1 KB: one CTA of up to 8 warps for the
+    // large classes, two (or more) CTAs of up to 8 warps for the small ones
+    static constexpr int FIT1 = (227 * 1024) / WARP_BYTES;                                // warps of a CTA that has the SM to itself
+    static constexpr int FIT2 = ((228 * 1024 - 2 * 1024) / 2) / WARP_BYTES;               // warps per CTA when two CTAs share the SM
+    static constexpr int CTAS = FIT1 <= 8 ? 1 : 2;                                        // CTAs per SM the kernel is compiled for (register budget)
+    static constexpr int WARPS = FIT1 <= 8 ? (FIT1 < 1 ? 1 : FIT1) : (FIT2 < 8 ? FIT2 : 8);
 };
 
 
 template <int CM>
-__global__ void __launch_bounds__(OrgCfg<CM>::WARPS * 32) k_org_solve(WORLD_ARG, Workspace W, StepK K, int cls) {
+__global__ void __launch_bounds__(OrgCfg<CM>::WARPS * 32, OrgCfg<CM>::CTAS) k_org_solve(WORLD_ARG, Workspace W, StepK K, int cls) {
     constexpr int G = OrgCfg<CM>::G, NG = OrgCfg<CM>::NG;
     constexpr bool GC = OrgCfg<CM>::GC;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -625,6 +655,12 @@ __global__ void __launch_bounds__(OrgCfg<CM>::WARPS * 32) k_org_solve(WORLD_ARG,
     const float dt_coef = w.g_stepped[0] ? 1.0f : 0.0f;   // prev_dt == 0 on the very first step
     const int iterations = w.p.iterations;
     int nic_sum = 0;
+#ifdef ORG_PHASE_PROF
+    long long ph[10] = {0}; long long tk = clock64(); int cnt_org = 0, sum_n = 0, sum_nic = 0, sum_ns = 0;
+#define PH(k) do { long long t_ = clock64(); ph[k] += t_ - tk; tk = t_; } while (0)
+#else
+#define PH(k) do { } while (0)
+#endif
     for (;;) {
         int q = 0;
         if (lane == 0) q = atomicAdd(&W.flags[FL_WORK0 + cls], 1);          // dynamic scheduling: organisms differ in cost
@@ -632,18 +668,29 @@ __global__ void __launch_bounds__(OrgCfg<CM>::WARPS * 32) k_org_solve(WORLD_ARG,
         if (q >= n_items) break;
         const int idx = end - 1 - (q * NG + lane / G);                        // largest organisms of the class first
         OrgCtx<CM, G, GC> c(s, w, K, idx >= start ? W.sorted_orgs[idx] : -1, cst);
-        c.load();
-        c.prestep_pairs();
-        c.match_prev();
-        c.schedule();
-        c.template prestep_contacts<true>();
+        PH(0);
+        c.load(); PH(1);
+        c.prestep_pairs(); PH(2);
+        c.schedule(); PH(3);
+        c.template prestep_contacts<true>(); PH(4);
         const int nsteps_max = OrgCtx<CM, G, GC>::wmax(s.nsteps), tmax = 2 * OrgCtx<CM, G, GC>::wmax(c.n) - 3;
         if (dt_coef != 0.f) c.warm_start(dt_coef, nullptr);
         else c.zero_pin_acc();
-        for (int it = 0; it < iterations; it++) { c.template contacts_pass<false>(0.f, nsteps_max); c.template joints_pass<false>(0.f, tmax); }
+        PH(5);
+        for (int it = 0; it < iterations; it++) { c.template contacts_pass<false>(0.f, nsteps_max); PH(6); c.template joints_pass<false>(0.f, tmax); PH(7); }
         if (c.o >= 0) { c.store_vel(); c.store_contacts(nullptr, nullptr); if (c.sl == 0) nic_sum += s.nic; }
         __syncwarp();
+        PH(8);
+#ifdef ORG_PHASE_PROF
+        cnt_org++; sum_n += c.n; sum_nic += s.nic; sum_ns += s.nsteps;
+#endif
     }
+#ifdef ORG_PHASE_PROF
+    if (blockIdx.x == 0 && threadIdx.x == 0 && (w.g_tick[0] % 1000) == 7)
+        printf("ORGPH cls %d tick %d orgs %d n %d nic %d nsteps %d | fetch %lld load %lld pairs %lld sched %lld cprestep %lld warm %lld contacts %lld joints %lld store %lld\n",
+               cls, (int)w.g_tick[0], cnt_org, sum_n, sum_nic, sum_ns, ph[0], ph[1], ph[2], ph[3], ph[4], ph[5], ph[6], ph[7], ph[8]);
+#endif
+#undef PH
     if (nic_sum) atomicAdd(&W.flags[FL_NIC], nic_sum);
 }
 

@@ -184,11 +184,27 @@ __global__ void __launch_bounds__(128) k_cross_prestep(WORLD_ARG, Workspace W, S
     }
 }
 
-// organisms -> two lists sorted by cell rows (counting sort: histogram, scan, scatter): coupled organisms and the rest
+// organisms -> two lists sorted by LIVING cells (counting sort: histogram, scan, scatter): coupled organisms and the rest. The solver
+// works in rank space (living cells compacted), so what sizes an organism's slab, its lanes and its chain of wavefronts is the number
+// of living cells, not the rows it occupies (an old organism carries the markers of the cells it lost).
 __global__ void k_classify_count(WORLD_ARG, Workspace W) {
     for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < w.p.n_org; o += gridDim.x * blockDim.x) {
         if (w.org_state[o] != 1) continue;
-        const int nc = min(max(w.org_ncells[o], 1), MAXC);
+        const int rows = min(max(w.org_ncells[o], 0), MAXC);
+        const uint4 *al = reinterpret_cast<const uint4 *>(w.c_alive + (size_t)o * MAXC);          // 64 bytes per organism, 16-byte aligned
+        int live = 0;
+#pragma unroll
+        for (int q = 0; q < MAXC / 16; q++) {
+            if (q * 16 >= rows) break;
+            const uint4 v = al[q];
+            const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+#pragma unroll
+                for (int bb = 0; bb < 4; bb++) { const int k = q * 16 + u * 4 + bb; live += (k < rows && ((wds[u] >> (8 * bb)) & 255u) == SAPIO_CELL_ALIVE); }
+        }
+        W.org_nlive[o] = (uint8_t)live;
+        const int nc = min(max(live, 1), MAXC);
         if (W.org_coupled[o]) { atomicAdd(&W.flags[FL_NCOUPLED], 1); atomicAdd(&W.flags[FL_CHIST + nc], 1); }
         else atomicAdd(&W.size_hist[nc], 1);
     }
@@ -206,7 +222,7 @@ __global__ void k_classify_scan(Workspace W) {
 __global__ void k_classify_scatter(WORLD_ARG, Workspace W) {
     for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < w.p.n_org; o += gridDim.x * blockDim.x) {
         if (w.org_state[o] != 1) continue;
-        const int nc = min(max(w.org_ncells[o], 1), MAXC);
+        const int nc = min(max((int)W.org_nlive[o], 1), MAXC);
         if (W.org_coupled[o]) W.coupled_list[atomicAdd(&W.flags[FL_CHIST + nc], 1)] = o;
         else W.sorted_orgs[atomicAdd(&W.size_hist[nc], 1)] = o;
     }

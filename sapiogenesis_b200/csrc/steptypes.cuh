@@ -23,6 +23,7 @@ struct Workspace {
     uint32_t *adj_tmp;              // partner runs in discovery order [2*x_cap]
     int2 *hit_list;                 // (body, start of its run) [2*x_cap]
     uint8_t *org_coupled;           // [n_org]
+    uint8_t *org_nlive;             // [n_org] living cells of every organism (k_classify_count): what sizes its solver slab
     int *coupled_list;              // [n_org]
     int *sorted_orgs;               // [n_org] uncoupled organisms sorted by cell rows
     int *size_hist;                 // [MAXC + 1] inside the flags block: histogram, then scatter cursors
@@ -71,6 +72,7 @@ static inline size_t carve_workspace(const SapioParams &p, char *base, Workspace
     W->adj_tmp = (uint32_t *)take(2 * XC * 4);
     W->hit_list = (int2 *)take(2 * XC * 8);
     W->org_coupled = (uint8_t *)take((size_t)p.n_org);
+    W->org_nlive = (uint8_t *)take((size_t)p.n_org);
     W->coupled_list = (int *)take((size_t)p.n_org * 4);
     W->sorted_orgs = (int *)take((size_t)p.n_org * 4);
     W->ic_bounce = (float *)take((size_t)p.n_org * SAPIO_ICAP * 4);

@@ -234,6 +234,7 @@ def compare_worlds(wg, w, tag, brain_tol=TOL, check_brain=True, skip=(), verbose
                 rep.bad.append(f"{name}[untouched organisms]: {ndiff} bytes differ")
             if name not in ("org_ldim", "org_incell") and len(detail) == 0:
                 G.drop(name); O.drop(name)
+    ties = 0
     for o in detail:
         nl = int(O["org_nlayers"][o]); ld = O["org_ldim"][o]
         rep.exact(f"org_ldim[{o}]", G["org_ldim"][o][: nl + 1], ld[: nl + 1])
@@ -243,7 +244,15 @@ def compare_worlds(wg, w, tag, brain_tol=TOL, check_brain=True, skip=(), verbose
             continue
         I = int(ld[0])
         P = sum(int(ld[l + 1]) * int(ld[l]) + int(ld[l + 1]) for l in range(nl))
-        if check_brain:
+        # Rounding cliff: the network output is rounded to 3 decimals (neural.py:292); at a tie the fp32 forward's 1e-7
+        # flips the last digit, and the flipped row is a training TARGET of the same tick (|output - target| <= 5e-4 becomes 1.5e-3):
+        # the gradient of that organism is a different one on the two sides. Such organisms are counted, held to the 1.5e-3 of the
+        # rounded outputs below, and left out of the brain / optimiser comparison; at most 2 (or 0.2 %) per comparison.
+        hn_ = min(int(O["org_hist_n"][o]), HIST); sn_ = min(int(O["org_stm_n"][o]), STM); mn_ = int(O["org_mem_n"][o])
+        tie = any(float(np.max(np.abs(G[k][o][: c * 4].astype(np.float64) - O[k][o][: c * 4]), initial=0.0)) > 5e-4
+                  for k, c in (("org_hist_out", hn_), ("org_stm_out", sn_), ("org_mem_out", mn_)))
+        ties += tie
+        if check_brain and not tie:
             gb, ob = G["org_brain"][o][:P].astype(np.float64), O["org_brain"][o][:P].astype(np.float64)
             scale = np.maximum(np.abs(ob), np.sqrt(np.mean(ob ** 2)) if P else 1.0)
             rel = np.abs(gb - ob) / scale
@@ -276,5 +285,10 @@ def compare_worlds(wg, w, tag, brain_tol=TOL, check_brain=True, skip=(), verbose
             rep.exact(f"org_mem_in[{o}]", G["org_mem_in"][o].reshape(MEMROWS, IN)[:M, :I], O["org_mem_in"][o].reshape(MEMROWS, IN)[:M, :I])
             rep.close("org_mem_out", G["org_mem_out"][o][: M * 4], O["org_mem_out"][o][: M * 4], tol=1.5e-3, floor=1.0)
             rep.close("org_mem_rew", G["org_mem_rew"][o][:M], O["org_mem_rew"][o][:M], floor=DOPA_FLOOR)
+    if ties:
+        print(f"{tag}: {ties} of {len(detail)} organisms at a 3-decimal rounding tie of their outputs (brain / optimiser comparison skipped for them)")
+        if ties > max(2, 0.002 * len(detail)):
+            rep.bad.append(f"rounding ties: {ties} of {len(detail)} organisms")
+    rep.ties = ties
     rep.finish(verbose)
     return rep
