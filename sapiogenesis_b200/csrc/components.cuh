@@ -20,14 +20,17 @@
 #include "orgsolve.cuh"
 
 // ---- tiers: warps (organisms) per CTA, shared memory, table capacities -------------------------------------------------------
-#define COMP_TIERS 5
+#define COMP_TIERS 6
 struct CompTier { int warps; int smem; int xmax; int dmax; };
+// A warp is an organism: the three one-warp tiers take one organism of up to 24 / 40 / 64 living cells with its debris (half of the
+// coupled organisms touch dead bodies only), so that no CTA carries a warp without work.
 __host__ __device__ inline CompTier comp_tier(int t) {
     switch (t) {
         case 0: return CompTier{1, 12 * 1024, 24, 24};          // a small organism with its debris, or debris alone: 18 CTAs per SM
-        case 1: return CompTier{1, 24 * 1024, 48, 48};          // one medium organism: 9 per SM
-        case 2: return CompTier{2, 54 * 1024, 96, 64};          // two organisms, or one large: 4 per SM
-        case 3: return CompTier{4, 110 * 1024, 192, 128};       // up to four organisms: 2 per SM
+        case 1: return CompTier{1, 25 * 1024, 40, 40};          // one organism of up to 40 cells: 8 per SM
+        case 2: return CompTier{1, 50 * 1024, 64, 48};          // one organism of any size: 4 per SM
+        case 3: return CompTier{2, 55 * 1024, 96, 64};          // two organisms: 4 per SM
+        case 4: return CompTier{4, 110 * 1024, 192, 128};       // up to four organisms: 2 per SM
         default: return CompTier{16, 220 * 1024, 384, 192};     // up to sixteen: 1 per SM
     }
 }
