@@ -11,7 +11,7 @@ import os
 from .world import SapioParams, SapioWorldStruct
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libsapio_b200.so")
+SO_PATH = os.environ.get("SAPIO_SO") or os.path.join(_HERE, "libsapio_b200.so")      # SAPIO_SO: an A/B build of the same sources (build.py, SAPIO_BUILD_TAG)
 _lib = None
 
 

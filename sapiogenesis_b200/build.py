@@ -14,8 +14,9 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(CSRC, "_obj")
-SO = os.path.join(HERE, "libsapio_b200.so")
+_TAG = os.environ.get("SAPIO_BUILD_TAG", "")            # diagnostic / A-B builds: their own object cache and library name (SAPIO_SO selects one at run time)
+OBJ = os.path.join(CSRC, "_obj" + ("_" + _TAG if _TAG else ""))
+SO = os.path.join(HERE, "libsapio_b200" + ("_" + _TAG if _TAG else "") + ".so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"] + os.environ.get("SAPIO_NVCC_DEFS", "").split()      # e.g. -DORG_PHASE_PROF (diagnostic builds)

@@ -7,7 +7,7 @@
 // bodies (sprites.py:300-323) and free dead cells. p = fma(v + v_bias, dt, p): the single fp32 op sequence the oracle mirrors.
 // Also writes the broadphase key of every solid body (grid cell index, or ~0 for "no body in this slot").
 template <bool INTEGRATE>
-__global__ void __launch_bounds__(256) k_integrate(WORLD_ARG, uint32_t *__restrict__ grid_key, uint32_t *__restrict__ grid_val) {
+__global__ void __launch_bounds__(256) k_integrate(WORLD_ARG, uint32_t *__restrict__ grid_key, uint32_t *__restrict__ live_list, int *__restrict__ cell_cnt, int *__restrict__ n_live) {
     const SapioParams &p = w.p;
     const int NC = p.n_org * MAXC, NB = NC + p.n_dead;
     const float dt = p.dt_phys;
@@ -60,7 +60,20 @@ __global__ void __launch_bounds__(256) k_integrate(WORLD_ARG, uint32_t *__restri
                 cx = min(max(cx, 0), p.grid_nx - 1); cy = min(max(cy, 0), p.grid_ny - 1);
                 key = (uint32_t)(cy * p.grid_nx + cx);
             }
-            grid_key[b] = key; grid_val[b] = (uint32_t)b;
+            grid_key[b] = key;
+            // the cells of an organism share a handful of grid cells and sit in consecutive slots: one atomic per (warp, cell), not per body
+            const uint32_t peers = __match_any_sync(__activemask(), key);
+            if (solid && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&cell_cnt[key], __popc(peers));
+        }
+        // the living bodies as a list (order immaterial: grid.cuh ranks them inside their cells), one atomic per warp
+        if (grid_key) {
+            const uint32_t m = __ballot_sync(__activemask(), solid);
+            if (m) {
+                const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+                int base = 0;
+                if (lane == leader) base = atomicAdd(n_live, __popc(m));
+                if (solid) { base = __shfl_sync(m, base, leader); live_list[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)b; }
+            }
         }
     }
 }

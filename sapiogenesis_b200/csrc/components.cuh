@@ -28,7 +28,7 @@ __host__ __device__ inline CompTier comp_tier(int t) {
     switch (t) {
         case 0: return CompTier{1, 12 * 1024, 24, 24};          // a small organism with its debris, or debris alone: 18 CTAs per SM
         case 1: return CompTier{1, 25 * 1024, 40, 40};          // one organism of up to 40 cells: 8 per SM
-        case 2: return CompTier{1, 50 * 1024, 64, 48};          // one organism of any size: 4 per SM
+        case 2: return CompTier{1, 51 * 1024, 64, 48};          // one organism of any size: 4 per SM
         case 3: return CompTier{2, 55 * 1024, 96, 64};          // two organisms: 4 per SM
         case 4: return CompTier{4, 110 * 1024, 192, 128};       // up to four organisms: 2 per SM
         default: return CompTier{16, 220 * 1024, 384, 192};     // up to sixteen: 1 per SM
@@ -44,7 +44,8 @@ __host__ __device__ inline int comp_slab_bytes(int k) {
 struct alignas(16) XCon {
     uint32_t vmA, bbA, vmB, bbB;                 // float4 (vx, vy, w, 1/m) and float4 (bias vx, bias vy, r/I, r) of the two bodies
     float nx, ny, bias, bounce;
-    float mu, jn, jt, jb;
+    float nMass, tMass, mu, pad0;                // effective masses: constant for the whole solve, computed once when the record is built
+    float jn, jt, jb, pad1;
 };
 __host__ __device__ inline int comp_table_bytes(const CompTier &T) {
     // contacts, dead bodies (two float4 each) + wall entry, sorted ids, contact order / steps, per-organism row -> rank maps, header
@@ -122,6 +123,9 @@ __global__ void __launch_bounds__(256) k_comp_assign(WORLD_ARG, Workspace W, int
         }
         if (force_fallback) tier = -1;
         W.cn_tier[root] = tier;
+#ifdef COMP_DIAG
+        if (tier < 0) printf("OVERSIZE tick %d organisms %d contacts %d dead %d slab bytes %d\n", (int)w.g_tick[0], no, cnt, nd, need);
+#endif
         if (tier < 0) { W.flags[FL_COMP_OVERFLOW] = 1; continue; }            // this component goes to the cooperative kernel (coupled.cuh)
         W.cn_xoff[root] = atomicAdd(&W.flags[FL_COMP_POOL], cnt);
         const int q = atomicAdd(&W.flags[FL_COMP_N0 + tier], 1);
@@ -145,32 +149,34 @@ struct CompS {                                   // CTA header, at the start of 
 };
 __device__ __forceinline__ void comp_sync() { __syncthreads(); }
 
-// cpArbiterApplyImpulse on two bodies resident in shared memory (the arithmetic of contact_apply in steptypes.cuh)
+// cpArbiterApplyImpulse on two bodies resident in shared memory (the arithmetic of contact_apply in steptypes.cuh; the effective
+// masses come from the record, and accumulators below 256 are clamped in fp32 like the intra contacts of OrgCtx::contacts_pass)
 __device__ __forceinline__ void xcon_apply(unsigned char *sm, XCon &c) {
     float4 va = *reinterpret_cast<float4 *>(sm + c.vmA), ba = *reinterpret_cast<float4 *>(sm + c.bbA);
     float4 vb = *reinterpret_cast<float4 *>(sm + c.vmB), bb = *reinterpret_cast<float4 *>(sm + c.bbB);
-    CBody A{va.x, va.y, va.z, ba.x, ba.y, va.w, 0.f, ba.w}, B{vb.x, vb.y, vb.z, bb.x, bb.y, vb.w, 0.f, bb.w};
-    const float iar = ba.z, ibr = bb.z;                                               // r / I
-    const float nx = c.nx, ny = c.ny;
-    float nMass = 1.0f / (A.minv + B.minv);
-    float tMass = 1.0f / (A.minv + B.minv + iar * A.r + ibr * B.r);
-    float dvx = B.vx - A.vx, dvy = B.vy - A.vy;
-    float vbn = (B.vbx - A.vbx) * nx + (B.vby - A.vby) * ny;
-    float vrn = dvx * nx + dvy * ny;
-    float vrt = (dvy * nx - dvx * ny) - B.r * B.w - A.r * A.w;
-    float jbn = (c.bias - vbn) * nMass, jbnOld = c.jb;
-    float jBias = fmaxf(jbnOld + jbn, 0.0f);
-    const double jnOld = (double)c.jn, jnNew = fmax(jnOld + (double)(-(c.bounce + vrn) * nMass), 0.0);
-    const double jtMax = (double)c.mu * jnNew;
-    const double jtOld = (double)c.jt, jtNew = fmin(fmax(jtOld + (double)(-vrt * tMass), -jtMax), jtMax);
-    c.jn = (float)jnNew; c.jt = (float)jtNew; c.jb = jBias;
-    float bj = jBias - jbnOld;
-    ba.x -= nx * bj * A.minv; ba.y -= ny * bj * A.minv;
-    bb.x += nx * bj * B.minv; bb.y += ny * bj * B.minv;
-    float dn = (float)(jnNew - jnOld), dtg = (float)(jtNew - jtOld);
-    float jx = nx * dn - ny * dtg, jy = nx * dtg + ny * dn;
-    va.x -= jx * A.minv; va.y -= jy * A.minv; va.z -= iar * dtg;
-    vb.x += jx * B.minv; vb.y += jy * B.minv; vb.z -= ibr * dtg;
+    const float4 g = *reinterpret_cast<const float4 *>(&c.nx), k = *reinterpret_cast<const float4 *>(&c.nMass), ac = *reinterpret_cast<const float4 *>(&c.jn);
+    const float nx = g.x, ny = g.y, nMass = k.x, tMass = k.y, mu = k.z;
+    const float dvx = vb.x - va.x, dvy = vb.y - va.y;
+    const float vbn = (bb.x - ba.x) * nx + (bb.y - ba.y) * ny;
+    const float vrn = dvx * nx + dvy * ny;
+    const float vrt = (dvy * nx - dvx * ny) - bb.w * vb.z - ba.w * va.z;
+    const float jbnOld = ac.z, jBias = fmaxf(jbnOld + (g.z - vbn) * nMass, 0.0f);
+    const float jnO = ac.x, jtO = ac.y, jnI = -(g.w + vrn) * nMass, jtI = -vrt * tMass;
+    float dn, dtg, jnS, jtS;
+    if (fabsf(jnO) < 256.f && fabsf(jtO) < 256.f) {
+        const float jnA = fmaxf(jnO + jnI, 0.0f), jtM = mu * jnA, jtA = fminf(fmaxf(jtO + jtI, -jtM), jtM);
+        jnS = jnA; jtS = jtA; dn = jnA - jnO; dtg = jtA - jtO;
+    } else {
+        const double jnA = fmax((double)jnO + (double)jnI, 0.0), jtM = (double)mu * jnA, jtA = fmin(fmax((double)jtO + (double)jtI, -jtM), jtM);
+        jnS = (float)jnA; jtS = (float)jtA; dn = (float)(jnA - (double)jnO); dtg = (float)(jtA - (double)jtO);
+    }
+    *reinterpret_cast<float4 *>(&c.jn) = make_float4(jnS, jtS, jBias, 0.f);
+    const float bj = jBias - jbnOld;
+    ba.x -= nx * bj * va.w; ba.y -= ny * bj * va.w;
+    bb.x += nx * bj * vb.w; bb.y += ny * bj * vb.w;
+    const float jx = nx * dn - ny * dtg, jy = nx * dtg + ny * dn;
+    va.x -= jx * va.w; va.y -= jy * va.w; va.z -= ba.z * dtg;
+    vb.x += jx * vb.w; vb.y += jy * vb.w; vb.z -= bb.z * dtg;
     *reinterpret_cast<float4 *>(sm + c.vmA) = va; *reinterpret_cast<float2 *>(sm + c.bbA) = make_float2(ba.x, ba.y);
     *reinterpret_cast<float4 *>(sm + c.vmB) = vb; *reinterpret_cast<float2 *>(sm + c.bbB) = make_float2(bb.x, bb.y);
 }
@@ -356,6 +362,13 @@ __global__ void __launch_bounds__(TW * 32, TW == 1 ? 16 : (TW == 2 ? 5 : (TW == 
             }
             const float2 n = W.nx_n[g];
             x.nx = n.x; x.ny = n.y; x.bias = W.nx_bias[g]; x.bounce = W.nx_bounce[g]; x.mu = ua * ub;
+            {   // k_n = 1/ma + 1/mb, k_t = k_n + ra^2/Ia + rb^2/Ib (circles: r x n = 0); a wall has 1/m = r/I = 0
+                const float4 va = *reinterpret_cast<const float4 *>(V.sm + x.vmA), ba = *reinterpret_cast<const float4 *>(V.sm + x.bbA);
+                const float4 vb = *reinterpret_cast<const float4 *>(V.sm + x.vmB), bb = *reinterpret_cast<const float4 *>(V.sm + x.bbB);
+                x.nMass = 1.0f / (va.w + vb.w);
+                x.tMass = 1.0f / (va.w + vb.w + ba.z * ba.w + bb.z * bb.w);
+            }
+            x.pad0 = 0.f; x.pad1 = 0.f;
             x.jn = W.nx_jn[g]; x.jt = W.nx_jt[g]; x.jb = 0.f;
             V.xc[i] = x;
         }

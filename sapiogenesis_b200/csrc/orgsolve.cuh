@@ -14,6 +14,9 @@
 #pragma once
 #include "common.cuh"
 #include "solver_api.h"
+#ifndef JOINT_PREFETCH
+#define JOINT_PREFETCH 1      /* pair record of the next wavefront fetched a step ahead */
+#endif
 
 // GC ("global constants"): the read-only part of a pin joint (nx, ny, bias) lives in a per-warp scratch in global memory (L2
 // resident: it is rewritten for every organism the warp takes) and is fetched three wavefronts ahead; shared memory keeps only
@@ -144,19 +147,24 @@ struct OrgCtx {
                 const float jn_cached = gj[pair_index(s.row_of[i], s.row_of[j])];
                 const float2 pi = s.p[i], pj = s.p[j], ri = s.rel[i], rj = s.rel[j];
                 const float radi = s.bb[i].w, radj = s.bb[j].w;
+                // Squared lengths exactly in double (the contact predicate below is bit-exact against the oracle), everything else in fp32:
+                // d - rest = (d^2 - rest^2) / (d + rest) keeps the cancellation in the exact numerator, so the unit vector, d + rest and the
+                // division only need fp32's 1e-7 -- no double square root or division per pin (four of them used to be 15 % of the kernel).
                 double dx = __dsub_rn((double)pj.x, (double)pi.x), dy = __dsub_rn((double)pj.y, (double)pi.y);
                 double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-                double d = sqrt(d2);
-                if (d != 0.0) { double inv = 1.0 / d; nxf = (float)(dx * inv); nyf = (float)(dy * inv); }
                 double lx = (double)rj.x - (double)ri.x, ly = (double)rj.y - (double)ri.y;
-                double rest = sqrt(lx * lx + ly * ly);                 // |relative_pos_i - relative_pos_j| (connectTo at spawn)
-                float bias = (float)(-K.bc_joint * (d - rest) / K.dt);
+                double r2 = lx * lx + ly * ly;                       // |relative_pos_i - relative_pos_j|^2 (connectTo at spawn)
+                const float d2f = (float)d2, r2f = (float)r2;
+                float invd = 0.f, df = 0.f;
+                if (d2f > 0.f) { invd = rsqrtf(d2f); invd = invd * fmaf(-0.5f * d2f * invd, invd, 1.5f); df = d2f * invd; nxf = (float)dx * invd; nyf = (float)dy * invd; }
+                const float sum = df + sqrtf(r2f);
+                float bias = sum > 0.f ? (float)(-(K.bc_joint / K.dt) * (d2 - r2)) / sum : 0.f;
                 const int q = slot_of(i, j);
                 if (GC) { cst[q] = make_float4(nxf, nyf, bias, 0.f); s.jn[q] = jn_cached; }
                 else s.pair[q] = make_float4(nxf, nyf, bias, jn_cached);
                 double md = __dadd_rn((double)radi, (double)radj);
                 hit = d2 < __dmul_rn(md, md);
-                if (hit) { if (d == 0.0) { nxf = 1.f; nyf = 0.f; } bias_c = contact_bias(d, radi, radj, w.p, K); }   // coincident centres: cpv(1, 0)
+                if (hit) { if (d2 == 0.0) { nxf = 1.f; nyf = 0.f; } bias_c = contact_bias(sqrt(d2), radi, radj, w.p, K); }   // coincident centres: cpv(1, 0)
             }
             const uint32_t m = gballot(hit);
             if (hit) {
@@ -476,29 +484,40 @@ struct OrgCtx {
         int T16 = 16, Q16 = S16, H16 = 16;                      // 16 t; 16 (off(t) + sl); 16 (h + 1)
         int M = max(T16 - N16, 0), I = S16 + M, J = T16 - I;
         bool act = I < J;
+        float4 *pp = reinterpret_cast<float4 *>(pqb + Q16);
+        float4 pr = *pp;                                          // constants and accumulator of the pair about to run: fetched a step ahead
         for (int t = 1; t <= tmax; t += 2, H16 += 16) {
 #pragma unroll
             for (int u = 0; u < 2; u++) {
                 // an idle lane reads whatever lies at its cursors (always inside the CTA's shared memory: |J| < 16 G < the size of the pair
                 // table in front of vm, I and Q run at most 32 entries past their arrays) and stores nothing
-                float4 *const pp = reinterpret_cast<float4 *>(pqb + Q16);
                 float2 *const pi = reinterpret_cast<float2 *>(vmb + I), *const pj = reinterpret_cast<float2 *>(vmb + J);
-                const float4 pr = *pp, vi = *reinterpret_cast<const float4 *>(pi), vj = *reinterpret_cast<const float4 *>(pj);
+                const float4 vi = *reinterpret_cast<const float4 *>(pi), vj = *reinterpret_cast<const float4 *>(pj);
                 const bool act_now = act;
-                Q16 += max(H16 - M, 0);                          // the next step's cursors and addresses, under the latency of the loads
+                float4 *const pp_now = pp;
+                Q16 += max(H16 - M, 0);                          // the next step's cursors, under the latency of the loads
                 T16 += 16;
                 M = max(T16 - N16, 0); I = S16 + M; J = T16 - I; act = I < J;
+                pp = reinterpret_cast<float4 *>(pqb + Q16);
+#if JOINT_PREFETCH
+                const float4 prn = *pp;                          // nobody writes the next pair's record during this step
+#endif
                 float jnv;
                 if (WARM) jnv = pr.w * dt_coef;
                 else jnv = fmaf(-(vj.x - vi.x), pr.x, fmaf(-(vj.y - vi.y), pr.y, pr.z)) * rcp_approx(vi.w + vj.w);
                 const float jx = pr.x * jnv, jy = pr.y * jnv;
                 const float2 ni = make_float2(fmaf(-jx, vi.w, vi.x), fmaf(-jy, vi.w, vi.y)), nj = make_float2(fmaf(jx, vj.w, vj.x), fmaf(jy, vj.w, vj.y));
                 if (act_now) {
-                    if (!WARM) reinterpret_cast<float *>(pp)[3] = pr.w + jnv;
+                    if (!WARM) reinterpret_cast<float *>(pp_now)[3] = pr.w + jnv;
                     *pi = ni;
                     *pj = nj;
                 }
                 __syncwarp();
+#if JOINT_PREFETCH
+                pr = prn;
+#else
+                pr = *pp;
+#endif
             }
         }
     }

@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(RULES_WARPS * 32, RULES_MAIN_MINB) k_rules_mai
             // take_energy of every cell's usage from every living cell (sprites.py:1400-1407, O(C^2) in the reference): the shares are
             // uniform, and max(max(e - a, 0) - b, 0) == max(e - a - b, 0), so they are summed and taken when somebody looks
             double pending = 0.0;
-            uint64_t rot_am = 0; double rot = 0.0;                                               // Organism.rotation, cached per set of living cells
+            uint64_t rot_am = 0; double push_c = 1.0, push_s = 0.0;                              // unit vector of the push direction, cached per set of living cells
             // Organism.rotation (sprites.py:1179-1201) is only used as an angle: cur - old (the % 360 cancels in cos/sin)
             for (int k = 0; k < g.nc; k++) {                                                     // _update_cell, sprites.py:1470-1606
                 float hk = bcast2(g.health[0], g.health[1], k);
@@ -346,16 +346,24 @@ __global__ void __launch_bounds__(RULES_WARPS * 32, RULES_MAIN_MINB) k_rules_mai
                         // that into 0.01 .. 0.08 px/s of bias velocity -- single-tick parity at 10k organisms and more hangs on this.
                         const uint64_t am = g.alive_mask() & ~1ull;
                         if (am != rot_am) {                                                      // Organism.rotation (sprites.py:1179-1201)
+                            // The push direction is atan2(dir_y, dir_x) + rotation, rotation = angle(heart -> first other living cell now) -
+                            // angle(the same cell in the genome's frame). Its cosine and sine follow from dot and cross products of the three
+                            // vectors -- the angle itself is never needed, and the four double-precision atan2 / sin / cos per organism were a
+                            // quarter of this kernel's instructions. Agrees with the trigonometric form to the last bits of a double.
                             rot_am = am;
-                            int rel = __ffsll((long long)am) - 1, rrow = o * MAXC + rel;
-                            double rx = (double)bcast2(g.px[0], g.px[1], rel) - (double)bcast2(g.px[0], g.px[1], 0), ry = (double)bcast2(g.py[0], g.py[1], rel) - (double)bcast2(g.py[0], g.py[1], 0);
-                            double deg = (atan2(ry, rx) - atan2((double)w.c_rel[2 * rrow + 1], (double)w.c_rel[2 * rrow])) * (180.0 / 3.14159265358979323846);
-                            deg = fmod(deg, 360.0); if (deg < 0.0) deg += 360.0;
-                            rot = deg * (3.14159265358979323846 / 180.0);
+                            const int rel = __ffsll((long long)am) - 1, rrow = o * MAXC + rel;
+                            const double rx = (double)bcast2(g.px[0], g.px[1], rel) - (double)bcast2(g.px[0], g.px[1], 0), ry = (double)bcast2(g.py[0], g.py[1], rel) - (double)bcast2(g.py[0], g.py[1], 0);
+                            const double ox = (double)w.c_rel[2 * rrow], oy = (double)w.c_rel[2 * rrow + 1];
+                            const double nr = sqrt(rx * rx + ry * ry), no = sqrt(ox * ox + oy * oy), nm = sqrt((double)mv2 * (double)mv2 + (double)mv3 * (double)mv3);
+                            const double cx = nr > 0.0 ? rx / nr : 1.0, cy = nr > 0.0 ? ry / nr : 0.0;        // atan2(0, 0) = 0
+                            const double qx = no > 0.0 ? ox / no : 1.0, qy = no > 0.0 ? oy / no : 0.0;
+                            const double mx = nm > 0.0 ? (double)mv2 / nm : 1.0, my = nm > 0.0 ? (double)mv3 / nm : 0.0;
+                            const double rc = cx * qx + cy * qy, rs = cy * qx - cx * qy;                     // cos, sin of the rotation
+                            push_c = mx * rc - my * rs; push_s = my * rc + mx * rs;
                         }
                         if (mine) {
-                            const double ang = atan2((double)mv3, (double)mv2) + rot, speed = (double)mv1 * (double)p.max_push * (double)dt;
-                            const double dvx = cos(ang) * speed, dvy = sin(ang) * speed;
+                            const double speed = (double)mv1 * (double)p.max_push * (double)dt;
+                            const double dvx = push_c * speed, dvy = push_s * speed;
                             if (hsel) { g.vx[1] = (float)((double)g.vx[1] + dvx); g.vy[1] = (float)((double)g.vy[1] + dvy); }
                             else { g.vx[0] = (float)((double)g.vx[0] + dvx); g.vy[0] = (float)((double)g.vy[0] + dvy); }
                         }

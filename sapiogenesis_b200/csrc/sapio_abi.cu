@@ -44,14 +44,10 @@ static int stream_grid(long items, int threads = 256) {
     return (int)wave;
 }
 
+// scratch shared by the gas scan (one Aff per chunk of organisms) and the reductions (REDUCE_CTAS doubles)
 static size_t cub_need(const SapioParams &p) {
-    size_t a = 0, b = 0, c = 0, d = 0;
-    cub::DeviceScan::InclusiveScan(nullptr, a, (Aff *)nullptr, (Aff *)nullptr, AffCompose(), p.n_org);
-    cub::DeviceReduce::Sum(nullptr, b, (double *)nullptr, (double *)nullptr, p.n_org);
-    cub::DeviceReduce::Reduce(nullptr, c, (double *)nullptr, (double *)nullptr, p.n_dead, MulD(), 1.0);
-    cub::DeviceScan::ExclusiveSum(nullptr, d, (int *)nullptr, (int *)nullptr, (p.n_org > p.n_dead ? p.n_org : p.n_dead) + 1);
-    size_t m = a > b ? a : b; m = m > c ? m : c; m = m > d ? m : d;
-    return m;
+    size_t a = ((size_t)p.n_org / GAS_CHUNK + 2) * sizeof(Aff), b = (size_t)REDUCE_CTAS * sizeof(double);
+    return (a > b ? a : b) + 256;
 }
 
 struct AllWs { Workspace step; RulesWs rules; TrainWs train; ReproWs repro; FrameWs frame, frame2; MigWs mig; HaloWs halo; int train_ctas; int *probe; };
@@ -130,12 +126,12 @@ static int check(const SapioWorld *w, void *ws, size_t ws_bytes, AllWs *out) {
 // ---- stage launchers ----------------------------------------------------------------------------------------------
 static int launch_grid_only(const SapioWorld &w, const Workspace &W, cudaStream_t st) {
     const int NC = w.p.n_org * MAXC, NB = NC + w.p.n_dead, NG = w.p.grid_nx * w.p.grid_ny;
-    k_integrate<false><<<stream_grid(NB), 256, 0, st>>>(w, W.gkey, W.gval);
-    size_t tmp = W.cub_bytes;
-    CUDA_TRY(cub::DeviceRadixSort::SortPairs(W.cub_tmp, tmp, W.gkey, W.skey, W.gval, W.sval, NB, 0, grid_key_bits(NG), st));
-    CUDA_TRY(cudaMemsetAsync(W.cell_start, 0, (size_t)NG * 4, st));
-    CUDA_TRY(cudaMemsetAsync(W.cell_end, 0, (size_t)NG * 4, st));
-    k_cell_bounds<<<stream_grid(NB), 256, 0, st>>>(W.skey, NB, NG, W.cell_start, W.cell_end);
+    CUDA_TRY(cudaMemsetAsync(W.cell_cnt, 0, (size_t)(NG + 1) * 4, st));
+    CUDA_TRY(cudaMemsetAsync(W.flags + FL_NLIVE, 0, sizeof(int), st));
+    k_integrate<false><<<stream_grid(NB), 256, 0, st>>>(w, W.gkey, W.gval, W.cell_cnt, W.flags + FL_NLIVE);
+    scan_exclusive_i32(W.cell_cnt, W.cell_start, NG + 1, W.scan_parts, st);
+    k_grid_scatter<<<stream_grid(NB / 3), 256, 0, st>>>(W, W.flags + FL_NLIVE);
+    k_grid_rank<<<stream_grid(NB / 3), 256, 0, st>>>(w, W, W.flags + FL_NLIVE);
     return 0;
 }
 
@@ -171,8 +167,7 @@ static int launch_rules(const SapioWorld &w, AllWs &A, uint32_t phases, cudaStre
     if (!(part & 2)) { prof_mark(st, PT_END); LAUNCH_CHECK(); return 0; }
     prof_mark(st, PT_RULES_MAIN);
     k_rules_main<<<org_grid, RULES_WARPS * 32, 0, st>>>(w, R, phases);
-    size_t tmp = A.step.cub_bytes;
-    CUDA_TRY(cub::DeviceReduce::Sum(A.step.cub_tmp, tmp, w.org_gas_refund, R.refund_sum, p.n_org, st));
+    reduce_doubles<false>(w.org_gas_refund, p.n_org, R.refund_sum, (double *)A.step.cub_tmp, st);
     k_rules_finish<<<1, 1, 0, st>>>(w, R);
     LAUNCHES(3);
     prof_mark(st, PT_END);
@@ -199,15 +194,12 @@ static int launch_settle(const SapioWorld &w, AllWs &A, cudaStream_t st) {
     prof_mark(st, PT_SETTLE);
     k_settle_gather<<<stream_grid(NB), 256, 0, st>>>(w);
     k_settle_count<<<stream_grid((p.n_org > p.n_dead ? p.n_org : p.n_dead) + 1), 256, 0, st>>>(w, R);
-    size_t tmp = A.step.cub_bytes;
-    CUDA_TRY(cub::DeviceScan::ExclusiveSum(A.step.cub_tmp, tmp, R.dying_cnt, R.dying_off, p.n_org + 1, st));
-    tmp = A.step.cub_bytes;
-    CUDA_TRY(cub::DeviceScan::ExclusiveSum(A.step.cub_tmp, tmp, R.free_flag, R.free_off, p.n_dead + 1, st));
+    scan_exclusive_i32(R.dying_cnt, R.dying_off, p.n_org + 1, A.step.scan_parts, st);
+    scan_exclusive_i32(R.free_flag, R.free_off, p.n_dead + 1, A.step.scan_parts, st);
     k_settle_freelist<<<stream_grid(p.n_dead), 256, 0, st>>>(w, R);
     k_settle_deaths<<<stream_grid(p.n_org), 256, 0, st>>>(w, R);
     k_settle_disperse<<<stream_grid(NB), 256, 0, st>>>(w, R);
-    tmp = A.step.cub_bytes;
-    CUDA_TRY(cub::DeviceReduce::Reduce(A.step.cub_tmp, tmp, R.disp_factor, R.disp_prod, p.n_dead, MulD(), 1.0, st));
+    reduce_doubles<true>(R.disp_factor, p.n_dead, R.disp_prod, (double *)A.step.cub_tmp, st);
     k_settle_gas<<<1, 1, 0, st>>>(w, R);
     LAUNCHES(6);
     prof_mark(st, PT_END);
@@ -221,10 +213,8 @@ static int launch_reproduce(const SapioWorld &w, AllWs &A, cudaStream_t st) {
     prof_mark(st, PT_REPRODUCE);
     for (int sib = 0; sib < p.offspring_amount; sib++) {
         k_repro_flags<<<stream_grid(p.n_org + 1), 256, 0, st>>>(w, Q);
-        size_t tmp = A.step.cub_bytes;
-        CUDA_TRY(cub::DeviceScan::ExclusiveSum(A.step.cub_tmp, tmp, Q.req_flag, Q.req_off, p.n_org + 1, st));
-        tmp = A.step.cub_bytes;
-        CUDA_TRY(cub::DeviceScan::ExclusiveSum(A.step.cub_tmp, tmp, Q.free_flag, Q.free_off, p.n_org + 1, st));
+        scan_exclusive_i32(Q.req_flag, Q.req_off, p.n_org + 1, A.step.scan_parts, st);
+        scan_exclusive_i32(Q.free_flag, Q.free_off, p.n_org + 1, A.step.scan_parts, st);
         k_repro_lists<<<stream_grid(p.n_org), 256, 0, st>>>(w, Q);
         int blocks = (Q.birth_cap + REPRO_WARPS - 1) / REPRO_WARPS;
         int cap = (sm_count() > 0 ? sm_count() : 148) * 8;

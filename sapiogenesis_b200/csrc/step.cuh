@@ -26,19 +26,11 @@
 namespace cg = cooperative_groups;
 
 #include "steptypes.cuh"
+#include "grid.cuh"
 #include "solver_api.h"
 // ------------------------------------------------------------------------------------------------------------------
 // broadphase
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_cell_bounds(const uint32_t *__restrict__ skey, int n, int ncell, int *__restrict__ cell_start, int *__restrict__ cell_end) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        uint32_t k = skey[i];
-        if (k >= (uint32_t)ncell) continue;
-        if (i == 0 || skey[i - 1] != k) cell_start[k] = i;
-        if (i == n - 1 || skey[i + 1] != k) cell_end[k] = i + 1;
-    }
-}
-
 __device__ __forceinline__ void body_circle(const SapioWorld &w, int b, int NC, float &x, float &y, float &r) {
     if (b < NC) { float2 p = reinterpret_cast<const float2 *>(w.c_pos)[b]; x = p.x; y = p.y; r = w.c_size[b] * 0.5f; }
     else { int d = b - NC; float2 p = reinterpret_cast<const float2 *>(w.d_pos)[d]; x = p.x; y = p.y; r = w.d_size[d] * 0.5f; }
@@ -52,12 +44,12 @@ __device__ __forceinline__ void body_circle(const SapioWorld &w, int b, int NC, 
 __global__ void __launch_bounds__(128) k_narrow_find(WORLD_ARG, Workspace W) {
     const SapioParams &p = w.p;
     const int NC = p.n_org * MAXC, NB = NC + p.n_dead, WALL0 = NB;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < NB; idx += gridDim.x * blockDim.x) {
+    const int n_live = W.flags[FL_NLIVE];
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_live; idx += gridDim.x * blockDim.x) {
         const uint32_t key = W.skey[idx];
-        if (key == 0xFFFFFFFFu) continue;                    // empty slots sort to the end
-        const int b = (int)W.sval[idx];
-        float mx, my, mr;
-        body_circle(w, b, NC, mx, my, mr);
+        const float4 me = W.srec[idx];
+        const int b = __float_as_int(me.w);
+        const float mx = me.x, my = me.y, mr = me.z;
         const int my_org = b < NC ? (b >> 6) : -1;
         const int cx = (int)(key % (uint32_t)p.grid_nx), cy = (int)(key / (uint32_t)p.grid_nx);
         uint32_t loc[NARROW_LOCAL];
@@ -65,20 +57,16 @@ __global__ void __launch_bounds__(128) k_narrow_find(WORLD_ARG, Workspace W) {
         bool over = false;
         for (int yy = cy - 1; yy <= cy + 1; yy++) {
             if (yy < 0 || yy >= p.grid_ny) continue;
-            for (int xx = cx - 1; xx <= cx + 1; xx++) {
-                if (xx < 0 || xx >= p.grid_nx) continue;
-                int c = yy * p.grid_nx + xx;
-                int s = W.cell_start[c], e = W.cell_end[c];
-                for (int i = s; i < e; i++) {
-                    int j = (int)W.sval[i];
-                    if (j == b) continue;
-                    if (my_org >= 0 && j < NC && (j >> 6) == my_org) continue;
-                    float ox, oy, orad;
-                    body_circle(w, j, NC, ox, oy, orad);
-                    double d2;
-                    if (!circles_overlap(mx, my, mr, ox, oy, orad, &d2)) continue;
-                    if (n < NARROW_LOCAL) { loc[n] = (uint32_t)j; n++; up += (j > b); } else over = true;
-                }
+            // the three cells of a grid row are neighbours in the cell-ordered list: one run of records
+            const int c0 = yy * p.grid_nx + max(cx - 1, 0), c1 = yy * p.grid_nx + min(cx + 1, p.grid_nx - 1);
+            for (int i = W.cell_start[c0], e = W.cell_start[c1 + 1]; i < e; i++) {
+                const float4 ot = W.srec[i];
+                const int j = __float_as_int(ot.w);
+                if (j == b) continue;
+                if (my_org >= 0 && j < NC && (j >> 6) == my_org) continue;
+                double d2;
+                if (!circles_overlap(mx, my, mr, ot.x, ot.y, ot.z, &d2)) continue;
+                if (n < NARROW_LOCAL) { loc[n] = (uint32_t)j; n++; up += (j > b); } else over = true;
             }
         }
         if (b >= NC) {
@@ -284,20 +272,17 @@ static int launch_space_step(const SapioWorld &w, const Workspace &W, cudaStream
     prof_mark(st, PT_BROADPHASE);
     STEP_TRY(cudaMemsetAsync(W.flags, 0, FL_BYTES, st));
     STEP_TRY(cudaMemsetAsync(W.org_coupled, 0, (size_t)p.n_org, st));
-    k_integrate<true><<<sgrid(NB, 256), 256, 0, st>>>(w, W.gkey, W.gval);
-    size_t tmp = W.cub_bytes;
-    STEP_TRY(cub::DeviceRadixSort::SortPairs(W.cub_tmp, tmp, W.gkey, W.skey, W.gval, W.sval, NB, 0, grid_key_bits(NG), st));
-    STEP_TRY(cudaMemsetAsync(W.cell_start, 0, (size_t)NG * 4, st));
-    STEP_TRY(cudaMemsetAsync(W.cell_end, 0, (size_t)NG * 4, st));
-    k_cell_bounds<<<sgrid(NB, 256), 256, 0, st>>>(W.skey, NB, NG, W.cell_start, W.cell_end);
+    STEP_TRY(cudaMemsetAsync(W.cell_cnt, 0, (size_t)(NG + 1) * 4, st));
+    k_integrate<true><<<sgrid(NB, 256), 256, 0, st>>>(w, W.gkey, W.gval, W.cell_cnt, W.flags + FL_NLIVE);
+    scan_exclusive_i32(W.cell_cnt, W.cell_start, NG + 1, W.scan_parts, st);
+    k_grid_scatter<<<sgrid(NB / 3, 256), 256, 0, st>>>(W, W.flags + FL_NLIVE);
+    k_grid_rank<<<sgrid(NB / 3, 256), 256, 0, st>>>(w, W, W.flags + FL_NLIVE);
     prof_mark(st, PT_NARROW);
     STEP_TRY(cudaMemsetAsync(W.cnt_up, 0, (size_t)(NB + 1) * 4, st));
     STEP_TRY(cudaMemsetAsync(W.cnt_all, 0, (size_t)(NB + 1) * 4, st));
-    k_narrow_find<<<sgrid(NB, 128), 128, 0, st>>>(w, W);
-    tmp = W.cub_bytes;
-    STEP_TRY(cub::DeviceScan::ExclusiveSum(W.cub_tmp, tmp, W.cnt_up, W.off_up, NB + 1, st));
-    tmp = W.cub_bytes;
-    STEP_TRY(cub::DeviceScan::ExclusiveSum(W.cub_tmp, tmp, W.cnt_all, W.off_all, NB + 1, st));
+    k_narrow_find<<<sgrid(NB / 3, 128), 128, 0, st>>>(w, W);
+    scan_exclusive_i32(W.cnt_up, W.off_up, NB + 1, W.scan_parts, st);
+    scan_exclusive_i32(W.cnt_all, W.off_all, NB + 1, W.scan_parts, st);
     k_narrow_totals<<<1, 1, 0, st>>>(w, W);
     k_narrow_fill<<<sgrid(2 * (long)p.x_cap, 128), 128, 0, st>>>(w, W);
     STEP_TRY(cudaMemsetAsync(W.nx_prev_a, 0xFF, (size_t)p.x_cap * 4, st));
@@ -307,7 +292,7 @@ static int launch_space_step(const SapioWorld &w, const Workspace &W, cudaStream
     k_classify_count<<<sgrid(p.n_org, 256), 256, 0, st>>>(w, W);
     k_classify_scan<<<1, 32, 0, st>>>(W);
     k_classify_scatter<<<sgrid(p.n_org, 256), 256, 0, st>>>(w, W);
-    LAUNCHES(11);
+    LAUNCHES(20);
     // connected components of the cross-contact graph (components.cuh): planned here, solved next to the organisms without contacts
     prof_mark(st, PT_COMP_PLAN);
     component_plan_launch(w, W, g_force_fallback, sgrid(p.x_cap, 256), st);

@@ -9,9 +9,11 @@
 struct Workspace {
     int *pop;                       // population reduction scratch
     int *flags;                     // FL_*
-    uint32_t *gkey, *gval, *skey, *sval;   // broadphase keys/values, unsorted and sorted [NB]
+    uint32_t *gkey, *gval, *skey, *sval;   // grid: cell key of every body slot [NB], list of living bodies, (cell key, body) in cell order [living]
+    uint32_t *stmp; float4 *srec;   // bodies in cell order before the ranking pass; (x, y, radius, id bits) in cell order (grid.cuh)
+    int *cell_cnt, *scan_parts;     // [grid cells + 1] bodies per cell (zero between builds); tile sums of the scans
     void *cub_tmp; size_t cub_bytes;
-    int *cell_start, *cell_end;     // [grid cells]
+    int *cell_start;                // [grid cells + 1] run of cell c in the cell-ordered lists: [cell_start[c], cell_start[c + 1])
     int *cnt_up, *cnt_all;          // per body counts [NB + 1]
     int *off_up, *off_all;          // exclusive scans [NB + 1]
     uint64_t *nx_key;               // new contact list [x_cap]
@@ -36,7 +38,7 @@ struct Workspace {
     char *cp_state; int cp_cap;     // parked solver state of the first cp_cap coupled organisms (sizeof(OrgS<MAXC>) each)
 };
 enum { FL_NX = 0, FL_NADJ = 1, FL_OVERFLOW = 2, FL_MAXLEVEL = 3, FL_NCOUPLED = 5, FL_NIC = 6, FL_CLS0 = 8 /* ..16: class starts + end */,
-       FL_WORK0 = 20 /* ..27 */, FL_TMPTOP = 28, FL_NHIT = 29, FL_RARE = 30, FL_HIST = 32 /* ..96 */, FL_CHIST = 100 /* ..164: coupled organisms by rows */,
+       FL_WORK0 = 20 /* ..27 */, FL_TMPTOP = 28, FL_NHIT = 29, FL_RARE = 30, FL_NLIVE = 31 /* living bodies in the grid */, FL_HIST = 32 /* ..96 */, FL_CHIST = 100 /* ..164: coupled organisms by rows */,
        FL_CCLS0 = 168 /* ..176: class starts + end in coupled_list */, FL_CHG0 = 180 /* ..182 */, FL_CWORK0 = 200 /* ..203: two alternating pairs of work counters of k_coupled */,
        FL_COMP_OVERFLOW = 210 /* a component exceeds the largest CTA tier: the tick falls back to the cooperative kernel */, FL_COMP_POOL = 211, FL_BIGLEVEL = 209,
        FL_COMP_N0 = 212 /* ..217: components per tier */, FL_COMP_WORK0 = 220 /* ..225: work counters */, FL_BYTES = 1024 };
@@ -55,11 +57,12 @@ static inline size_t carve_workspace(const SapioParams &p, char *base, Workspace
     W->gkey = (uint32_t *)take(NB * 4); W->gval = (uint32_t *)take(NB * 4);
     W->skey = (uint32_t *)take(NB * 4); W->sval = (uint32_t *)take(NB * 4);
     size_t sort_bytes = 0, scan_bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)NB);
     cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (int *)nullptr, (int *)nullptr, (int)NB + 1);
     W->cub_bytes = sort_bytes > scan_bytes ? sort_bytes : scan_bytes;
     W->cub_tmp = take(W->cub_bytes);
-    W->cell_start = (int *)take(NG * 4); W->cell_end = (int *)take(NG * 4);
+    W->cell_start = (int *)take((NG + 1) * 4); W->cell_cnt = (int *)take((NG + 1) * 4);
+    W->stmp = (uint32_t *)take(NB * 4); W->srec = (float4 *)take(NB * 16);
+    { const size_t big = (NG > NB ? NG : NB) + 1; W->scan_parts = (int *)take(((big + 2047) / 2048 + 1) * 4); }
     W->cnt_up = (int *)take((NB + 1) * 4); W->cnt_all = (int *)take((NB + 1) * 4);
     W->off_up = (int *)take((NB + 1) * 4); W->off_all = (int *)take((NB + 1) * 4);
     W->nx_key = (uint64_t *)take(XC * 8);

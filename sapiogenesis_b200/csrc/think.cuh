@@ -32,7 +32,7 @@ __device__ __forceinline__ void sense_enumerate(const SapioWorld &w, const Works
     if (nbx <= 0 || nby <= 0) return;
     for (int idx = lane; idx < nbx * nby; idx += 32) {
         int c = (cy0 + idx / nbx) * p.grid_nx + cx0 + idx % nbx;
-        for (int i = W.cell_start[c], e = W.cell_end[c]; i < e; i++) {
+        for (int i = W.cell_start[c], e = W.cell_start[c + 1]; i < e; i++) {
             int j = (int)W.sval[i];
             float x, y, r; bool dead;
             if (j < NC) {
@@ -52,7 +52,7 @@ __device__ __forceinline__ void sense_enumerate(const SapioWorld &w, const Works
 
 // Encodes the view relative to the cell at (px, py) (neural.py:123-218).
 template <bool EYE>
-__device__ __forceinline__ void sense(const SapioWorld &w, const Workspace &W, int o, int64_t uid, float sx, float sy, float R, float px, float py, double rot, SenseOut &out) {
+__device__ __forceinline__ void sense(const SapioWorld &w, const Workspace &W, int o, int64_t uid, float sx, float sy, float R, float px, float py, double rot_c, double rot_s, SenseOut &out) {
     double eye[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
     double smell = 0.; int hits = 0;
     sense_enumerate(w, W, o, uid, sx, sy, R, [&](int, float x, float y, float r, bool dead) {
@@ -63,8 +63,11 @@ __device__ __forceinline__ void sense(const SapioWorld &w, const Workspace &W, i
         double dist = sqrt(ddx * ddx + ddy * ddy);
         double val = fabs(((double)R - (dist + (double)r)) / (double)R);
         if (EYE) {
-            double ang = atan2(ddy, ddx) - rot;
-            double dx = cos(ang), dy = sin(ang);
+            // (cos, sin) of atan2(ddy, ddx) - rotation: the direction of the hit turned back by the organism's rotation -- a dot and a cross
+            // product with the rotation's unit vector over the distance already at hand, instead of three double-precision
+            // transcendentals per hit (same value to the last bits of a double; atan2(0, 0) = 0)
+            const double ux = dist > 0.0 ? ddx / dist : 1.0, uy = dist > 0.0 ? ddy / dist : 0.0;
+            const double dx = ux * rot_c + uy * rot_s, dy = uy * rot_c - ux * rot_s;
             int s;
             if (dx >= 0.0) { if (dy < 0.0) s = dx < .707 ? 0 : 1; else s = dx >= .707 ? 2 : 3; }
             else { if (dy >= 0.0) s = dy >= .707 ? 4 : 5; else s = dx < -.707 ? 6 : 7; }
@@ -101,15 +104,16 @@ __global__ void __launch_bounds__(THINK_WARPS * 32) k_think(WORLD_ARG, Workspace
         uint32_t a0 = __ballot_sync(FULL, lane < nc && w.c_alive[o * MAXC + lane] == SAPIO_CELL_ALIVE);
         uint32_t a1 = __ballot_sync(FULL, lane + 32 < nc && w.c_alive[o * MAXC + lane + 32] == SAPIO_CELL_ALIVE);
         uint64_t alive = ((uint64_t)a1 << 32) | a0;
-        double rot = 0.0;
+        double rot_c = 1.0, rot_s = 0.0;                                               // cos, sin of the rotation: angle(heart -> first other living cell) now minus in the genome's frame
         {
             uint64_t am = alive & ~1ull;
             if (am) {
                 int rel = __ffsll((long long)am) - 1, r0 = o * MAXC, rr = r0 + rel;
-                double deg = (atan2((double)w.c_pos[2 * rr + 1] - (double)w.c_pos[2 * r0 + 1], (double)w.c_pos[2 * rr] - (double)w.c_pos[2 * r0])
-                              - atan2((double)w.c_rel[2 * rr + 1], (double)w.c_rel[2 * rr])) * (180.0 / 3.14159265358979323846);
-                deg = fmod(deg, 360.0); if (deg < 0.0) deg += 360.0;                   // math.degrees(angleDiff) % 360
-                rot = deg * (3.14159265358979323846 / 180.0);                           // math.radians
+                const double rx = (double)w.c_pos[2 * rr] - (double)w.c_pos[2 * r0], ry = (double)w.c_pos[2 * rr + 1] - (double)w.c_pos[2 * r0 + 1];
+                const double ox = (double)w.c_rel[2 * rr], oy = (double)w.c_rel[2 * rr + 1];
+                const double nr = sqrt(rx * rx + ry * ry), no = sqrt(ox * ox + oy * oy);
+                const double cx = nr > 0.0 ? rx / nr : 1.0, cy = nr > 0.0 ? ry / nr : 0.0, qx = no > 0.0 ? ox / no : 1.0, qy = no > 0.0 ? oy / no : 0.0;
+                rot_c = cx * qx + cy * qy; rot_s = cy * qx - cx * qy;
             }
         }
         int n = 0;
@@ -121,7 +125,7 @@ __global__ void __launch_bounds__(THINK_WARPS * 32) k_think(WORLD_ARG, Workspace
             if (t == SAPIO_T_EYE) {
 #pragma unroll
                 for (int s = 0; s < 8; s++) so.eye[s] = 0.;
-                if (live) sense<true>(w, W, o, uid, sp.x, sp.y, w.c_size[row] * p.eyesight_mult, cp.x, cp.y, rot, so);
+                if (live) sense<true>(w, W, o, uid, sp.x, sp.y, w.c_size[row] * p.eyesight_mult, cp.x, cp.y, rot_c, rot_s, so);
                 if (lane < 8) { double v = 0.;
 #pragma unroll
                     for (int s = 0; s < 8; s++) if (s == lane) v = so.eye[s];
@@ -129,7 +133,7 @@ __global__ void __launch_bounds__(THINK_WARPS * 32) k_think(WORLD_ARG, Workspace
                 n += 8;
             } else {
                 so.smell = 0.;
-                if (live) sense<false>(w, W, o, uid, sp.x, sp.y, w.c_size[row] * p.olfactory_mult, cp.x, cp.y, rot, so);
+                if (live) sense<false>(w, W, o, uid, sp.x, sp.y, w.c_size[row] * p.olfactory_mult, cp.x, cp.y, rot_c, rot_s, so);
                 if (lane == 0) x[n] = (float)so.smell;
                 n += 1;
             }

@@ -116,13 +116,39 @@ def dumps_reference_pickle(dna: dict, protocol: int = 4) -> bytes:
             sys.modules["sprites"] = saved
 
 
+# What a pickled sprites.DNA can legitimately reference: plain containers and scalars, tensors / arrays of numbers. Exact (module, name)
+# pairs only -- a prefix rule would admit builtins.eval, torch.load, numpy.load and the like, i.e. arbitrary code from a genome file.
+_PICKLE_ALLOWED = {
+    ("collections", "OrderedDict"), ("collections", "defaultdict"), ("collections", "deque"),
+    ("builtins", "list"), ("builtins", "dict"), ("builtins", "set"), ("builtins", "frozenset"), ("builtins", "tuple"), ("builtins", "int"),
+    ("builtins", "float"), ("builtins", "bool"), ("builtins", "str"), ("builtins", "bytes"), ("builtins", "bytearray"), ("builtins", "complex"),
+    ("builtins", "slice"), ("builtins", "range"),
+    ("copyreg", "_reconstructor"), ("builtins", "object"), ("_codecs", "encode"),
+    ("torch._utils", "_rebuild_tensor_v2"), ("torch._utils", "_rebuild_parameter"), ("torch", "Size"), ("torch", "device"), ("torch", "dtype"),
+    ("torch.storage", "_load_from_bytes"),
+    ("torch", "FloatStorage"), ("torch", "DoubleStorage"), ("torch", "HalfStorage"), ("torch", "LongStorage"), ("torch", "IntStorage"),
+    ("torch", "ShortStorage"), ("torch", "CharStorage"), ("torch", "ByteStorage"), ("torch", "BoolStorage"), ("torch", "BFloat16Storage"),
+    ("numpy", "ndarray"), ("numpy", "dtype"), ("numpy.core.multiarray", "_reconstruct"), ("numpy.core.multiarray", "scalar"),
+    ("numpy._core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "scalar"), ("numpy.core.numeric", "_frombuffer"),
+    ("numpy._core.numeric", "_frombuffer"),
+}
+
+
 class _Unpickler(pickle.Unpickler):
     def find_class(self, module, name):
         if (module, name) == ("sprites", "DNA"):
             return _DNAStub
-        if module.split(".")[0] in ("torch", "collections", "numpy", "builtins", "copyreg", "_codecs"):
+        if (module, name) == ("torch.storage", "_load_from_bytes"):
+            return _load_storage_bytes
+        if (module, name) in _PICKLE_ALLOWED:
             return super().find_class(module, name)
         raise pickle.UnpicklingError(f"refusing to load {module}.{name} from a genome file")
+
+
+def _load_storage_bytes(b: bytes):
+    """torch.storage._load_from_bytes is torch.load(weights_only=False) on the bytes: replaced by the restricted loader."""
+    import torch
+    return torch.load(io.BytesIO(b), weights_only=True)
 
 
 def loads_reference_pickle(blob: bytes) -> dict:

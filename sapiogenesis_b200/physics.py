@@ -110,6 +110,50 @@ class Sprite:
         vel = self._f("c_vel", "d_vel")
         vel[self._i] += torch.tensor([k * math.cos(d) * speed, k * math.sin(d) * speed], device=vel.device)
 
+    # -- collisions and joints (physics.py:219-248) -----------------------------------------------------------------------
+    def collision(self, item):                          # physics.py:219-220: a hook the reference leaves empty
+        pass
+
+    @property
+    def _organism(self):
+        return self._i // MAXC if self._kind == "cell" else -1
+
+    @property
+    def connections(self) -> dict:
+        """physics.py:143 / :222-248: the pin joints of this sprite. In the world step the joints of an organism are implicit -- every
+        pair of its LIVING cells is pinned (sprites.py:1721-1726), a joint dies with either of its cells (sprites.py:1340-1343) and a free
+        dead cell has none -- so the dict is derived from the living-cell set."""
+        if self._kind != "cell":
+            return {}
+        t = self.environment.world.t
+        o, base = self._organism, self._organism * MAXC
+        if int(t["c_alive"][self._i]) != 1:
+            return {}
+        rows = torch.nonzero(t["c_alive"][base: base + int(t["org_ncells"][o])] == 1).view(-1).tolist()
+        return {Sprite(self.environment, "cell", base + k): "PinJoint" for k in rows if base + k != self._i}
+
+    def connectTo(self, sprite, rigid=True):            # physics.py:222-241
+        """Two living cells of one organism are pinned already (a no-op, like the reference's early return for an existing connection,
+        physics.py:223-224). Any other joint is not part of the per-tick world step this library implements: it fails loudly instead of
+        being dropped silently."""
+        if self._kind == "cell" and sprite._kind == "cell" and self._organism == sprite._organism:
+            return
+        raise NotImplementedError("pin joints exist between the living cells of one organism only (sprites.py:1721-1726); "
+                                  "a joint across organisms or to a free body is outside the world step (SURVEY.md section 8)")
+
+    def disconnectFrom(self, sprite):                   # physics.py:243-248
+        """The reference removes a joint when one of its cells dies (sprites.py:1340-1343); the world step does the same inside the death
+        cascade. Disconnecting two living cells of an organism by hand is not representable (the joint set is the living-cell set)."""
+        if sprite not in self.connections:
+            return                                      # physics.py:244: nothing to do
+        raise NotImplementedError("the joints of an organism follow its living cells; kill the cell (removeSprite) to remove its joints")
+
+    def __eq__(self, o):
+        return isinstance(o, Sprite) and o.environment is self.environment and (o._kind, o._i) == (self._kind, self._i)
+
+    def __hash__(self):
+        return hash((self._kind, self._i))
+
     def updateSprite(self):
         """Per-sprite form of the friction pass (physics.py:250-275); the batch form is Environment.update."""
         f = 1.0 - self.environment.friction / 100.0 * self.environment.world.p.dt_wall
@@ -293,6 +337,25 @@ class Environment:
         import_dna(self.world, slot, pos, dna)
         self.engine._grid_valid = False
         return Organism(self, slot)
+
+    def add_sprite(self, sprite: Sprite):                # physics.py:453-456
+        """Puts a sprite (back) into the space. Bodies live in the world's tables, so a view made by add_ball_sprite is in the space
+        already; a free body taken out with removeSprite comes back with the state its row still holds."""
+        if sprite.environment is not self:
+            raise ValueError("the sprite belongs to another environment")
+        if sprite._kind == "dead":
+            if int(self.world.t["d_state"][sprite._i]) == 0:
+                self.world.t["d_state"][sprite._i] = 1
+                self.engine._grid_valid = False
+            return sprite
+        if int(self.world.t["c_alive"][sprite._i]) != 1:
+            raise NotImplementedError("a cell that died cannot be re-added: it has left through the death cascade (sprites.py:1326-1354)")
+        return sprite
+
+    def collision(self, arbiter=None, space=None, data=None):   # physics.py:379-386
+        """The reference's collision handler forwards every cell / cell arbiter to the two sprites' (empty) collision hooks; the contact
+        adjacency the rules use (sprite.colliding) is built by Space.step on the device, so there is nothing to forward here."""
+        return True
 
     def removeSprite(self, sprite: Sprite):              # physics.py:444-451
         t = self.world.t

@@ -131,3 +131,20 @@ def test_imported_organism_lives_on_the_gpu_like_in_the_oracle(oracle):
         # double accumulators of large contact impulses exist for
         compare_worlds(wg2, w, f"imported organism, tick {w.tick}", verbose=False)
     assert int(w.np("org_state")[free]) == 1 and int(w.np("org_hist_n")[free]) > int(dna_io.export_dna(w, donor)["generation"]) * 0
+
+
+def test_genome_file_cannot_reach_arbitrary_callables():
+    """the unpickler admits exact (module, name) pairs only -- a crafted genome file must not reach eval / exec /
+    __import__ / torch.load / numpy.load through REDUCE."""
+    import pickle
+    from sapiogenesis_b200 import dna_io
+
+    class Evil:
+        def __init__(self, fn, *args): self.fn, self.args = fn, args
+        def __reduce__(self): return (self.fn, self.args)
+
+    import builtins, os
+    for fn, args in ((builtins.eval, ("1+1",)), (builtins.__import__, ("os",)), (os.system, ("true",)), (builtins.exec, ("pass",))):
+        blob = pickle.dumps({"cells": Evil(fn, *args), "growth_pattern": [], "brain_structure": {}, "base_info": {}})
+        with pytest.raises(pickle.UnpicklingError):
+            dna_io.loads_reference_pickle(blob)

@@ -18,11 +18,13 @@ def test_reference_entry_points_exist_with_the_reference_parameters():
     params = lambda f: list(inspect.signature(f).parameters)
     assert params(physics.Environment.__init__)[:8] == ["self", "worldView", "scene", "width", "height", "friction", "gravity", "frameWidth"]
     assert params(physics.Environment.update) == ["self", "event"]
-    for name in ("preUpdateEvent", "postUpdateEvent", "pause_world", "resume_world", "removeSprite", "add_ball_sprite", "stop"):
+    for name in ("preUpdateEvent", "postUpdateEvent", "pause_world", "resume_world", "removeSprite", "add_ball_sprite", "add_sprite", "collision", "stop"):
         assert callable(getattr(physics.Environment, name))
     assert params(physics.Environment.add_ball_sprite)[:7] == ["self", "xy", "width", "height", "mass", "friction", "elasticity"]
     assert params(physics.setupEnvironment)[:4] == ["worldView", "scene", "friction", "gravity"]
-    for name in ("getPos", "getCenter", "getWidth", "getHeight", "bump", "updateSprite"):
+    assert params(physics.Environment.add_sprite) == ["self", "sprite"] and params(physics.Environment.collision) == ["self", "arbiter", "space", "data"]
+    assert params(physics.Sprite.connectTo) == ["self", "sprite", "rigid"] and params(physics.Sprite.disconnectFrom) == ["self", "sprite"]
+    for name in ("getPos", "getCenter", "getWidth", "getHeight", "bump", "updateSprite", "collision", "connectTo", "disconnectFrom"):
         assert callable(getattr(physics.Sprite, name))
     assert params(sprites.update_organisms) == ["environment"]
     assert params(sprites.disperse_all_dead) == ["environment"]
@@ -146,3 +148,34 @@ def test_manual_controls_and_headless_runner(oracle, tmp_path):
     run.main(["--organisms", "6", "--ticks", "20", "--every", "10", "--dump", str(out)])
     z = np.load(out)
     assert z["cells"].shape[1] == 4 and len(z["cells"]) > 6
+
+
+@pytest.mark.gpu
+def test_sprite_joints_add_sprite_and_collision_hooks(oracle):
+    """Environment.add_sprite (physics.py:453), Sprite.connectTo / disconnectFrom / connections (:222-248), Environment.collision
+    (:379-386): the joints of an organism are its living-cell set, free bodies come and go through add_sprite / removeSprite."""
+    from sapiogenesis_b200 import physics
+    w = make_world(oracle, n_org=6, seed=9, n_food=6, crowd=0.9, extra_slots=2, n_dead_cap=64 * 8)
+    env = _env_from(w)
+    t = env.world.t
+    org = env.info["organism_list"][0]
+    base = org.slot * MAXC
+    live = [base + k for k in range(int(t["org_ncells"][org.slot])) if int(t["c_alive"][base + k]) == 1]
+    a, b = physics.Sprite(env, "cell", live[0]), physics.Sprite(env, "cell", live[1])
+    conn = a.connections
+    assert len(conn) == len(live) - 1 and b in conn and a not in conn            # all-pairs pins among the living cells (sprites.py:1721-1726)
+    a.connectTo(b)                                                               # already connected: the reference returns early too
+    other = physics.Sprite(env, "cell", env.info["organism_list"][1].slot * MAXC)
+    with pytest.raises(NotImplementedError):
+        a.connectTo(other)
+    with pytest.raises(NotImplementedError):
+        a.disconnectFrom(b)
+    a.disconnectFrom(other)                                                      # not connected: nothing to do (physics.py:244)
+    food = env.add_ball_sprite((400.0, 400.0), 30, 30, mass=12)
+    assert food.connections == {} and env.collision(None, None, None) is True and food.collision(a) is None
+    n0 = len(env.sprites)
+    env.removeSprite(food)
+    assert len(env.sprites) == n0 - 1
+    assert env.add_sprite(food) is food and len(env.sprites) == n0                # back in the space with the state its row holds
+    env.update(None)
+    assert int(t["d_state"][food._i]) > 0
