@@ -392,10 +392,11 @@ def run_ours(args):
         clocks = clk.summary()
         mhz = clocks["sm_mhz"] or 1965.0
         kernels = {
-            "org_solve": ("k_org_solve<8|16|24|32|40|48|56|64> (organisms without cross contacts: intra contacts + sensor pins + all-pairs pin joints, warm start + 10 "
-                          "Gauss-Seidel sweeps in shared memory; one launch per size class, concurrent streams)", solver_bytes(shape["free"])),
-            "coupled": ("coupled pass (organisms and dead bodies that share a cross contact: the same per-organism solve interleaved with the cross contacts)",
-                        solver_bytes(shape["coupled"]) + 64 * shape["cross_contacts"] + 36 * shape["dead_coupled"]),
+            "org_solve": ("k_org_solve<8|16|24|32|40|48|56|64> + k_component<1|2|4|16> (Space.step's solver: per organism its intra contacts, sensor pins and "
+                          "all-pairs pin joints, exact warm start + 10 Gauss-Seidel sweeps with everything resident in shared memory; organisms without cross "
+                          "contacts by size class, organisms and dead bodies that touch each other one connected component per CTA; 15 concurrent launches)",
+                          solver_bytes(shape["free"]) + solver_bytes(shape["coupled"]) + 64 * shape["cross_contacts"] + 36 * shape["dead_coupled"]),
+            "coupled": ("k_coupled_simple (cooperative fallback for components beyond the largest CTA tier)", 64 * shape["cross_contacts"]),
         }
         roof = None
         rk = dom if dom in kernels else "org_solve"

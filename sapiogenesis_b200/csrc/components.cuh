@@ -20,7 +20,7 @@
 #include "orgsolve.cuh"
 
 // ---- tiers: warps (organisms) per CTA, shared memory, table capacities -------------------------------------------------------
-#define COMP_TIERS 6
+#define COMP_TIERS 7
 struct CompTier { int warps; int smem; int xmax; int dmax; };
 // A warp is an organism: the three one-warp tiers take one organism of up to 24 / 40 / 64 living cells with its debris (half of the
 // coupled organisms touch dead bodies only), so that no CTA carries a warp without work.
@@ -31,7 +31,9 @@ __host__ __device__ inline CompTier comp_tier(int t) {
         case 2: return CompTier{1, 51 * 1024, 64, 48};          // one organism of any size: 4 per SM
         case 3: return CompTier{2, 55 * 1024, 96, 64};          // two organisms: 4 per SM
         case 4: return CompTier{4, 110 * 1024, 192, 128};       // up to four organisms: 2 per SM
-        default: return CompTier{16, 220 * 1024, 384, 192};     // up to sixteen: 1 per SM
+        case 5: return CompTier{16, 220 * 1024, 384, 192};      // up to sixteen: 1 per SM
+        default: return CompTier{16, 227 * 1024 - 512, 48, 32};     // a handful of LARGE organisms touching each other (5-8 x 27-44 KB of slabs, few contacts):
+                                                                // small tables leave 221 KB for the slabs -- what used to fall back to the cooperative kernel on most ticks
     }
 }
 // slab class of an organism by its cell rows

@@ -20,7 +20,7 @@ static const OrgLaunchFn ORG_LAUNCH_FN[ORG_CLASSES] = {org_launch_8, org_launch_
 // coupled.cu: the cooperative fallback; component.cu: connected components of the cross-contact graph, one per CTA
 cudaError_t coupled_plan(int sms, int *simple_blocks, size_t *simple_smem);
 cudaError_t coupled_launch(const SapioWorld &w, const Workspace &W, const StepK &K, int blocks, size_t smem, cudaStream_t st);
-#define COMP_TIERS_N 6
+#define COMP_TIERS_N 7
 cudaError_t component_plan(int sms, int *blocks);
 void component_plan_launch(const SapioWorld &w, const Workspace &W, int force_fallback, int grid, cudaStream_t st);
 void component_launch(const SapioWorld &w, const Workspace &W, const StepK &K, int tier, int blocks, cudaStream_t st);

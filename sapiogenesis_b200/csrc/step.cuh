@@ -307,7 +307,7 @@ static int launch_space_step(const SapioWorld &w, const Workspace &W, cudaStream
         auto side_end = [&]() { cudaEventRecord(g_plan.join[k], g_plan.side[k]); cudaStreamWaitEvent(st, g_plan.join[k], 0); k++; };
         auto org = [&](int cls) { cudaStream_t ss = side_begin(); ORG_LAUNCH_FN[cls](w, W, K, cls, g_plan.org_blocks[cls], g_plan.org_smem[cls], ss); side_end(); };
         auto comp = [&](int t) { cudaStream_t ss = side_begin(); component_launch(w, W, K, t, g_plan.comp_blocks[t], ss); side_end(); };
-        comp(5); comp(4); org(7); org(6); comp(3); org(5); org(4); comp(2); org(3); org(2); comp(1); org(1); org(0); comp(0);
+        comp(6); comp(5); comp(4); org(7); org(6); comp(3); org(5); org(4); comp(2); org(3); org(2); comp(1); org(1); org(0); comp(0);
     }
     LAUNCHES(8 + COMP_TIERS_N);
     // the cooperative kernel only has work (decided on the device) when a component exceeds the largest tier

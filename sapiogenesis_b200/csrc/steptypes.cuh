@@ -41,7 +41,7 @@ enum { FL_NX = 0, FL_NADJ = 1, FL_OVERFLOW = 2, FL_MAXLEVEL = 3, FL_NCOUPLED = 5
        FL_WORK0 = 20 /* ..27 */, FL_TMPTOP = 28, FL_NHIT = 29, FL_RARE = 30, FL_NLIVE = 31 /* living bodies in the grid */, FL_HIST = 32 /* ..96 */, FL_CHIST = 100 /* ..164: coupled organisms by rows */,
        FL_CCLS0 = 168 /* ..176: class starts + end in coupled_list */, FL_CHG0 = 180 /* ..182 */, FL_CWORK0 = 200 /* ..203: two alternating pairs of work counters of k_coupled */,
        FL_COMP_OVERFLOW = 210 /* a component exceeds the largest CTA tier: the tick falls back to the cooperative kernel */, FL_COMP_POOL = 211, FL_BIGLEVEL = 209,
-       FL_COMP_N0 = 212 /* ..217: components per tier */, FL_COMP_WORK0 = 220 /* ..225: work counters */, FL_BYTES = 1024 };
+       FL_COMP_N0 = 212 /* ..218: components per tier */, FL_COMP_WORK0 = 220 /* ..226: work counters */, FL_BYTES = 1024 };
 
 #define COUPLED_STATE_BYTES 49152      /* >= sizeof(OrgS<MAXC>), checked where the struct is known */
 // sort only the bits a grid key can have; the key of an empty slot (all ones) still sorts behind every cell: its low bits are all ones
@@ -85,7 +85,7 @@ static inline size_t carve_workspace(const SapioParams &p, char *base, Workspace
         const size_t NN = (size_t)p.n_org + p.n_dead;
         W->cn_parent = (int *)take(NN * 4); W->cn_nx = (int *)take(NN * 4); W->cn_norg = (int *)take(NN * 4); W->cn_ndead = (int *)take(NN * 4);
         W->cn_need = (int *)take(NN * 4); W->cn_xoff = (int *)take(NN * 4); W->cn_fill = (int *)take(NN * 4); W->cn_seen = (int *)take(NN * 4); W->cn_tier = (int *)take(NN * 4);
-        W->comp_of = (int *)take(XC * 4); W->comp_pool = (int *)take(XC * 4); W->comp_list = (int *)take((size_t)6 * 2 * XC * 4);
+        W->comp_of = (int *)take(XC * 4); W->comp_pool = (int *)take(XC * 4); W->comp_list = (int *)take((size_t)7 * 2 * XC * 4);
     }
     W->cp_cap = p.n_org < 8192 ? p.n_org : 8192;      // parked state of the fallback kernel (beyond: recomputed per pass)
     W->cp_state = take((size_t)W->cp_cap * COUPLED_STATE_BYTES);
