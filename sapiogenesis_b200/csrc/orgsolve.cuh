@@ -147,24 +147,30 @@ struct OrgCtx {
                 const float jn_cached = gj[pair_index(s.row_of[i], s.row_of[j])];
                 const float2 pi = s.p[i], pj = s.p[j], ri = s.rel[i], rj = s.rel[j];
                 const float radi = s.bb[i].w, radj = s.bb[j].w;
-                // Squared lengths exactly in double (the contact predicate below is bit-exact against the oracle), everything else in fp32:
-                // d - rest = (d^2 - rest^2) / (d + rest) keeps the cancellation in the exact numerator, so the unit vector, d + rest and the
-                // division only need fp32's 1e-7 -- no double square root or division per pin (four of them used to be 15 % of the kernel).
+                // Squared lengths exactly in double (the contact predicate below is bit-exact against the oracle). The two lengths and the
+                // reciprocal are fp32 hardware approximations refined by ONE Newton step in double (error 1e-7 squared), so unit vector and
+                // bias come out as the correctly rounded fp32 values the double-precision sqrt / divide gave -- for 11 double-pipe
+                // instructions per pin instead of ~100 (four library routines that used to be 15 % of the kernel).
                 double dx = __dsub_rn((double)pj.x, (double)pi.x), dy = __dsub_rn((double)pj.y, (double)pi.y);
                 double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
                 double lx = (double)rj.x - (double)ri.x, ly = (double)rj.y - (double)ri.y;
                 double r2 = lx * lx + ly * ly;                       // |relative_pos_i - relative_pos_j|^2 (connectTo at spawn)
                 const float d2f = (float)d2, r2f = (float)r2;
-                float invd = 0.f, df = 0.f;
-                if (d2f > 0.f) { invd = rsqrtf(d2f); invd = invd * fmaf(-0.5f * d2f * invd, invd, 1.5f); df = d2f * invd; nxf = (float)dx * invd; nyf = (float)dy * invd; }
-                const float sum = df + sqrtf(r2f);
-                float bias = sum > 0.f ? (float)(-(K.bc_joint / K.dt) * (d2 - r2)) / sum : 0.f;
+                double d = 0.0, rest = 0.0;
+                if (d2f > 0.f) {
+                    const float iv = rsqrtf(d2f);
+                    d = (double)(d2f * iv); d = fma(fma(-d, d, d2), (double)(0.5f * iv), d);                 // sqrt(d2)
+                    double y = (double)iv; y = fma(y, fma(-d, y, 1.0), y);                                   // 1 / d
+                    nxf = (float)(dx * y); nyf = (float)(dy * y);
+                }
+                if (r2f > 0.f) { const float iv = rsqrtf(r2f); rest = (double)(r2f * iv); rest = fma(fma(-rest, rest, r2), (double)(0.5f * iv), rest); }
+                float bias = (float)(-(K.bc_joint / K.dt) * (d - rest));
                 const int q = slot_of(i, j);
                 if (GC) { cst[q] = make_float4(nxf, nyf, bias, 0.f); s.jn[q] = jn_cached; }
                 else s.pair[q] = make_float4(nxf, nyf, bias, jn_cached);
                 double md = __dadd_rn((double)radi, (double)radj);
                 hit = d2 < __dmul_rn(md, md);
-                if (hit) { if (d2 == 0.0) { nxf = 1.f; nyf = 0.f; } bias_c = contact_bias(sqrt(d2), radi, radj, w.p, K); }   // coincident centres: cpv(1, 0)
+                if (hit) { if (d2 == 0.0) { nxf = 1.f; nyf = 0.f; } bias_c = contact_bias(d, radi, radj, w.p, K); }   // coincident centres: cpv(1, 0)
             }
             const uint32_t m = gballot(hit);
             if (hit) {

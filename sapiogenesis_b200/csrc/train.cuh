@@ -250,11 +250,25 @@ __global__ void __launch_bounds__(TRAIN_THREADS, 4) k_train(WORLD_ARG, RulesWs R
             for (int e = tid; e < np_in + np_out; e += TRAIN_THREADS) {
                 // Adam divides by |g| + 1e-8: gradients are summed over the batch in double so that their own rounding noise does not
                 // decide the update of near-zero components
+                // both factors are stored sample-fastest (dz0T / dOT rows, X^T and the last hidden layer's activations): four samples per
+                // pair of 16-byte loads, added in ascending sample order like the scalar loop (the padding samples beyond M are skipped)
                 double gd = 0.0; float *prm;
-                if (e < h0 * I) { int r = e / I, c = e % I; for (int m = 0; m < M; m++) gd += (double)__fmul_rn(dz0T[r * TR_S + m], min_[(size_t)m * IN + c]); prm = &Win[e]; }
-                else if (e < np_in) { int r = e - h0 * I; for (int m = 0; m < M; m++) gd += (double)dz0T[r * TR_S + m]; prm = &bin[r]; }
-                else if (e < np_in + 4 * hl) { int z = (e - np_in) / hl, c = (e - np_in) % hl; for (int m = 0; m < M; m++) gd += (double)__fmul_rn(dOT[z * TR_S + m], hlastT[c * TR_S + m]); prm = &Wout[e - np_in]; }
-                else { int z = e - np_in - 4 * hl; for (int m = 0; m < M; m++) gd += (double)dOT[z * TR_S + m]; prm = &bout[z]; }
+                const float *fa, *fb = nullptr;
+                if (e < h0 * I) { const int r = e / I, c = e % I; fa = dz0T + r * TR_S; fb = XT + c * TR_S; prm = &Win[e]; }
+                else if (e < np_in) { const int r = e - h0 * I; fa = dz0T + r * TR_S; prm = &bin[r]; }
+                else if (e < np_in + 4 * hl) { const int z = (e - np_in) / hl, c = (e - np_in) % hl; fa = dOT + z * TR_S; fb = hlastT + c * TR_S; prm = &Wout[e - np_in]; }
+                else { const int z = e - np_in - 4 * hl; fa = dOT + z * TR_S; prm = &bout[z]; }
+                const int Mq = M & ~3;
+                if (fb) {
+                    for (int m = 0; m < Mq; m += 4) {
+                        const float4 a = *reinterpret_cast<const float4 *>(fa + m), b = *reinterpret_cast<const float4 *>(fb + m);
+                        gd += (double)__fmul_rn(a.x, b.x); gd += (double)__fmul_rn(a.y, b.y); gd += (double)__fmul_rn(a.z, b.z); gd += (double)__fmul_rn(a.w, b.w);
+                    }
+                    for (int m = Mq; m < M; m++) gd += (double)__fmul_rn(fa[m], fb[m]);
+                } else {
+                    for (int m = 0; m < Mq; m += 4) { const float4 a = *reinterpret_cast<const float4 *>(fa + m); gd += (double)a.x; gd += (double)a.y; gd += (double)a.z; gd += (double)a.w; }
+                    for (int m = Mq; m < M; m++) gd += (double)fa[m];
+                }
                 const float g = (float)gd;
                 float m1 = b1 * am[e] + (1.0f - b1) * g, v1 = b2 * av[e] + (1.0f - b2) * g * g;
                 am[e] = m1; av[e] = v1;

@@ -266,7 +266,7 @@ def split_world(whole: World, n_slabs: int, device, halo: float = HALO, slot_fac
     for r in range(n_slabs):
         mo, md = org[owner_o == r], dead[owner_d == r]
         n_org = int(math.ceil((len(mo) * slot_factor + 64) / 64.0) * 64)
-        n_dead = max(1024, int(len(md) * 2 + 512))
+        n_dead = max(1024, int(len(md) * 2 + 512), int(whole.p.n_dead * 1.5 / n_slabs))     # the slab's share of the whole world's dead pool, with room for ghosts
         p = slab_params(whole.p, r, n_slabs, n_org, n_dead, halo, cuts=cuts)
         ws = World(p)
         place(ws, mo, md)

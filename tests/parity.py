@@ -146,6 +146,14 @@ def compare_worlds(wg, w, tag, brain_tol=TOL, check_brain=True, skip=(), verbose
     O = _Lazy(w)
     rep.exact("org_state", G["org_state"], O["org_state"])
     orgs = np.nonzero(O["org_state"] == 1)[0]
+    # organisms whose network output sits on a 3-decimal rounding tie this tick (see below): their movement command differs by 1e-3 on
+    # the two sides, the push actuator turns that into a different velocity of their own cells -- left out of the fp32 comparisons
+    tie_orgs = np.zeros(p.n_org, dtype=bool)
+    if detail_orgs is not None and len(detail_orgs):
+        dsel = np.intersect1d(orgs, np.asarray(detail_orgs, dtype=np.int64))
+        mv = np.abs(G["org_move"][dsel].astype(np.float64) - O["org_move"][dsel]).reshape(len(dsel), -1).max(axis=1) if len(dsel) else np.zeros(0)
+        tie_orgs[dsel[mv > 5e-4]] = True
+    tie_rows = np.repeat(tie_orgs, MAXC)
     alive_org = O["org_state"] == 1
     org_rows = ((np.arange(MAXC)[None, :] < O["org_ncells"].astype(np.int64)[:, None]) & alive_org[:, None]).reshape(-1)
     rep.exact("c_alive", G["c_alive"][org_rows], O["c_alive"][org_rows])
@@ -159,10 +167,13 @@ def compare_worlds(wg, w, tag, brain_tol=TOL, check_brain=True, skip=(), verbose
             continue
         g, o = G[name], O[name]
         if f.scope == "ORG":
-            g, o = g[orgs], o[orgs]
+            sel = orgs[~tie_orgs[orgs]] if f.ctype in ("float", "double") else orgs
+            g, o = g[sel], o[sel]
         elif f.scope == "CELL":
             m = org_rows if name in ("c_type", "c_parent", "c_mirror", "c_gorder", "c_id", "c_size", "c_mass", "c_elast", "c_fric", "c_rel",
                                      "c_grow", "c_maxhealth", "c_use_idle", "c_use_act", "c_storage", "c_damage") else live
+            if f.ctype in ("float", "double"):
+                m = m & ~tie_rows
             g, o = g[m], o[m]
         elif f.scope == "DEAD":
             g, o = g[dead], o[dead]
@@ -186,8 +197,10 @@ def compare_worlds(wg, w, tag, brain_tol=TOL, check_brain=True, skip=(), verbose
     # the pin joints turn it into 0.01 .. 0.08 px/s of bias velocity)
     rep.exact("c_pos[exact]", G["c_pos"][live], O["c_pos"][live]); rep.exact("d_pos[exact]", G["d_pos"][dead], O["d_pos"][dead])
     # sensors
+    sens_x = sens                                           # exact fields keep every sensor
+    sens = sens & ~tie_rows
     for name in ("c_spos",):
-        rep.exact(name, G[name][sens], O[name][sens])
+        rep.exact(name, G[name][sens_x], O[name][sens_x])
     rep.close("c_svel", G["c_svel"][sens], O["c_svel"][sens])
     rep.close("c_spin_jn", G["c_spin_jn"][sens], O["c_spin_jn"][sens], floor=max(1e-3, velocity_rms(w)))   # sensor body: mass 1
     rep.close("c_wbias", G["c_wbias"][live], O["c_wbias"][live]); rep.close("d_wbias", G["d_wbias"][dead], O["d_wbias"][dead])
@@ -202,16 +215,17 @@ def compare_worlds(wg, w, tag, brain_tol=TOL, check_brain=True, skip=(), verbose
     na = int(O["xa_off"][-1])
     rep.exact("xa_other", G["xa_other"].reshape(-1)[:na], O["xa_other"].reshape(-1)[:na])
     icm = ((np.arange(ICAP)[None, :] < O["org_ic_n"].astype(np.int64)[:, None]) & alive_org[:, None]).reshape(-1)
-    al2 = live.reshape(p.n_org, MAXC)
+    icm_f = icm & np.repeat(~tie_orgs, ICAP)                # impulses of a tie organism's own contacts and pins: see tie_orgs
+    al2 = (live & ~tie_rows).reshape(p.n_org, MAXC)
     jm = np.empty((p.n_org, NPAIR), dtype=bool)
     for s0 in range(0, p.n_org, 8192):                   # pin (i, j) exists iff both cells live
         jm[s0:s0 + 8192] = al2[s0:s0 + 8192][:, _PAIR_I] & al2[s0:s0 + 8192][:, _PAIR_J]
     jm = jm.reshape(-1)
     rep.exact("ic_code", G["ic_code"][icm], O["ic_code"][icm])
-    rep.close("ic_jn", G["ic_jn"][icm], O["ic_jn"][icm], floor=pf); rep.close("ic_jt", G["ic_jt"][icm], O["ic_jt"][icm], floor=max(pf, rms(O["ic_jn"][icm])))
+    rep.close("ic_jn", G["ic_jn"][icm_f], O["ic_jn"][icm_f], floor=pf); rep.close("ic_jt", G["ic_jt"][icm_f], O["ic_jt"][icm_f], floor=max(pf, rms(O["ic_jn"][icm_f])))
     rep.close("j_jn", G["j_jn"][jm], O["j_jn"][jm], floor=pf)
     G.drop("j_jn", "ic_jn", "ic_jt", "ic_code"); O.drop("j_jn", "ic_jn", "ic_jt", "ic_code")
-    del jm, icm
+    del jm, icm, icm_f
     # brains and memories
     IN = p.in_cap
     detail = orgs if detail_orgs is None else np.intersect1d(orgs, np.asarray(detail_orgs, dtype=np.int64))
