@@ -249,6 +249,9 @@ uint64_t sapio_launch_count(void);
  * warp per organism, or lane-packed size classes. The packed one is launched when the previous tick counted more than `n`
  * coupled organisms (default 2400; -1 = always, INT_MAX = never). Returns the previous threshold. Tuning / test knob. */
 int sapio_set_coupled_pack_from(int n);
+/* Diagnostic builds (-DSAPIO_DEBUG_FLAGS) honour A/B switches (bit 0: solver classes by rows in use, bit 1: library sqrt / divide in the
+ * pin prestep); the production build ignores them. Returns the previous value. */
+int sapio_debug_flags(int flags);
 /* Residency of the organism solver, per size class cls (cell rows <= 8 (cls + 1)): out6 = {lanes per organism, organisms per warp,
  * warps per CTA, shared-memory bytes per warp, resident CTAs on the device (0 before the first step), SMs}. Measurement hook: the
  * solver is bound by a dependent chain of wavefront steps per organism times the organisms in flight, not by memory. */

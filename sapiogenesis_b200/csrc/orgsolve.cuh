@@ -157,13 +157,19 @@ struct OrgCtx {
                 double r2 = lx * lx + ly * ly;                       // |relative_pos_i - relative_pos_j|^2 (connectTo at spawn)
                 const float d2f = (float)d2, r2f = (float)r2;
                 double d = 0.0, rest = 0.0;
+#ifdef SAPIO_DEBUG_FLAGS                               /* A/B switch 2: the library sqrt / divide of round 1 */
+                if (K.dbg & 2) {
+                    d = sqrt(d2); rest = sqrt(r2);
+                    if (d != 0.0) { const double inv = 1.0 / d; nxf = (float)(dx * inv); nyf = (float)(dy * inv); }
+                } else
+#endif
                 if (d2f > 0.f) {
                     const float iv = rsqrtf(d2f);
                     d = (double)(d2f * iv); d = fma(fma(-d, d, d2), (double)(0.5f * iv), d);                 // sqrt(d2)
                     double y = (double)iv; y = fma(y, fma(-d, y, 1.0), y);                                   // 1 / d
                     nxf = (float)(dx * y); nyf = (float)(dy * y);
                 }
-                if (r2f > 0.f) { const float iv = rsqrtf(r2f); rest = (double)(r2f * iv); rest = fma(fma(-rest, rest, r2), (double)(0.5f * iv), rest); }
+                if (r2f > 0.f && !(K.dbg & 2)) { const float iv = rsqrtf(r2f); rest = (double)(r2f * iv); rest = fma(fma(-rest, rest, r2), (double)(0.5f * iv), rest); }
                 float bias = (float)(-(K.bc_joint / K.dt) * (d - rest));
                 const int q = slot_of(i, j);
                 if (GC) { cst[q] = make_float4(nxf, nyf, bias, 0.f); s.jn[q] = jn_cached; }

@@ -664,6 +664,7 @@ int sapio_solver_info(int cls, int32_t *out6) {
     out6[4] = g_plan.ready ? g_plan.org_blocks[cls] : 0; out6[5] = g_plan.ready ? g_plan.sms : 0;
     return 0;
 }
+int sapio_debug_flags(int f) { const int old = g_debug_flags; g_debug_flags = f; return old; }      // honoured by builds with -DSAPIO_DEBUG_FLAGS only
 int sapio_set_coupled_pack_from(int n) { const int old = g_force_fallback ? 2147483647 : 2400; g_force_fallback = n == 2147483647; return old; }
 
 }  // extern "C"

@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(128) k_cross_prestep(WORLD_ARG, Workspace W, S
 // organisms -> two lists sorted by LIVING cells (counting sort: histogram, scan, scatter): coupled organisms and the rest. The solver
 // works in rank space (living cells compacted), so what sizes an organism's slab, its lanes and its chain of wavefronts is the number
 // of living cells, not the rows it occupies (an old organism carries the markers of the cells it lost).
-__global__ void k_classify_count(WORLD_ARG, Workspace W) {
+__global__ void k_classify_count(WORLD_ARG, Workspace W, int dbg) {
     for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < w.p.n_org; o += gridDim.x * blockDim.x) {
         if (w.org_state[o] != 1) continue;
         const int rows = min(max(w.org_ncells[o], 0), MAXC);
@@ -191,6 +191,9 @@ __global__ void k_classify_count(WORLD_ARG, Workspace W) {
 #pragma unroll
                 for (int bb = 0; bb < 4; bb++) { const int k = q * 16 + u * 4 + bb; live += (k < rows && ((wds[u] >> (8 * bb)) & 255u) == SAPIO_CELL_ALIVE); }
         }
+#ifdef SAPIO_DEBUG_FLAGS                               /* A/B switch 1: round-1 classes (rows in use) */
+        if (dbg & 1) live = rows;
+#endif
         W.org_nlive[o] = (uint8_t)live;
         const int nc = min(max(live, 1), MAXC);
         if (W.org_coupled[o]) { atomicAdd(&W.flags[FL_NCOUPLED], 1); atomicAdd(&W.flags[FL_CHIST + nc], 1); }
@@ -240,6 +243,7 @@ __global__ void __launch_bounds__(256) k_step_finish(WORLD_ARG, Workspace W, int
 // ------------------------------------------------------------------------------------------------------------------
 struct StepPlan { bool ready; int sms; int simple_blocks; size_t simple_smem; int comp_blocks[COMP_TIERS_N]; int org_blocks[ORG_CLASSES]; size_t org_smem[ORG_CLASSES]; cudaStream_t side[ORG_CLASSES + COMP_TIERS_N]; cudaEvent_t fork, join[ORG_CLASSES + COMP_TIERS_N]; };
 static StepPlan g_plan = {};
+static int g_debug_flags = 0;                             // sapio_debug_flags (diagnostic builds only)
 static int g_force_fallback = 0;                          // sapio_set_coupled_pack_from(INT_MAX): tests compare the two implementations
 
 static int launch_space_step(const SapioWorld &w, const Workspace &W, cudaStream_t st, char *err, size_t errlen) {
@@ -267,7 +271,7 @@ static int launch_space_step(const SapioWorld &w, const Workspace &W, cudaStream
     K.dt = (double)p.dt_phys;
     K.bc_contact = 1.0 - pow((double)p.collision_bias, K.dt);        // cpSpaceStep: biasCoef = 1 - collisionBias^dt
     K.bc_joint = 1.0 - pow((double)p.joint_error_bias, K.dt);        // bias_coef(errorBias, dt)
-    K.dt_coef_unused = 0.f;
+    K.dbg = g_debug_flags;
 
     prof_mark(st, PT_BROADPHASE);
     STEP_TRY(cudaMemsetAsync(W.flags, 0, FL_BYTES, st));
@@ -289,7 +293,7 @@ static int launch_space_step(const SapioWorld &w, const Workspace &W, cudaStream
     STEP_TRY(cudaMemsetAsync(W.nx_prev_b, 0xFF, (size_t)p.x_cap * 4, st));
     k_cross_links<<<sgrid(NB, 128), 128, 0, st>>>(w, W);
     k_cross_prestep<<<sgrid(p.x_cap, 128), 128, 0, st>>>(w, W, K);
-    k_classify_count<<<sgrid(p.n_org, 256), 256, 0, st>>>(w, W);
+    k_classify_count<<<sgrid(p.n_org, 256), 256, 0, st>>>(w, W, K.dbg);
     k_classify_scan<<<1, 32, 0, st>>>(W);
     k_classify_scatter<<<sgrid(p.n_org, 256), 256, 0, st>>>(w, W);
     LAUNCHES(20);

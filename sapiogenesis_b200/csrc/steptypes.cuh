@@ -100,7 +100,7 @@ static inline size_t carve_workspace(const SapioParams &p, char *base, Workspace
 //   v_rel.n = (vb - va).n     v_rel.t = (vb - va).t - rb*wb - ra*wa
 //   torque of impulse (jn, jt): a: -ia*ra*jt   b: -ib*rb*jt      bias impulses (along n) never touch w_bias
 // ------------------------------------------------------------------------------------------------------------------
-struct StepK { double bc_contact, bc_joint, dt; float dt_coef_unused; };
+struct StepK { double bc_contact, bc_joint, dt; int dbg; };      // dbg: A/B switches of diagnostic builds (SAPIO_DEBUG_FLAGS), 0 otherwise
 
 struct CBody { float vx, vy, w, vbx, vby, minv, iinv, r; };
 

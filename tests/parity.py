@@ -153,6 +153,23 @@ def compare_worlds(wg, w, tag, brain_tol=TOL, check_brain=True, skip=(), verbose
         dsel = np.intersect1d(orgs, np.asarray(detail_orgs, dtype=np.int64))
         mv = np.abs(G["org_move"][dsel].astype(np.float64) - O["org_move"][dsel]).reshape(len(dsel), -1).max(axis=1) if len(dsel) else np.zeros(0)
         tie_orgs[dsel[mv > 5e-4]] = True
+    tie_dead = np.zeros(p.n_dead, dtype=bool)
+    if tie_orgs.any():
+        # ... and so does everything the contact solver couples to them in this tick: the connected component of the cross-contact graph
+        nx_ = int(O["g_x_n"][0]); key = O["x_key"][:nx_].astype(np.uint64)
+        NCb = p.n_org * MAXC
+        ka = (key >> np.uint64(32)).astype(np.int64); kb = (key & np.uint64(0xFFFFFFFF)).astype(np.int64)
+        node = lambda b: np.where(b < NCb, b // MAXC, np.where(b < NCb + p.n_dead, p.n_org + (b - NCb), -1))
+        na_, nb_ = node(ka), node(kb)
+        ok = nb_ >= 0
+        tainted = np.concatenate([tie_orgs, tie_dead])
+        for _ in range(64):
+            grow = np.zeros_like(tainted)
+            grow[nb_[ok][tainted[na_[ok]]]] = True; grow[na_[ok][tainted[nb_[ok]]]] = True
+            if not (grow & ~tainted).any():
+                break
+            tainted |= grow
+        tie_orgs, tie_dead = tainted[: p.n_org].copy(), tainted[p.n_org:].copy()
     tie_rows = np.repeat(tie_orgs, MAXC)
     alive_org = O["org_state"] == 1
     org_rows = ((np.arange(MAXC)[None, :] < O["org_ncells"].astype(np.int64)[:, None]) & alive_org[:, None]).reshape(-1)
@@ -176,7 +193,8 @@ def compare_worlds(wg, w, tag, brain_tol=TOL, check_brain=True, skip=(), verbose
                 m = m & ~tie_rows
             g, o = g[m], o[m]
         elif f.scope == "DEAD":
-            g, o = g[dead], o[dead]
+            md = dead & ~tie_dead if f.ctype in ("float", "double") else dead
+            g, o = g[md], o[md]
         elif f.scope == "GLOB":
             pass
         else:
@@ -193,6 +211,18 @@ def compare_worlds(wg, w, tag, brain_tol=TOL, check_brain=True, skip=(), verbose
             rep.exact(name, g, o)
         if G[name].nbytes > (1 << 26) and name not in ("c_vel", "d_vel", "c_type", "c_mass", "d_mass"):
             G.drop(name); O.drop(name)
+    if verbose:                                             # where the largest velocity error sits: organism, size, contacts, its own velocity scale
+        gv, ov = G["c_vel"].astype(np.float64), O["c_vel"].astype(np.float64)
+        err = np.abs(gv - ov).max(axis=1) * (live & ~tie_rows)
+        r = int(np.argmax(err)); oo = r // MAXC
+        rows = slice(oo * MAXC, oo * MAXC + int(O["org_ncells"][oo]))
+        lv = O["c_alive"][rows] == 1
+        deg = O["xa_off"][oo * MAXC + 1: oo * MAXC + MAXC + 1] - O["xa_off"][oo * MAXC: oo * MAXC + MAXC]
+        vmag = np.sqrt((ov[rows][lv] ** 2).sum(axis=1))
+        bmag = np.sqrt((before.np("c_vel").astype(np.float64)[rows][lv] ** 2).sum(axis=1)) if before is not None else vmag * 0
+        print(f"{tag}: largest c_vel error {err[r]:.3e} px/s at row {r} (organism {oo}, cell {r % MAXC}): rows {int(O['org_ncells'][oo])}, living {int(lv.sum())}, "
+              f"intra contacts {int(O['org_ic_n'][oo])}, cross partners {int(deg.sum())}, |v| of its cells max {vmag.max():.2f} (before the tick {bmag.max():.2f}), "
+              f"gpu {gv[r]} oracle {ov[r]}")
     # integrated positions are one fp32 fma of identical inputs: bit-exact (an ulp of position is 0.002 .. 0.016 px in a large world, and
     # the pin joints turn it into 0.01 .. 0.08 px/s of bias velocity)
     rep.exact("c_pos[exact]", G["c_pos"][live], O["c_pos"][live]); rep.exact("d_pos[exact]", G["d_pos"][dead], O["d_pos"][dead])
@@ -210,7 +240,13 @@ def compare_worlds(wg, w, tag, brain_tol=TOL, check_brain=True, skip=(), verbose
     # friction impulses are bounded by mu * jn: their error is measured on the scale of the normal impulses
     rms = lambda a: float(np.sqrt(np.mean(np.asarray(a, dtype=np.float64) ** 2))) if len(a) else 0.0
     pf = max(1e-3, momentum_scale(w))
-    rep.close("x_jn", G["x_jn"][:nx], O["x_jn"][:nx], floor=pf); rep.close("x_jt", G["x_jt"][:nx], O["x_jt"][:nx], floor=max(pf, rms(O["x_jn"][:nx])))
+    xm = np.ones(nx, dtype=bool)
+    if tie_orgs.any():                                      # contacts of a tie organism's component (see tie_orgs)
+        kk = O["x_key"][:nx].astype(np.uint64); NCb = p.n_org * MAXC
+        for b in ((kk >> np.uint64(32)).astype(np.int64), (kk & np.uint64(0xFFFFFFFF)).astype(np.int64)):
+            io = b < NCb; idd = (b >= NCb) & (b < NCb + p.n_dead)
+            xm[io] &= ~tie_orgs[b[io] // MAXC]; xm[idd] &= ~tie_dead[b[idd] - NCb]
+    rep.close("x_jn", G["x_jn"][:nx][xm], O["x_jn"][:nx][xm], floor=pf); rep.close("x_jt", G["x_jt"][:nx][xm], O["x_jt"][:nx][xm], floor=max(pf, rms(O["x_jn"][:nx])))
     rep.exact("xa_off", G["xa_off"], O["xa_off"])
     na = int(O["xa_off"][-1])
     rep.exact("xa_other", G["xa_other"].reshape(-1)[:na], O["xa_other"].reshape(-1)[:na])

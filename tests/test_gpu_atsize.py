@@ -29,6 +29,7 @@ def one_tick_parity(oracle, w, eng, phases, tag, **kw):
     host = w.to("cpu")
     t1 = time.time()
     before = None; kw.pop("check_untouched", None)
+    tail = kw.pop("tail", None)                                               # (level in units of the rms, largest admitted fraction of the living bodies above it)
     w.t["g_stats"].view(-1)[14] = 0                                           # rare-path bits: evidence of THIS tick only
     st0 = w.stats()
     eng.tick(1, phases); eng.synchronize()
@@ -36,6 +37,9 @@ def one_tick_parity(oracle, w, eng, phases, tag, **kw):
     t2 = time.time()
     st = w.stats()
     so = host.stats()
+    icn = host.np("org_ic_n")[host.np("org_state") == 1]
+    print(f"{tag}: overflow counter {st['overflow']} (oracle {so['overflow']}), most intra contacts of one organism {int(icn.max()) if icn.size else 0}")
+    assert st["overflow"] == so["overflow"] == 0, "a capacity overflow (contacts per organism, cross contacts, partners per body) voids the comparison"
     for k in ("births", "deaths", "cell_deaths", "dead_removed", "thinks", "trains", "xcontacts", "icontacts", "birth_fail_place", "org_ticks"):
         assert st[k] == so[k], (k, st[k], so[k])
     req = host.np("org_req")
@@ -43,6 +47,13 @@ def one_tick_parity(oracle, w, eng, phases, tag, **kw):
     newborn = np.nonzero(host.np("org_birth_tick") == host.tick - 1)[0]
     detail = np.union1d(detail, newborn)
     rep = compare_worlds(w, host, tag, detail_orgs=detail, before=before, **kw)
+    if tail is not None:
+        live = (host.np("c_alive") == 1) & np.repeat(host.np("org_state") == 1, MAXC)
+        gv, ov = w.np("c_vel").astype(np.float64)[live], host.np("c_vel").astype(np.float64)[live]
+        rms = float(np.sqrt((ov ** 2).mean())); err = np.abs(gv - ov).max(axis=1)
+        above = int((err > tail[0] * rms).sum())
+        print(f"{tag}: {above} of {len(err)} living cells above {tail[0]:g} of the velocity rms {rms:.1f} px/s ({int((err > 1e-4 * rms).sum())} above 1e-4, {int((err > 3e-5 * rms).sum())} above 3e-5)")
+        assert above <= tail[1] * len(err), "the tail of the solver's fp32 error is heavier than stated"
     rare = st["rare_paths"]
     print(f"{tag}: host copy {t1 - t0:.1f} s, both ticks {t2 - t1:.1f} s, comparison {time.time() - t2:.1f} s")
     print(f"{tag}: organisms {int((host.np('org_state') == 1).sum())}, cross contacts {st['xcontacts']}, intra {st['icontacts']}, coupled {st['coupled']}, "
@@ -103,7 +114,12 @@ def test_aged_world_tick_matches_oracle(oracle, aged_world):
         # the worst body is off by 1.1e-5 of the velocity change of its own organism, tools/debug_aged.py), which is 1e-4 of the
         # world's rms; 1 % of the bodies exceed 1e-5 of the rms, 34 of 372k exceed 3e-5, none 1e-4. Energies O(2e3) pass through
         # ~2n dependent fp32 updates per tick (2 cells of 372k above 1e-5); the Adam moments of a 200-row batch sum 800 terms.
-        st, _ = one_tick_parity(oracle, w, eng, PH_ALL, f"aged world, tick {w.tick}", phys_tol=3e-4, adam_tol=5e-4, extra_tols={"c_energy": 3e-5})
+        # Round 2 measured the tail on one state with every solver variant (tools/debug_accuracy.py: classes by rows or by living cells,
+        # library or Newton-refined square roots give the same errors to four digits): of 372k bodies 36-86 are above 3e-5 of the rms, 2-12
+        # above 1e-4, and ONE organism (10 living cells of 22 rows, flying at 82 px/s, three times the rms) sits at 1.3e-4 .. 6.2e-4 tick
+        # after tick -- 2e-4 of its own speed. The bound is therefore 1e-3 of the rms for the worst body, with the tail counted below.
+        st, _ = one_tick_parity(oracle, w, eng, PH_ALL, f"aged world, tick {w.tick}", phys_tol=1e-3, adam_tol=5e-4, extra_tols={"c_energy": 3e-5},
+                                tail=(3e-4, 1e-4))
         eng.tick(16)                                                          # another phase of the think / train stagger each time
     assert st["coupled"] > 2400 and st["xcontacts"] > 4096
 

@@ -104,7 +104,7 @@ def test_ownership_moves_with_the_heart_and_births_cross_the_cut():
     from sapiogenesis_b200.engine import Engine
     from sapiogenesis_b200.slabs import LocalComm, SlabDriver, split_world
     from sapiogenesis_b200.synth import build_world
-    w, eng = build_world(1500, seed=5, area_per_org=120_000.0, food_per_org=1.0)
+    w, eng = build_world(1500, seed=5, area_per_org=120_000.0, food_per_org=1.0, slot_factor=3.4)     # room for the birth wave up to the population limit
     w.p.repro_ticks = 40; w.p.population_limit = 4000; eng.refresh()
     w.t["c_vel"][:, 0] += 200.0 * torch.sign(torch.randn(w.t["c_vel"].shape[0], device="cuda"))      # everybody on the move, left or right
     eng.tick(30); eng.synchronize()
@@ -120,6 +120,7 @@ def test_ownership_moves_with_the_heart_and_births_cross_the_cut():
             for s in slabs: s.world.t["c_energy"][:] = s.world.t["c_storage"]
             pw.t["c_energy"][:] = pw.t["c_storage"]
         drv.tick(1); pe.tick(1)
+    drv.exchange()                                                           # ownership follows the heart at the next exchange: apply the hand-over of the last tick's motion
     drv.synchronize(); pe.synchronize()
     seen, moved = {}, 0
     for s in slabs:
