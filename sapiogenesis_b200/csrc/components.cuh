@@ -152,7 +152,7 @@ struct CompS {                                   // CTA header, at the start of 
 __device__ __forceinline__ void comp_sync() { __syncthreads(); }
 
 // cpArbiterApplyImpulse on two bodies resident in shared memory (the arithmetic of contact_apply in steptypes.cuh; the effective
-// masses come from the record, and accumulators below 256 are clamped in fp32 like the intra contacts of OrgCtx::contacts_pass)
+// masses come from the record; accumulate-and-clamp as contact_accumulate, like the intra contacts of OrgCtx::contacts_pass)
 __device__ __forceinline__ void xcon_apply(unsigned char *sm, XCon &c) {
     float4 va = *reinterpret_cast<float4 *>(sm + c.vmA), ba = *reinterpret_cast<float4 *>(sm + c.bbA);
     float4 vb = *reinterpret_cast<float4 *>(sm + c.vmB), bb = *reinterpret_cast<float4 *>(sm + c.bbB);
@@ -163,15 +163,8 @@ __device__ __forceinline__ void xcon_apply(unsigned char *sm, XCon &c) {
     const float vrn = dvx * nx + dvy * ny;
     const float vrt = (dvy * nx - dvx * ny) - bb.w * vb.z - ba.w * va.z;
     const float jbnOld = ac.z, jBias = fmaxf(jbnOld + (g.z - vbn) * nMass, 0.0f);
-    const float jnO = ac.x, jtO = ac.y, jnI = -(g.w + vrn) * nMass, jtI = -vrt * tMass;
     float dn, dtg, jnS, jtS;
-    if (fabsf(jnO) < 256.f && fabsf(jtO) < 256.f) {
-        const float jnA = fmaxf(jnO + jnI, 0.0f), jtM = mu * jnA, jtA = fminf(fmaxf(jtO + jtI, -jtM), jtM);
-        jnS = jnA; jtS = jtA; dn = jnA - jnO; dtg = jtA - jtO;
-    } else {
-        const double jnA = fmax((double)jnO + (double)jnI, 0.0), jtM = (double)mu * jnA, jtA = fmin(fmax((double)jtO + (double)jtI, -jtM), jtM);
-        jnS = (float)jnA; jtS = (float)jtA; dn = (float)(jnA - (double)jnO); dtg = (float)(jtA - (double)jtO);
-    }
+    contact_accumulate(ac.x, ac.y, -(g.w + vrn) * nMass, -vrt * tMass, mu, jnS, jtS, dn, dtg);
     *reinterpret_cast<float4 *>(&c.jn) = make_float4(jnS, jtS, jBias, 0.f);
     const float bj = jBias - jbnOld;
     ba.x -= nx * bj * va.w; ba.y -= ny * bj * va.w;

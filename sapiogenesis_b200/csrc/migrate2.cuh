@@ -22,7 +22,8 @@ struct MigWs {
     int *emig;            // [MAX_RECORDS] chosen slots
     int *counters;        // 0 chosen, 1 packed, 2 accepted, 3 dropped (no viable place / no free slot), 4..7 totals since the world began
     double *rect;         // [MAX_RECORDS][6] box relative to the heart (4), heart position (2)
-    uint32_t *mask;       // [MAX_RECORDS][12] viable candidates
+    uint32_t *mask;       // [MAX_RECORDS][12] viable candidates among the first upto[r] (the rest: not evaluated)
+    int *upto;            // [MAX_RECORDS] candidates evaluated by k_mig_viable (a multiple of 32, or all of them)
     int *slot;            // [MAX_RECORDS] destination slot or -1
     double *delta;        // [MAX_RECORDS][2] translation
     double *acc_rect;     // [MAX_RECORDS][4] boxes of the accepted arrivals (absolute)
@@ -183,40 +184,58 @@ __device__ __forceinline__ void mig_candidate(const SapioWorld &w, int r, int k,
     rng4(w.p.seed, w.g_next_uid[0] + r, (int32_t)w.g_tick[0], RNG_MIGRATE, (uint32_t)k, q);
     *x = (double)u01(q[0]) * (double)w.p.width; *y = (double)u01(q[1]) * (double)w.p.height;
 }
-// candidates of one arrival (one CTA, a thread per candidate) against the world's bounds and every living organism's box
-#define MIG_TILE 256
-__global__ void __launch_bounds__(384) k_mig_viable(WORLD_ARG, MigWs M, const char *buf) {
+// One candidate of arrival r against the world's bounds and every living organism's box, by the lanes of a warp (strided over the
+// organisms). A conservative fp32 test (boxes rounded outwards) rejects almost every pair; the exact double predicate decides the rest.
+__device__ __forceinline__ bool mig_blocked_by_residents(const SapioWorld &w, const double d[4], int first, int stride) {
+    const float f0 = __double2float_rd(d[0]), f1 = __double2float_rd(d[1]), f2 = __double2float_ru(d[2]), f3 = __double2float_ru(d[3]);
+    bool blocked = false;
+    for (int o = first; o < w.p.n_org && !blocked; o += stride) {
+        if (w.org_state[o] != 1) continue;
+        const double *R = w.org_rect + 4 * o;
+        const double r0 = R[0], r1 = R[1], r2 = R[2], r3 = R[3];
+        if (f2 < __double2float_rd(r0) || f0 > __double2float_ru(r2) || f3 < __double2float_rd(r1) || f1 > __double2float_ru(r3)) continue;
+        const double rr[4] = {r0, r1, r2, r3};
+        blocked = mig_rects_block(d, rr);
+    }
+    return blocked;
+}
+// Candidates are tried in order and the first viable one wins (get_new_organism_position, sprites.py:194-219), so they are evaluated
+// lazily: 32 at a time (MIG_VTHREADS / 32 slices of the organisms per candidate), stopping after the first round that holds a viable
+// one. In a world that is 5 % covered that is the first round; k_mig_resolve evaluates further candidates itself in the rare case
+// that every evaluated one is blocked by an earlier arrival. (All 360 x every organism used to cost 24 ms per exchange.)
+#define MIG_VTHREADS 512
+__global__ void __launch_bounds__(MIG_VTHREADS) k_mig_viable(WORLD_ARG, MigWs M, const char *buf) {
     const SapioMigBufHeader *H = reinterpret_cast<const SapioMigBufHeader *>(buf);
     const int n = H->magic == SAPIO_MIG_MAGIC ? min(H->n_records, SAPIO_MIG_MAX_RECORDS) : 0;
-    __shared__ double tile[MIG_TILE][4];
-    __shared__ int tile_n;
-    const int k = threadIdx.x;
+    __shared__ int blocked_by[32];
+    __shared__ uint32_t round_mask;
+    const int cand = threadIdx.x & 31, slice = threadIdx.x >> 5, slices = MIG_VTHREADS / 32;
     for (int r = blockIdx.x; r < n; r += gridDim.x) {
         const double *R = M.rect + 6 * r;
-        double d[4] = {0, 0, 0, 0};
-        bool ok = k < SAPIO_MIG_CANDIDATES;
-        if (ok) {
-            double x, y; mig_candidate(w, r, k, &x, &y);
-            d[0] = R[0] + x; d[1] = R[1] + y; d[2] = R[2] + x; d[3] = R[3] + y;
-            ok = !(d[0] < 0 || d[2] > (double)w.p.width || d[1] < 0 || d[3] > (double)w.p.height);         // sprites.py:170-171
-        }
-        for (int o0 = 0; o0 < w.p.n_org; o0 += MIG_TILE) {
+        int upto = 0;
+        for (int k0 = 0; k0 < SAPIO_MIG_CANDIDATES; k0 += 32) {
             __syncthreads();
-            if (threadIdx.x == 0) tile_n = 0;
+            if (threadIdx.x < 32) blocked_by[threadIdx.x] = 0;
             __syncthreads();
-            if (threadIdx.x < MIG_TILE) {
-                const int o = o0 + threadIdx.x;
-                if (o < w.p.n_org && w.org_state[o] == 1) {
-                    const int t = atomicAdd(&tile_n, 1);
-                    tile[t][0] = w.org_rect[4 * o]; tile[t][1] = w.org_rect[4 * o + 1]; tile[t][2] = w.org_rect[4 * o + 2]; tile[t][3] = w.org_rect[4 * o + 3];
-                }
+            const int k = k0 + cand;
+            bool ok = k < SAPIO_MIG_CANDIDATES;
+            double d[4] = {0, 0, 0, 0};
+            if (ok) {
+                double x, y; mig_candidate(w, r, k, &x, &y);
+                d[0] = R[0] + x; d[1] = R[1] + y; d[2] = R[2] + x; d[3] = R[3] + y;
+                ok = !(d[0] < 0 || d[2] > (double)w.p.width || d[1] < 0 || d[3] > (double)w.p.height);         // sprites.py:170-171
+            }
+            if (ok && mig_blocked_by_residents(w, d, slice, slices)) blocked_by[cand] = 1;
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                const uint32_t m = __ballot_sync(FULL, ok && !blocked_by[cand]);
+                if (threadIdx.x == 0) { M.mask[12 * r + (k0 >> 5)] = m; round_mask = m; }
             }
             __syncthreads();
-            if (ok) for (int t = 0; t < tile_n; t++) if (mig_rects_block(d, tile[t])) { ok = false; break; }
+            upto = min(k0 + 32, SAPIO_MIG_CANDIDATES);
+            if (round_mask) break;
         }
-        const uint32_t b = __ballot_sync(FULL, ok);
-        if ((threadIdx.x & 31) == 0) M.mask[12 * r + (threadIdx.x >> 5)] = b;
-        __syncthreads();
+        if (threadIdx.x == 0) M.upto[r] = upto;
     }
 }
 // in record order: the first viable candidate that no earlier arrival's box blocks; the j-th accepted takes the j-th smallest free slot
@@ -227,11 +246,16 @@ __global__ void __launch_bounds__(32) k_mig_resolve(WORLD_ARG, MigWs M, const ch
     int n_acc = 0, n_drop = 0, cursor = 0;
     for (int r = 0; r < n; r++) {
         const double *R = M.rect + 6 * r;
+        const int upto = M.upto[r];
         int chosen = -1; double cx = 0, cy = 0;
         for (int k = 0; k < SAPIO_MIG_CANDIDATES && chosen < 0; k++) {
-            if (!((M.mask[12 * r + (k >> 5)] >> (k & 31)) & 1u)) continue;
             double x, y; mig_candidate(w, r, k, &x, &y);
             const double d[4] = {R[0] + x, R[1] + y, R[2] + x, R[3] + y};
+            if (k < upto) { if (!((M.mask[12 * r + (k >> 5)] >> (k & 31)) & 1u)) continue; }
+            else {                                                   // beyond what k_mig_viable evaluated: the warp does it (rare)
+                if (d[0] < 0 || d[2] > (double)w.p.width || d[1] < 0 || d[3] > (double)w.p.height) continue;
+                if (__any_sync(FULL, mig_blocked_by_residents(w, d, lane, 32))) continue;
+            }
             bool blocked = false;
             for (int a = lane; a < n_acc; a += 32) blocked |= mig_rects_block(d, M.acc_rect + 4 * a);
             if (!__any_sync(FULL, blocked)) { chosen = k; cx = x; cy = y; }

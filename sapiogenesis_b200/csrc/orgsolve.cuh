@@ -336,18 +336,9 @@ struct OrgCtx {
                 const float vbn = (bbv.x - ba.x) * nx + (bbv.y - ba.y) * ny;
                 const float vrn = dvx * nx + dvy * ny;
                 const float vrt = (dvy * nx - dvx * ny) - bbv.w * vb.z - ba.w * va.z;
-                // accumulate and clamp in double, apply the difference: a resting contact squeezed between pinned cells carries
-                // 1e5 of impulse, and ulp(1e5) = 0.008 in fp32 would quantise what a sweep can add to it
                 const float jbnOld = ac.z, jBias = fmaxf(jbnOld + (e0.z - vbn) * nMass, 0.0f);
-                const float jnO = ac.x, jtO = ac.y, jnI = -(e0.w + vrn) * nMass, jtI = -vrt * tMass, mu = e1.z;
                 float dn, dtg, jnS, jtS;
-                if (fabsf(jnO) < 256.f && fabsf(jtO) < 256.f) {           // ordinary contact: fp32 resolves its accumulators to 3e-5
-                    const float jnA = fmaxf(jnO + jnI, 0.0f), jtM = mu * jnA, jtA = fminf(fmaxf(jtO + jtI, -jtM), jtM);
-                    jnS = jnA; jtS = jtA; dn = jnA - jnO; dtg = jtA - jtO;
-                } else {
-                    const double jnA = fmax((double)jnO + (double)jnI, 0.0), jtM = (double)mu * jnA, jtA = fmin(fmax((double)jtO + (double)jtI, -jtM), jtM);
-                    jnS = (float)jnA; jtS = (float)jtA; dn = (float)(jnA - (double)jnO); dtg = (float)(jtA - (double)jtO);
-                }
+                contact_accumulate(ac.x, ac.y, -(e0.w + vrn) * nMass, -vrt * tMass, e1.z, jnS, jtS, dn, dtg);       // steptypes.cuh: double accuracy in fp32
                 s.cacc[pos] = make_float4(jnS, jtS, jBias, 0.f);
                 const float bj = jBias - jbnOld;
                 ba.x -= nx * bj * va.w; ba.y -= ny * bj * va.w;

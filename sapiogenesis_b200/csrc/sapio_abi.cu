@@ -80,7 +80,7 @@ static size_t carve_all(const SapioParams &p, char *base, AllWs *A) {
     A->probe = (int *)take(256);
     {
         MigWs &M = A->mig; const size_t R = SAPIO_MIG_MAX_RECORDS;
-        M.emig = (int *)take(R * 4); M.counters = (int *)take(256); M.rect = (double *)take(R * 6 * 8); M.mask = (uint32_t *)take(R * 12 * 4);
+        M.emig = (int *)take(R * 4); M.counters = (int *)take(256); M.rect = (double *)take(R * 6 * 8); M.mask = (uint32_t *)take(R * 12 * 4); M.upto = (int *)take(R * 4);
         M.slot = (int *)take(R * 4); M.delta = (double *)take(R * 2 * 8); M.acc_rect = (double *)take(R * 4 * 8);
     }
     if (p.slab_mode) {
@@ -554,7 +554,7 @@ int sapio_migrate_in(const SapioWorld *w, void *ws, size_t ws_bytes, void *d_buf
     const int cap = SAPIO_MIG_MAX_RECORDS;                              // the count lives in the buffer, on the device
     k_org_rects<<<stream_grid(w->p.n_org), 256, 0, st>>>(*w, nullptr);
     k_mig_prepare<<<(cap + 127) / 128, 128, 0, st>>>(*w, T, A.mig, (const char *)d_buf);
-    k_mig_viable<<<148, 384, 0, st>>>(*w, A.mig, (const char *)d_buf);
+    k_mig_viable<<<SAPIO_MIG_MAX_RECORDS < 592 ? SAPIO_MIG_MAX_RECORDS : 592, MIG_VTHREADS, 0, st>>>(*w, A.mig, (const char *)d_buf);
     k_mig_resolve<<<1, 32, 0, st>>>(*w, A.mig, (const char *)d_buf);
     k_mig_unpack<<<148, 256, 0, st>>>(*w, T, A.mig, (char *)d_buf);
     k_mig_clear_dead<<<stream_grid(w->p.n_dead), 256, 0, st>>>(*w, A.mig);

@@ -110,6 +110,28 @@ __device__ __forceinline__ float contact_bias(double d, float ra, float rb, cons
 }
 __device__ __forceinline__ float contact_vrn(const CBody &A, const CBody &B, float nx, float ny) { return (B.vx - A.vx) * nx + (B.vy - A.vy) * ny; }
 
+// The accumulate-and-clamp of cpArbiterApplyImpulse,
+//     jnAcc' = max(jnAcc + jn, 0)          jtAcc' = clamp(jtAcc + jt, -mu jnAcc', mu jnAcc')         apply (jnAcc' - jnAcc, jtAcc' - jtAcc),
+// to the accuracy of a double-precision evaluation but in fp32 arithmetic: a resting contact squeezed between pinned cells carries 1e5 of
+// impulse, and ulp(1e5) = 0.008 would quantise what a sweep adds if the DIFFERENCE of the rounded accumulators were applied. Unclamped, the
+// difference is the increment itself, exactly; the sign of a rounded sum is the sign of the exact one; and the friction bound mu * jnAcc' is
+// carried as an unevaluated sum of two floats (the product's and the sum's rounding errors from an FMA and a TwoSum), so the clamped branch
+// loses nothing either. Replaces ~30 double-pipe instructions on the chain of every level step of an aged organism (most of its contacts
+// carry more than the 256 below which round 1 stayed in fp32).
+__device__ __forceinline__ void contact_accumulate(float jnO, float jtO, float jnI, float jtI, float mu, float &jnS, float &jtS, float &dn, float &dtg) {
+    const float sN = jnO + jnI;
+    const bool pos = sN > 0.0f;
+    jnS = pos ? sN : 0.0f; dn = pos ? jnI : -jnO;
+    const float bN = sN - jnO, eN = pos ? (jnO - (sN - bN)) + (jnI - bN) : 0.0f;          // jnAcc' == jnS + eN exactly
+    const float mh = mu * jnS, ml = fmaf(mu, jnS, -mh) + mu * eN;                          // mu * jnAcc' == mh + ml to ~1e-14
+    const float sT = jtO + jtI, bT = sT - jtO, eT = (jtO - (sT - bT)) + (jtI - bT);        // jtAcc + jt == sT + eT exactly
+    const float sg = sT < 0.0f ? -1.0f : 1.0f;
+    if ((fabsf(sT) - mh) + (sg * eT - ml) > 0.0f) {                                        // beyond the friction cone: clamp to +-(mh + ml)
+        jtS = sg * (mh + ml);
+        dtg = (sg * mh - jtO) + sg * ml;
+    } else { jtS = sT; dtg = jtI; }
+}
+
 // cpArbiterApplyCachedImpulse
 __device__ __forceinline__ void contact_warm(CBody &A, CBody &B, float nx, float ny, float jn, float jt, float dt_coef) {
     jn *= dt_coef; jt *= dt_coef;
@@ -127,15 +149,12 @@ __device__ __forceinline__ void contact_apply(CBody &A, CBody &B, float nx, floa
     float vrt = (dvy * nx - dvx * ny) - B.r * B.w - A.r * A.w;
     float jbn = (bias - vbn) * nMass, jbnOld = jBias;
     jBias = fmaxf(jbnOld + jbn, 0.0f);
-    // accumulate and clamp in double, apply the difference (see OrgCtx::contacts_pass)
-    const double jnOld = (double)jnAcc, jnNew = fmax(jnOld + (double)(-(bounce + vrn) * nMass), 0.0);
-    const double jtMax = (double)mu * jnNew;
-    const double jtOld = (double)jtAcc, jtNew = fmin(fmax(jtOld + (double)(-vrt * tMass), -jtMax), jtMax);
-    jnAcc = (float)jnNew; jtAcc = (float)jtNew;
+    float jnS, jtS, dn, dtg;
+    contact_accumulate(jnAcc, jtAcc, -(bounce + vrn) * nMass, -vrt * tMass, mu, jnS, jtS, dn, dtg);
+    jnAcc = jnS; jtAcc = jtS;
     float bj = jBias - jbnOld;
     A.vbx -= nx * bj * A.minv; A.vby -= ny * bj * A.minv;
     B.vbx += nx * bj * B.minv; B.vby += ny * bj * B.minv;
-    float dn = (float)(jnNew - jnOld), dtg = (float)(jtNew - jtOld);
     float jx = nx * dn - ny * dtg, jy = nx * dtg + ny * dn;
     A.vx -= jx * A.minv; A.vy -= jy * A.minv; A.w -= A.iinv * A.r * dtg;
     B.vx += jx * B.minv; B.vy += jy * B.minv; B.w -= B.iinv * B.r * dtg;

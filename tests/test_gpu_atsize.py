@@ -118,7 +118,8 @@ def test_aged_world_tick_matches_oracle(oracle, aged_world):
         # library or Newton-refined square roots give the same errors to four digits): of 372k bodies 36-86 are above 3e-5 of the rms, 2-12
         # above 1e-4, and ONE organism (10 living cells of 22 rows, flying at 82 px/s, three times the rms) sits at 1.3e-4 .. 6.2e-4 tick
         # after tick -- 2e-4 of its own speed. The bound is therefore 1e-3 of the rms for the worst body, with the tail counted below.
-        st, _ = one_tick_parity(oracle, w, eng, PH_ALL, f"aged world, tick {w.tick}", phys_tol=1e-3, adam_tol=5e-4, extra_tols={"c_energy": 3e-5},
+        st, _ = one_tick_parity(oracle, w, eng, PH_ALL, f"aged world, tick {w.tick}", phys_tol=1e-3, adam_tol=5e-4,
+                                extra_tols={"c_energy": 3e-5, "org_gas_refund": 5e-4},          # the refund is a difference of energies up to 2e3: ulp(2048) = 2.4e-4
                                 tail=(3e-4, 1e-4))
         eng.tick(16)                                                          # another phase of the think / train stagger each time
     assert st["coupled"] > 2400 and st["xcontacts"] > 4096
