@@ -25,28 +25,25 @@ struct HaloWs {
 struct DeadRec { float pos[2], vel[2], ang, angvel, vbias[2], wbias, mass, mass0, size, elast, fric; int64_t owner; int32_t state, src_slot; };   // 72 bytes
 struct DeadBufHeader { int32_t magic, n, dropped, pad; };
 
-// owned living organisms with the heart in [x_lo, x_hi), ascending slot (deterministic), at most `cap`
-__global__ void __launch_bounds__(256) k_halo_choose(WORLD_ARG, MigWs M, float x_lo, float x_hi, int cap) {
-    __shared__ int s_base, s_warp[8];
-    const int n_org = w.p.n_org, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) s_base = 0;
-    __syncthreads();
-    for (int i0 = 0; i0 < n_org; i0 += 256) {
-        const int o = i0 + tid;
+// owned living organisms with the heart in [x_lo, x_hi), ascending slot (deterministic), at most `cap`: flags, an exclusive scan
+// (grid.cuh), scatter -- three grid-wide launches instead of one CTA walking every slot
+__global__ void __launch_bounds__(256) k_halo_flag(WORLD_ARG, float x_lo, float x_hi, int *__restrict__ flag) {
+    const int n_org = w.p.n_org;
+    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o <= n_org; o += gridDim.x * blockDim.x) {
         bool in = false;
         if (o < n_org && w.org_state[o] == 1 && !(w.org_flags[o] & SAPIO_F_GHOST)) { const float hx = w.c_pos[2 * (o * MAXC)]; in = hx >= x_lo && hx < x_hi; }
-        const uint32_t b = __ballot_sync(FULL, in);
-        if (lane == 0) s_warp[wid] = __popc(b);
-        __syncthreads();
-        int before = s_base;
-        for (int k = 0; k < wid; k++) before += s_warp[k];
-        const int pos = before + __popc(b & ((1u << lane) - 1u));
-        if (in && pos < cap) M.emig[pos] = o;
-        __syncthreads();
-        if (tid == 0) { int t = s_base; for (int k = 0; k < 8; k++) t += s_warp[k]; s_base = t; }
-        __syncthreads();
+        flag[o] = in;
     }
-    if (tid == 0) { M.counters[MC_CHOSEN] = min(s_base, cap); if (s_base > cap) atomicAdd((unsigned long long *)&w.g_stats[SAPIO_STAT_OVERFLOW], 1ull); }
+}
+__global__ void __launch_bounds__(256) k_halo_choose(WORLD_ARG, MigWs M, const int *__restrict__ flag, const int *__restrict__ off, int cap) {
+    const int n_org = w.p.n_org;
+    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n_org; o += gridDim.x * blockDim.x)
+        if (flag[o] && off[o] < cap) M.emig[off[o]] = o;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const int total = off[n_org];
+        M.counters[MC_CHOSEN] = min(total, cap);
+        if (total > cap) atomicAdd((unsigned long long *)&w.g_stats[SAPIO_STAT_OVERFLOW], 1ull);
+    }
 }
 // owned dead cells with the centre in [x_lo, x_hi): records straight into the buffer (order: atomic, the receiver maps by sender slot)
 __global__ void __launch_bounds__(256) k_halo_pack_dead(WORLD_ARG, RulesWs R, float x_lo, float x_hi, char *buf, size_t cap_bytes) {
@@ -68,40 +65,59 @@ __global__ void __launch_bounds__(256) k_halo_pack_dead(WORLD_ARG, RulesWs R, fl
 }
 __global__ void k_halo_dead_header(char *buf) { DeadBufHeader *H = reinterpret_cast<DeadBufHeader *>(buf); H->magic = SAPIO_MIG_MAGIC; H->n = 0; H->dropped = 0; H->pad = 0; }
 
-// ---- arriving: slots. One warp, in record order: last tick's slot if the ghost is still there (same uid), else the highest free slot.
-__global__ void __launch_bounds__(32) k_halo_assign(WORLD_ARG, const __grid_constant__ SapioMigTable T, MigWs M, HaloWs Hw, int side, const char *buf) {
+// ---- arriving: slots. A ghost that is still here keeps last tick's slot (same uid): a thread per record. The others -- new ghosts,
+// organisms that changed their mapping -- are served by one warp in record order: the slot that already holds the uid, else the highest
+// free slot (deterministic; a handful per tick, where the serial form walked ~900 records with four dependent global loads each).
+__global__ void __launch_bounds__(256) k_halo_assign_kept(WORLD_ARG, const __grid_constant__ SapioMigTable T, MigWs M, HaloWs Hw, int side, const char *buf) {
     const SapioMigBufHeader *H = reinterpret_cast<const SapioMigBufHeader *>(buf);
     const int n = H->magic == SAPIO_MIG_MAGIC ? min(H->n_records, SAPIO_MIG_MAX_RECORDS) : 0;
-    const int lane = lane_id();
-    int cursor = w.p.n_org - 1, n_acc = 0, n_drop = 0;
-    for (int r = 0; r < n; r++) {
+    const int stamp = (int)w.g_tick[0] + 1;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
         const char *rec = buf + H->offset[r];
         const SapioMigHeader h = *reinterpret_cast<const SapioMigHeader *>(rec);
         const int64_t uid = *reinterpret_cast<const int64_t *>(rec + mig_field_offset(T, h, T.i_uid));
         int slot = Hw.ghost_slot[side][h.src_slot] - 1;
         if (slot >= 0 && !(w.org_state[slot] == 1 && w.org_uid[slot] == uid)) slot = -1;
-        if (slot < 0) {
+        M.slot[r] = slot >= 0 ? slot : -2;                           // -2: k_halo_assign decides
+        if (slot >= 0) Hw.refreshed[slot] = stamp;
+    }
+}
+__global__ void __launch_bounds__(32) k_halo_assign(WORLD_ARG, const __grid_constant__ SapioMigTable T, MigWs M, HaloWs Hw, int side, const char *buf) {
+    const SapioMigBufHeader *H = reinterpret_cast<const SapioMigBufHeader *>(buf);
+    const int n = H->magic == SAPIO_MIG_MAGIC ? min(H->n_records, SAPIO_MIG_MAX_RECORDS) : 0;
+    const int lane = lane_id();
+    int cursor = w.p.n_org - 1, n_acc = 0, n_drop = 0;
+    for (int r0 = 0; r0 < n; r0 += 32) {
+        const int mine = r0 + lane < n ? M.slot[r0 + lane] : 0;
+        n_acc += __popc(__ballot_sync(FULL, r0 + lane < n && mine >= 0));
+        uint32_t pending = __ballot_sync(FULL, r0 + lane < n && mine == -2);
+        while (pending) {
+            const int r = r0 + __ffs(pending) - 1; pending &= pending - 1;
+            const char *rec = buf + H->offset[r];
+            const SapioMigHeader h = *reinterpret_cast<const SapioMigHeader *>(rec);
+            const int64_t uid = *reinterpret_cast<const int64_t *>(rec + mig_field_offset(T, h, T.i_uid));
+            int slot = -1;
             // the same organism may already live here under another mapping (it was ours, or came from the other side): look for its uid
             for (int base = 0; base < w.p.n_org && slot < 0; base += 32) {
                 const int o = base + lane;
                 const uint32_t hit = __ballot_sync(FULL, o < w.p.n_org && w.org_state[o] == 1 && w.org_uid[o] == uid);
                 if (hit) slot = base + __ffs(hit) - 1;
             }
-        }
-        if (slot < 0) {
-            while (cursor >= 0) {                                   // highest free slot: the owned organisms keep the low ones
-                const int o = cursor - lane;
-                const uint32_t fb = __ballot_sync(FULL, o >= 0 && w.org_state[o] == 0 && Hw.refreshed[o] != (int)w.g_tick[0] + 1);
-                if (fb) { slot = cursor - (__ffs(fb) - 1); cursor = slot - 1; break; }
-                cursor -= 32;
+            if (slot < 0) {
+                while (cursor >= 0) {                               // highest free slot: the owned organisms keep the low ones
+                    const int o = cursor - lane;
+                    const uint32_t fb = __ballot_sync(FULL, o >= 0 && w.org_state[o] == 0 && Hw.refreshed[o] != (int)w.g_tick[0] + 1);
+                    if (fb) { slot = cursor - (__ffs(fb) - 1); cursor = slot - 1; break; }
+                    cursor -= 32;
+                }
             }
+            if (lane == 0) {
+                M.slot[r] = slot;
+                if (slot >= 0) { Hw.ghost_slot[side][h.src_slot] = slot + 1; Hw.refreshed[slot] = (int)w.g_tick[0] + 1; }
+            }
+            if (slot >= 0) n_acc++; else n_drop++;
+            __syncwarp();
         }
-        if (lane == 0) {
-            M.slot[r] = slot;
-            if (slot >= 0) { Hw.ghost_slot[side][h.src_slot] = slot + 1; Hw.refreshed[slot] = (int)w.g_tick[0] + 1; }
-        }
-        if (slot >= 0) n_acc++; else n_drop++;
-        __syncwarp();
     }
     if (lane == 0) { M.counters[MC_ACCEPTED] = n_acc; M.counters[MC_DROPPED] = n_drop; if (n_drop) atomicAdd((unsigned long long *)&w.g_stats[SAPIO_STAT_OVERFLOW], (unsigned long long)n_drop); }
 }

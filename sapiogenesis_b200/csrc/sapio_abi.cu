@@ -470,7 +470,9 @@ int sapio_halo_pack(const SapioWorld *w, void *ws, size_t ws_bytes, float x_lo, 
     if (!w->p.slab_mode) return fail(SAPIO_E_ARG, "sapio_halo_pack: not a slab world%s");
     cudaStream_t st = (cudaStream_t)stream;
     SapioMigTable T; sapio_mig_table(&w->p, w, &T);
-    k_halo_choose<<<1, 256, 0, st>>>(*w, A.mig, x_lo, x_hi, SAPIO_MIG_MAX_RECORDS);
+    k_halo_flag<<<stream_grid(w->p.n_org + 1), 256, 0, st>>>(*w, x_lo, x_hi, A.repro.req_flag);          // the reproduction scratch is idle here
+    scan_exclusive_i32(A.repro.req_flag, A.repro.req_off, w->p.n_org + 1, A.step.scan_parts, st);
+    k_halo_choose<<<stream_grid(w->p.n_org), 256, 0, st>>>(*w, A.mig, A.repro.req_flag, A.repro.req_off, SAPIO_MIG_MAX_RECORDS);
     k_mig_sizes<<<1, 256, 0, st>>>(*w, T, A.mig, (char *)d_buf, buf_bytes);
     k_mig_pack<<<148 * 4, 256, 0, st>>>(*w, T, A.mig, (char *)d_buf);
     k_halo_dead_header<<<1, 1, 0, st>>>((char *)d_dead);
@@ -483,6 +485,7 @@ int sapio_halo_unpack(const SapioWorld *w, void *ws, size_t ws_bytes, int side, 
     if (!w->p.slab_mode || side < 0 || side > 1) return fail(SAPIO_E_ARG, "sapio_halo_unpack: not a slab world, or side not 0 / 1%s");
     cudaStream_t st = (cudaStream_t)stream;
     SapioMigTable T; sapio_mig_table(&w->p, w, &T);
+    k_halo_assign_kept<<<16, 256, 0, st>>>(*w, T, A.mig, A.halo, side, (const char *)d_buf);
     k_halo_assign<<<1, 32, 0, st>>>(*w, T, A.mig, A.halo, side, (const char *)d_buf);
     k_halo_unpack<<<148 * 4, 256, 0, st>>>(*w, T, A.mig, (char *)d_buf);
     k_halo_assign_dead<<<1, 32, 0, st>>>(*w, A.rules, A.halo, side, (const char *)d_dead);
