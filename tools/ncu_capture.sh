@@ -21,6 +21,10 @@ timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:
     --log-file $OUT/${TAG}_launches.csv $BENCH > $OUT/${TAG}_ncu_launch.log 2>&1
 timeout 1500 ncu --set full --import-source on --clock-control none -k regex:"k_org_solve|k_component|k_coupled" -s $SKIP -c $PER_TICK -f -o $OUT/${TAG}_solver \
     $BENCH > $OUT/${TAG}_ncu_full.log 2>&1
+# every kernel of a few ticks of a 600-tick world (the streaming stages do not depend on the age): grid build, narrowphase, rules, think, train
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 30000 -c 300 --csv --log-file $OUT/${TAG}_launches_tick.csv \
+    python bench.py --no-cpu --no-forward-record --organisms $ORG --age 600 --steps 10 --warmup 5 > $OUT/${TAG}_ncu_tick.log 2>&1
+python tools/ncu_summary.py launches $OUT/${TAG}_launches_tick.csv > profiles/${TAG}_launches_tick.txt 2>&1
 python tools/ncu_traffic.py $OUT/${TAG}_solver.ncu-rep $ORG $AGE profiles/ncu_traffic.json
 python tools/ncu_summary.py launches $OUT/${TAG}_launches.csv > profiles/${TAG}_launches.txt 2>&1
 python tools/ncu_summary.py full $OUT/${TAG}_solver.ncu-rep > profiles/${TAG}_solver_full.txt 2>&1
