@@ -34,6 +34,8 @@ extern "C" {
 #define SAPIO_HIST   10                         /* neural.stimulation_memory (neural.py:34) */
 #define SAPIO_STM    30                         /* short-term memory cap (neural.py:315) */
 #define SAPIO_MEMROWS 232                       /* memory_limit 200 (+30 appended before the trim, neural.py:392-404) */
+#define SAPIO_RNN_MAXH 16                       /* largest hidden_rnn_size (physics.py:308 default 6) */
+#define SAPIO_HM 90                             /* dna.hidden_memory: <= 30 own entries + <= 60 inherited ones (sprites.py:386 is not erased at birth) */
 
 /* ---- cell types: sprites.cell_types (sprites.py:22) + "heart" (sprites.py:573) ---- */
 enum {
@@ -80,7 +82,8 @@ enum { SAPIO_OK = 0, SAPIO_E_ARG = -1, SAPIO_E_CUDA = -2, SAPIO_E_WORKSPACE = -3
 /* Frozen world parameters. Defaults and their reference sources: SURVEY.md Appendix B. */
 typedef struct SapioParams {
     /* capacities */
-    int32_t n_org, n_dead, x_cap, in_cap, brain_cap, adam_cap, width_cap, pad0;
+    int32_t n_org, n_dead, x_cap, in_cap, brain_cap, adam_cap, width_cap;
+    int32_t rnn_cap;          /* capacity of the recurrent-state arrays (RNNH of sapio_fields.def): 0 = a world without RNN brains, else <= SAPIO_RNN_MAXH */
     /* world: environment_settings.json:1, physics.py:280-345 */
     float width, height, frame_width, wall_elast, wall_fric;
     float dt_wall;            /* update_speed/1000 = 0.030 s: the uDiff of every rule (virtual clock) */
@@ -113,7 +116,10 @@ typedef struct SapioParams {
     int32_t slab_mode;
     float grid_x0;            /* x of the first grid column (0 for a whole world) */
     float slab_x0, slab_x1;
-    int32_t pad1;
+    /* Environment.info["use_rnn"] / ["hidden_rnn_size"] (physics.py:305,308) as ONE number: the hidden-state size of the brains built from
+     * now on (spawn, birth; sprites.py:1683-1690), 0 = feed-forward networks.Network. 0 or rnn_cap: the reference cannot change the size
+     * while RNN organisms live either (torch.tensor(trainingHidden) of ragged rows raises, neural.py:412). */
+    int32_t rnn_hidden;
 } SapioParams;
 
 /* The world: one raw pointer per SoA array of include/sapio_fields.def. */

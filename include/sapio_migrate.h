@@ -19,7 +19,7 @@
 #define MAXC SAPIO_MAXC               /* the field list writes per-row extents with this name */
 #endif
 
-#define SAPIO_MIG_MAX_FIELDS 96
+#define SAPIO_MIG_MAX_FIELDS 112
 #define SAPIO_MIG_MAX_RECORDS 4096
 #define SAPIO_MIG_MAGIC 0x53415031           /* "SAP1" */
 #define SAPIO_MIG_CANDIDATES 360             /* placement candidates per arrival, like the 360 bearings of get_new_organism_position */
@@ -61,8 +61,8 @@ static inline int sapio_mig_kind(const char *name, const char *scope) {
 
 /* the field table of a world (w may be NULL: sizes only) */
 static inline void sapio_mig_table(const SapioParams *p, const SapioWorld *w, SapioMigTable *T) {
-    const size_t IN = (size_t)p->in_cap, BRAIN = (size_t)p->brain_cap, ADAM = (size_t)p->adam_cap;
-    (void)IN; (void)BRAIN; (void)ADAM;
+    const size_t IN = (size_t)p->in_cap, BRAIN = (size_t)p->brain_cap, ADAM = (size_t)p->adam_cap, RNNH = (size_t)p->rnn_cap;
+    (void)IN; (void)BRAIN; (void)ADAM; (void)RNNH;
     const size_t M_ORG = 1, M_CELL = SAPIO_MAXC, M_PAIR = SAPIO_NPAIR, M_ICON = SAPIO_ICAP, M_DEAD = 0, M_XCON = 0, M_BODY1 = 0, M_GLOB = 0;
     T->n = 0; T->in_cap = p->in_cap;
     T->i_uid = T->i_cpos = T->i_cspos = T->i_orgpos = T->i_calive = T->i_csize = T->i_ncells = T->i_state = -1;
@@ -123,6 +123,10 @@ SAPIO_HD static inline void sapio_mig_header(const SapioWorld *w, int o, SapioMi
     h->I = nl > 0 ? ld[0] : 0; h->P = 0; h->npar = 0;
     for (int l = 0; l < nl; l++) h->P += ld[l + 1] * ld[l] + ld[l + 1];
     if (nl > 0) h->npar = ld[1] * ld[0] + ld[1] + 4 * ld[nl - 1] + 4;            /* the input and output layers (networks.py:221) */
+    if (nl > 0 && w->org_rnn_h[o] > 0) {                                        /* RNN brain: wider input layer, second head (networks.py:151-166) */
+        const int H = w->org_rnn_h[o];
+        h->P += H * ld[1] + H * ld[nl - 1] + H;
+    }
     h->mem_n = w->org_mem_n[o] < SAPIO_MEMROWS ? w->org_mem_n[o] : SAPIO_MEMROWS;
     h->stm_n = w->org_stm_n[o] < SAPIO_STM ? w->org_stm_n[o] : SAPIO_STM;       /* rings: slots 0 .. min(count, capacity) - 1 are in use */
     h->hist_n = w->org_hist_n[o] < SAPIO_HIST ? w->org_hist_n[o] : SAPIO_HIST;

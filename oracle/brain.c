@@ -9,21 +9,26 @@
 #include <stdlib.h>
 #include <string.h>
 
-static int layer_off(const int32_t *ldim, int layer) {
+/* H = hidden-state columns of an RNN brain's input layer on top of ldim[0] (networks.py:116); 0 for networks.Network */
+static int layer_off(const int32_t *ldim, int layer, int H) {
     int off = 0;
-    for (int l = 0; l < layer; l++) off += ldim[l + 1] * ldim[l] + ldim[l + 1];
+    for (int l = 0; l < layer; l++) off += ldim[l + 1] * (ldim[l] + (l == 0 ? H : 0)) + ldim[l + 1];
     return off;
 }
 
 /* Network.forward: out = W_out(...W_1(sigmoid(W_in x + b_in)) + b_1...) + b_out -- sigmoid after the first layer only */
-void oracle_forward(const float *brain, const int32_t *ldim, int nl, const float *x, float *out, float *acts) {
+/* RNNetwork.forward (networks.py:160-175) when H > 0: x holds ldim[0] inputs followed by the H hidden values (torch.cat), and the
+ * second head outputLayerH -- stored after the output layer -- maps the last hidden activation to the next hidden state `hid`. */
+void oracle_forward_rnn(const float *brain, const int32_t *ldim, int nl, int H, const float *x, float *out, float *acts, float *hid) {
     float buf[2][1024];
-    const float *cur = x;
+    const float *cur = x, *last = x;
     int off = 0;
-    for (int l = 0; l < nl; l++) {
-        int fin = ldim[l], fout = ldim[l + 1];
+    for (int l = 0; l < nl + (H > 0 ? 1 : 0); l++) {
+        int fin = l == nl ? ldim[nl - 1] : ldim[l] + (l == 0 ? H : 0), fout = l == nl ? H : ldim[l + 1];
         const float *W = brain + off, *b = W + fout * fin;
-        float *dst = (l == nl - 1) ? out : buf[l & 1];
+        float *dst = (l == nl - 1) ? out : (l == nl) ? hid : buf[l & 1];
+        if (l == nl - 1) last = cur;
+        if (l == nl) cur = last;
         for (int r = 0; r < fout; r++) {
             float s = 0.0f;
             for (int c = 0; c < fin; c++) s += W[r * fin + c] * cur[c];
@@ -35,6 +40,9 @@ void oracle_forward(const float *brain, const int32_t *ldim, int nl, const float
         cur = dst;
         off += fout * fin + fout;
     }
+}
+void oracle_forward(const float *brain, const int32_t *ldim, int nl, const float *x, float *out, float *acts) {
+    oracle_forward_rnn(brain, ldim, nl, 0, x, out, acts, NULL);
 }
 
 /* Python round(x, 1) of a float, times 10, as an integer key (neural.py:77-78). Correctly rounded, ties decided on the
@@ -161,7 +169,11 @@ int oracle_think(SapioWorld *w, int o, const double *health, const double *energ
     if (n != I) return -1;
     for (int i = 0; i < I; i++) x[i] = rintf((float)raw[i] * 1000.0f) / 1000.0f;      /* neural.py:285 (torch.round: half-even) */
     const float *brain = w->org_brain + (size_t)o * p->brain_cap;
-    oracle_forward(brain, ldim, nl, x, out, NULL);
+    const int H = w->org_rnn_h[o], RC = p->rnn_cap;
+    float *lasth = w->org_last_hidden + (size_t)o * RC, hid[SAPIO_RNN_MAXH];
+    for (int i = 0; i < H; i++) x[I + i] = lasth[i];                                   /* network.forward(flat_inputs, network.lastHidden), neural.py:287-288 */
+    oracle_forward_rnn(brain, ldim, nl, H, x, out, NULL, hid);
+    for (int i = 0; i < H; i++) lasth[i] = hid[i];
     for (int i = 0; i < 4; i++) w->org_out_raw[4 * o + i] = out[i];
     for (int i = 0; i < 4; i++) out[i] = rintf(out[i] * 1000.0f) / 1000.0f;            /* neural.py:292 */
     int32_t T = (int32_t)w->g_tick[0];
@@ -190,6 +202,12 @@ int oracle_think(SapioWorld *w, int o, const double *health, const double *energ
         double d2 = hdo[(cnt - 2) % SAPIO_HIST], d1 = hdo[(cnt - 1) % SAPIO_HIST];
         w->org_stm_rew[o * SAPIO_STM + slot] = (float)((((0.0 + d2) + d1) + dopamine) / 3);
         w->org_stm_n[o] = sc + 1;
+        if (H > 0) {                                                                   /* hidden_memory: append, and pop with the short-term memory (neural.py:312-318) */
+            int32_t *hn = w->org_hm_n + 2 * o;
+            memcpy(w->org_hm + ((size_t)o * SAPIO_HM + (size_t)(hn[0] % SAPIO_HM)) * RC, hid, sizeof(float) * (size_t)H);
+            hn[0]++;
+            if (sc + 1 > SAPIO_STM) hn[1]++;
+        }
     }
     int slot = cnt % SAPIO_HIST;
     memcpy(hin + (size_t)slot * IN, x, sizeof(float) * (size_t)I);
@@ -220,6 +238,68 @@ int oracle_think(SapioWorld *w, int o, const double *health, const double *energ
     return 0;
 }
 
+/* Trainer.train_rnn (networks.py:56-73) as neural.train_network calls it (neural.py:407-413), with everything it does restated:
+ *  - the model runs over every memory row but only the LAST result is kept: input = the last row of trainingInput (list order: the
+ *    most recently appended), hidden = trainingHidden[M - 1] -- the (M-1)-th entry EVER appended, since remove_memory never pops
+ *    that list (neural.py:83-87);
+ *  - targetData.resize_(result.shape) leaves the FIRST row of trainingOutput as the target;
+ *  - MSELoss(mean) over the 4 outputs, backward, then plain SGD  p += -lr * grad  on model.parameters() that have a gradient: the
+ *    input and output layers (the hidden layers sit in a Python list, networks.py:143; outputLayerH gets no gradient);
+ *  - side effect: network.lastHidden = outputLayerH of that last row under the old weights. */
+static void oracle_train_rnn(SapioWorld *w, int o, int M) {
+    const SapioParams *p = &w->p;
+    const int IN = p->in_cap, RC = p->rnn_cap, H = w->org_rnn_h[o];
+    const int32_t *ldim = w->org_ldim + o * 16, *seq = w->org_mem_seq + (size_t)o * SAPIO_MEMROWS;
+    const int nl = w->org_nlayers[o], I = ldim[0], F0 = I + H, h0 = ldim[1], hl = ldim[nl - 1];
+    int last = 0, first = 0;
+    for (int m = 1; m < M; m++) { if (seq[m] > seq[last]) last = m; if (seq[m] < seq[first]) first = m; }
+    float x[1024], act[SAPIO_MAXL + 1][1024], out[4], hid[SAPIO_RNN_MAXH];
+    memcpy(x, w->org_mem_in + ((size_t)o * SAPIO_MEMROWS + last) * IN, sizeof(float) * (size_t)I);
+    for (int i = 0; i < H; i++) x[I + i] = (M - 1 < w->org_th_n[o]) ? w->org_th[((size_t)o * SAPIO_MEMROWS + (M - 1)) * RC + i] : 0.0f;
+    float *brain = w->org_brain + (size_t)o * p->brain_cap;
+    const float *cur = x; int off = 0;
+    for (int l = 0; l < nl + 1; l++) {
+        int fin = l == nl ? hl : ldim[l] + (l == 0 ? H : 0), fout = l == nl ? H : ldim[l + 1];
+        const float *W = brain + off, *b = W + fout * fin;
+        const float *src = l == nl ? act[nl - 1] : cur;
+        float *dst = l == nl - 1 ? out : l == nl ? hid : act[l + 1];
+        if (nl == 1 && l == nl) src = x;
+        for (int r = 0; r < fout; r++) {
+            float s = 0.0f;
+            for (int c = 0; c < fin; c++) s += W[r * fin + c] * src[c];
+            s += b[r];
+            if (l == 0) s = 1.0f / (1.0f + expf(-s));
+            dst[r] = s;
+        }
+        if (l < nl - 1) cur = dst;
+        off += fout * fin + fout;
+    }
+    const float *y = w->org_mem_out + ((size_t)o * SAPIO_MEMROWS + first) * 4, *Hl = act[nl - 1], *H0 = act[1];
+    float dO[4]; double loss = 0;
+    for (int q = 0; q < 4; q++) { float e = out[q] - y[q]; loss += (double)e * e; dO[q] = 2.0f * e / 4.0f; }
+    w->org_loss[o] = (float)(loss / 4);
+    float *Win = brain, *bin = brain + h0 * F0, *Wout = brain + layer_off(ldim, nl - 1, H), *bout = Wout + 4 * hl;
+    float d[2][1024]; int cd = 0;
+    for (int c = 0; c < hl; c++) { float s = 0; for (int q = 0; q < 4; q++) s += dO[q] * Wout[q * hl + c]; d[0][c] = s; }
+    for (int l = nl - 2; l >= 1; l--) {
+        int fin = ldim[l], fout = ldim[l + 1];
+        const float *W = brain + layer_off(ldim, l, H);
+        for (int c = 0; c < fin; c++) { float s = 0; for (int r = 0; r < fout; r++) s += d[cd][r] * W[r * fin + c]; d[cd ^ 1][c] = s; }
+        cd ^= 1;
+    }
+    const float lr = p->learning_rate;
+    for (int q = 0; q < 4; q++) {
+        for (int c = 0; c < hl; c++) { float g = dO[q] * Hl[c]; Wout[q * hl + c] = Wout[q * hl + c] + (-lr) * g; }
+        bout[q] = bout[q] + (-lr) * dO[q];
+    }
+    for (int r = 0; r < h0; r++) {
+        float dz = d[cd][r] * H0[r] * (1.0f - H0[r]);
+        for (int c = 0; c < F0; c++) { float g = dz * x[c]; Win[r * F0 + c] = Win[r * F0 + c] + (-lr) * g; }
+        bin[r] = bin[r] + (-lr) * dz;
+    }
+    for (int i = 0; i < H; i++) w->org_last_hidden[(size_t)o * RC + i] = hid[i];
+}
+
 /* neural.train_network (neural.py:369-423) for organism o.
  * Storage policy for the curated memory (a Python list in the reference): a replaced key is overwritten in place and the
  * trim moves the last row into the hole, instead of list.pop + append. Keys are unique, so only the fp summation order of the
@@ -233,6 +313,8 @@ int oracle_train_one(SapioWorld *w, int o) {
     float *min_ = w->org_mem_in + (size_t)o * SAPIO_MEMROWS * IN, *mout = w->org_mem_out + (size_t)o * SAPIO_MEMROWS * 4;
     float *mrew = w->org_mem_rew + (size_t)o * SAPIO_MEMROWS;
     int M = w->org_mem_n[o];
+    const int H = w->org_rnn_h[o], RC = p->rnn_cap;
+    int32_t *seq = w->org_mem_seq + (size_t)o * SAPIO_MEMROWS;
     for (int i = 0; i < sn; i++) {                                                     /* chronological */
         int si = (sc - sn + i) % SAPIO_STM;
         const float *xin = w->org_stm_in + ((size_t)o * SAPIO_STM + si) * IN;
@@ -261,6 +343,15 @@ int oracle_train_one(SapioWorld *w, int o) {
             memcpy(min_ + (size_t)dst * IN, xin, sizeof(float) * (size_t)I);          /* roundList(mem[0], 3) == the fp32 value again */
             memcpy(mout + dst * 4, w->org_stm_out + (o * SAPIO_STM + best) * 4, sizeof(float) * 4);
             mrew[dst] = w->org_stm_rew[o * SAPIO_STM + si];                             /* sic: mem[2], not bestReward (neural.py:395) */
+            seq[dst] = w->org_mem_stamp[o]++;                                           /* remove_memory + append: the row is now the LAST of the list */
+            if (H > 0) {                                                                /* trainingHidden.append(hidden_memory[i]) (neural.py:396-397) */
+                int tn = w->org_th_n[o];
+                if (tn < SAPIO_MEMROWS) {
+                    const int32_t *hn = w->org_hm_n + 2 * o;
+                    memcpy(w->org_th + ((size_t)o * SAPIO_MEMROWS + tn) * RC, w->org_hm + ((size_t)o * SAPIO_HM + (size_t)((hn[1] + i) % SAPIO_HM)) * RC, sizeof(float) * (size_t)H);
+                    w->org_th_n[o] = tn + 1;
+                }
+            }
         }
     }
     while (M > p->memory_limit && (w->org_flags[o] & SAPIO_F_FINITE_MEMORY)) {          /* neural.py:399-404 */
@@ -270,15 +361,16 @@ int oracle_train_one(SapioWorld *w, int o) {
         if (lo != M) {
             memcpy(min_ + (size_t)lo * IN, min_ + (size_t)M * IN, sizeof(float) * (size_t)I);
             memcpy(mout + lo * 4, mout + M * 4, sizeof(float) * 4);
-            mrew[lo] = mrew[M];
+            mrew[lo] = mrew[M]; seq[lo] = seq[M];
         }
     }
     w->org_mem_n[o] = M;
-    if (M > 0) {
+    if (M > 0 && H > 0) oracle_train_rnn(w, o, M);
+    else if (M > 0) {
         /* Trainer.train_epoch (networks.py:75-87): full batch, MSELoss(mean), Adam on input+output layers only */
         float *brain = w->org_brain + (size_t)o * p->brain_cap;
         int h0 = ldim[1], hl = ldim[nl - 1];
-        int off_out = layer_off(ldim, nl - 1);
+        int off_out = layer_off(ldim, nl - 1, 0);
         float *Win = brain, *bin = brain + h0 * I, *Wout = brain + off_out, *bout = Wout + 4 * hl;
         int np_in = h0 * I + h0, np_out = 4 * hl + 4;
         double *g = (double *)calloc((size_t)(np_in + np_out), sizeof(double));
@@ -315,7 +407,7 @@ int oracle_train_one(SapioWorld *w, int o) {
             for (int c = 0; c < hl; c++) { float s = 0; for (int q = 0; q < 4; q++) s += dO[q] * Wout[q * hl + c]; d[0][c] = s; }
             for (int l = nl - 2; l >= 1; l--) {
                 int fin = ldim[l], fout = ldim[l + 1];
-                const float *W = brain + layer_off(ldim, l);
+                const float *W = brain + layer_off(ldim, l, 0);
                 for (int c = 0; c < fin; c++) { float s = 0; for (int r = 0; r < fout; r++) s += d[cur_d][r] * W[r * fin + c]; d[cur_d ^ 1][c] = s; }
                 cur_d ^= 1;
             }

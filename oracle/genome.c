@@ -180,10 +180,11 @@ int og_brain_params(const OGenome *g) {
 }
 int og_fits_caps(const OGenome *g, const SapioParams *p) {
     if (g->n > MAXC) return 0;
-    if (og_input_size(g) > p->in_cap) return 0;
+    const int H = p->rnn_hidden;                  /* RNN brain (networks.py:111-166): H more input columns, a second head of H rows */
+    if (og_input_size(g) + H > p->in_cap) return 0;
     if (g->n_hidden < 1 || g->n_hidden + 1 > SAPIO_MAXL) return 0;
     for (int i = 0; i < g->n_hidden; i++) if (g->hidden[i] > p->width_cap) return 0;
-    if (og_brain_params(g) > p->brain_cap) return 0;
+    if (og_brain_params(g) + H * g->hidden[0] + H * g->hidden[g->n_hidden - 1] + H > p->brain_cap) return 0;
     return 1;
 }
 

@@ -72,6 +72,7 @@ int  og_fits_caps(const OGenome *g, const SapioParams *p);
 /* world <-> genome */
 void ow_genome_from_world(const SapioWorld *w, int org, OGenome *g);
 int  ow_materialize(SapioWorld *w, int org, const OGenome *g, double px, double py, int64_t uid, int32_t tick, USrc *u_init);
+void ow_inherit_recurrent(SapioWorld *w, int parent, int child);
 void ow_org_rect(const SapioWorld *w, int org, double r[4]);
 int  ow_viable_position(const SapioWorld *w, const OGenome *g, double px, double py);
 

@@ -81,6 +81,7 @@ int oracle_reproduce(SapioWorld *w) {
             cg.generation = pg.generation + 1;
             USrc ui = stream_src(p, uid, T, SAPIO_RNG_BRAIN_INIT, 0);
             if (ow_materialize(w, slot, &cg, pos[0], pos[1], uid, T, &ui) < 0) { w->g_stats[SAPIO_STAT_BIRTH_FAIL_CAPS]++; w->org_state[slot] = 0; break; }
+            ow_inherit_recurrent(w, o, slot);
             w->g_stats[SAPIO_STAT_BIRTHS]++;
         }
     }

@@ -6,9 +6,10 @@
 #include <stdlib.h>
 #include <string.h>
 
-static int brain_layer_offset(const int32_t *ldim, int layer) {
+/* H = hidden-state columns the input layer of an RNN brain has on top of ldim[0] (networks.py:116) */
+static int brain_layer_offset(const int32_t *ldim, int layer, int H) {
     int off = 0;
-    for (int l = 0; l < layer; l++) off += ldim[l + 1] * ldim[l] + ldim[l + 1];
+    for (int l = 0; l < layer; l++) off += ldim[l + 1] * (ldim[l] + (l == 0 ? H : 0)) + ldim[l + 1];
     return off;
 }
 
@@ -47,7 +48,7 @@ void ow_genome_from_world(const SapioWorld *w, int org, OGenome *g) {
     int off = 0;
     for (int l = 1; l + 1 < nl; l++) {
         int n = ldim[l + 1] * ldim[l];
-        memcpy(g->hw + off, brain + brain_layer_offset(ldim, l), sizeof(float) * (size_t)n);
+        memcpy(g->hw + off, brain + brain_layer_offset(ldim, l, w->org_rnn_h[org]), sizeof(float) * (size_t)n);
         off += n;
     }
 }
@@ -138,10 +139,16 @@ int ow_materialize(SapioWorld *w, int org, const OGenome *g, double px, double p
     ldim[nd++] = 4;
     int nl = nd - 1;
     w->org_nlayers[org] = nl;
+    /* build_brain (sprites.py:1683-1690): an RNNetwork when Environment.info["use_rnn"] is set now -- the input layer takes
+     * hiddenSize more columns and a second head outputLayerH is constructed after the output layer (networks.py:116,151-166) */
+    const int H = p->rnn_hidden;
+    w->org_rnn_h[org] = H;
+    w->org_hm_n[2 * org] = w->org_hm_n[2 * org + 1] = 0; w->org_th_n[org] = 0; w->org_mem_stamp[org] = 0;
+    for (int i = 0; i < p->rnn_cap; i++) w->org_last_hidden[(size_t)org * p->rnn_cap + i] = 0;      /* lastHidden = zeros (networks.py:149) */
     float *brain = w->org_brain + (size_t)org * p->brain_cap;
     int off = 0, hoff = 0;
-    for (int l = 0; l < nl; l++) {
-        int fin = ldim[l], fout = ldim[l + 1];
+    for (int l = 0; l < nl + (H > 0 ? 1 : 0); l++) {
+        int fin = l == nl ? ldim[nl - 1] : ldim[l] + (l == 0 ? H : 0), fout = l == nl ? H : ldim[l + 1];
         double bound = 1.0 / sqrt((double)fin);
         for (int e = 0; e < fout * fin; e++) brain[off + e] = (float)((2.0 * usrc_next(u_init) - 1.0) * bound);
         if (l >= 1 && l + 1 < nl) {                                         /* inherited hidden weights */
@@ -156,6 +163,25 @@ int ow_materialize(SapioWorld *w, int org, const OGenome *g, double px, double p
     memset(w->org_adam_m + (size_t)org * ac, 0, sizeof(float) * ac);
     memset(w->org_adam_v + (size_t)org * ac, 0, sizeof(float) * ac);
     return 0;
+}
+
+/* What DNA.mutate's deepcopy carries over and erase_memory (sprites.py:413-421) forgets to clear: hidden_memory and trainingHidden
+ * (sprites.py:377,386). The child's hidden_memory therefore starts with the parent's entries and runs out of step with its own
+ * short-term memory. Cap (ours): the first SAPIO_HM - SAPIO_STM entries are inherited, so that the list never exceeds SAPIO_HM (the
+ * reference's list grows by up to 30 entries per generation without bound). */
+void ow_inherit_recurrent(SapioWorld *w, int parent, int child) {
+    const int RC = w->p.rnn_cap;
+    if (RC <= 0) return;
+    const int app = w->org_hm_n[2 * parent], pop = w->org_hm_n[2 * parent + 1];
+    int n = app - pop;
+    if (n > SAPIO_HM - SAPIO_STM) n = SAPIO_HM - SAPIO_STM;
+    const float *ph = w->org_hm + (size_t)parent * SAPIO_HM * RC;
+    float *ch = w->org_hm + (size_t)child * SAPIO_HM * RC;
+    for (int i = 0; i < n; i++) memcpy(ch + (size_t)i * RC, ph + (size_t)((pop + i) % SAPIO_HM) * RC, sizeof(float) * (size_t)RC);
+    w->org_hm_n[2 * child] = n; w->org_hm_n[2 * child + 1] = 0;
+    const int tn = w->org_th_n[parent];
+    memcpy(w->org_th + (size_t)child * SAPIO_MEMROWS * RC, w->org_th + (size_t)parent * SAPIO_MEMROWS * RC, sizeof(float) * (size_t)tn * RC);
+    w->org_th_n[child] = tn;
 }
 
 /* Organism.get_rect (sprites.py:1211-1232): seeded with the first cell's centre, widened by living cells' discs */

@@ -155,9 +155,10 @@ __device__ __forceinline__ int g_brain_params(const DGenome &g) {
     return tot + 4 * prev + 4;
 }
 __device__ __forceinline__ bool g_fits_caps(const DGenome &g, const SapioParams &p) {
-    if (g.n > MAXC || g_input_size(g) > p.in_cap || g.n_hidden < 1 || g.n_hidden + 1 > SAPIO_MAXL) return false;
+    const int H = p.rnn_hidden;                   // RNN brain (networks.py:111-166): H more input columns, a second head of H rows
+    if (g.n > MAXC || g_input_size(g) + H > p.in_cap || g.n_hidden < 1 || g.n_hidden + 1 > SAPIO_MAXL) return false;
     for (int i = 0; i < g.n_hidden; i++) if (g.hidden[i] > p.width_cap) return false;
-    return g_brain_params(g) <= p.brain_cap;
+    return g_brain_params(g) + H * g.hidden[0] + H * g.hidden[g.n_hidden - 1] + H <= p.brain_cap;
 }
 // DNA._setup_brain_structure (sprites.py:827-866), structure only (the tempNet's weights are drawn by the caller)
 __device__ __forceinline__ void g_setup_brain_structure(DGenome &g, const SapioParams &p, RngStream &u) {

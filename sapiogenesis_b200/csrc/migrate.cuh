@@ -7,13 +7,13 @@
 #pragma once
 #include "common.cuh"
 
-#define MIG_MAX_FIELDS 96
+#define MIG_MAX_FIELDS 112
 struct MigField { char *base; uint32_t bytes; uint32_t off; };          // bytes per organism, offset inside a record
 struct MigTable { MigField f[MIG_MAX_FIELDS]; int n; uint32_t record_bytes; uint32_t uid_off; };
 
 static inline void mig_table(const SapioParams &p, const SapioWorld *w, MigTable &T) {
-    const size_t IN = (size_t)p.in_cap, BRAIN = (size_t)p.brain_cap, ADAM = (size_t)p.adam_cap;
-    (void)IN; (void)BRAIN; (void)ADAM;
+    const size_t IN = (size_t)p.in_cap, BRAIN = (size_t)p.brain_cap, ADAM = (size_t)p.adam_cap, RNNH = (size_t)p.rnn_cap;
+    (void)IN; (void)BRAIN; (void)ADAM; (void)RNNH;
     const size_t M_ORG = 1, M_CELL = MAXC, M_PAIR = SAPIO_NPAIR, M_ICON = SAPIO_ICAP, M_DEAD = 0, M_XCON = 0, M_BODY1 = 0, M_GLOB = 0;
     T.n = 0; uint32_t off = 0; T.uid_off = 0;
 #define SAPIO_FIELD(name, ctype, scope, per) \

@@ -236,6 +236,7 @@ __global__ void __launch_bounds__(REPRO_WARPS * 32) k_repro_place(WORLD_ARG, Rep
 // g, order and row_of live in shared memory
 __device__ __forceinline__ void write_rows(const SapioWorld &w, int slot, const DGenome &g, const uint8_t *order, uint8_t *row_of, double px, double py, int64_t uid, int32_t tick) {
     const int lane = lane_id(), nc = g.n;
+    const SapioParams &p_ = w.p;
     float sum_h = 0.f, sum_mh = 0.f, sum_e = 0.f, sum_st = 0.f;
     for (int k = lane; k < nc; k += 32) row_of[order[k]] = (uint8_t)k;
     __syncwarp();
@@ -274,6 +275,9 @@ __device__ __forceinline__ void write_rows(const SapioWorld &w, int slot, const 
         w.org_curiosity[slot] = (float)g.curiosity; w.org_boredom[slot] = w.org_stimulation[slot] = 0.f;
         for (int i = 0; i < 10; i++) w.org_stim_hist[10 * slot + i] = 0.f;
         w.org_hist_n[slot] = w.org_stm_n[slot] = w.org_mem_n[slot] = 0; w.org_adam_t[slot] = 0; w.org_loss[slot] = 0.f;
+        // build_brain (sprites.py:1683-1690): an RNNetwork when use_rnn is set now; lastHidden = zeros (networks.py:149)
+        w.org_rnn_h[slot] = p_.rnn_hidden; w.org_hm_n[2 * slot] = w.org_hm_n[2 * slot + 1] = 0; w.org_th_n[slot] = 0; w.org_mem_stamp[slot] = 0;
+        for (int i = 0; i < p_.rnn_cap; i++) w.org_last_hidden[(size_t)slot * p_.rnn_cap + i] = 0.f;
         w.org_ic_n[slot] = 0; w.org_req[slot] = 0;
         w.org_gas_a[slot] = 1.0; w.org_gas_b[slot] = 0.0; w.org_gas_in[slot] = 0.0; w.org_gas_refund[slot] = 0.0;
         w.org_last_health[slot] = (sum_mh > 0.f && sum_h != 0.f) ? sum_h / sum_mh * 100.0f : 0.f;      // build_body tail (sprites.py:1728-1729)
@@ -385,18 +389,20 @@ __device__ void build_brain(const SapioWorld &w, int slot, int64_t uid, int32_t 
     const int32_t *ldim = w.org_ldim + slot * 16;
     const int nl = w.org_nlayers[slot];
     float *brain = w.org_brain + (size_t)slot * p.brain_cap;
+    // RNN brain (networks.py:111-166): H more columns in the input layer, and the second head outputLayerH constructed after the output layer
+    const int H = w.org_rnn_h[slot];
     int off = 0;
-    for (int l = 0; l < nl; l++) {
-        int fin = ldim[l], n = ldim[l + 1] * fin + ldim[l + 1];
+    for (int l = 0; l < nl + (H > 0 ? 1 : 0); l++) {
+        const int fin = l == nl ? ldim[nl - 1] : ldim[l] + (l == 0 ? H : 0), fout = l == nl ? H : ldim[l + 1], n = fout * fin + fout;
         for (int e = lane; e < n; e += 32) brain[off + e] = init_param(p.seed, uid, tick, RNG_BRAIN_INIT, off + e, fin);
         off += n;
     }
     __syncwarp();
     // hidden layers
-    off = ldim[1] * ldim[0] + ldim[1];
+    off = ldim[1] * (ldim[0] + H) + ldim[1];
     int poff = 0, fill_base = 0, garb_base = 0;
     const float *pbrain = nullptr; const int32_t *pldim = nullptr;
-    if (mode == 1) { pbrain = w.org_brain + (size_t)parent * p.brain_cap; pldim = w.org_ldim + parent * 16; poff = pldim[1] * pldim[0] + pldim[1]; }
+    if (mode == 1) { pbrain = w.org_brain + (size_t)parent * p.brain_cap; pldim = w.org_ldim + parent * 16; poff = pldim[1] * (pldim[0] + w.org_rnn_h[parent]) + pldim[1]; }
     const int n_old_layers = old_n - 1 > 0 ? old_n - 1 : 0;
     for (int l = 1; l + 1 < nl; l++) {
         const int hl = l - 1, cols = ldim[l], rows = ldim[l + 1];
@@ -429,6 +435,16 @@ __device__ void build_brain(const SapioWorld &w, int slot, int64_t uid, int32_t 
             if (have) poff += old_len + orows;        // next old hidden layer in the parent's brain (skip this one's W and b)
         }
         off += rows * cols + rows;
+    }
+    // what DNA.mutate's deepcopy carries over and erase_memory (sprites.py:413-421) does not clear: hidden_memory (its first
+    // SAPIO_HM - SAPIO_STM entries: the list never exceeds SAPIO_HM here) and trainingHidden -- see oracle/world.c ow_inherit_recurrent
+    if (mode == 1 && p.rnn_cap > 0) {
+        const int RC = p.rnn_cap, app = w.org_hm_n[2 * parent], pop = w.org_hm_n[2 * parent + 1], n = min(app - pop, SAPIO_HM - SAPIO_STM), tn = w.org_th_n[parent];
+        const float *ph = w.org_hm + (size_t)parent * SAPIO_HM * RC; float *ch = w.org_hm + (size_t)slot * SAPIO_HM * RC;
+        for (int e = lane; e < n * RC; e += 32) { const int i = e / RC, c = e - i * RC; ch[e] = ph[(size_t)((pop + i) % SAPIO_HM) * RC + c]; }
+        const float *pt = w.org_th + (size_t)parent * SAPIO_MEMROWS * RC; float *ct = w.org_th + (size_t)slot * SAPIO_MEMROWS * RC;
+        for (int e = lane; e < tn * RC; e += 32) ct[e] = pt[e];
+        if (lane == 0) { w.org_hm_n[2 * slot] = n; w.org_hm_n[2 * slot + 1] = 0; w.org_th_n[slot] = tn; }
     }
     // optimizer state, joint impulses
     const size_t ac = (size_t)p.adam_cap;

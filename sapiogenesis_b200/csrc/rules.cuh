@@ -355,9 +355,10 @@ __global__ void __launch_bounds__(RULES_WARPS * 32, RULES_MAIN_MINB) k_rules_mai
                             const double rx = (double)bcast2(g.px[0], g.px[1], rel) - (double)bcast2(g.px[0], g.px[1], 0), ry = (double)bcast2(g.py[0], g.py[1], rel) - (double)bcast2(g.py[0], g.py[1], 0);
                             const double ox = (double)w.c_rel[2 * rrow], oy = (double)w.c_rel[2 * rrow + 1];
                             const double nr = sqrt(rx * rx + ry * ry), no = sqrt(ox * ox + oy * oy), nm = sqrt((double)mv2 * (double)mv2 + (double)mv3 * (double)mv3);
-                            const double cx = nr > 0.0 ? rx / nr : 1.0, cy = nr > 0.0 ? ry / nr : 0.0;        // atan2(0, 0) = 0
+                            const double cx = nr > 0.0 ? rx / nr : 1.0, cy = nr > 0.0 ? ry / nr : 0.0;        // atan2(0, 0) = 0 (a difference of positions is never -0)
                             const double qx = no > 0.0 ? ox / no : 1.0, qy = no > 0.0 ? oy / no : 0.0;
-                            const double mx = nm > 0.0 ? (double)mv2 / nm : 1.0, my = nm > 0.0 ? (double)mv3 / nm : 0.0;
+                            // a command rounded to -0.0 keeps its sign (neural.py:292): atan2(+-0, -0) = +-pi, atan2(+-0, +0) = +-0
+                            const double mx = nm > 0.0 ? (double)mv2 / nm : (signbit(mv2) ? -1.0 : 1.0), my = nm > 0.0 ? (double)mv3 / nm : 0.0;
                             const double rc = cx * qx + cy * qy, rs = cy * qx - cx * qy;                     // cos, sin of the rotation
                             push_c = mx * rc - my * rs; push_s = my * rc + mx * rs;
                         }

@@ -157,7 +157,7 @@ static int launch_rules(const SapioWorld &w, AllWs &A, uint32_t phases, cudaStre
         prof_mark(st, PT_GRID);
         if (!(phases & SAPIO_PH_REUSE_GRID)) { int rc = launch_grid_only(w, A.step, st); if (rc) return rc; }
         prof_mark(st, PT_THINK);
-        size_t smem = (size_t)THINK_WARPS * (p.in_cap + 2 * (p.width_cap > 4 ? p.width_cap : 4)) * sizeof(float);
+        size_t smem = (size_t)THINK_WARPS * (p.in_cap + 2 * (p.width_cap > SAPIO_RNN_MAXH ? p.width_cap : SAPIO_RNN_MAXH)) * sizeof(float);
         static size_t smem_set = 0;
         if (smem > smem_set) { CUDA_TRY(cudaFuncSetAttribute(k_think, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_set = smem; }
         k_think<<<stream_grid((long)p.n_org * 32 / 4 + 1, THINK_WARPS * 32), THINK_WARPS * 32, smem, st>>>(w, A.step, R);
@@ -322,7 +322,7 @@ int sapio_activate(const SapioWorld *w, void *ws, size_t ws_bytes, const int32_t
     const SapioParams &p = w->p;
     k_fill_list<<<(n + 255) / 256, 256, 0, st>>>(A.rules.think_list, A.rules.counters + RC_NTHINK, d_orgs, n);
     if ((rc = launch_grid_only(*w, A.step, st))) return rc;
-    size_t smem = (size_t)THINK_WARPS * (p.in_cap + 2 * (p.width_cap > 4 ? p.width_cap : 4)) * sizeof(float);
+    size_t smem = (size_t)THINK_WARPS * (p.in_cap + 2 * (p.width_cap > SAPIO_RNN_MAXH ? p.width_cap : SAPIO_RNN_MAXH)) * sizeof(float);
     CUDA_TRY(cudaFuncSetAttribute(k_think, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_think<<<stream_grid((long)n * 32, THINK_WARPS * 32), THINK_WARPS * 32, smem, st>>>(*w, A.step, A.rules);
     LAUNCHES(4);

@@ -84,13 +84,13 @@ __device__ __forceinline__ void sense(const SapioWorld &w, const Workspace &W, i
 }
 
 #define THINK_WARPS 4
-// dynamic shared memory per warp: in_cap + 2 * width_cap floats
+// dynamic shared memory per warp: in_cap + 2 * max(width_cap, SAPIO_RNN_MAXH) floats
 __global__ void __launch_bounds__(THINK_WARPS * 32) k_think(WORLD_ARG, Workspace W, RulesWs R) {
     extern __shared__ float think_smem[];
     const SapioParams &p = w.p;
     const int IN = p.in_cap, lane = lane_id();
-    float *x = think_smem + (size_t)(threadIdx.x >> 5) * (IN + 2 * max(p.width_cap, 4));
-    float *act0 = x + IN, *act1 = act0 + max(p.width_cap, 4);
+    float *x = think_smem + (size_t)(threadIdx.x >> 5) * (IN + 2 * max(p.width_cap, SAPIO_RNN_MAXH));
+    float *act0 = x + IN, *act1 = act0 + max(p.width_cap, SAPIO_RNN_MAXH);
     const int n_think = R.counters[RC_NTHINK];
     const int32_t T = (int32_t)w.g_tick[0];
     const int warps = gridDim.x * THINK_WARPS;
@@ -99,6 +99,7 @@ __global__ void __launch_bounds__(THINK_WARPS * 32) k_think(WORLD_ARG, Workspace
         const int nc = w.org_ncells[o], nl = w.org_nlayers[o];
         const int32_t *ldim = w.org_ldim + o * 16;
         const int I = ldim[0];
+        const int H = w.org_rnn_h[o], RC = p.rnn_cap;                                  // RNN brain: H hidden values follow the I inputs (I + H <= in_cap: g_fits_caps)
         const int64_t uid = w.org_uid[o];
         // Organism.rotation (sprites.py:1179-1201) as an angle
         uint32_t a0 = __ballot_sync(FULL, lane < nc && w.c_alive[o * MAXC + lane] == SAPIO_CELL_ALIVE);
@@ -147,14 +148,17 @@ __global__ void __launch_bounds__(THINK_WARPS * 32) k_think(WORLD_ARG, Workspace
         }
         __syncwarp();
         for (int i = lane; i < I; i += 32) x[i] = rintf(x[i] * 1000.0f) / 1000.0f;                 // neural.py:285 (round half to even)
+        if (lane < H) x[I + lane] = w.org_last_hidden[(size_t)o * RC + lane];                      // torch.cat((inputs, hidden)) (networks.py:164), neural.py:287-288
         __syncwarp();
-        // Network.forward: sigmoid after the first layer only
+        // Network.forward: sigmoid after the first layer only. RNNetwork.forward (networks.py:160-175): one more "layer" after the
+        // output layer -- the head outputLayerH on the same last hidden activation -- gives the next lastHidden
         const float *brain = w.org_brain + (size_t)o * p.brain_cap;
         const float *cur = x; float *dst = act0;
         float out4[4] = {0.f, 0.f, 0.f, 0.f};
         int off = 0;
-        for (int l = 0; l < nl; l++) {
-            const int fin = ldim[l], fout = ldim[l + 1];
+        for (int l = 0; l < nl + (H > 0 ? 1 : 0); l++) {
+            const bool head = l == nl;
+            const int fin = head ? ldim[nl - 1] : ldim[l] + (l == 0 ? H : 0), fout = head ? H : ldim[l + 1];
             const float *Wm = brain + off, *b = Wm + fout * fin;
             // eight output rows at a time: their weights (cold, straight from HBM) are all requested before the first is used.
             // Per row the summation order is unchanged: lane-strided partial sums in ascending column order, then the butterfly.
@@ -192,9 +196,11 @@ __global__ void __launch_bounds__(THINK_WARPS * 32) k_think(WORLD_ARG, Workspace
                 }
             }
             __syncwarp();
-            cur = dst; dst = (dst == act0) ? act1 : act0;
+            if (l < nl - 1) { cur = dst; dst = (dst == act0) ? act1 : act0; }                   // the output layer wrote registers: `dst` stays free for the head, `cur` stays its input
             off += fout * fin + fout;
         }
+        const float *hid = dst;                                                                    // H values when H > 0
+        if (lane < H) w.org_last_hidden[(size_t)o * RC + lane] = hid[lane];
         if (lane < 4) { float v = 0.f;
 #pragma unroll
             for (int z = 0; z < 4; z++) if (z == lane) v = out4[z];
@@ -227,6 +233,11 @@ __global__ void __launch_bounds__(THINK_WARPS * 32) k_think(WORLD_ARG, Workspace
                 double d2 = hdo[(cnt - 2) % SAPIO_HIST], d1 = hdo[(cnt - 1) % SAPIO_HIST];
                 w.org_stm_rew[o * SAPIO_STM + slot] = (float)((((0.0 + d2) + d1) + (double)dopamine) / 3);
                 w.org_stm_n[o] = sc + 1;
+            }
+            if (H > 0) {                                                                           // hidden_memory: append, pop with the short-term memory (neural.py:312-318)
+                const int app = w.org_hm_n[2 * o];
+                if (lane < H) w.org_hm[((size_t)o * SAPIO_HM + (size_t)(app % SAPIO_HM)) * RC + lane] = hid[lane];
+                if (lane == 0) { w.org_hm_n[2 * o] = app + 1; if (sc + 1 > SAPIO_STM) w.org_hm_n[2 * o + 1]++; }
             }
         }
         __syncwarp();

@@ -54,11 +54,100 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
     return v;
 }
 
+// Trainer.train_rnn (networks.py:56-73) as neural.train_network calls it (neural.py:407-413); see oracle/brain.c oracle_train_rnn for what
+// the reference's loop amounts to: ONE sample -- input = the last row of the memory list, hidden = trainingHidden[M - 1] (the (M-1)-th entry
+// ever appended), target = the first row's action -- MSE over the 4 outputs, plain SGD p += -lr * grad on the input and output layers, and
+// network.lastHidden = the hidden head of that sample under the old weights. Whole CTA, one thread per output unit; scratch = the CTA's
+// activation buffer (x | h0 | two ping-pong rows | hl copy | two gradient rows), seq_s = append stamps of the rows, red = a small shared array.
+__device__ __forceinline__ void train_rnn_step(const SapioWorld &w, int o, int M, const int *seq_s, float *red, float *scratch) {
+    const SapioParams &p = w.p;
+    const int IN = p.in_cap, RC = p.rnn_cap, H = w.org_rnn_h[o], tid = threadIdx.x;
+    const int32_t *ldim = w.org_ldim + o * 16;
+    const int nl = w.org_nlayers[o], I = ldim[0], F0 = I + H, h0 = ldim[1], hl = ldim[nl - 1];
+    float *x = scratch, *a0 = x + 256, *pa = a0 + TRAIN_MAXW, *pb = pa + TRAIN_MAXW, *ah = pb + TRAIN_MAXW, *da = ah + TRAIN_MAXW, *db = da + TRAIN_MAXW;
+    float *brain = w.org_brain + (size_t)o * p.brain_cap;
+    __shared__ int sh_last, sh_first;
+    if (tid == 0) {
+        int last = 0, first = 0;
+        for (int m = 1; m < M; m++) { if (seq_s[m] > seq_s[last]) last = m; if (seq_s[m] < seq_s[first]) first = m; }
+        sh_last = last; sh_first = first;
+    }
+    __syncthreads();
+    const int last = sh_last, first = sh_first;
+    if (tid < I) x[tid] = w.org_mem_in[((size_t)o * SAPIO_MEMROWS + last) * IN + tid];
+    else if (tid < F0) x[tid] = (M - 1 < w.org_th_n[o]) ? w.org_th[((size_t)o * SAPIO_MEMROWS + (M - 1)) * RC + (tid - I)] : 0.f;
+    __syncthreads();
+    // forward: layers 0 .. nl-1, then the hidden head on the last hidden activation
+    const float *cur = x; float *dst = a0;
+    int off = 0, off_out = 0;
+    for (int l = 0; l < nl - 1; l++) {
+        const int fin = l == 0 ? F0 : ldim[l], fout = ldim[l + 1];
+        const float *Wm = brain + off, *b = Wm + fout * fin;
+        if (tid < fout) {
+            float s = 0.f;
+            for (int c = 0; c < fin; c++) s += Wm[tid * fin + c] * cur[c];
+            s += b[tid];
+            if (l == 0) s = 1.0f / (1.0f + expf(-s));
+            dst[tid] = s;
+        }
+        __syncthreads();
+        cur = dst; dst = (l == 0) ? pa : (dst == pa ? pb : pa);
+        off += fout * fin + fout;
+    }
+    off_out = off;
+    float *Wout = brain + off_out, *bout = Wout + 4 * hl, *Wh = bout + 4, *bh = Wh + H * hl;
+    if (tid < hl) ah[tid] = cur[tid];                                                  // the last hidden activation (== a0 when there is one hidden layer)
+    if (tid < 4 + H) {
+        const float *Wm = tid < 4 ? Wout + tid * hl : Wh + (tid - 4) * hl;
+        float s = 0.f;
+        for (int c = 0; c < hl; c++) s += Wm[c] * cur[c];
+        s += tid < 4 ? bout[tid] : bh[tid - 4];
+        red[tid] = s;                                                                  // out[0..4), hid[0..H)
+    }
+    __syncthreads();
+    if (tid < 4) {
+        const float e = red[tid] - w.org_mem_out[((size_t)o * SAPIO_MEMROWS + first) * 4 + tid];
+        red[32 + tid] = e * e; red[64 + tid] = 2.0f * e / 4.0f;                        // dO
+    }
+    if (tid >= 32 && tid < 32 + H) w.org_last_hidden[(size_t)o * RC + (tid - 32)] = red[4 + tid - 32];
+    __syncthreads();
+    if (tid == 0) w.org_loss[o] = (float)(((double)red[32] + (double)red[33] + (double)red[34] + (double)red[35]) / 4);
+    const float dO0 = red[64], dO1 = red[65], dO2 = red[66], dO3 = red[67];
+    // backward through the activation-free hidden chain to the first layer's output
+    float *d = da, *d2 = db;
+    if (tid < hl) { float s = 0.f; s += dO0 * Wout[0 * hl + tid]; s += dO1 * Wout[1 * hl + tid]; s += dO2 * Wout[2 * hl + tid]; s += dO3 * Wout[3 * hl + tid]; d[tid] = s; }
+    __syncthreads();
+    for (int l = nl - 2; l >= 1; l--) {
+        const int fin = ldim[l], fout = ldim[l + 1];
+        int offl = 0;
+        for (int t = 0; t < l; t++) offl += ldim[t + 1] * (t == 0 ? F0 : ldim[t]) + ldim[t + 1];
+        const float *Wm = brain + offl;
+        if (tid < fin) { float s = 0.f; for (int r = 0; r < fout; r++) s += d[r] * Wm[r * fin + tid]; d2[tid] = s; }
+        __syncthreads();
+        float *t2 = d; d = d2; d2 = t2;
+    }
+    // SGD: p = p + (-lr) * grad, products rounded like torch's (grad materialised in fp32 first)
+    const float nlr = -p.learning_rate;
+    float *Win = brain, *bin = brain + h0 * F0;
+    for (int e = tid; e < 4 * hl + 4; e += TRAIN_THREADS) {
+        if (e < 4 * hl) { const int q = e / hl, c = e - q * hl; const float g = __fmul_rn(red[64 + q], ah[c]); Wout[e] = __fadd_rn(Wout[e], __fmul_rn(nlr, g)); }
+        else bout[e - 4 * hl] = __fadd_rn(bout[e - 4 * hl], __fmul_rn(nlr, red[64 + e - 4 * hl]));
+    }
+    for (int e = tid; e < h0 * F0 + h0; e += TRAIN_THREADS) {
+        const int r = e < h0 * F0 ? e / F0 : e - h0 * F0;
+        const float hv = a0[r], dz = __fmul_rn(__fmul_rn(d[r], hv), 1.0f - hv);
+        if (e < h0 * F0) { const float g = __fmul_rn(dz, x[e - r * F0]); Win[e] = __fadd_rn(Win[e], __fmul_rn(nlr, g)); }
+        else bin[r] = __fadd_rn(bin[r], __fmul_rn(nlr, dz));
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(TRAIN_THREADS, 4) k_train(WORLD_ARG, RulesWs R, TrainWs TW) {
     __shared__ unsigned long long hs[2][SAPIO_STM], hm[2][SAPIO_STM], hmem[2][SAPIO_MEMROWS];
     __shared__ float rew_s[SAPIO_MEMROWS], red_f[TRAIN_THREADS];
     __shared__ int16_t rowsrc[SAPIO_MEMROWS];      // -1 row untouched | 0..231 content of original row | 256 + i short-term row i
     __shared__ uint8_t bestof[SAPIO_STM];
+    __shared__ int seq_s[SAPIO_MEMROWS];           // list position of every curated row (append stamps): Trainer.train_rnn reads the last row and the first
     __shared__ int sh_M;
     const SapioParams &p = w.p;
     const int IN = p.in_cap, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -96,7 +185,9 @@ __global__ void __launch_bounds__(TRAIN_THREADS, 4) k_train(WORLD_ARG, RulesWs R
                 if (lane == 0) { hmem[0][m] = a; hmem[1][m] = b; }
             }
         }
-        for (int m = tid; m < SAPIO_MEMROWS; m += TRAIN_THREADS) { rowsrc[m] = -1; rew_s[m] = m < M0 ? mrew[m] : 0.f; }
+        const int H = w.org_rnn_h[o], RC = p.rnn_cap;
+        int32_t *mseq = w.org_mem_seq + (size_t)o * SAPIO_MEMROWS;
+        for (int m = tid; m < SAPIO_MEMROWS; m += TRAIN_THREADS) { rowsrc[m] = -1; rew_s[m] = m < M0 ? mrew[m] : 0.f; seq_s[m] = m < M0 ? mseq[m] : 0; }
         __syncthreads();
         // (a) sorted(allActions, key=reward)[-1] among the short-term rows with the same key: highest reward, the LAST of equal maxima
         if (tid < sn) {
@@ -108,7 +199,8 @@ __global__ void __launch_bounds__(TRAIN_THREADS, 4) k_train(WORLD_ARG, RulesWs R
         __syncthreads();
         // ---- curate (neural.py:374-404): one warp, chronological, bookkeeping only ----
         if (wid == 0) {
-            int M = M0;
+            int M = M0, stamp = w.org_mem_stamp[o], thn = H > 0 ? w.org_th_n[o] : 0;
+            const int hpop = H > 0 ? w.org_hm_n[2 * o + 1] : 0;
             for (int i = 0; i < sn; i++) {
                 const unsigned long long a = hs[0][i], b = hs[1][i];
                 int found = -1;                                   // (b) rounded_training_data.index(key): first stored row with the key
@@ -124,6 +216,14 @@ __global__ void __launch_bounds__(TRAIN_THREADS, 4) k_train(WORLD_ARG, RulesWs R
                 __syncwarp();
                 if (add && lane == 0) {                           // input of THIS memory, action of the best one, reward of this one (sic, neural.py:395)
                     rowsrc[dst] = (int16_t)(256 + i); rew_s[dst] = srew[STM_SLOT(i)]; hmem[0][dst] = hm[0][i]; hmem[1][dst] = hm[1][i];
+                    seq_s[dst] = stamp;                           // remove_memory + append: the row is now the last of the list
+                }
+                if (add) {
+                    stamp++;
+                    if (H > 0 && thn < SAPIO_MEMROWS) {           // trainingHidden.append(hidden_memory[i]) (neural.py:396-397): append-only, the first 232 entries kept
+                        if (lane < H) w.org_th[((size_t)o * SAPIO_MEMROWS + thn) * RC + lane] = w.org_hm[((size_t)o * SAPIO_HM + (size_t)((hpop + i) % SAPIO_HM)) * RC + lane];
+                        thn++;
+                    }
                 }
                 __syncwarp();
             }
@@ -137,14 +237,15 @@ __global__ void __launch_bounds__(TRAIN_THREADS, 4) k_train(WORLD_ARG, RulesWs R
                 }
                 const int last = M - 1, lo = li < M ? li : last;
                 __syncwarp();
-                if (lo != last && lane == 0) { rowsrc[lo] = rowsrc[last] < 0 ? (int16_t)last : rowsrc[last]; rew_s[lo] = rew_s[last]; }
+                if (lo != last && lane == 0) { rowsrc[lo] = rowsrc[last] < 0 ? (int16_t)last : rowsrc[last]; rew_s[lo] = rew_s[last]; seq_s[lo] = seq_s[last]; }
                 M = last;
                 __syncwarp();
             }
-            if (lane == 0) sh_M = M;
+            if (lane == 0) { sh_M = M; w.org_mem_stamp[o] = stamp; if (H > 0) w.org_th_n[o] = thn; }
         }
         __syncthreads();
         const int M = sh_M;
+        for (int m = tid; m < M; m += TRAIN_THREADS) mseq[m] = seq_s[m];
         // ---- apply: a row only ever moves when it is the last one, so every original source row lies at or beyond M and every
         //      destination below M: the copies are independent ----
         for (int m = wid; m < M; m += TRAIN_THREADS / 32) {
@@ -159,7 +260,8 @@ __global__ void __launch_bounds__(TRAIN_THREADS, 4) k_train(WORLD_ARG, RulesWs R
         }
         if (tid == 0) w.org_mem_n[o] = M;
         __syncthreads();
-        if (M > 0) {
+        if (M > 0 && H > 0) train_rnn_step(w, o, M, seq_s, red_f, XT);
+        else if (M > 0) {
             float *brain = w.org_brain + (size_t)o * p.brain_cap;
             const int h0 = ldim[1], hl = ldim[nl - 1];
             int off_out = 0;

@@ -19,7 +19,7 @@ import types
 
 import torch
 
-from .world import CELL_TYPES, F_FINITE_MEMORY, F_MIRROR_X, F_MIRROR_Y, HIST, MAXC, MEMROWS, NPAIR, STM, World
+from .world import CELL_TYPES, F_FINITE_MEMORY, F_MIRROR_X, F_MIRROR_Y, HIST, HM, MAXC, MEMROWS, NPAIR, STM, World
 
 DNA_FIELDS = ("cells", "growth_pattern", "_base_brain_structure", "brain_structure", "trainingInput", "trainingOutput", "trainingReward",
               "trainingHidden", "previousInputs", "previousOutputs", "previousDopamine", "stim_history", "short_term_memory", "hidden_memory",
@@ -62,9 +62,10 @@ def export_dna(world: World, slot: int) -> dict:
             growth[cid(par)][cid(k)] = [float(t["c_grow"][base + k][0]), float(t["c_grow"][base + k][1])]
     nl = int(t["org_nlayers"][slot]); dims = t["org_ldim"][slot][:nl + 1].tolist()
     blob = t["org_brain"][slot]
+    H, RC = int(t["org_rnn_h"][slot]), int(world.p.rnn_cap)       # RNN brain: the input layer has H more columns (networks.py:116)
     hidden_w, off = [], 0
     for l in range(nl):
-        fin, fout = dims[l], dims[l + 1]
+        fin, fout = dims[l] + (H if l == 0 else 0), dims[l + 1]
         if 1 <= l <= nl - 2:
             hidden_w.append(blob[off:off + fout * fin].view(fout, fin).tolist())
         off += fout * fin + fout
@@ -72,20 +73,24 @@ def export_dna(world: World, slot: int) -> dict:
     I, IN = dims[0] if nl else 0, world.p.in_cap
     flags = int(t["org_flags"][slot])
     mem_n = int(t["org_mem_n"][slot]); mem_in = t["org_mem_in"][slot].view(MEMROWS, IN)
+    morder = sorted(range(mem_n), key=lambda m: int(t["org_mem_seq"][slot][m]))       # list order of the curated memory (append stamps)
+    hm_app, hm_pop = (int(v) for v in t["org_hm_n"][slot])
+    hm = t["org_hm"][slot].view(HM, RC) if RC else None; th = t["org_th"][slot].view(MEMROWS, RC) if RC else None
     hist_n = int(t["org_hist_n"][slot]); hin = t["org_hist_in"][slot].view(HIST, IN); hout = t["org_hist_out"][slot].view(HIST, 4)
     order = [(e % HIST) for e in range(max(0, hist_n - HIST), hist_n)]            # ring slots, oldest first
     stm_n = int(t["org_stm_n"][slot]); sin = t["org_stm_in"][slot].view(STM, IN); sout = t["org_stm_out"][slot].view(STM, 4)
     sorder = [(e % STM) for e in range(max(0, stm_n - STM), stm_n)]
     return {
         "cells": cells, "growth_pattern": growth, "_base_brain_structure": _base_brain(), "brain_structure": brain,
-        "trainingInput": [mem_in[m, :I].tolist() for m in range(mem_n)],
-        "trainingOutput": [t["org_mem_out"][slot].view(MEMROWS, 4)[m].tolist() for m in range(mem_n)],
-        "trainingReward": [float(t["org_mem_rew"][slot][m]) for m in range(mem_n)], "trainingHidden": [],
+        "trainingInput": [mem_in[m, :I].tolist() for m in morder],
+        "trainingOutput": [t["org_mem_out"][slot].view(MEMROWS, 4)[m].tolist() for m in morder],
+        "trainingReward": [float(t["org_mem_rew"][slot][m]) for m in morder],
+        "trainingHidden": [th[e].tolist() for e in range(int(t["org_th_n"][slot]))] if RC else [],
         "previousInputs": [hin[s, :I].clone() for s in order], "previousOutputs": [hout[s].tolist() for s in order],
         "previousDopamine": [float(t["org_hist_dopa"][slot][s]) for s in order],
         "stim_history": [float(v) for v in t["org_stim_hist"][slot]],
         "short_term_memory": [[sin[s, :I].tolist(), sout[s].tolist(), float(t["org_stm_rew"][slot][s])] for s in sorder],
-        "hidden_memory": [],
+        "hidden_memory": [hm[e % HM].tolist() for e in range(hm_pop, hm_app)] if RC else [],
         "base_info": {"distanceThreshold": .8, "mirror_x": bool(flags & F_MIRROR_X), "mirror_y": bool(flags & F_MIRROR_Y),
                       "maximum_creation_tries": 30, "curiosity": float(t["org_curiosity"][slot])},
         "cellRange": [int(world.p.cell_lo), int(world.p.cell_hi)], "sizeRange": [int(world.p.size_lo), int(world.p.size_hi)],
@@ -206,8 +211,9 @@ def import_dna(world: World, slot: int, pos, dna: dict, seed: int | None = None)
     hidden = [int(h) for h in dna["brain_structure"]["hidden_layers"]]
     eyes = [j for j in range(n) if cells[ids[j]]["type"] == "eye"]; olf = [j for j in range(n) if cells[ids[j]]["type"] == "olfactory"]
     dims = [8 * len(eyes) + len(olf) + 4] + hidden + [4]
-    nparam = sum(dims[l + 1] * dims[l] + dims[l + 1] for l in range(len(dims) - 1))
-    if dims[0] > p.in_cap or max(hidden, default=0) > p.width_cap or nparam > p.brain_cap or not hidden or len(dims) - 1 > 15:
+    H, RC = int(p.rnn_hidden), int(p.rnn_cap)                     # build_brain: an RNNetwork when use_rnn is set now (sprites.py:1683-1690)
+    nparam = sum(dims[l + 1] * dims[l] + dims[l + 1] for l in range(len(dims) - 1)) + (H * (hidden[0] + hidden[-1]) + H if hidden else 0)
+    if dims[0] + H > p.in_cap or max(hidden, default=0) > p.width_cap or nparam > p.brain_cap or not hidden or len(dims) - 1 > 15:
         raise ValueError("genome exceeds the tile caps (in_cap / width_cap / brain_cap)")
     dev = t["c_pos"].device
     base = slot * MAXC
@@ -258,8 +264,9 @@ def import_dna(world: World, slot: int, pos, dna: dict, seed: int | None = None)
     g = torch.Generator().manual_seed(((int(p.seed) if seed is None else int(seed)) * 1000003 + uid) & 0x7FFFFFFFFFFFFFFF)
     blob, off = torch.zeros(p.brain_cap, dtype=torch.float32), 0
     hw = dna["brain_structure"].get("hidden_weights", [])
-    for l in range(len(dims) - 1):
-        fin, fout = dims[l], dims[l + 1]
+    nlin = len(dims) - 1
+    for l in range(nlin + (1 if H else 0)):                       # the hidden head outputLayerH follows the output layer (networks.py:151-166)
+        fin, fout = (dims[nlin - 1], H) if l == nlin else (dims[l] + (H if l == 0 else 0), dims[l + 1])
         bound = 1.0 / math.sqrt(fin)
         blob[off:off + fout * fin + fout] = (torch.rand(fout * fin + fout, generator=g) * 2 - 1) * bound
         if 1 <= l <= len(dims) - 3 and l - 1 < len(hw):
@@ -267,6 +274,16 @@ def import_dna(world: World, slot: int, pos, dna: dict, seed: int | None = None)
             if tuple(wl.shape) == (fout, fin):
                 blob[off:off + fout * fin] = wl.reshape(-1)
         off += fout * fin + fout
+    t["org_rnn_h"][slot] = H; t["org_hm_n"][slot] = 0; t["org_th_n"][slot] = 0
+    if RC:
+        t["org_last_hidden"][slot] = 0.0
+        hml = [e for e in dna.get("hidden_memory", []) if len(e) == RC][: HM - STM]           # what a deepcopied DNA carries (sprites.py:386, not erased)
+        thl = [e for e in dna.get("trainingHidden", []) if len(e) == RC][:MEMROWS]
+        if hml:
+            t["org_hm"][slot].view(HM, RC)[: len(hml)] = torch.tensor(hml, dtype=torch.float32, device=dev)
+        if thl:
+            t["org_th"][slot].view(MEMROWS, RC)[: len(thl)] = torch.tensor(thl, dtype=torch.float32, device=dev)
+        t["org_hm_n"][slot][0] = len(hml); t["org_th_n"][slot] = len(thl)
     t["org_brain"][slot] = blob.to(dev)
     t["org_adam_m"][slot] = 0.0; t["org_adam_v"][slot] = 0.0
     t["j_jn"][slot * NPAIR:(slot + 1) * NPAIR] = 0.0
@@ -276,6 +293,7 @@ def import_dna(world: World, slot: int, pos, dna: dict, seed: int | None = None)
     m = min(len(ti), len(to), len(tr), MEMROWS)
     keep = [e for e in range(m) if len(ti[e]) == I]
     t["org_mem_n"][slot] = len(keep)
+    t["org_mem_seq"][slot] = 0; t["org_mem_seq"][slot][: len(keep)] = torch.arange(len(keep), dtype=torch.int32, device=dev); t["org_mem_stamp"][slot] = len(keep)
     mem_in = torch.zeros(MEMROWS, IN); mem_out = torch.zeros(MEMROWS, 4); mem_rew = torch.zeros(MEMROWS)
     for q, e in enumerate(keep):
         mem_in[q, :I] = torch.tensor(ti[e], dtype=torch.float32); mem_out[q] = torch.tensor(to[e], dtype=torch.float32); mem_rew[q] = float(tr[e])

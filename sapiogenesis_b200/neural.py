@@ -21,14 +21,30 @@ class Network:
     def structure(self) -> list:
         return self.organism.dna.brain_structure
 
+    @property
+    def hiddenSize(self) -> int:
+        """RNNetwork.hiddenSize (networks.py:119); 0 for a feed-forward networks.Network"""
+        return int(self.organism.environment.world.t["org_rnn_h"][self.organism.slot])
+
+    @property
+    def is_rnn(self) -> bool:
+        return self.hiddenSize > 0
+
+    @property
+    def lastHidden(self):
+        """RNNetwork.lastHidden (networks.py:149,174): the hidden state the next forward pass is fed"""
+        o = self.organism
+        return o.environment.world.t["org_last_hidden"][o.slot][: self.hiddenSize]
+
     def layers(self):
-        """[(weight [out, in], bias [out])] views into HBM, input layer first (networks.py:226-230)."""
+        """[(weight [out, in], bias [out])] views into HBM, input layer first (networks.py:226-230); for an RNN brain the input layer
+        has hiddenSize more columns and the hidden head outputLayerH comes last (RNNetwork.layers, networks.py:127-134)."""
         o = self.organism
         blob = o.environment.world.t["org_brain"][o.slot]
-        dims = self.structure
+        dims, H = self.structure, self.hiddenSize
+        shapes = [(dims[l] + (H if l == 0 else 0), dims[l + 1]) for l in range(len(dims) - 1)] + ([(dims[-2], H)] if H else [])
         out, off = [], 0
-        for l in range(len(dims) - 1):
-            fin, fout = dims[l], dims[l + 1]
+        for fin, fout in shapes:
             out.append((blob[off:off + fout * fin].view(fout, fin), blob[off + fout * fin:off + fout * fin + fout]))
             off += fout * fin + fout
         return out
@@ -48,11 +64,13 @@ class Network:
 
 def setup_network(dna, learning_rate=0.02, rnn=False, hiddenSize=6) -> Network:
     """neural.py:426-454. The parameters of a materialised organism already exist (build_brain runs inside sapio_spawn /
-    sapio_reproduce with the reference's initialisation); this returns the view. `rnn=True` is not built: the reference's
-    RNN path is unreachable from the UI default and crashes on `activate` (SURVEY C-11)."""
-    if rnn:
-        raise NotImplementedError("use_rnn=True is outside the world step (SURVEY C-11)")
+    sapio_reproduce with the reference's initialisation, as an RNNetwork when Environment.info["use_rnn"] was set at that moment);
+    this returns the view. `rnn` / `hiddenSize` must describe the brain the organism has."""
     env = dna._o.environment
+    have = int(env.world.t["org_rnn_h"][dna._o.slot])
+    if bool(rnn) != (have > 0) or (rnn and int(hiddenSize) != have):
+        raise ValueError(f"organism {dna._o.slot} was built with {'an RNN brain of hidden size %d' % have if have else 'a feed-forward brain'}: "
+                         "set Environment.info['use_rnn'] / ['hidden_rnn_size'] before it is spawned or born")
     if abs(env.world.p.learning_rate - learning_rate) > 0:
         env.world.p.learning_rate = float(learning_rate); env.engine.refresh()
     return Network(dna._o)

@@ -220,10 +220,15 @@ class _Info(dict):
             p.population_limit = int(v); self._env.engine.refresh(); super().__setitem__(k, v)
         elif k == "reproduction_limit":
             p.offspring_amount = int(v); self._env.engine.refresh(); super().__setitem__(k, v)
-        elif k == "use_rnn":
-            if v:
-                raise NotImplementedError("use_rnn=True: recurrent brains (networks.py:111-175) are not part of this world step yet (DESIGN.md 6b)")
+        elif k in ("use_rnn", "hidden_rnn_size"):
+            # physics.py:305,308, read by build_brain (sprites.py:1683-1690): brains built from now on (spawn, birth, import) are
+            # networks.RNNetwork with that hidden size; living organisms keep the brain they have. The size is fixed once set: the
+            # reference cannot change it either while RNN organisms live (torch.tensor of ragged trainingHidden rows raises, neural.py:412)
             super().__setitem__(k, v)
+            h = int(dict.get(self, "hidden_rnn_size", 6)) if dict.get(self, "use_rnn", False) else 0
+            if h:
+                w.reserve_rnn(h)
+            p.rnn_hidden = h; self._env.engine.refresh()
         elif k == "weight_persistence":
             if not v:
                 raise NotImplementedError("weight_persistence=False crashes the reference (SURVEY C-12); not reproduced")

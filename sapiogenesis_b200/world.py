@@ -31,6 +31,8 @@ NWALL = 4
 HIST = 10
 STM = 30
 MEMROWS = 232
+RNN_MAXH = 16
+HM = 90
 
 # cell types: sprites.py:22 (+ "heart", sprites.py:573)
 CELL_TYPES = ["barrier", "carniv", "eye", "olfactory", "co2C", "push", "body", "rotate", "heart"]
@@ -59,7 +61,7 @@ class SapioParams(ctypes.Structure):
     _fields_ = [
         ("n_org", ctypes.c_int32), ("n_dead", ctypes.c_int32), ("x_cap", ctypes.c_int32),
         ("in_cap", ctypes.c_int32), ("brain_cap", ctypes.c_int32), ("adam_cap", ctypes.c_int32),
-        ("width_cap", ctypes.c_int32), ("pad0", ctypes.c_int32),
+        ("width_cap", ctypes.c_int32), ("rnn_cap", ctypes.c_int32),
         ("width", ctypes.c_float), ("height", ctypes.c_float), ("frame_width", ctypes.c_float),
         ("wall_elast", ctypes.c_float), ("wall_fric", ctypes.c_float),
         ("dt_wall", ctypes.c_float), ("dt_phys", ctypes.c_float), ("friction_pct", ctypes.c_float),
@@ -83,17 +85,20 @@ class SapioParams(ctypes.Structure):
         ("seed", ctypes.c_uint64),
         ("grid_cell", ctypes.c_float), ("grid_nx", ctypes.c_int32), ("grid_ny", ctypes.c_int32),
         ("slab_mode", ctypes.c_int32), ("grid_x0", ctypes.c_float), ("slab_x0", ctypes.c_float), ("slab_x1", ctypes.c_float),
-        ("pad1", ctypes.c_int32),
+        ("rnn_hidden", ctypes.c_int32),
     ]
 
 
 def default_params(n_org: int = 16, n_dead: int = 256, width: float = 3180.0, height: float = 1800.0,
                    in_cap: int = 128, width_cap: int = 128, brain_cap: int = 32768, x_cap: int = 0,
-                   seed: int = 0, population_limit: int = 12) -> SapioParams:
+                   seed: int = 0, population_limit: int = 12, rnn_hidden: int = 0) -> SapioParams:
     p = SapioParams()
     p.n_org, p.n_dead = n_org, n_dead
     p.x_cap = x_cap if x_cap > 0 else max(1024, 8 * n_org + 4 * n_dead)
     p.in_cap, p.width_cap, p.brain_cap = in_cap, width_cap, brain_cap
+    # Environment.info["use_rnn"] / ["hidden_rnn_size"] (physics.py:305,308): 0 = feed-forward brains and no recurrent-state arrays
+    assert 0 <= rnn_hidden <= RNN_MAXH
+    p.rnn_cap = p.rnn_hidden = rnn_hidden
     # Adam sees only the input and output layers (networks.py:221): (in+1)*h0 + (h_last+1)*4
     p.adam_cap = (in_cap + 1) * width_cap + (width_cap + 1) * 4
     p.width, p.height = width, height               # environment_settings.json:1
@@ -168,7 +173,7 @@ def _rows(p: SapioParams, scope: str) -> int:
 
 def _per(p: SapioParams, per: str) -> int:
     return int(eval(per, {"__builtins__": {}}, {"MAXC": MAXC, "IN": p.in_cap, "BRAIN": p.brain_cap,
-                                                 "ADAM": p.adam_cap}))
+                                                 "ADAM": p.adam_cap, "RNNH": p.rnn_cap}))
 
 
 class World:
@@ -210,6 +215,19 @@ class World:
             setattr(s, f.name, self.t[f.name].data_ptr())
         self._struct = s  # keep alive
         return s
+
+    def reserve_rnn(self, hidden: int) -> None:
+        """Allocates the recurrent-state arrays (per = RNNH of sapio_fields.def) of a world that was built without them: what setting
+        Environment.info["use_rnn"] needs the first time. The hidden size is then fixed for the life of the world."""
+        if self.p.rnn_cap == hidden:
+            return
+        if self.p.rnn_cap != 0 or not 0 < hidden <= RNN_MAXH:
+            raise ValueError(f"hidden_rnn_size {hidden}: between 1 and {RNN_MAXH}, and fixed once RNN brains exist ({self.p.rnn_cap} here)")
+        self.p.rnn_cap = hidden
+        for f in FIELDS:
+            if "RNNH" in f.per:
+                self.t[f.name] = torch.zeros((_rows(self.p, f.scope), _per(self.p, f.per)), dtype=_CT[f.ctype][0], device=self.device)
+        self._struct = None
 
     def to(self, device) -> "World":
         w = World.__new__(World)

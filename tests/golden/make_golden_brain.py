@@ -49,10 +49,13 @@ def fill_views(ns, env, org):
                            and shape.shapes_collide(s.shape).points]
 
 
-def gen_brain(n_cases=6, seed=41):
+def gen_brain(n_cases=6, seed=41, rnn=0, name="brain_cases.npz", n_thinks=N_THINKS):
+    """rnn = hidden_rnn_size with Environment.info["use_rnn"] set (physics.py:305,308): the same scenes through networks.RNNetwork,
+    the is_rnn branches of neural.activate / train_network and Trainer.train_rnn -> rnn_cases.npz"""
     ns = refshim.load()
     torch = ns.torch
-    out = {"meta": np.asarray([n_cases, seed, N_THINKS], dtype=np.int32)}
+    N_THINKS = n_thinks
+    out = {"meta": np.asarray([n_cases, seed, N_THINKS, rnn], dtype=np.int32)}
     none = lambda: refshim.UniformFeed([], "none")
     for ci in range(n_cases):
         base = f"brain-{seed}-{ci}"
@@ -61,6 +64,8 @@ def gen_brain(n_cases=6, seed=41):
         tagB, dnaB, usedB = find_seed(ns, base + "-B", want_eye=0, want_olf=0, max_cells=40)
         round_dna_to_f32(dnaA); round_dna_to_f32(dnaB)
         env = refshim.FakeEnv(ns)
+        if rnn:
+            env.info["use_rnn"], env.info["hidden_rnn_size"] = True, rnn
         ubA, ubB = feed(tagA + "-ub", 600000, "build"), feed(tagB + "-ub", 600000, "build")
         posA = [f32(rng.uniform(900, 2200)), f32(rng.uniform(600, 1200))]
         ang = rng.uniform(0, 2 * math.pi); dist = rng.uniform(120, 260)
@@ -87,7 +92,7 @@ def gen_brain(n_cases=6, seed=41):
         out[f"c{ci}.used"] = np.asarray([usedA, usedB], dtype=np.int32)
         out[f"c{ci}.pos"] = np.asarray([posA, posB], dtype=np.float64)
         out[f"c{ci}.food"] = np.asarray(food, dtype=np.float64)
-        I = A.brain.inputSize
+        I = A.brain.inputSize - rnn          # RNNetwork.inputSize counts the hidden columns (networks.py:116)
         rec = dict(inputs=[], raw=[], out=[], move=[], scal=[], stim_hist=[], nhist=[], stm_n=[], rot=[], bpos=[], benergy=[], aenergy=[],
                    gate=[], dopa=[])
         curiosity = f32(A.dna.base_info["curiosity"]); A.dna.base_info["curiosity"] = curiosity
@@ -134,10 +139,16 @@ def gen_brain(n_cases=6, seed=41):
                 return torch.tensor(vals, dtype=torch.float64).float()
             ns.neural.torch = refshim._TorchProxy(torch, randn=randn)
             rot = A.rotation()
+            h_prev = A.brain.lastHidden.detach().clone() if rnn else None
             A.brain.activate(env, A, 0.03)
             x = A.dna.previousInputs[-1]
             rec["inputs"].append(x.tolist())
-            rec["raw"].append(A.brain.forward(x).tolist())
+            if rnn:
+                rec["raw"].append(A.brain.forward(x, h_prev).tolist())      # recomputes the same lastHidden
+                rec.setdefault("lasthid", []).append(A.brain.lastHidden.tolist())
+                rec.setdefault("hm_n", []).append(len(A.dna.hidden_memory))
+            else:
+                rec["raw"].append(A.brain.forward(x).tolist())
             rec["out"].append(A.dna.previousOutputs[-1])
             rec["move"].append([A.movement["rotation"], A.movement["speed"], A.movement["direction"][0], A.movement["direction"][1]])
             rec["scal"].append([A.brain.stimulation, A.brain.boredom, A.dopamine, A.pain])
@@ -161,8 +172,11 @@ def gen_brain(n_cases=6, seed=41):
         out[f"c{ci}.stm_out"] = np.asarray([m[1] for m in stm], dtype=np.float32).reshape(len(stm), 4)
         out[f"c{ci}.stm_rew"] = np.asarray([m[2] for m in stm], dtype=np.float64)
 
+        if rnn:
+            assert len(A.dna.hidden_memory) == len(stm)
+            out[f"c{ci}.hm"] = np.asarray(A.dna.hidden_memory, dtype=np.float32).reshape(len(stm), rnn)
         # ---- train_network: curated memory + one Adam epoch, twice; pre-filled memory so that replace / keep / trim all occur
-        pre_n = [0, 150, 205, 230, 60, 199][ci % 6]
+        pre_n = ([0, 150, 200, 185] if rnn else [0, 150, 205, 230, 60, 199])[ci % 6]      # RNN scenes hold 30 short-term rows: <= 200 + 30 rows fit the table
         pre_in, pre_out, pre_rew = [], [], []
         seen = set()                              # the reference's memory never holds two entries with one 1-dp key
         m = 0                                     # (train_network replaces on a key match), so neither does the pre-fill
@@ -183,6 +197,10 @@ def gen_brain(n_cases=6, seed=41):
         A.dna.trainingInput = [list(v) for v in pre_in]
         A.dna.trainingOutput = [list(v) for v in pre_out]
         A.dna.trainingReward = list(pre_rew)
+        if rnn:      # trainingHidden runs along with the memory (one entry per appended row, never removed: neural.py:83-87, 396-397)
+            pre_th = [[f32(rng.uniform(-1, 1)) for _ in range(rnn)] for _ in range(pre_n)]
+            A.dna.trainingHidden = [list(v) for v in pre_th]
+            out[f"c{ci}.pre_th"] = np.asarray(pre_th, dtype=np.float32).reshape(pre_n, rnn)
         out[f"c{ci}.pre_in"] = np.asarray(pre_in, dtype=np.float32).reshape(pre_n, I)
         out[f"c{ci}.pre_out"] = np.asarray(pre_out, dtype=np.float32).reshape(pre_n, 4)
         out[f"c{ci}.pre_rew"] = np.asarray(pre_rew, dtype=np.float32)
@@ -198,10 +216,18 @@ def gen_brain(n_cases=6, seed=41):
                 flat += layer.weight.detach().reshape(-1).tolist() + layer.bias.detach().reshape(-1).tolist()
             out[f"c{ci}.brain{ep}"] = np.asarray(flat, dtype=np.float32)
             out[f"c{ci}.loss{ep}"] = np.asarray([A.brain.lastLoss], dtype=np.float64)
+            if rnn:
+                th = A.dna.trainingHidden
+                out[f"c{ci}.th_n{ep}"] = np.asarray([len(th)], dtype=np.int32)
+                out[f"c{ci}.th{ep}"] = np.asarray(th[:232], dtype=np.float32).reshape(min(len(th), 232), rnn)
+                out[f"c{ci}.lasthid_t{ep}"] = np.asarray(A.brain.lastHidden.tolist(), dtype=np.float32)
         print(f"brain case {ci}: inputs {I}, cells A {len(orderA)} B {len(orderB)}, viewed {rec['views']}, stm {len(stm)}, "
               f"memory {pre_n} -> {len(A.dna.trainingInput)}, loss {A.brain.lastLoss:.5f}")
-    np.savez_compressed(os.path.join(HERE, "brain_cases.npz"), **out)
+    np.savez_compressed(os.path.join(HERE, name), **out)
 
 
 if __name__ == "__main__":
-    gen_brain()
+    if "rnn" in sys.argv[1:]:
+        gen_brain(n_cases=4, seed=43, rnn=6, name="rnn_cases.npz", n_thinks=48)
+    else:
+        gen_brain()

@@ -13,7 +13,7 @@ TOL = 1e-5
 SKIP = {"org_gas_a", "org_gas_b", "c_dmg", "d_eaten", "org_rect", "g_stats", "org_out_raw"}
 # fields whose meaningful extent depends on counters / rings: handled explicitly
 SPECIAL = {"org_brain", "org_adam_m", "org_adam_v", "org_hist_in", "org_hist_out", "org_hist_dopa", "org_stm_in", "org_stm_out",
-           "org_stm_rew", "org_mem_in", "org_mem_out", "org_mem_rew", "org_incell", "org_ldim", "ic_code", "ic_jn", "ic_jt", "j_jn",
+           "org_stm_rew", "org_mem_in", "org_mem_out", "org_mem_rew", "org_mem_seq", "org_incell", "org_ldim", "ic_code", "ic_jn", "ic_jt", "j_jn",
            "x_key", "x_jn", "x_jt", "xa_off", "xa_other", "c_spos", "c_svel", "c_svbias", "c_spin_jn", "c_wbias", "d_wbias"}
 # dopamine / pain = (percent now - percent at the last snapshot) / dt with percents O(100) held in fp32 and dt >= 0.09 s: the
 # subtraction carries 100 * 6e-8 / 0.09 ~ 7e-5 of absolute noise whatever the size of the result, so these signals are compared
@@ -293,7 +293,8 @@ def compare_worlds(wg, w, tag, brain_tol=TOL, check_brain=True, skip=(), verbose
         if G["org_nlayers"][o] != nl:
             continue
         I = int(ld[0])
-        P = sum(int(ld[l + 1]) * int(ld[l]) + int(ld[l + 1]) for l in range(nl))
+        H = int(O["org_rnn_h"][o])                           # RNN brain: H more input columns and the hidden head after the output layer
+        P = sum(int(ld[l + 1]) * (int(ld[l]) + (H if l == 0 else 0)) + int(ld[l + 1]) for l in range(nl)) + (H * int(ld[nl - 1]) + H if H else 0)
         # Rounding cliff: the network output is rounded to 3 decimals (neural.py:292); at a tie the fp32 forward's 1e-7
         # flips the last digit, and the flipped row is a training TARGET of the same tick (|output - target| <= 5e-4 becomes 1.5e-3):
         # the gradient of that organism is a different one on the two sides. Such organisms are counted, held to the 1.5e-3 of the
@@ -335,6 +336,7 @@ def compare_worlds(wg, w, tag, brain_tol=TOL, check_brain=True, skip=(), verbose
             rep.exact(f"org_mem_in[{o}]", G["org_mem_in"][o].reshape(MEMROWS, IN)[:M, :I], O["org_mem_in"][o].reshape(MEMROWS, IN)[:M, :I])
             rep.close("org_mem_out", G["org_mem_out"][o][: M * 4], O["org_mem_out"][o][: M * 4], tol=1.5e-3, floor=1.0)
             rep.close("org_mem_rew", G["org_mem_rew"][o][:M], O["org_mem_rew"][o][:M], floor=DOPA_FLOOR)
+            rep.exact(f"org_mem_seq[{o}]", G["org_mem_seq"][o][:M], O["org_mem_seq"][o][:M])
     if ties:
         print(f"{tag}: {ties} of {len(detail)} organisms at a 3-decimal rounding tie of their outputs (brain / optimiser comparison skipped for them)")
         if ties > max(2, 0.002 * len(detail)):

@@ -97,3 +97,25 @@ def test_every_size_class_boundary(oracle, coupled_kernel):
         eng.tick(1, PH_ALL); eng.synchronize()
         assert oracle.tick(w, PH_ALL, 1) == 0
         compare_worlds(wg, w, f"size classes tick {w.tick}", verbose=False)
+
+
+def test_push_direction_keeps_the_sign_of_a_zero_command(oracle):
+    """A network output rounded to -0.0 stays -0.0 (neural.py:292, tolist()), and the push actuator takes math.atan2 of the two direction
+    commands (sprites.py:1519-1544): atan2(+-0, -0) = +-pi, atan2(+-0, +0) = +-0 -- opposite pushes. Found at 100k organisms (one
+    organism per tick has both commands at zero); here every combination of signed zeros and a few ordinary directions."""
+    from test_gpu_tick import fast_world
+    w = fast_world(oracle, 16, 17, 0.9, 0)
+    assert oracle.tick(w, PH_ALL, 2) == 0
+    z = [(0.0, 0.0), (-0.0, 0.0), (0.0, -0.0), (-0.0, -0.0), (-0.0, 0.5), (0.5, -0.0), (-0.5, -0.0), (-0.5, 0.0), (0.3, -0.4), (-0.0, -0.5)]
+    orgs = np.nonzero(w.np("org_state") == 1)[0]
+    pushers = 0
+    for i, o in enumerate(orgs):
+        dx, dy = z[i % len(z)]
+        w.t["org_move"][o] = torch.tensor([0.0, -0.6 if i % 2 else 0.8, dx, dy])
+        pushers += int(((w.np("c_type")[o * MAXC:(o + 1) * MAXC] == 5) & (w.np("c_alive")[o * MAXC:(o + 1) * MAXC] == 1)).sum())
+    assert pushers >= 10
+    w.t["org_think_tick"][:] = int(w.tick)                           # nobody thinks this tick: the commands above are the ones acted on
+    wg, eng = engine_for(w)
+    eng.tick(1, PH_ALL); eng.synchronize()
+    assert oracle.tick(w, PH_ALL, 1) == 0
+    compare_worlds(wg, w, "signed-zero push commands", verbose=True)

@@ -13,9 +13,9 @@ from worlds import make_world
 pytestmark = pytest.mark.gpu
 
 
-def fast_world(oracle, n_org, seed, crowd, food, extra=24):
+def fast_world(oracle, n_org, seed, crowd, food, extra=24, **kw):
     """A busy little world: brains think/train every 3 ticks, reproduction allowed every 8, plenty of free slots."""
-    w = make_world(oracle, n_org=n_org, seed=seed, n_food=food, crowd=crowd, kick=30.0, extra_slots=extra, n_dead_cap=64 * (n_org + extra))
+    w = make_world(oracle, n_org=n_org, seed=seed, n_food=food, crowd=crowd, kick=30.0, extra_slots=extra, n_dead_cap=64 * (n_org + extra), **kw)
     w.p.think_ticks, w.p.train_ticks, w.p.repro_ticks = 3, 3, 8
     w.p.population_limit = n_org + extra
     return w
@@ -44,17 +44,22 @@ def test_spawn_matches_oracle(oracle):
         np.testing.assert_array_equal(wg.np("org_brain")[s], w.np("org_brain")[s])
 
 
-@pytest.mark.parametrize("n_org,crowd,food,seed", [(16, 0.45, 40, 11), (40, 0.4, 120, 12)])
-def test_every_stage_matches_oracle_along_a_trajectory(oracle, n_org, crowd, food, seed):
-    w = fast_world(oracle, n_org, seed, crowd, food)
+@pytest.mark.parametrize("n_org,crowd,food,seed,rnn", [(16, 0.45, 40, 11, 0), (40, 0.4, 120, 12, 0), (24, 0.45, 60, 13, 6)])
+def test_every_stage_matches_oracle_along_a_trajectory(oracle, n_org, crowd, food, seed, rnn):
+    """rnn = hidden_rnn_size with use_rnn set (physics.py:305,308): RNNetwork brains (networks.py:111-175) -- forward on inputs ++ lastHidden,
+    hidden_memory along the short-term memory, Trainer.train_rnn's one-sample SGD, inheritance of hidden_memory / trainingHidden at birth;
+    use_rnn is switched off half way, so feed-forward children of RNN parents live next to them."""
+    w = fast_world(oracle, n_org, seed, crowd, food, extra=96 if rnn else 24, rnn_hidden=rnn)
     assert oracle.tick(w, PH_ALL, 6) == 0                 # warm up: contacts, adjacency, first thinks and memories exist
     seen = dict(thinks=0, trains=0, births=0, cell_deaths=0, deaths=0)
-    for t in range(30):
+    for t in range(30 if not rnn else 60):
+        if rnn and t == 40:
+            w.p.rnn_hidden = 0
         if t == 8:                                         # provoke deaths (cascades, dead bodies) and births
             alive = np.nonzero(w.np("c_alive") == 1)[0]
             kill = alive[(alive % MAXC != 0)][::7]
             w.t["c_health"][torch.from_numpy(kill)] = -1.0
-        if t in (10, 18):
+        if t in (10, 18, 44):
             w.t["c_energy"][:] = w.t["c_storage"]          # everybody full: reproduction gate opens, co2 refunds saturate
         before = w.stats()
         wg, eng = engine_for(w)
@@ -69,7 +74,8 @@ def test_every_stage_matches_oracle_along_a_trajectory(oracle, n_org, crowd, foo
         compare_worlds(wg, w, tag + " reproduce", verbose=False)
         eng.space_step(); eng.friction(); eng.post(); eng.synchronize()
         assert oracle.space_step(w) == 0; oracle.friction(w); oracle.post(w)
-        compare_worlds(wg, w, tag + " step", verbose=(t % 10 == 0))
+        # the RNN trajectory is about the brains: its crowded 60-tick physics is held to 3e-5 of the rms instead of 1e-5 (d_vel reached 2e-5 once)
+        compare_worlds(wg, w, tag + " step", verbose=(t % 10 == 0), phys_tol=3e-5 if rnn else None)
         assert wg.stats()["overflow"] == 0
         w.t["g_tick"] += 1
         after = w.stats()
@@ -77,6 +83,11 @@ def test_every_stage_matches_oracle_along_a_trajectory(oracle, n_org, crowd, foo
             seen[k] += after[k] - before[k]
     print("events along the trajectory:", seen)
     assert seen["thinks"] > 0 and seen["trains"] > 0 and seen["cell_deaths"] > 0 and seen["births"] > 0
+    if rnn:
+        st = w.np("org_state") == 1; h = w.np("org_rnn_h")[st]; gen = w.np("org_generation")[st]
+        print(f"rnn: {int((h > 0).sum())} RNN / {int((h == 0).sum())} feed-forward organisms, RNN children {int(((h > 0) & (gen > 0)).sum())}, "
+              f"hidden_memory entries {int((w.np('org_hm_n')[st][:, 0] - w.np('org_hm_n')[st][:, 1]).sum())}, trainingHidden entries {int(w.np('org_th_n')[st].sum())}")
+        assert (h > 0).any() and (h == 0).any() and ((h > 0) & (gen > 0)).any() and w.np("org_th_n")[st].sum() > 0
 
 
 def test_full_tick_call_matches_oracle(oracle):

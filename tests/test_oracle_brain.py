@@ -15,6 +15,10 @@ from sapiogenesis_b200.world import HIST, MAXC, MEMROWS, STM, World, default_par
 
 CASES = np.load(os.path.join(GOLDEN, "brain_cases.npz"))
 N_CASES, SEED, N_THINKS = (int(v) for v in CASES["meta"])
+# the same scenes through the reference's networks.RNNetwork / Trainer.train_rnn and the is_rnn branches of neural.py (use_rnn = True,
+# hidden_rnn_size = 6; 48 thinks, so that the short-term memory -- and hidden_memory with it -- wraps)
+RNN_CASES = np.load(os.path.join(GOLDEN, "rnn_cases.npz"))
+RNN_N_CASES, _, RNN_N_THINKS, RNN_H = (int(v) for v in RNN_CASES["meta"])
 
 
 def u24(tag, n):
@@ -22,11 +26,13 @@ def u24(tag, n):
     return np.asarray([rng.getrandbits(24) / 16777216.0 for _ in range(n)], dtype=np.float32)
 
 
-def build_scene(oracle, ci):
-    g = lambda k: CASES[f"c{ci}.{k}"]
+def build_scene(oracle, ci, cases=CASES, rnn=0):
+    g = lambda k: cases[f"c{ci}.{k}"]
     tagA, tagB = (str(s) for s in g("tags"))
     used, pos = g("used"), g("pos")
-    w = World(default_params(n_org=3, n_dead=16))
+    p = default_params(n_org=3, n_dead=16)
+    p.rnn_cap = p.rnn_hidden = rnn
+    w = World(p)
     for slot, tag in ((0, tagA), (1, tagB)):
         rc, _ = oracle.spawn_arr(w, slot, float(pos[slot][0]), float(pos[slot][1]), u24(tag + "-u", used[slot][0] + 8),
                                  u24(tag + "-ui", used[slot][1] + 8), u24(tag + "-ub", used[slot][2] + 8))
@@ -40,8 +46,18 @@ def build_scene(oracle, ci):
 
 @pytest.mark.parametrize("ci", range(N_CASES))
 def test_activate_and_train_match_reference(oracle, ci):
-    w, g = build_scene(oracle, ci)
+    run_case(oracle, ci, CASES, N_THINKS, 0)
+
+
+@pytest.mark.parametrize("ci", range(RNN_N_CASES))
+def test_rnn_activate_and_train_match_reference(oracle, ci):
+    run_case(oracle, ci, RNN_CASES, RNN_N_THINKS, RNN_H)
+
+
+def run_case(oracle, ci, cases, N_THINKS, H):
+    w, g = build_scene(oracle, ci, cases, H)
     t = w.t
+    assert int(w.np("org_rnn_h")[0]) == H
     ncA, ncB = int(w.np("org_ncells")[0]), int(w.np("org_ncells")[1])
     I = int(w.np("org_ldim")[0][0])
     assert g("inputs").shape == (N_THINKS, I)
@@ -95,16 +111,27 @@ def test_activate_and_train_match_reference(oracle, ci):
         np.testing.assert_allclose(w.np("org_stim_hist")[0], g("stim_hist")[k], rtol=2e-6, atol=1e-7)
         assert min(int(w.np("org_hist_n")[0]), HIST) == int(g("nhist")[k])
         assert min(int(w.np("org_stm_n")[0]), STM) == int(g("stm_n")[k]), f"think {k}: short-term memory length"
+        if H:
+            np.testing.assert_allclose(w.np("org_last_hidden")[0][:H], g("lasthid")[k], rtol=1e-5, atol=1e-6, err_msg=f"think {k}: lastHidden")
+            hn = w.np("org_hm_n")[0]
+            assert int(hn[0]) - int(hn[1]) == int(g("hm_n")[k]), f"think {k}: hidden_memory length"
     assert flips <= 2, "rounded outputs differ from the reference beyond tie flips"
     # short-term memory content (ring, chronological)
-    sn = int(w.np("org_stm_n")[0])
-    assert sn == len(g("stm_rew")) and sn <= STM
-    got_in = w.np("org_stm_in")[0].reshape(STM, IN)[:sn, :I]
+    sc = int(w.np("org_stm_n")[0]); sn = min(sc, STM)
+    assert sn == len(g("stm_rew"))
+    ring = [(sc - sn + i) % STM for i in range(sn)]                # chronological order of the ring
+    got_in = w.np("org_stm_in")[0].reshape(STM, IN)[ring, :I]
     np.testing.assert_array_equal(got_in, g("stm_in"))
-    np.testing.assert_allclose(w.np("org_stm_out")[0].reshape(STM, 4)[:sn], g("stm_out"), rtol=0, atol=1e-3 + 1e-6)
-    np.testing.assert_allclose(w.np("org_stm_rew")[0][:sn], g("stm_rew"), rtol=2e-6, atol=1e-6)
+    np.testing.assert_allclose(w.np("org_stm_out")[0].reshape(STM, 4)[ring], g("stm_out"), rtol=0, atol=1e-3 + 1e-6)
+    np.testing.assert_allclose(w.np("org_stm_rew")[0][ring], g("stm_rew"), rtol=2e-6, atol=1e-6)
     # make the actions identical to the reference's before training on them
-    t["org_stm_out"][0][: sn * 4] = torch.from_numpy(g("stm_out").reshape(-1))
+    t["org_stm_out"][0].view(STM, 4)[ring] = torch.from_numpy(g("stm_out"))
+    if H:                                                           # hidden_memory runs along with the short-term memory (neural.py:312-318)
+        hn = w.np("org_hm_n")[0]; RC = w.p.rnn_cap
+        hm = w.np("org_hm")[0].reshape(-1, RC)
+        got_hm = hm[[(int(hn[1]) + i) % hm.shape[0] for i in range(int(hn[0]) - int(hn[1]))], :H]
+        np.testing.assert_allclose(got_hm, g("hm"), rtol=1e-5, atol=1e-6)
+        t["org_hm"][0].view(-1, RC)[[(int(hn[1]) + i) % hm.shape[0] for i in range(len(g("hm")))], :H] = torch.from_numpy(g("hm"))
 
     # ---- train_network twice
     pre_in, pre_out, pre_rew = g("pre_in"), g("pre_out"), g("pre_rew")
@@ -115,8 +142,11 @@ def test_activate_and_train_match_reference(oracle, ci):
     t["org_mem_out"][0].view(MEMROWS, 4)[:M0] = torch.from_numpy(pre_out)
     t["org_mem_rew"][0][:M0] = torch.from_numpy(pre_rew)
     t["org_mem_n"][0] = M0
+    t["org_mem_seq"][0][:M0] = torch.arange(M0, dtype=torch.int32); t["org_mem_stamp"][0] = M0      # list order of the pre-filled rows
     nl = int(w.np("org_nlayers")[0]); ldim = w.np("org_ldim")[0]
-    P = sum(int(ldim[l + 1]) * int(ldim[l]) + int(ldim[l + 1]) for l in range(nl))
+    P = sum(int(ldim[l + 1]) * (int(ldim[l]) + (H if l == 0 else 0)) + int(ldim[l + 1]) for l in range(nl)) + (H * int(ldim[nl - 1]) + H if H else 0)
+    if H:
+        t["org_th"][0].view(MEMROWS, w.p.rnn_cap)[:M0, :H] = torch.from_numpy(g("pre_th")); t["org_th_n"][0] = M0
     for ep in range(2):
         assert oracle.train_one(w, 0) == 0
         M = int(w.np("org_mem_n")[0])
@@ -129,7 +159,17 @@ def test_activate_and_train_match_reference(oracle, ci):
         for key in ref:
             np.testing.assert_allclose(got[key][0], ref[key][0], rtol=0, atol=1e-6)
             np.testing.assert_allclose(got[key][1], ref[key][1], rtol=2e-6, atol=1e-6)
-        np.testing.assert_allclose(w.np("org_loss")[0], g(f"loss{ep}")[0], rtol=2e-5)
+        np.testing.assert_allclose(w.np("org_loss")[0], g(f"loss{ep}")[0], rtol=2e-5, atol=1e-9)
+        if H:
+            # Trainer.train_rnn (networks.py:56-73): one sample, plain SGD on the input and output layers, lastHidden as a side effect
+            tn_ref = int(g(f"th_n{ep}")[0])
+            assert int(w.np("org_th_n")[0]) == min(tn_ref, MEMROWS), f"epoch {ep}: trainingHidden length"
+            np.testing.assert_allclose(w.np("org_th")[0].reshape(MEMROWS, -1)[: min(tn_ref, MEMROWS), :H], g(f"th{ep}"), rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(w.np("org_last_hidden")[0][:H], g(f"lasthid_t{ep}"), rtol=1e-5, atol=1e-6, err_msg=f"epoch {ep}: lastHidden after train_rnn")
+            got_w, ref_w = w.np("org_brain")[0][:P].astype(np.float64), g(f"brain{ep}").astype(np.float64)
+            assert len(ref_w) == P
+            np.testing.assert_allclose(got_w, ref_w, rtol=1e-5, atol=1e-6, err_msg=f"epoch {ep}: weights after train_rnn")
+            continue
         # Adam's first steps move every weight by ~lr * g / (|g| + 1e-8): where |g| is within a few orders of eps the update is
         # ill-conditioned in the gradient's own fp32 summation noise (torch's sgemm order is not reproducible). So: 1e-5 relative to
         # the weight scale for >= 99 % of the parameters, and never more than 1e-3 of one learning-rate step (lr = 0.02).
