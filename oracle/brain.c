@@ -339,7 +339,7 @@ int oracle_train_one(SapioWorld *w, int o) {
         int dst = M;
         if (found >= 0) { if ((double)mrew[found] > best_r) add = 0; else dst = found; }
         if (add) {
-            if (dst == M) { if (M >= SAPIO_MEMROWS) continue; M++; }
+            if (dst == M) { if (M >= SAPIO_MEMROWS) { w->g_stats[SAPIO_STAT_OVERFLOW]++; continue; } M++; }      /* the row table is full (only without finite_memory): dropped and counted */
             memcpy(min_ + (size_t)dst * IN, xin, sizeof(float) * (size_t)I);          /* roundList(mem[0], 3) == the fp32 value again */
             memcpy(mout + dst * 4, w->org_stm_out + (o * SAPIO_STM + best) * 4, sizeof(float) * 4);
             mrew[dst] = w->org_stm_rew[o * SAPIO_STM + si];                             /* sic: mem[2], not bestReward (neural.py:395) */

@@ -6,11 +6,17 @@
 // cpBodyUpdatePosition (Chipmunk cpBody.c; SURVEY A-2 step 1) for every dynamic body: living cells, their sensor
 // bodies (sprites.py:300-323) and free dead cells. p = fma(v + v_bias, dt, p): the single fp32 op sequence the oracle mirrors.
 // Also writes the broadphase key of every solid body (grid cell index, or ~0 for "no body in this slot").
+#define INTEGRATE_STAGE 256
 template <bool INTEGRATE>
 __global__ void __launch_bounds__(256) k_integrate(WORLD_ARG, uint32_t *__restrict__ grid_key, uint32_t *__restrict__ live_list, int *__restrict__ cell_cnt, int *__restrict__ n_live) {
     const SapioParams &p = w.p;
     const int NC = p.n_org * MAXC, NB = NC + p.n_dead;
     const float dt = p.dt_phys;
+    // the list of living bodies is staged per warp in shared memory and appended in runs of ~200 entries: one atomic on the list's counter
+    // per run instead of one per warp and iteration (300k atomics on ONE address per tick were most of this kernel's time)
+    __shared__ uint32_t stage[8][INTEGRATE_STAGE];
+    uint32_t *mine = stage[threadIdx.x >> 5];
+    int staged = 0;                                          // warp-uniform among the lanes still in the loop (lane 0 leaves last)
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < NB; b += gridDim.x * blockDim.x) {
         uint32_t key = 0xFFFFFFFFu;
         float2 pos;
@@ -53,27 +59,48 @@ __global__ void __launch_bounds__(256) k_integrate(WORLD_ARG, uint32_t *__restri
                 solid = true;
             }
         }
+        // Only living bodies have a grid key, a place in their cell's count and in the list (its consumers -- k_grid_scatter / k_grid_rank --
+        // read the key through the list): two thirds of the slots are empty, most of them in runs longer than a warp (the unused rows of an
+        // organism, the free tail of the dead pool), and those warps leave here after one ballot.
         if (grid_key) {
+            const int left = NB - (b - (int)(threadIdx.x & 31));             // the lanes of this warp that are in this iteration: slots b0 .. b0 + 31 below NB
+            const uint32_t act = left >= 32 ? FULL : ((1u << left) - 1u);
+            const uint32_t m = __ballot_sync(act, solid);
             if (solid) {
                 // same cell function as the oracle's candidate grid; any superset generator is exact
                 int cx = (int)floorf((pos.x - p.grid_x0) / p.grid_cell) + 1, cy = (int)floorf(pos.y / p.grid_cell) + 1;
                 cx = min(max(cx, 0), p.grid_nx - 1); cy = min(max(cy, 0), p.grid_ny - 1);
                 key = (uint32_t)(cy * p.grid_nx + cx);
+                grid_key[b] = key;
+                // the cells of an organism share a handful of grid cells and sit in consecutive slots: one atomic per (warp, cell), not per body
+                const uint32_t peers = __match_any_sync(m, key);
+                const int lane = threadIdx.x & 31;
+                if (lane == __ffs(peers) - 1) atomicAdd(&cell_cnt[key], __popc(peers));
+                // the living bodies as a list (order immaterial: grid.cuh ranks them inside their cells)
+                mine[staged + __popc(m & ((1u << lane) - 1u))] = (uint32_t)b;
             }
-            grid_key[b] = key;
-            // the cells of an organism share a handful of grid cells and sit in consecutive slots: one atomic per (warp, cell), not per body
-            const uint32_t peers = __match_any_sync(__activemask(), key);
-            if (solid && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&cell_cnt[key], __popc(peers));
-        }
-        // the living bodies as a list (order immaterial: grid.cuh ranks them inside their cells), one atomic per warp
-        if (grid_key) {
-            const uint32_t m = __ballot_sync(__activemask(), solid);
-            if (m) {
-                const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+            staged += __popc(m);
+            if (staged > INTEGRATE_STAGE - 32) {             // flush: every lane of this iteration takes part (lanes 0 .. popc(act) - 1)
+                __syncwarp(act);
+                const int lane = threadIdx.x & 31;
                 int base = 0;
-                if (lane == leader) base = atomicAdd(n_live, __popc(m));
-                if (solid) { base = __shfl_sync(m, base, leader); live_list[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)b; }
+                if (lane == 0) base = atomicAdd(n_live, staged);
+                base = __shfl_sync(act, base, 0);
+                for (int i = lane; i < staged; i += __popc(act)) live_list[base + i] = mine[i];
+                __syncwarp(act);
+                staged = 0;
             }
+        }
+    }
+    if (grid_key) {                                          // the rest (lane 0 was in every iteration of its warp: its count is the warp's)
+        __syncwarp();
+        staged = __shfl_sync(FULL, staged, 0);
+        if (staged) {
+            const int lane = threadIdx.x & 31;
+            int base = 0;
+            if (lane == 0) base = atomicAdd(n_live, staged);
+            base = __shfl_sync(FULL, base, 0);
+            for (int i = lane; i < staged; i += 32) live_list[base + i] = mine[i];
         }
     }
 }

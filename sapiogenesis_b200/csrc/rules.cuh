@@ -36,7 +36,7 @@ struct RulesWs {
     double *slab_co2_in;            // [1]
     uint8_t *dead_ghost;            // [n_dead]
 };
-enum { RC_NTHINK = 0, RC_NTRAIN = 1, RC_NREPRO = 2, RC_NDYING = 3, RC_NFREE = 4, RC_TRAIN_TICKET = 8 /* work counter of k_train */ };
+enum { RC_NTHINK = 0, RC_NTRAIN = 1, RC_NREPRO = 2, RC_NDYING = 3, RC_NFREE = 4, RC_TRAIN_TICKET = 8 /* work counter of k_train */, RC_THINK_TICKET = 9 /* work counter of k_think */ };
 
 __device__ __forceinline__ float warp_sum(float v) { for (int s = 16; s; s >>= 1) v += __shfl_xor_sync(FULL, v, s); return v; }
 __device__ __forceinline__ float bcast2(float v0, float v1, int k) { return __shfl_sync(FULL, (k >> 5) ? v1 : v0, k & 31); }
@@ -280,6 +280,7 @@ __global__ void __launch_bounds__(RULES_WARPS * 32, RULES_MAIN_MINB) k_rules_mai
     const double co2_0 = w.g_co2[0], Ttot = co2_0 + w.g_o2[0];
     const int NC = p.n_org * MAXC, ND = p.n_dead;
     const int warps = gridDim.x * RULES_WARPS, lane = lane_id();
+    int org_ticks = 0;
     for (int o = blockIdx.x * RULES_WARPS + (threadIdx.x >> 5); o < p.n_org; o += warps) {
         if (w.org_state[o] != 1) { if (lane == 0) w.org_gas_refund[o] = 0.0; continue; }
         OrgR g; g.load(w, o, true);
@@ -402,7 +403,7 @@ __global__ void __launch_bounds__(RULES_WARPS * 32, RULES_MAIN_MINB) k_rules_mai
             }
             g.take_energy_sum(pending);
             if ((phases & SAPIO_PH_TRAIN) && !(w.org_flags[o] & SAPIO_F_MALADAPTIVE) && w.org_nlayers[o] > 0 && T - w.org_train_tick[o] >= p.train_ticks) req |= SAPIO_REQ_TRAIN;
-            if (lane == 0 && !ghost) stat_add(w, SAPIO_STAT_ORG_TICKS, 1);
+            org_ticks += !ghost;                                                                 // counted per warp, added once (124k atomics on one address otherwise)
         }
         g.store(w, true);
         if (lane == 0) {
@@ -411,6 +412,7 @@ __global__ void __launch_bounds__(RULES_WARPS * 32, RULES_MAIN_MINB) k_rules_mai
             if (req & SAPIO_REQ_TRAIN) R.train_list[atomicAdd(&R.counters[RC_NTRAIN], 1)] = o;
         }
     }
+    if (lane == 0) stat_add(w, SAPIO_STAT_ORG_TICKS, org_ticks);
 }
 
 // gases after the rules phase: the composed map of every organism, plus the refunds handed back at the end (C4)

@@ -65,7 +65,7 @@ static size_t carve_all(const SapioParams &p, char *base, AllWs *A) {
     R.free_flag = (int *)take((ND + 1) * 4); R.free_off = (int *)take((ND + 1) * 4); R.free_list = (int *)take(ND * 4);
     R.disp_factor = (double *)take(ND * 8); R.disp_prod = (double *)take(256);
     R.slab_co2_in = (double *)take(256); R.dead_ghost = (uint8_t *)take(ND);
-    A->train_ctas = (int)std::min<long>(8 * 148, std::max<long>(8, NO / 8));      // 8 CTAs of 256 threads per SM; ~1/17 of the organisms train per tick
+    A->train_ctas = (int)std::min<long>(2 * TRAIN_CTAS_PER_SM * 148, std::max<long>(8, NO / 8));      // two waves of resident CTAs (work counter); ~1/17 of the organisms train per tick
     TrainWs &T = A->train;
     T.per_cta = (size_t)(p.in_cap + 4 * TRAIN_MAXW + 4) * SAPIO_MEMROWS;
     T.buf = (float *)take((size_t)A->train_ctas * T.per_cta * 4);
@@ -135,6 +135,13 @@ static int launch_grid_only(const SapioWorld &w, const Workspace &W, cudaStream_
     return 0;
 }
 
+// k_think pulls organisms from a work counter: one wave of resident CTAs (or fewer, for a short list)
+static int think_grid(long organisms) {
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    const long want = (organisms + THINK_WARPS - 1) / THINK_WARPS, wave = (long)sms * THINK_MINB;
+    return (int)(want < wave ? (want > 0 ? want : 1) : wave);
+}
+
 static int launch_rules(const SapioWorld &w, AllWs &A, uint32_t phases, cudaStream_t st, int part = 3) {   // part: 1 begin + gas scan + think, 2 main + finish
     const SapioParams &p = w.p;
     RulesWs &R = A.rules;
@@ -160,7 +167,8 @@ static int launch_rules(const SapioWorld &w, AllWs &A, uint32_t phases, cudaStre
         size_t smem = (size_t)THINK_WARPS * (p.in_cap + 2 * (p.width_cap > SAPIO_RNN_MAXH ? p.width_cap : SAPIO_RNN_MAXH)) * sizeof(float);
         static size_t smem_set = 0;
         if (smem > smem_set) { CUDA_TRY(cudaFuncSetAttribute(k_think, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_set = smem; }
-        k_think<<<stream_grid((long)p.n_org * 32 / 4 + 1, THINK_WARPS * 32), THINK_WARPS * 32, smem, st>>>(w, A.step, R);
+        CUDA_TRY(cudaMemsetAsync(R.counters + RC_THINK_TICKET, 0, sizeof(int), st));
+        k_think<<<think_grid((long)p.n_org / 4 + 1), THINK_WARPS * 32, smem, st>>>(w, A.step, R);
         LAUNCHES(3);
     }
     }
@@ -324,7 +332,8 @@ int sapio_activate(const SapioWorld *w, void *ws, size_t ws_bytes, const int32_t
     if ((rc = launch_grid_only(*w, A.step, st))) return rc;
     size_t smem = (size_t)THINK_WARPS * (p.in_cap + 2 * (p.width_cap > SAPIO_RNN_MAXH ? p.width_cap : SAPIO_RNN_MAXH)) * sizeof(float);
     CUDA_TRY(cudaFuncSetAttribute(k_think, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_think<<<stream_grid((long)n * 32, THINK_WARPS * 32), THINK_WARPS * 32, smem, st>>>(*w, A.step, A.rules);
+    CUDA_TRY(cudaMemsetAsync(A.rules.counters + RC_THINK_TICKET, 0, sizeof(int), st));
+    k_think<<<think_grid(n), THINK_WARPS * 32, smem, st>>>(*w, A.step, A.rules);
     LAUNCHES(4);
     LAUNCH_CHECK();
     return 0;

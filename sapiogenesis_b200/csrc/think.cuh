@@ -84,8 +84,11 @@ __device__ __forceinline__ void sense(const SapioWorld &w, const Workspace &W, i
 }
 
 #define THINK_WARPS 4
+#ifndef THINK_MINB
+#define THINK_MINB 4          // resident CTAs per SM the kernel is compiled for. Measured (A/B builds, 100k organisms aged 1500 ticks): 8 CTAs at <= 64
+#endif                        // registers 0.55 ms, 4 CTAs at 117 registers 0.52 ms -- the organisms in flight are not what bounds the stage
 // dynamic shared memory per warp: in_cap + 2 * max(width_cap, SAPIO_RNN_MAXH) floats
-__global__ void __launch_bounds__(THINK_WARPS * 32) k_think(WORLD_ARG, Workspace W, RulesWs R) {
+__global__ void __launch_bounds__(THINK_WARPS * 32, THINK_MINB) k_think(WORLD_ARG, Workspace W, RulesWs R) {
     extern __shared__ float think_smem[];
     const SapioParams &p = w.p;
     const int IN = p.in_cap, lane = lane_id();
@@ -93,8 +96,11 @@ __global__ void __launch_bounds__(THINK_WARPS * 32) k_think(WORLD_ARG, Workspace
     float *act0 = x + IN, *act1 = act0 + max(p.width_cap, SAPIO_RNN_MAXH);
     const int n_think = R.counters[RC_NTHINK];
     const int32_t T = (int32_t)w.g_tick[0];
-    const int warps = gridDim.x * THINK_WARPS;
-    for (int q = blockIdx.x * THINK_WARPS + (threadIdx.x >> 5); q < n_think; q += warps) {
+    for (;;) {                                          // organisms differ by their sensors and brains: pulled from a work counter, not dealt
+        int q = 0;
+        if (lane == 0) q = atomicAdd(&R.counters[RC_THINK_TICKET], 1);
+        q = __shfl_sync(FULL, q, 0);
+        if (q >= n_think) break;
         const int o = R.think_list[q];
         const int nc = w.org_ncells[o], nl = w.org_nlayers[o];
         const int32_t *ldim = w.org_ldim + o * 16;

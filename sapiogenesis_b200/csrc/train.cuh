@@ -18,7 +18,10 @@
 #include "common.cuh"
 #include "rules.cuh"
 
+#ifndef TRAIN_THREADS
 #define TRAIN_THREADS 256
+#endif
+#define TRAIN_CTAS_PER_SM (1024 / TRAIN_THREADS)
 #define TRAIN_MAXW 128
 
 // Python round(v, 1) * 10 for a double v, exactly (ties resolved on the exact binary value, half to even when exact)
@@ -74,8 +77,8 @@ __device__ __forceinline__ void train_rnn_step(const SapioWorld &w, int o, int M
     }
     __syncthreads();
     const int last = sh_last, first = sh_first;
-    if (tid < I) x[tid] = w.org_mem_in[((size_t)o * SAPIO_MEMROWS + last) * IN + tid];
-    else if (tid < F0) x[tid] = (M - 1 < w.org_th_n[o]) ? w.org_th[((size_t)o * SAPIO_MEMROWS + (M - 1)) * RC + (tid - I)] : 0.f;
+    for (int c = tid; c < F0; c += TRAIN_THREADS)
+        x[c] = c < I ? w.org_mem_in[((size_t)o * SAPIO_MEMROWS + last) * IN + c] : (M - 1 < w.org_th_n[o]) ? w.org_th[((size_t)o * SAPIO_MEMROWS + (M - 1)) * RC + (c - I)] : 0.f;
     __syncthreads();
     // forward: layers 0 .. nl-1, then the hidden head on the last hidden activation
     const float *cur = x; float *dst = a0;
@@ -83,12 +86,12 @@ __device__ __forceinline__ void train_rnn_step(const SapioWorld &w, int o, int M
     for (int l = 0; l < nl - 1; l++) {
         const int fin = l == 0 ? F0 : ldim[l], fout = ldim[l + 1];
         const float *Wm = brain + off, *b = Wm + fout * fin;
-        if (tid < fout) {
+        for (int r = tid; r < fout; r += TRAIN_THREADS) {
             float s = 0.f;
-            for (int c = 0; c < fin; c++) s += Wm[tid * fin + c] * cur[c];
-            s += b[tid];
+            for (int c = 0; c < fin; c++) s += Wm[r * fin + c] * cur[c];
+            s += b[r];
             if (l == 0) s = 1.0f / (1.0f + expf(-s));
-            dst[tid] = s;
+            dst[r] = s;
         }
         __syncthreads();
         cur = dst; dst = (l == 0) ? pa : (dst == pa ? pb : pa);
@@ -96,7 +99,7 @@ __device__ __forceinline__ void train_rnn_step(const SapioWorld &w, int o, int M
     }
     off_out = off;
     float *Wout = brain + off_out, *bout = Wout + 4 * hl, *Wh = bout + 4, *bh = Wh + H * hl;
-    if (tid < hl) ah[tid] = cur[tid];                                                  // the last hidden activation (== a0 when there is one hidden layer)
+    for (int c = tid; c < hl; c += TRAIN_THREADS) ah[c] = cur[c];                      // the last hidden activation (== a0 when there is one hidden layer)
     if (tid < 4 + H) {
         const float *Wm = tid < 4 ? Wout + tid * hl : Wh + (tid - 4) * hl;
         float s = 0.f;
@@ -115,14 +118,14 @@ __device__ __forceinline__ void train_rnn_step(const SapioWorld &w, int o, int M
     const float dO0 = red[64], dO1 = red[65], dO2 = red[66], dO3 = red[67];
     // backward through the activation-free hidden chain to the first layer's output
     float *d = da, *d2 = db;
-    if (tid < hl) { float s = 0.f; s += dO0 * Wout[0 * hl + tid]; s += dO1 * Wout[1 * hl + tid]; s += dO2 * Wout[2 * hl + tid]; s += dO3 * Wout[3 * hl + tid]; d[tid] = s; }
+    for (int c = tid; c < hl; c += TRAIN_THREADS) { float s = 0.f; s += dO0 * Wout[0 * hl + c]; s += dO1 * Wout[1 * hl + c]; s += dO2 * Wout[2 * hl + c]; s += dO3 * Wout[3 * hl + c]; d[c] = s; }
     __syncthreads();
     for (int l = nl - 2; l >= 1; l--) {
         const int fin = ldim[l], fout = ldim[l + 1];
         int offl = 0;
         for (int t = 0; t < l; t++) offl += ldim[t + 1] * (t == 0 ? F0 : ldim[t]) + ldim[t + 1];
         const float *Wm = brain + offl;
-        if (tid < fin) { float s = 0.f; for (int r = 0; r < fout; r++) s += d[r] * Wm[r * fin + tid]; d2[tid] = s; }
+        for (int c = tid; c < fin; c += TRAIN_THREADS) { float s = 0.f; for (int r = 0; r < fout; r++) s += d[r] * Wm[r * fin + c]; d2[c] = s; }
         __syncthreads();
         float *t2 = d; d = d2; d2 = t2;
     }
@@ -142,7 +145,7 @@ __device__ __forceinline__ void train_rnn_step(const SapioWorld &w, int o, int M
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(TRAIN_THREADS, 4) k_train(WORLD_ARG, RulesWs R, TrainWs TW) {
+__global__ void __launch_bounds__(TRAIN_THREADS, TRAIN_CTAS_PER_SM) k_train(WORLD_ARG, RulesWs R, TrainWs TW) {
     __shared__ unsigned long long hs[2][SAPIO_STM], hm[2][SAPIO_STM], hmem[2][SAPIO_MEMROWS];
     __shared__ float rew_s[SAPIO_MEMROWS], red_f[TRAIN_THREADS];
     __shared__ int16_t rowsrc[SAPIO_MEMROWS];      // -1 row untouched | 0..231 content of original row | 256 + i short-term row i
@@ -212,7 +215,7 @@ __global__ void __launch_bounds__(TRAIN_THREADS, 4) k_train(WORLD_ARG, RulesWs R
                 const float best_r = srew[STM_SLOT(bestof[i])];
                 int add = 1, dst = M;
                 if (found >= 0) { if (rew_s[found] > best_r) add = 0; else dst = found; }
-                if (add && dst == M) { if (M >= SAPIO_MEMROWS) add = 0; else M++; }
+                if (add && dst == M) { if (M >= SAPIO_MEMROWS) { add = 0; if (lane == 0) stat_add(w, SAPIO_STAT_OVERFLOW, 1); } else M++; }   // table full (only without finite_memory): dropped and counted
                 __syncwarp();
                 if (add && lane == 0) {                           // input of THIS memory, action of the best one, reward of this one (sic, neural.py:395)
                     rowsrc[dst] = (int16_t)(256 + i); rew_s[dst] = srew[STM_SLOT(i)]; hmem[0][dst] = hm[0][i]; hmem[1][dst] = hm[1][i];
@@ -296,12 +299,12 @@ __global__ void __launch_bounds__(TRAIN_THREADS, 4) k_train(WORLD_ARG, RulesWs R
                 if (l == nl - 2) hlastT = dst;
                 cur = dst; off += fout * fin + fout;
             }
-            // MSELoss(mean) and its gradient at the outputs (one thread per sample: M <= 232 < TRAIN_THREADS)
+            // MSELoss(mean) and its gradient at the outputs (thread per sample)
             float lsum = 0.f;
-            if (tid < M) {
-                const float *y = mout + tid * 4;
+            for (int m = tid; m < M; m += TRAIN_THREADS) {
+                const float *y = mout + m * 4;
 #pragma unroll
-                for (int z = 0; z < 4; z++) { float e = dOT[z * TR_S + tid] - y[z]; lsum += e * e; dOT[z * TR_S + tid] = 2.0f * e / (float)(M * 4); }
+                for (int z = 0; z < 4; z++) { float e = dOT[z * TR_S + m] - y[z]; lsum += e * e; dOT[z * TR_S + m] = 2.0f * e / (float)(M * 4); }
             }
             red_f[tid] = lsum;
             __syncthreads();

@@ -148,3 +148,37 @@ def test_genome_file_cannot_reach_arbitrary_callables():
         blob = pickle.dumps({"cells": Evil(fn, *args), "growth_pattern": [], "brain_structure": {}, "base_info": {}})
         with pytest.raises(pickle.UnpicklingError):
             dna_io.loads_reference_pickle(blob)
+
+
+def test_rnn_organism_round_trip(oracle):
+    """An organism with an RNNetwork brain (use_rnn, physics.py:305): hidden_memory and trainingHidden travel with the genome, the curated
+    memory in list order, and the import builds a brain with the wider input layer and the hidden head."""
+    from sapiogenesis_b200.world import HM, MEMROWS
+    w = make_world(oracle, n_org=6, seed=13, n_food=12, crowd=0.7, kick=20.0, extra_slots=6, rnn_hidden=6)
+    w.p.think_ticks = w.p.train_ticks = 3
+    assert oracle.tick(w, PH_ALL, 60) == 0
+    slot = int(np.nonzero((w.np("org_th_n") > 0) & (w.np("org_mem_n") > 1))[0][0])
+    dna = dna_io.export_dna(w, slot)
+    hn = w.np("org_hm_n")[slot]
+    assert len(dna["hidden_memory"]) == int(hn[0] - hn[1]) > 0 and len(dna["trainingHidden"]) == int(w.np("org_th_n")[slot])
+    assert all(len(e) == 6 for e in dna["hidden_memory"] + dna["trainingHidden"])
+    seq = w.np("org_mem_seq")[slot][: int(w.np("org_mem_n")[slot])]
+    first, last = int(np.argmin(seq)), int(np.argmax(seq))                      # train_rnn's target row and input row (networks.py:59-62)
+    I = int(w.np("org_ldim")[slot][0])
+    np.testing.assert_array_equal(np.float32(dna["trainingInput"][-1]), w.np("org_mem_in")[slot].reshape(MEMROWS, -1)[last, :I])
+    np.testing.assert_array_equal(np.float32(dna["trainingOutput"][0]), w.np("org_mem_out")[slot].reshape(MEMROWS, 4)[first])
+    back = dna_io.loads_reference_pickle(dna_io.dumps_reference_pickle(dna))
+    free = int(np.nonzero(w.np("org_state") == 0)[0][0])
+    dna_io.import_dna(w, free, (1500.0, 900.0), back)
+    again = dna_io.export_dna(w, free)
+    same_genome(dna, again)
+    keep = min(len(dna["hidden_memory"]), HM - 30)
+    assert int(w.np("org_rnn_h")[free]) == 6 and again["hidden_memory"] == dna["hidden_memory"][:keep] and again["trainingHidden"] == dna["trainingHidden"]
+    for k in ("trainingInput", "trainingOutput", "trainingReward"):
+        assert again[k] == dna[k], k
+    assert oracle.post(w) == 0 and oracle.tick(w, PH_ALL, 6) == 0 and int(w.np("org_state")[free]) == 1
+    # a feed-forward world opens the same file: the recurrent lists are dropped, the brain is a networks.Network
+    w2 = World(default_params(n_org=4, n_dead=16, seed=3))
+    dna_io.import_dna(w2, 0, (800.0, 600.0), back)
+    assert int(w2.np("org_rnn_h")[0]) == 0 and dna_io.export_dna(w2, 0)["hidden_memory"] == []
+    assert oracle.post(w2) == 0 and oracle.tick(w2, PH_ALL, 3) == 0

@@ -179,3 +179,37 @@ def test_sprite_joints_add_sprite_and_collision_hooks(oracle):
     assert env.add_sprite(food) is food and len(env.sprites) == n0                # back in the space with the state its row holds
     env.update(None)
     assert int(t["d_state"][food._i]) > 0
+
+
+@pytest.mark.gpu
+def test_use_rnn_switch_builds_recurrent_brains(oracle):
+    """Environment.info["use_rnn"] / ["hidden_rnn_size"] (physics.py:305,308; the UI checkbox, Sapiogenesis.py:381-386): organisms created
+    while it is set get a networks.RNNetwork -- input layer widened by the hidden size, hidden head last (networks.py:111-166) -- the
+    others keep their feed-forward brain; both kinds think and train in the same world."""
+    from sapiogenesis_b200 import neural, physics
+    env = physics.Environment(None, None, 3180, 1800, capacity=16)
+    a = env.add_creature((600.0, 600.0))
+    env.info["hidden_rnn_size"] = 5
+    env.info["use_rnn"] = True
+    assert env.world.p.rnn_cap == 5 and env.world.p.rnn_hidden == 5 and env.world.t["org_hm"].shape[1] == 90 * 5
+    b = env.add_creature((1600.0, 900.0))
+    env.info["use_rnn"] = False
+    c = env.add_creature((2400.0, 600.0))
+    assert (a.brain.hiddenSize, b.brain.hiddenSize, c.brain.hiddenSize) == (0, 5, 0) and b.brain.is_rnn
+    dims = b.brain.structure
+    shapes = [tuple(W.shape) for W, _ in b.brain.layers()]
+    assert shapes == [(dims[1], dims[0] + 5)] + [(dims[i + 1], dims[i]) for i in range(1, len(dims) - 1)] + [(5, dims[-2])]
+    assert neural.setup_network(b.dna, rnn=True, hiddenSize=5).is_rnn
+    with pytest.raises(ValueError):
+        neural.setup_network(a.dna, rnn=True)
+    with pytest.raises(ValueError):
+        env.info["hidden_rnn_size"] = 7; env.info["use_rnn"] = True                # the size is fixed once RNN brains exist
+    env.info["hidden_rnn_size"] = 5; env.info["use_rnn"] = False
+    env.world.p.think_ticks = env.world.p.train_ticks = 3; env.engine.refresh()
+    assert float(b.brain.lastHidden.abs().sum()) == 0.0
+    env.engine.tick(40); env.engine.synchronize()
+    assert float(b.brain.lastHidden.abs().sum()) > 0.0 and env.world.stats()["thinks"] >= 30
+    host = env.world.to("cpu")
+    env.engine.tick(3); env.engine.synchronize()
+    assert oracle.tick(host, PH_ALL, 3) == 0
+    compare_worlds(env.world, host, "three ticks of a mixed RNN / feed-forward world", verbose=False)

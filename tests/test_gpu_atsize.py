@@ -144,3 +144,19 @@ def test_birth_wave_with_crowded_placement_matches_oracle(oracle):
     print("birth wave:", {k: st[k] for k in ("births", "birth_fail_place", "full_scans", "rare_paths")})
     compare_worlds(wg, w, "birth wave", phys_tol=1e-4)
     assert st["full_scans"] > 0 and st["rare_paths"] & 4 and st["births"] >= 5 and st["birth_fail_place"] > 100
+
+
+def test_organism_cut_out_of_the_100k_world(oracle):
+    """tests/golden/cut_100k_signed_zero.npz: organism 21934 of the 100k-organism bench world at tick 34, cut out by tools/debug_extract.py
+    when test_100k_full_tick_matches_oracle failed on it (its direction commands are (-0.0, -0.0): atan2 = -pi). One tick, every field."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tools"))
+    from conftest import GOLDEN
+    from debug_extract import load
+    from sapiogenesis_b200.engine import Engine
+    host, n = load(os.path.join(GOLDEN, "cut_100k_signed_zero.npz"))
+    assert n == 1 and np.signbit(host.np("org_move")[0][2:]).all()
+    wg = host.to("cuda"); eng = Engine(wg)
+    eng.tick(1, PH_ALL); eng.synchronize()
+    assert oracle.tick(host, PH_ALL, 1) == 0
+    compare_worlds(wg, host, "organism 21934 of the 100k world")
