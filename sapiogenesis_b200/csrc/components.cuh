@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256) k_comp_assign(WORLD_ARG, Workspace W, int
 #ifdef COMP_DIAG
         if (tier < 0) printf("OVERSIZE tick %d organisms %d contacts %d dead %d slab bytes %d\n", (int)w.g_tick[0], no, cnt, nd, need);
 #endif
-        if (tier < 0) { W.flags[FL_COMP_OVERFLOW] = 1; continue; }            // this component goes to the cooperative kernel (coupled.cuh)
+        if (tier < 0) { W.flags[FL_COMP_OVERFLOW] = 1; atomicAdd(&W.flags[FL_BIG_NORG], no); continue; }   // this component goes to the fallback kernel (coupled.cuh)
         W.cn_xoff[root] = atomicAdd(&W.flags[FL_COMP_POOL], cnt);
         const int q = atomicAdd(&W.flags[FL_COMP_N0 + tier], 1);
         W.comp_list[(size_t)tier * 2 * w.p.x_cap + q] = root;

@@ -18,7 +18,8 @@ __device__ __forceinline__ bool cross_levels_relax(const Workspace &W, int c) {
     W.nx_level[c] = L; atomicMax(&W.flags[FL_MAXLEVEL], L); atomicMax(&W.flags[FL_BIGLEVEL], L);
     return true;
 }
-__device__ __forceinline__ void cross_levels(cg::grid_group &grid, const Workspace &W, int nx, int gtid, int gthreads) {
+template <class Sync>
+__device__ __forceinline__ void cross_levels(Sync &sync, const Workspace &W, int nx, int gtid, int gthreads) {
     if (nx <= LEVELS_ONE_CTA) {
         if (blockIdx.x == 0) {
             __shared__ int s_changed;
@@ -33,7 +34,7 @@ __device__ __forceinline__ void cross_levels(cg::grid_group &grid, const Workspa
                 if (!s_changed) break;
             }
         }
-        grid.sync();
+        sync();
         return;
     }
     if (gtid == 0) W.flags[FL_RARE] |= SAPIO_RARE_GRID_LEVELS;
@@ -42,7 +43,7 @@ __device__ __forceinline__ void cross_levels(cg::grid_group &grid, const Workspa
         bool ch = false;
         for (int c = gtid; c < nx; c += gthreads) if (W.cn_tier[W.comp_of[c]] < 0) ch |= cross_levels_relax(W, c);
         if (ch) W.flags[FL_CHG0 + r % 3] = 1;
-        grid.sync();
+        sync();
         if (!W.flags[FL_CHG0 + r % 3]) break;
     }
 }
@@ -100,26 +101,35 @@ __device__ __forceinline__ void cross_warm_dead(const SapioWorld &w, const Works
 // It runs when a connected component exceeds the largest CTA tier (or when a test forces it), and is the second, independent
 // implementation the component solver is compared with (tests: fixture `coupled_kernel`).
 #define SIMPLE_WARPS 4
-__global__ void __launch_bounds__(SIMPLE_WARPS * 32) k_coupled_simple(WORLD_ARG, Workspace W, StepK K) {
-    cg::grid_group grid = cg::this_grid();
+#define CLUSTER_CTAS 8                                        // portable cluster size: 32 warps, one organism each
+#define CLUSTER_ORGS (CLUSTER_CTAS * SIMPLE_WARPS)
+// The body of both launch forms. `sync` is the barrier between phases: a grid barrier of the cooperative launch, or -- when the oversize
+// components hold no more organisms than one thread-block cluster has warps, which is what an aged world produces (one cluster of
+// 5-20 organisms now and then) -- the hardware barrier of a cluster of 8 CTAs, an order of magnitude cheaper (~170 barriers per tick).
+template <class Sync>
+__device__ __forceinline__ void coupled_body(const SapioWorld &w, const Workspace &W, const StepK &K, Sync &sync) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     OrgS<MAXC> &s = reinterpret_cast<OrgS<MAXC> *>(smem_raw)[threadIdx.x >> 5];
     typedef OrgCtx<MAXC, 32> Ctx;
     const int nx = W.flags[FL_NX];
-    if (nx == 0 || !W.flags[FL_COMP_OVERFLOW]) return;         // uniform over the grid: no barrier has been entered. Fallback only (components.cuh)
     if (blockIdx.x == 0 && threadIdx.x == 0) W.flags[FL_RARE] |= SAPIO_RARE_PACKED_COUPLED;
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
     const int gwarp = gtid >> 5, gwarps = gthreads >> 5;
     const int ncoupled = W.flags[FL_NCOUPLED];
     const float dt_coef = w.g_stepped[0] ? 1.0f : 0.0f;
-    cross_levels(grid, W, nx, gtid, gthreads);
+    // the organisms of the oversize components as a list (order immaterial: within a phase they touch nothing of each other)
+    for (int q = gwarp; q < ncoupled; q += gwarps) {
+        const int o = W.coupled_list[q];
+        if (comp_is_big(W, o) && lane_id() == 0) W.big_list[atomicAdd(&W.flags[FL_BIG_N], 1)] = o;
+    }
+    cross_levels(sync, W, nx, gtid, gthreads);              // ends with a barrier: the list is complete
+    const int nbig = W.flags[FL_BIG_N];
     const int maxL = max(W.flags[FL_BIGLEVEL], 1);
     // stage A: coupled organisms detect their intra contacts and take their bounce before any velocity changes
     static_assert(sizeof(OrgS<MAXC>) <= COUPLED_STATE_BYTES, "COUPLED_STATE_BYTES too small");
     auto parked = [&](int q) { return q < W.cp_cap ? reinterpret_cast<OrgS<MAXC> *>(W.cp_state + (size_t)q * COUPLED_STATE_BYTES) : nullptr; };
-    for (int q = gwarp; q < ncoupled; q += gwarps) {
-        if (!comp_is_big(W, W.coupled_list[q])) continue;                        // warp-uniform
-        Ctx c(s, w, K, W.coupled_list[q]);
+    for (int q = gwarp; q < nbig; q += gwarps) {
+        Ctx c(s, w, K, W.big_list[q]);
         c.load(); c.prestep_pairs(); c.schedule(); c.template prestep_contacts<true>();
         if (dt_coef == 0.f) c.zero_pin_acc();                  // no warm start will consume the cached pin impulses
         c.store_contacts(W.ic_bounce, W.ic_jbias);
@@ -127,10 +137,10 @@ __global__ void __launch_bounds__(SIMPLE_WARPS * 32) k_coupled_simple(WORLD_ARG,
         if (lane_id() == 0) atomicAdd(&W.flags[FL_NIC], s.nic);
         __syncwarp();
     }
-    grid.sync();
+    sync();
     // one pass of a coupled organism's own arbiters and constraints between two rounds of cross contacts
     auto org_pass = [&](int q, bool warm, bool last) {
-        Ctx c(s, w, K, W.coupled_list[q]);
+        Ctx c(s, w, K, W.big_list[q]);
         c.load();
         OrgS<MAXC> *g = parked(q);
         if (g) c.restore_static(g);
@@ -146,14 +156,29 @@ __global__ void __launch_bounds__(SIMPLE_WARPS * 32) k_coupled_simple(WORLD_ARG,
     // cached impulses: cross contacts by level, then each coupled organism's own arbiters and constraints
     if (dt_coef != 0.f) {
         cross_warm_dead(w, W, dt_coef, gtid, gthreads);       // disjoint from what the organisms touch: no barrier in between
-        for (int q = gwarp; q < ncoupled; q += gwarps) if (comp_is_big(W, W.coupled_list[q])) org_pass(q, true, false);
-        grid.sync();
+        for (int q = gwarp; q < nbig; q += gwarps) org_pass(q, true, false);
+        sync();
     }
     const int iterations = w.p.iterations;
     for (int it = 0; it < iterations; it++) {
-        for (int L = 1; L <= maxL; L++) { cross_level_pass<false>(w, W, L, nx, 0.f, gtid, gthreads); grid.sync(); }
-        for (int q = gwarp; q < ncoupled; q += gwarps) if (comp_is_big(W, W.coupled_list[q])) org_pass(q, false, it == iterations - 1);
-        grid.sync();
+        for (int L = 1; L <= maxL; L++) { cross_level_pass<false>(w, W, L, nx, 0.f, gtid, gthreads); sync(); }
+        for (int q = gwarp; q < nbig; q += gwarps) org_pass(q, false, it == iterations - 1);
+        sync();
     }
 }
 
+struct GridSync { cg::grid_group g; __device__ void operator()() { g.sync(); } };
+struct ClusterSync { cg::cluster_group c; __device__ void operator()() { __threadfence(); c.sync(); } };
+
+// cooperative launch over a grid of CTAs: crowds (a component of dozens to hundreds of organisms), and the form the tests force
+__global__ void __launch_bounds__(SIMPLE_WARPS * 32) k_coupled_simple(WORLD_ARG, Workspace W, StepK K) {
+    if (W.flags[FL_NX] == 0 || !W.flags[FL_COMP_OVERFLOW] || W.flags[FL_BIG_NORG] <= CLUSTER_ORGS) return;   // uniform over the grid: no barrier has been entered
+    GridSync sync{cg::this_grid()};
+    coupled_body(w, W, K, sync);
+}
+// one thread-block cluster: the oversize components of an ordinary tick
+__global__ void __cluster_dims__(CLUSTER_CTAS, 1, 1) __launch_bounds__(SIMPLE_WARPS * 32) k_coupled_cluster(WORLD_ARG, Workspace W, StepK K) {
+    if (W.flags[FL_NX] == 0 || !W.flags[FL_COMP_OVERFLOW] || W.flags[FL_BIG_NORG] > CLUSTER_ORGS) return;
+    ClusterSync sync{cg::this_cluster()};
+    coupled_body(w, W, K, sync);
+}

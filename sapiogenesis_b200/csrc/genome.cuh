@@ -288,10 +288,12 @@ __device__ __forceinline__ int g_instance_order(const DGenome &g, uint8_t *order
     return n;
 }
 // rebuild the DNA of a living organism from its rows (dna.cells order via c_gorder); lane 0 only
+// whole warp: lane l loads the rows l and l + 32 (a single lane walking ~20 rows x 22 arrays of cold global memory, each row behind the load
+// of its genome index, was most of a birth's latency); g in shared memory, __syncwarp() before anybody reads it
 __device__ __forceinline__ void g_from_world(const SapioWorld &w, int org, DGenome &g) {
-    int nc = w.org_ncells[org];
-    g.n = nc;
-    for (int k = 0; k < nc; k++) {
+    const int nc = w.org_ncells[org], lane = lane_id();
+    if (lane == 0) g.n = nc;
+    for (int k = lane; k < nc; k += 32) {
         int row = org * MAXC + k, j = w.c_gorder[row];
         g.id[j] = w.c_id[row]; g.type[j] = (int8_t)w.c_type[row]; g.first[j] = w.c_parent[row] < 0;
         g.parent_id[j] = w.c_parent[row] < 0 ? 0 : w.c_id[org * MAXC + w.c_parent[row]];
@@ -300,9 +302,13 @@ __device__ __forceinline__ void g_from_world(const SapioWorld &w, int org, DGeno
         g.relx[j] = w.c_rel[2 * row]; g.rely[j] = w.c_rel[2 * row + 1]; g.growx[j] = w.c_grow[2 * row]; g.growy[j] = w.c_grow[2 * row + 1];
         g.maxhealth[j] = w.c_maxhealth[row]; g.use_idle[j] = w.c_use_idle[row]; g.use_act[j] = w.c_use_act[row]; g.storage[j] = w.c_storage[row]; g.damage[j] = w.c_damage[row];
     }
-    uint8_t fl = w.org_flags[org];
-    g.mirror_x = (fl & SAPIO_F_MIRROR_X) != 0; g.mirror_y = (fl & SAPIO_F_MIRROR_Y) != 0;
-    g.curiosity = w.org_curiosity[org]; g.generation = w.org_generation[org];
-    g.n_hidden = w.org_nlayers[org] - 1;
-    for (int i = 0; i < g.n_hidden; i++) g.hidden[i] = w.org_ldim[org * 16 + i + 1];
+    if (lane == 0) {
+        uint8_t fl = w.org_flags[org];
+        g.mirror_x = (fl & SAPIO_F_MIRROR_X) != 0; g.mirror_y = (fl & SAPIO_F_MIRROR_Y) != 0;
+        g.curiosity = w.org_curiosity[org]; g.generation = w.org_generation[org];
+        g.n_hidden = w.org_nlayers[org] - 1;
+    }
+    const int nh = w.org_nlayers[org] - 1;
+    for (int i = lane; i < nh; i += 32) g.hidden[i] = w.org_ldim[org * 16 + i + 1];
+    __syncwarp();
 }

@@ -93,10 +93,10 @@ __global__ void __launch_bounds__(REPRO_WARPS * 32) k_repro_prepare(WORLD_ARG, R
         const int parent = Q.req_list[r];
         DGenome &g = sg[threadIdx.x >> 5];                    // the dict-walking logic runs on shared memory, not on global
         GenomeSvc *svc = &ssvc[threadIdx.x >> 5];
+        g_from_world(w, parent, g);                           // whole warp
         if (lane != 0) g_svc_worker(g, svc, lane);            // serve lane 0's distance queries until it is done mutating
         else {
             B.parent = parent; B.accepted = 0; B.slot = -1; B.ok = 0;
-            g_from_world(w, parent, g);
             double prect[2]; g_get_size(g, prect);                                  // old_organism.dna.get_size()
             RngStream u(p.seed, w.org_uid[parent], T, RNG_GENOME, (uint32_t)sibling << 20);
             int rc = g_mutate_cells(g, p, (double)p.mutation_severity, u, svc);

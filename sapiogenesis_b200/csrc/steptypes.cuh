@@ -35,13 +35,15 @@ struct Workspace {
     int *cn_parent, *cn_nx, *cn_norg, *cn_ndead, *cn_need, *cn_xoff, *cn_fill, *cn_seen, *cn_tier;
     int *comp_of, *comp_pool;      // [x_cap] component (root node) of a contact; contacts grouped by component
     int *comp_list;                 // [COMP_TIERS][2 * x_cap] roots by CTA tier
+    int *big_list;                  // [n_org] organisms of the oversize components, compacted by the fallback kernel itself
     char *cp_state; int cp_cap;     // parked solver state of the first cp_cap coupled organisms (sizeof(OrgS<MAXC>) each)
 };
 enum { FL_NX = 0, FL_NADJ = 1, FL_OVERFLOW = 2, FL_MAXLEVEL = 3, FL_NCOUPLED = 5, FL_NIC = 6, FL_CLS0 = 8 /* ..16: class starts + end */,
        FL_WORK0 = 20 /* ..27 */, FL_TMPTOP = 28, FL_NHIT = 29, FL_RARE = 30, FL_NLIVE = 31 /* living bodies in the grid */, FL_HIST = 32 /* ..96 */, FL_CHIST = 100 /* ..164: coupled organisms by rows */,
        FL_CCLS0 = 168 /* ..176: class starts + end in coupled_list */, FL_CHG0 = 180 /* ..182 */, FL_CWORK0 = 200 /* ..203: two alternating pairs of work counters of k_coupled */,
        FL_COMP_OVERFLOW = 210 /* a component exceeds the largest CTA tier: the tick falls back to the cooperative kernel */, FL_COMP_POOL = 211, FL_BIGLEVEL = 209,
-       FL_COMP_N0 = 212 /* ..218: components per tier */, FL_COMP_WORK0 = 220 /* ..226: work counters */, FL_BYTES = 1024 };
+       FL_COMP_N0 = 212 /* ..218: components per tier */, FL_COMP_WORK0 = 220 /* ..226: work counters */,
+       FL_BIG_NORG = 230 /* organisms in components beyond the largest CTA tier */, FL_BIG_N = 231 /* length of big_list */, FL_BYTES = 1024 };
 
 #define COUPLED_STATE_BYTES 49152      /* >= sizeof(OrgS<MAXC>), checked where the struct is known */
 // sort only the bits a grid key can have; the key of an empty slot (all ones) still sorts behind every cell: its low bits are all ones
@@ -87,6 +89,7 @@ static inline size_t carve_workspace(const SapioParams &p, char *base, Workspace
         W->cn_need = (int *)take(NN * 4); W->cn_xoff = (int *)take(NN * 4); W->cn_fill = (int *)take(NN * 4); W->cn_seen = (int *)take(NN * 4); W->cn_tier = (int *)take(NN * 4);
         W->comp_of = (int *)take(XC * 4); W->comp_pool = (int *)take(XC * 4); W->comp_list = (int *)take((size_t)7 * 2 * XC * 4);
     }
+    W->big_list = (int *)take((size_t)p.n_org * 4);
     W->cp_cap = p.n_org < 8192 ? p.n_org : 8192;      // parked state of the fallback kernel (beyond: recomputed per pass)
     W->cp_state = take((size_t)W->cp_cap * COUPLED_STATE_BYTES);
     return off;

@@ -33,15 +33,18 @@ __device__ __forceinline__ void sense_enumerate(const SapioWorld &w, const Works
     for (int idx = lane; idx < nbx * nby; idx += 32) {
         int c = (cy0 + idx / nbx) * p.grid_nx + cx0 + idx % nbx;
         for (int i = W.cell_start[c], e = W.cell_start[c + 1]; i < e; i++) {
-            int j = (int)W.sval[i];
-            float x, y, r; bool dead;
+            // the grid's own record of the body -- position, radius, id as written by k_grid_rank from the same arrays (positions only change
+            // when the grid is rebuilt; every listed body is a living cell or an existing dead cell): one 16-byte load instead of the chain
+            // body id -> c_alive -> c_pos -> c_size of dependent cold loads
+            const float4 rec = W.srec[i];
+            const int j = __float_as_int(rec.w);
+            const float x = rec.x, y = rec.y, r = rec.z;
+            bool dead = false;
             if (j < NC) {
-                if ((j >> 6) == o || w.c_alive[j] == 0) continue;
-                float2 q = reinterpret_cast<const float2 *>(w.c_pos)[j]; x = q.x; y = q.y; r = w.c_size[j] * 0.5f; dead = false;
+                if ((j >> 6) == o) continue;
             } else {
-                int d = j - NC;
-                if (!w.d_state[d] || w.d_owner[d] == uid) continue;            // own dead cells are invisible (sprites.py:233)
-                float2 q = reinterpret_cast<const float2 *>(w.d_pos)[d]; x = q.x; y = q.y; r = w.d_size[d] * 0.5f; dead = true;
+                if (w.d_owner[j - NC] == uid) continue;                        // own dead cells are invisible (sprites.py:233)
+                dead = true;
             }
             double d2;
             if (!circles_overlap(sx, sy, R, x, y, r, &d2)) continue;
