@@ -210,10 +210,13 @@ def import_dna(world: World, slot: int, pos, dna: dict, seed: int | None = None)
     row_of = {j: k for k, j in enumerate(order)}
     hidden = [int(h) for h in dna["brain_structure"]["hidden_layers"]]
     eyes = [j for j in range(n) if cells[ids[j]]["type"] == "eye"]; olf = [j for j in range(n) if cells[ids[j]]["type"] == "olfactory"]
-    dims = [8 * len(eyes) + len(olf) + 4] + hidden + [4]
-    H, RC = int(p.rnn_hidden), int(p.rnn_cap)                     # build_brain: an RNNetwork when use_rnn is set now (sprites.py:1683-1690)
+    # neural.setup_network returns no network for a genome without hidden layers (neural.py:471): the organism lives without a brain
+    dims = [8 * len(eyes) + len(olf) + 4] + hidden + [4] if hidden else [8 * len(eyes) + len(olf) + 4]
+    H, RC = int(p.rnn_hidden), int(p.rnn_cap)
+    if not hidden:
+        H = 0                     # build_brain: an RNNetwork when use_rnn is set now (sprites.py:1683-1690)
     nparam = sum(dims[l + 1] * dims[l] + dims[l + 1] for l in range(len(dims) - 1)) + (H * (hidden[0] + hidden[-1]) + H if hidden else 0)
-    if dims[0] + H > p.in_cap or max(hidden, default=0) > p.width_cap or nparam > p.brain_cap or not hidden or len(dims) - 1 > 15:
+    if dims[0] + H > p.in_cap or max(hidden, default=0) > p.width_cap or nparam > p.brain_cap or len(dims) - 1 > 15:
         raise ValueError("genome exceeds the tile caps (in_cap / width_cap / brain_cap)")
     dev = t["c_pos"].device
     base = slot * MAXC

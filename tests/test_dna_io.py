@@ -182,3 +182,19 @@ def test_rnn_organism_round_trip(oracle):
     dna_io.import_dna(w2, 0, (800.0, 600.0), back)
     assert int(w2.np("org_rnn_h")[0]) == 0 and dna_io.export_dna(w2, 0)["hidden_memory"] == []
     assert oracle.post(w2) == 0 and oracle.tick(w2, PH_ALL, 3) == 0
+
+
+def test_genome_without_hidden_layers_imports_as_a_brainless_organism(oracle):
+    """neural.setup_network returns None for a genome whose hidden_layers list is empty (neural.py:471): the reference keeps such an organism
+    alive without a brain; the import maps it to org_nlayers = 0 (it never thinks, trains or -- its brain cannot mutate -- reproduces)."""
+    w = make_world(oracle, n_org=4, seed=3, n_food=4, extra_slots=4)
+    dna = dna_io.export_dna(w, 0)
+    dna["brain_structure"]["hidden_layers"] = []; dna["brain_structure"]["hidden_weights"] = []
+    for k in ("trainingInput", "trainingOutput", "trainingReward"):
+        dna[k] = []
+    dna_io.import_dna(w, 5, (1500.0, 900.0), dna)
+    assert int(w.np("org_nlayers")[5]) == 0
+    thinks0 = w.stats()["thinks"]
+    assert oracle.post(w) == 0 and oracle.tick(w, PH_ALL, 40) == 0
+    assert int(w.np("org_state")[5]) == 1 and int(w.np("org_hist_n")[5]) == 0 and w.stats()["thinks"] > thinks0
+    assert dna_io.export_dna(w, 5)["brain_structure"]["hidden_layers"] == []
