@@ -221,6 +221,13 @@ def gen_brain(n_cases=6, seed=41, rnn=0, name="brain_cases.npz", n_thinks=N_THIN
                 out[f"c{ci}.th_n{ep}"] = np.asarray([len(th)], dtype=np.int32)
                 out[f"c{ci}.th{ep}"] = np.asarray(th[:232], dtype=np.float32).reshape(min(len(th), 232), rnn)
                 out[f"c{ci}.lasthid_t{ep}"] = np.asarray(A.brain.lastHidden.tolist(), dtype=np.float32)
+        if rnn:
+            # what a child starts with: DNA.mutate's first two statements (sprites.py:1070-1072) on the trained parent -- copy(), erase_memory()
+            child = A.dna.copy(); child.erase_memory()
+            out[f"c{ci}.child_lens"] = np.asarray([len(child.trainingInput), len(child.short_term_memory), len(child.previousInputs),
+                                                   len(child.hidden_memory), len(child.trainingHidden)], dtype=np.int32)
+            out[f"c{ci}.child_hm"] = np.asarray(child.hidden_memory, dtype=np.float32).reshape(len(child.hidden_memory), rnn)
+            out[f"c{ci}.child_th"] = np.asarray(child.trainingHidden[:232], dtype=np.float32).reshape(min(len(child.trainingHidden), 232), rnn)
         print(f"brain case {ci}: inputs {I}, cells A {len(orderA)} B {len(orderB)}, viewed {rec['views']}, stm {len(stm)}, "
               f"memory {pre_n} -> {len(A.dna.trainingInput)}, loss {A.brain.lastLoss:.5f}")
     np.savez_compressed(os.path.join(HERE, name), **out)

@@ -180,6 +180,33 @@ def run_case(oracle, ci, cases, N_THINKS, H):
         assert np.max(np.abs(got_w - ref_w)) <= 1e-3 * 0.02, f"epoch {ep}: trained weights max abs diff {np.max(np.abs(got_w - ref_w)):.2e}"
 
 
+@pytest.mark.parametrize("ci", range(RNN_N_CASES))
+def test_rnn_lists_a_child_inherits_match_reference(oracle, ci):
+    """DNA.mutate starts with copy() + erase_memory() (sprites.py:1070-1072), and erase_memory (sprites.py:413-421) clears the training
+    and short-term lists but neither hidden_memory nor trainingHidden: the child starts with the parent's. ow_inherit_recurrent (oracle/world.c)
+    against the reference's own copy + erase on the parent of the scene, after its 48 thinks and two train_network calls."""
+    import ctypes
+    from oracle import oracle as omod
+    g = lambda k: RNN_CASES[f"c{ci}.{k}"]
+    n_train, n_stm, n_prev, n_hm, n_th = (int(v) for v in g("child_lens"))
+    assert (n_train, n_stm, n_prev) == (0, 0, 0) and n_hm == len(g("hm")) and n_th == int(g("th_n1")[0])
+    H = RNN_H
+    p = default_params(n_org=2, n_dead=4, rnn_hidden=H)
+    w = World(p); t = w.t
+    # the parent's lists as the scene left them: hidden_memory (30 entries, some popped before), trainingHidden after the second call
+    hm = g("hm"); pop = 7
+    ring = [(pop + i) % 90 for i in range(len(hm))]
+    t["org_hm"][0].view(90, H)[ring] = torch.from_numpy(hm); t["org_hm_n"][0] = torch.tensor([pop + len(hm), pop], dtype=torch.int32)
+    th = g("th1"); t["org_th"][0].view(MEMROWS, H)[: len(th)] = torch.from_numpy(th); t["org_th_n"][0] = len(th)
+    L = omod.lib(); L.ow_inherit_recurrent.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]; L.ow_inherit_recurrent.restype = None
+    s = w.struct(); L.ow_inherit_recurrent(ctypes.byref(s), 0, 1)
+    hn = w.np("org_hm_n")[1]
+    assert (int(hn[0]), int(hn[1])) == (min(n_hm, 60), 0)
+    np.testing.assert_array_equal(w.np("org_hm")[1].reshape(90, H)[: int(hn[0])], g("child_hm")[: int(hn[0])])
+    assert int(w.np("org_th_n")[1]) == min(n_th, MEMROWS)
+    np.testing.assert_array_equal(w.np("org_th")[1].reshape(MEMROWS, H)[: min(n_th, MEMROWS)], g("child_th"))
+
+
 def test_one_decimal_keys_follow_python_round(oracle):
     """roundList(x, 1) on the doubles the reference actually holds: fp32 values from tensor.tolist() (short-term memory)
     and round(x, 3) results (stored memory). neural.py:77-78, :375-393."""
