@@ -213,3 +213,24 @@ def test_use_rnn_switch_builds_recurrent_brains(oracle):
     env.engine.tick(3); env.engine.synchronize()
     assert oracle.tick(host, PH_ALL, 3) == 0
     compare_worlds(env.world, host, "three ticks of a mixed RNN / feed-forward world", verbose=False)
+
+
+def test_recurrent_state_arrays_are_reserved_on_demand():
+    """A world built without RNN brains carries empty recurrent-state arrays (per = RNNH of include/sapio_fields.def); World.reserve_rnn gives
+    them their columns once -- what Environment.info["use_rnn"] = True does the first time -- and the hidden size is fixed from then on."""
+    from sapiogenesis_b200.world import FIELDS, HM, MEMROWS, RNN_MAXH, World, default_params
+    w = World(default_params(n_org=8, n_dead=8))
+    rnn_fields = [f.name for f in FIELDS if "RNNH" in f.per]
+    assert set(rnn_fields) == {"org_last_hidden", "org_hm", "org_th"} and all(w.t[n].numel() == 0 for n in rnn_fields)
+    assert w.p.rnn_cap == 0 and w.p.rnn_hidden == 0 and w.t["org_rnn_h"].shape == (8,) and w.t["org_mem_seq"].shape == (8, MEMROWS)
+    w.reserve_rnn(6)
+    assert w.p.rnn_cap == 6 and w.t["org_last_hidden"].shape == (8, 6) and w.t["org_hm"].shape == (8, HM * 6) and w.t["org_th"].shape == (8, MEMROWS * 6)
+    w.reserve_rnn(6)                                         # idempotent
+    with pytest.raises(ValueError):
+        w.reserve_rnn(5)
+    with pytest.raises(ValueError):
+        World(default_params(n_org=8, n_dead=8)).reserve_rnn(RNN_MAXH + 1)
+    s = w.struct()                                           # the C struct sees the new buffers
+    assert s.p.rnn_cap == 6 and s.org_hm == w.t["org_hm"].data_ptr()
+    w2 = World(default_params(n_org=8, n_dead=8, rnn_hidden=4))
+    assert w2.p.rnn_cap == 4 and w2.p.rnn_hidden == 4 and w2.t["org_th"].shape == (8, MEMROWS * 4)
