@@ -111,7 +111,7 @@ def test_aged_world_tick_matches_oracle(oracle, aged_world):
     assert s0["xcontacts"] > 4096, "the aged world must hold more cross contacts than one CTA relaxes"
     assert s0["coupled"] > 2400, "the aged world must load the coupled pass"
     assert int(w.t["org_mem_n"].max()) >= w.p.memory_limit
-    for k in range(4):
+    for k in range(2):                                                        # two parity ticks 17 apart (33 s each, most of it the oracle's brute-force sensors)
         # Crowded and violent: dead bodies shot out of deep overlaps at 500 px/s against a field rms of 30, organisms whose cells change
         # their velocity by 250 px/s within the tick. An fp32 solver resolves those to an ulp of the LOCAL velocity scale (measured:
         # the worst body is off by 1.1e-5 of the velocity change of its own organism, tools/debug_aged.py), which is 1e-4 of the
