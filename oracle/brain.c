@@ -67,11 +67,71 @@ static int key_mem(float x) { return oracle_key1(stored_value(x)); }
  * cells not descended from this organism (eye_segment_handler, sprites.py:221-236; contract C3). Calls cb per member in
  * ascending body id. Predicate in double on fp32 positions, strict (SURVEY A-3). */
 typedef void (*view_cb)(void *ctx, uint32_t body, double x, double y, double r, int alive);
+
+/* Candidate index for the sensors of one rules phase (oracle_rules builds it, uses it and drops it): the bounding box of every living
+ * organism and the dead cells bucketed in a coarse grid. Nothing the index is built from changes during the phase (positions move in
+ * Space.step, dead cells are created in settle; a cell that dies becomes DYING, not absent), every candidate still goes through the exact
+ * predicate below, and eye / olfactory encodings are maxima over the view (order-free): results are bit-identical to the full scan, which
+ * stays the path of every call outside a rules phase (think_now, the sensor-view probe) and of ORACLE_BRUTE=1. At 100k organisms the full
+ * scan is 1e11 predicate evaluations per tick. */
+#define VI_CELL 1024.0
+typedef struct { const SapioWorld *w; double *bb; int gnx, gny; int *dstart; int *dlist; double rmax; } ViewIndex;
+static ViewIndex g_vi = {0};
+void oracle_view_index_drop(void) { free(g_vi.bb); free(g_vi.dstart); free(g_vi.dlist); memset(&g_vi, 0, sizeof(g_vi)); }
+static int vi_cell(double v, int n) { int c = (int)floor(v / VI_CELL); return c < 0 ? 0 : (c >= n ? n - 1 : c); }
+void oracle_view_index_build(const SapioWorld *w) {
+    oracle_view_index_drop();
+    const char *brute = getenv("ORACLE_BRUTE");
+    if (brute && brute[0] == '1') return;
+    const SapioParams *p = &w->p;
+    g_vi.bb = (double *)malloc(sizeof(double) * 4 * (size_t)(p->n_org > 0 ? p->n_org : 1));
+    for (int o = 0; o < p->n_org; o++) {
+        double *b = g_vi.bb + 4 * (size_t)o;
+        b[0] = b[1] = INFINITY; b[2] = b[3] = -INFINITY;
+        if (w->org_state[o] != 1) continue;
+        for (int k = 0; k < w->org_ncells[o]; k++) {
+            int r2 = o * MAXC + k;
+            if (w->c_alive[r2] == 0) continue;
+            double x = w->c_pos[2 * r2], y = w->c_pos[2 * r2 + 1], rad = w->c_size[r2] * 0.5;
+            if (x - rad < b[0]) b[0] = x - rad;
+            if (y - rad < b[1]) b[1] = y - rad;
+            if (x + rad > b[2]) b[2] = x + rad;
+            if (y + rad > b[3]) b[3] = y + rad;
+        }
+    }
+    double xmax = p->width, ymax = p->height;
+    if (p->slab_mode && p->slab_x1 > xmax) xmax = p->slab_x1;
+    g_vi.gnx = (int)ceil((xmax > 0 ? xmax : 1.0) / VI_CELL) + 1; g_vi.gny = (int)ceil((ymax > 0 ? ymax : 1.0) / VI_CELL) + 1;
+    const size_t ng = (size_t)g_vi.gnx * g_vi.gny;
+    g_vi.dstart = (int *)calloc(ng + 1, sizeof(int));
+    g_vi.dlist = (int *)malloc(sizeof(int) * (size_t)(p->n_dead > 0 ? p->n_dead : 1));
+    g_vi.rmax = 0;
+    for (int d = 0; d < p->n_dead; d++) {
+        if (!w->d_state[d]) continue;
+        g_vi.dstart[(size_t)vi_cell(w->d_pos[2 * d + 1], g_vi.gny) * g_vi.gnx + vi_cell(w->d_pos[2 * d], g_vi.gnx) + 1]++;
+        double rad = w->d_size[d] * 0.5; if (rad > g_vi.rmax) g_vi.rmax = rad;
+    }
+    for (size_t c = 0; c < ng; c++) g_vi.dstart[c + 1] += g_vi.dstart[c];
+    int *fill = (int *)malloc(sizeof(int) * (ng + 1));
+    memcpy(fill, g_vi.dstart, sizeof(int) * (ng + 1));
+    for (int d = 0; d < p->n_dead; d++) {
+        if (!w->d_state[d]) continue;
+        g_vi.dlist[fill[(size_t)vi_cell(w->d_pos[2 * d + 1], g_vi.gny) * g_vi.gnx + vi_cell(w->d_pos[2 * d], g_vi.gnx)]++] = d;
+    }
+    free(fill);
+    g_vi.w = w;
+}
+
 static void for_each_viewed(const SapioWorld *w, int o, int row, double R, view_cb cb, void *ctx) {
     const SapioParams *p = &w->p;
     double sx = w->c_spos[2 * row], sy = w->c_spos[2 * row + 1];
+    const int indexed = g_vi.w == w && g_vi.bb != NULL;
     for (int oo = 0; oo < p->n_org; oo++) {
         if (oo == o || w->org_state[oo] != 1) continue;
+        if (indexed) {                                                          /* the disc cannot reach the organism's box */
+            const double *b = g_vi.bb + 4 * (size_t)oo;
+            if (sx + R < b[0] || sx - R > b[2] || sy + R < b[1] || sy - R > b[3]) continue;
+        }
         for (int k = 0; k < w->org_ncells[oo]; k++) {
             int r2 = oo * MAXC + k;
             if (w->c_alive[r2] == 0) continue;
@@ -79,6 +139,19 @@ static void for_each_viewed(const SapioWorld *w, int o, int row, double R, view_
             double dx = x - sx, dy = y - sy, md = R + rad;
             if (dx * dx + dy * dy < md * md) cb(ctx, (uint32_t)r2, x, y, rad, 1);
         }
+    }
+    if (indexed) {
+        const double reach = R + g_vi.rmax;
+        const int cx0 = vi_cell(sx - reach, g_vi.gnx), cx1 = vi_cell(sx + reach, g_vi.gnx), cy0 = vi_cell(sy - reach, g_vi.gny), cy1 = vi_cell(sy + reach, g_vi.gny);
+        for (int cy = cy0; cy <= cy1; cy++)
+            for (int q = g_vi.dstart[(size_t)cy * g_vi.gnx + cx0], e = g_vi.dstart[(size_t)cy * g_vi.gnx + cx1 + 1]; q < e; q++) {
+                const int d = g_vi.dlist[q];
+                if (!w->d_state[d] || w->d_owner[d] == w->org_uid[o]) continue;
+                double x = w->d_pos[2 * d], y = w->d_pos[2 * d + 1], rad = w->d_size[d] * 0.5;
+                double dx = x - sx, dy = y - sy, md = R + rad;
+                if (dx * dx + dy * dy < md * md) cb(ctx, (uint32_t)(p->n_org * MAXC + d), x, y, rad, 0);
+            }
+        return;
     }
     for (int d = 0; d < p->n_dead; d++) {
         if (!w->d_state[d] || w->d_owner[d] == w->org_uid[o]) continue;

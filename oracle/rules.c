@@ -260,13 +260,17 @@ static void org_update(SapioWorld *w, int o, uint32_t phases, double *co2, doubl
     org_store(w, &g);
 }
 
+void oracle_view_index_build(const SapioWorld *w);
+void oracle_view_index_drop(void);
 int oracle_rules(SapioWorld *w, uint32_t phases) {
     double co2 = w->g_co2[0], o2 = w->g_o2[0], refund = 0;
+    if (phases & SAPIO_PH_THINK) oracle_view_index_build(w);                   /* candidates for this phase's sensors (brain.c) */
     for (int o = 0; o < w->p.n_org; o++) {
         if (w->org_state[o] != 1) continue;
         org_update(w, o, phases, &co2, &o2);
         refund += w->org_gas_refund[o];
     }
+    oracle_view_index_drop();
     co2 += refund; o2 -= refund;                                              /* contract C4: refunds at the end of the phase */
     w->g_co2[0] = co2; w->g_o2[0] = o2;
     return 0;
@@ -280,25 +284,51 @@ int oracle_settle(SapioWorld *w) {
     const uint32_t NC = (uint32_t)p->n_org * MAXC, ND = (uint32_t)p->n_dead;
     const double dt = p->dt_wall;
     int rc = 0;
-    /* C2: gather per victim, attackers in ascending body id == ascending position in the sorted contact list per victim */
-    for (uint32_t v = 0; v < NC + ND; v++) {
-        if (v < NC) { if (w->c_alive[v] != SAPIO_CELL_ALIVE) continue; }
-        else if (!w->d_state[v - NC]) continue;
-        double sum = 0; int hit = 0;
-        /* two passes keep attacker-id order: partners with smaller id first (they appear as `a`), then larger ones */
-        for (int pass = 0; pass < 2; pass++)
-            for (int c = 0; c < w->g_x_n[0]; c++) {
-                uint32_t a = (uint32_t)(w->x_key[c] >> 32), b = (uint32_t)(w->x_key[c] & 0xFFFFFFFFu), att;
-                if (pass == 0 && b == v) att = a; else if (pass == 1 && a == v) att = b; else continue;
-                if (att >= NC || w->c_alive[att] != SAPIO_CELL_ALIVE || w->c_type[att] != SAPIO_T_CARNIV) continue;
-                if (v < NC && att / MAXC == v / MAXC) continue;
-                if (v < NC) sum += (double)w->c_damage[att];
-                else sum += (double)w->c_damage[att] / (double)w->c_size[att];           /* sprites.py:1505 */
+    /* C2: gather per victim, attackers in ascending body id. The contact list is sorted by (a, b): for a victim v the partners with a
+     * smaller id are the `a` of the contacts with b == v, in list order, followed by the `b` of the contacts with a == v, in list order.
+     * Both runs are laid out per victim first (counting sort over the contacts), so the sums run over the same terms in the same order
+     * as a scan of the whole list per victim would -- without its bodies x contacts cost. */
+    {
+        const int nx = w->g_x_n[0];
+        const uint32_t NBody = NC + ND;
+        int *off = (int *)calloc((size_t)NBody + 2, sizeof(int));
+        uint32_t *att = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(2 * (nx > 0 ? nx : 1)));
+        /* slots per victim: first its smaller partners, then its larger ones */
+        for (int c = 0; c < nx; c++) {
+            uint32_t a = (uint32_t)(w->x_key[c] >> 32), b = (uint32_t)(w->x_key[c] & 0xFFFFFFFFu);
+            if (b < NBody) off[b + 1]++;
+            if (a < NBody) off[a + 1]++;
+        }
+        for (uint32_t v = 0; v < NBody; v++) off[v + 1] += off[v];
+        int *fill = (int *)malloc(sizeof(int) * ((size_t)NBody + 1));
+        memcpy(fill, off, sizeof(int) * ((size_t)NBody + 1));
+        for (int c = 0; c < nx; c++) {                                                   /* smaller partners, in list order */
+            uint32_t a = (uint32_t)(w->x_key[c] >> 32), b = (uint32_t)(w->x_key[c] & 0xFFFFFFFFu);
+            if (b < NBody) att[fill[b]++] = a;
+        }
+        for (int c = 0; c < nx; c++) {                                                   /* then the larger ones, in list order */
+            uint32_t a = (uint32_t)(w->x_key[c] >> 32), b = (uint32_t)(w->x_key[c] & 0xFFFFFFFFu);
+            if (a < NBody) att[fill[a]++] = b;
+        }
+        free(fill);
+        for (uint32_t v = 0; v < NBody; v++) {
+            if (off[v] == off[v + 1]) continue;
+            if (v < NC) { if (w->c_alive[v] != SAPIO_CELL_ALIVE) continue; }
+            else if (!w->d_state[v - NC]) continue;
+            double sum = 0; int hit = 0;
+            for (int q = off[v]; q < off[v + 1]; q++) {
+                const uint32_t at = att[q];
+                if (at >= NC || w->c_alive[at] != SAPIO_CELL_ALIVE || w->c_type[at] != SAPIO_T_CARNIV) continue;
+                if (v < NC && at / MAXC == v / MAXC) continue;
+                if (v < NC) sum += (double)w->c_damage[at];
+                else sum += (double)w->c_damage[at] / (double)w->c_size[at];             /* sprites.py:1505 */
                 hit = 1;
             }
-        if (!hit) continue;
-        if (v < NC) { if (w->c_type[v] != SAPIO_T_BARRIER) w->c_health[v] = (float)((double)w->c_health[v] - sum); }
-        else { double m = (double)w->d_mass[v - NC] - sum; w->d_mass[v - NC] = (float)(m > 0 ? m : 0); }
+            if (!hit) continue;
+            if (v < NC) { if (w->c_type[v] != SAPIO_T_BARRIER) w->c_health[v] = (float)((double)w->c_health[v] - sum); }
+            else { double m = (double)w->d_mass[v - NC] - sum; w->d_mass[v - NC] = (float)(m > 0 ? m : 0); }
+        }
+        free(off); free(att);
     }
     /* deaths -> dead pool: the j-th dying cell in (organism, row) order takes the j-th smallest free slot */
     uint32_t next_free = 0;
