@@ -157,7 +157,7 @@ def run_reference(args):
     n_org, ticks = args.ref_organisms, args.ref_ticks or 2
     v, step_s, cores = cpu_islands(n_org, args.warmup, args.steps, ticks)
     total_t = sum(step_s)
-    sample = (f"{cores} independent worlds (one per host core) x {n_org} organisms x {ticks} ticks per step, oracle/ C restatement of the reference "
+    sample = (f"{cores} independent worlds (one per host core) x {n_org} organisms x {ticks} ticks per step, oracle/ C restatement of the reference with indexed sensor candidates and per-victim contact lists "
               f"(pymunk/Chipmunk not installable: DESIGN.md)")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
