@@ -76,7 +76,7 @@ typedef void (*view_cb)(void *ctx, uint32_t body, double x, double y, double r, 
  * scan is 1e11 predicate evaluations per tick. */
 #define VI_CELL 1024.0
 typedef struct { const SapioWorld *w; double *bb; int gnx, gny; int *dstart; int *dlist; double rmax; } ViewIndex;
-static ViewIndex g_vi = {0};
+static __thread ViewIndex g_vi = {0};       /* per thread: independent worlds may be ticked from several threads of one process */
 void oracle_view_index_drop(void) { free(g_vi.bb); free(g_vi.dstart); free(g_vi.dlist); memset(&g_vi, 0, sizeof(g_vi)); }
 static int vi_cell(double v, int n) { int c = (int)floor(v / VI_CELL); return c < 0 ? 0 : (c >= n ? n - 1 : c); }
 void oracle_view_index_build(const SapioWorld *w) {
